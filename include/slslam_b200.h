@@ -1,0 +1,140 @@
+/* slslam_b200 — C ABI of the B200-native LBA / PO solver.
+ *
+ * This is the drop-in boundary: what the reference does inside `ceres::Solve(options, &problem, &summary)`
+ * for an LBAProblem (reference src/slam.cpp:663, 944) or a POProblem (reference src/slam.cpp:1293) is one call
+ * here.  Plain pointers and sizes only; no C++/torch types.  The reference-facing C++ classes
+ * (include/lba_problem.h, include/po_problem.h, include/ceres/ceres.h) are thin wrappers over these calls;
+ * see INTEGRATION.md.
+ *
+ * There is NO CPU fallback: every solve entry point returns SLSLAM_ERR_CUDA when no sm_100 device is usable.
+ * Never throws.  On any error `params_inout` is left untouched.
+ */
+#ifndef SLSLAM_B200_H_
+#define SLSLAM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  SLSLAM_OK = 0,
+  SLSLAM_ERR_INVALID = -1,      /* null pointer, negative size, index out of range */
+  SLSLAM_ERR_UNSUPPORTED = -2,  /* problem exceeds a kernel limit (see slslam_lba_limits) */
+  SLSLAM_ERR_CUDA = -3,         /* no device / CUDA runtime error (message via slslam_last_error) */
+  SLSLAM_ERR_NUMERICAL = -4     /* non-finite input parameters */
+};
+
+/* Solver::Summary::termination_type as far as this path can produce it (Ceres 1.7.0 names). */
+enum {
+  SLSLAM_NO_CONVERGENCE = 0,      /* max_num_iterations reached */
+  SLSLAM_GRADIENT_TOLERANCE = 1,
+  SLSLAM_FUNCTION_TOLERANCE = 2,
+  SLSLAM_PARAMETER_TOLERANCE = 3,
+  SLSLAM_NUMERICAL_FAILURE = 4    /* max_num_consecutive_invalid_steps reached */
+};
+
+/* One LBA window: the arrays LBAProblem holds (reference src/lba_problem.h:188-196, filled at
+ * src/slam.cpp:899-920) plus the constants that are literals in the reference.  Borrowed, never freed. */
+typedef struct slslam_lba_desc {
+  int32_t num_cameras;            /* lba_param_t::num_cameras       (lba_problem.h:123-130) */
+  int32_t num_lines;              /* lba_param_t::num_lines */
+  int32_t num_observations;       /* lba_param_t::num_observations */
+  int32_t max_iterations;         /* lba_param_t::num_iterations -> Solver::Options::max_num_iterations (lba_problem.cpp:124) */
+  const int32_t* camera_index;    /* [N]   LBAProblem::camera_index() */
+  const int32_t* line_index;      /* [N]   LBAProblem::line_index() */
+  const int32_t* fixed_index;     /* [2N]  [2i] camera constant, [2i+1] line constant; sticky per block (lba_problem.cpp:88-91) */
+  const double* observations;     /* [8N]  normalised endpoints x0 y0 x1 y1 (cam A)  x2 y2 x3 y3 (cam B) */
+  int32_t robust;                 /* FLAGS_robust (lba_problem.cpp:35): HuberLoss on the squared norm of the 4-vector */
+  double huber_delta;             /* 1/406.05 at lba_problem.cpp:78-80; <= 0 selects that default */
+  double baseline;                /* 0.12 literal at lba_problem.h:101; < 0 selects that default */
+  /* Ceres 1.7.0 Solver::Options the reference leaves at their defaults; a value <= 0 selects the default
+   * (1e-6, 1e-10, 1e-8, 1e4).  Pass a tiny positive number (e.g. 1e-300) to disable a tolerance. */
+  double function_tolerance;
+  double gradient_tolerance;
+  double parameter_tolerance;
+  double initial_trust_region_radius;
+} slslam_lba_desc;
+
+/* One pose graph: the arrays POProblem holds (reference src/po_problem.h:139-143, filled at src/slam.cpp:1261-1287). */
+typedef struct slslam_po_desc {
+  int32_t num_poses;              /* number of 6-vectors in the parameter array (kfs.size(), slam.cpp:1264) */
+  int32_t num_edges;              /* POProblem::num_size() */
+  int32_t max_iterations;         /* POProblem ctor arg n (=10 at slam.cpp:1283) */
+  const int32_t* pose_index_1;    /* [E] */
+  const int32_t* pose_index_2;    /* [E] */
+  const double* constraints;      /* [6E] measured T_{2<-1} as (angle-axis, t) */
+  double function_tolerance, gradient_tolerance, parameter_tolerance, initial_trust_region_radius;
+} slslam_po_desc;
+
+/* The fields of ceres::Solver::Summary the reference reads (src/slam.cpp:949-952) plus diagnostics. */
+typedef struct slslam_summary {
+  double initial_cost;            /* 1/2 sum rho, includes residual blocks whose parameter blocks are all constant */
+  double final_cost;
+  double fixed_cost;              /* the part contributed by all-constant residual blocks */
+  double gradient_max_norm;       /* max |J^T r| at the last linearisation */
+  int32_t num_successful_steps;
+  int32_t num_unsuccessful_steps;
+  int32_t termination_type;
+  int32_t iterations;             /* linear solves performed = successful + unsuccessful (+1 if stopped by a tolerance) */
+} slslam_summary;
+
+/* Per-iteration record, SLSLAM_TRACE_WIDTH doubles:
+ * cost, trial_cost, model_cost_change, radius, step_norm, accepted(1/0/-1 invalid), gradient_max_norm, relative_decrease */
+#define SLSLAM_TRACE_WIDTH 8
+
+typedef struct slslam_lba_limits {
+  int32_t max_cameras;            /* parameter blocks, free + constant */
+  int32_t max_free_cameras;       /* reduced camera system is 6*max_free_cameras square */
+  int32_t max_observations_per_line;
+  int32_t max_cluster_size;
+} slslam_lba_limits;
+
+int slslam_version(void);
+const char* slslam_strerror(int code);
+const char* slslam_last_error(void);          /* thread-local detail for the last SLSLAM_ERR_CUDA */
+int slslam_device_count(void);                /* usable sm_100 devices; 0 means every solve call fails */
+void slslam_lba_get_limits(slslam_lba_limits* out);
+
+/* ---- what replaces ceres::Solve for one LBAProblem: H2D, device LM loop, D2H; parameters updated in place ---- */
+int slslam_lba_solve(const slslam_lba_desc* desc, double* params_inout, slslam_summary* summary_out);
+
+/* Independent windows in one launch (one thread-block cluster per window).  params_inout[i] has 6C_i+4L_i doubles. */
+int slslam_lba_solve_batch(int32_t n, const slslam_lba_desc* descs, double* const* params_inout,
+                           slslam_summary* summaries_out);
+
+/* ---- device-resident form: plan + upload once, solve any number of times from the uploaded initial guess ---- */
+typedef struct slslam_lba_batch slslam_lba_batch;
+/* cluster_size 0 = choose automatically; device < 0 = current device. */
+int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const double* const* params,
+                            int32_t device, int32_t cluster_size, slslam_lba_batch** out);
+/* Enqueue one solve of every window on `cuda_stream` (a cudaStream_t, may be NULL); asynchronous. */
+int slslam_lba_batch_solve(slslam_lba_batch* b, void* cuda_stream);
+/* Re-upload the initial parameters of every window (H2D only; same sizes as at creation). */
+int slslam_lba_batch_upload_params(slslam_lba_batch* b, const double* const* params, void* cuda_stream);
+/* Synchronise with `cuda_stream` and copy results back.  Any of the output pointers may be NULL.
+ * trace_out[i] receives max_iterations_i * SLSLAM_TRACE_WIDTH doubles. */
+int slslam_lba_batch_download(slslam_lba_batch* b, void* cuda_stream, double* const* params_out,
+                              slslam_summary* summaries_out, double* const* trace_out);
+int slslam_lba_batch_info(const slslam_lba_batch* b, int32_t* cluster_size, int32_t* threads_per_cta,
+                          int32_t* smem_bytes_per_cta, int32_t* z_in_smem);
+void slslam_lba_batch_destroy(slslam_lba_batch* b);
+
+/* ---- K1 alone: residuals (Huber-unscaled) and analytic Jacobians of every observation, for parity tests ----
+ * residuals [4N]; jac_camera [24N] row-major 4x6; jac_line [16N] row-major 4x4; cost_out = 1/2 sum rho. */
+int slslam_lba_evaluate(const slslam_lba_desc* desc, const double* params, double* residuals, double* jac_camera,
+                        double* jac_line, double* cost_out);
+
+/* ---- what replaces ceres::Solve for one POProblem ---- */
+int slslam_po_solve(const slslam_po_desc* desc, double* poses_inout, slslam_summary* summary_out);
+int slslam_po_solve_trace(const slslam_po_desc* desc, double* poses_inout, slslam_summary* summary_out,
+                          double* trace_out);
+/* residuals [6E], jac_pose1 / jac_pose2 [36E] row-major 6x6 */
+int slslam_po_evaluate(const slslam_po_desc* desc, const double* poses, double* residuals, double* jac_pose1,
+                       double* jac_pose2, double* cost_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLSLAM_B200_H_ */

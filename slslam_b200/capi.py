@@ -1,0 +1,248 @@
+"""ctypes binding of libslslam_b200.so (the C ABI in include/slslam_b200.h).
+
+Used by tests/, bench.py and __graft_entry__.py.  It only marshals numpy arrays into the C structs: no arithmetic
+of the hot path lives here, and there is no fallback — if the library is missing or no sm_100 device is present the
+calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libslslam_b200.so")
+TRACE_WIDTH = 8
+TERMINATION = {0: "NO_CONVERGENCE", 1: "GRADIENT_TOLERANCE", 2: "FUNCTION_TOLERANCE", 3: "PARAMETER_TOLERANCE",
+               4: "NUMERICAL_FAILURE"}
+
+EXPORTS = [
+    "slslam_version", "slslam_strerror", "slslam_last_error", "slslam_device_count", "slslam_lba_get_limits",
+    "slslam_lba_solve", "slslam_lba_solve_batch", "slslam_lba_batch_create", "slslam_lba_batch_solve",
+    "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_destroy",
+    "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate",
+]
+
+dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+
+
+class LbaDesc(C.Structure):
+    _fields_ = [("num_cameras", C.c_int32), ("num_lines", C.c_int32), ("num_observations", C.c_int32),
+                ("max_iterations", C.c_int32), ("camera_index", ip), ("line_index", ip), ("fixed_index", ip),
+                ("observations", dp), ("robust", C.c_int32), ("huber_delta", C.c_double), ("baseline", C.c_double),
+                ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
+                ("parameter_tolerance", C.c_double), ("initial_trust_region_radius", C.c_double)]
+
+
+class PoDesc(C.Structure):
+    _fields_ = [("num_poses", C.c_int32), ("num_edges", C.c_int32), ("max_iterations", C.c_int32),
+                ("pose_index_1", ip), ("pose_index_2", ip), ("constraints", dp),
+                ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
+                ("parameter_tolerance", C.c_double), ("initial_trust_region_radius", C.c_double)]
+
+
+class Summary(C.Structure):
+    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double), ("fixed_cost", C.c_double),
+                ("gradient_max_norm", C.c_double), ("num_successful_steps", C.c_int32),
+                ("num_unsuccessful_steps", C.c_int32), ("termination_type", C.c_int32), ("iterations", C.c_int32)]
+
+
+class Limits(C.Structure):
+    _fields_ = [("max_cameras", C.c_int32), ("max_free_cameras", C.c_int32),
+                ("max_observations_per_line", C.c_int32), ("max_cluster_size", C.c_int32)]
+
+
+class SlslamError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        super().__init__(f"slslam error {code}: {detail}")
+
+
+_LIB = None
+
+
+def build_library(force: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a build of the in-tree shared library (cross-compiles without a GPU)."""
+    args = ["make", "-C", _HERE, "-s", "libslslam_b200.so"]
+    if force:
+        args.append("-B")
+    subprocess.check_call(args, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise SlslamError(-3, f"{LIB_PATH} is not built (run __graft_entry__.build()); there is no fallback path")
+        L = C.CDLL(LIB_PATH)
+        L.slslam_version.restype = C.c_int
+        L.slslam_strerror.restype = C.c_char_p
+        L.slslam_strerror.argtypes = [C.c_int]
+        L.slslam_last_error.restype = C.c_char_p
+        L.slslam_device_count.restype = C.c_int
+        L.slslam_lba_get_limits.argtypes = [C.POINTER(Limits)]
+        L.slslam_lba_solve.argtypes = [C.POINTER(LbaDesc), dp, C.POINTER(Summary)]
+        L.slslam_lba_solve_batch.argtypes = [C.c_int32, C.POINTER(LbaDesc), C.POINTER(dp), C.POINTER(Summary)]
+        L.slslam_lba_batch_create.argtypes = [C.c_int32, C.POINTER(LbaDesc), C.POINTER(dp), C.c_int32, C.c_int32,
+                                              C.POINTER(C.c_void_p)]
+        L.slslam_lba_batch_solve.argtypes = [C.c_void_p, C.c_void_p]
+        L.slslam_lba_batch_upload_params.argtypes = [C.c_void_p, C.POINTER(dp), C.c_void_p]
+        L.slslam_lba_batch_download.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(dp), C.POINTER(Summary), C.POINTER(dp)]
+        L.slslam_lba_batch_info.argtypes = [C.c_void_p, ip, ip, ip, ip]
+        L.slslam_lba_batch_destroy.argtypes = [C.c_void_p]
+        L.slslam_lba_batch_destroy.restype = None
+        L.slslam_lba_evaluate.argtypes = [C.POINTER(LbaDesc), dp, dp, dp, dp, dp]
+        L.slslam_po_solve.argtypes = [C.POINTER(PoDesc), dp, C.POINTER(Summary)]
+        L.slslam_po_solve_trace.argtypes = [C.POINTER(PoDesc), dp, C.POINTER(Summary), dp]
+        L.slslam_po_evaluate.argtypes = [C.POINTER(PoDesc), dp, dp, dp, dp, dp]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        L = lib()
+        raise SlslamError(rc, f"{L.slslam_strerror(rc).decode()} [{L.slslam_last_error().decode()}]")
+
+
+def _d(a):
+    return a.ctypes.data_as(dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(ip)
+
+
+class _Keep:
+    """A desc plus the numpy arrays it points into."""
+
+    def __init__(self, desc, arrays):
+        self.desc, self.arrays = desc, arrays
+
+
+def lba_desc(w, max_iters=10, robust=True, huber_delta=0.0, baseline=-1.0, lm_opts=None) -> _Keep:
+    ci = np.ascontiguousarray(w.camera_index, np.int32)
+    li = np.ascontiguousarray(w.line_index, np.int32)
+    fi = np.ascontiguousarray(w.fixed_index, np.int32)
+    ob = np.ascontiguousarray(w.observations, np.float64)
+    o = [0.0, 0.0, 0.0, 0.0] if lm_opts is None else list(lm_opts)
+    d = LbaDesc(w.num_cameras, w.num_lines, int(ci.shape[0]), max_iters, _i(ci), _i(li), _i(fi), _d(ob), int(robust),
+                huber_delta, baseline, o[0], o[1], o[2], o[3])
+    return _Keep(d, (ci, li, fi, ob))
+
+
+def summary_dict(s: Summary, trace=None):
+    d = dict(initial_cost=s.initial_cost, final_cost=s.final_cost, fixed_cost=s.fixed_cost,
+             gradient_max_norm=s.gradient_max_norm, num_successful_steps=s.num_successful_steps,
+             num_unsuccessful_steps=s.num_unsuccessful_steps, termination=TERMINATION.get(s.termination_type, "?"),
+             iterations=s.iterations)
+    if trace is not None:
+        d["trace"] = trace[:s.iterations].copy()
+    return d
+
+
+def lba_solve(w, params=None, **kw):
+    """One window through slslam_lba_solve (host buffers in, host buffers out)."""
+    k = lba_desc(w, **kw)
+    p = np.ascontiguousarray(w.parameters if params is None else params, np.float64).copy()
+    s = Summary()
+    _check(lib().slslam_lba_solve(C.byref(k.desc), _d(p), C.byref(s)))
+    return p, summary_dict(s)
+
+
+def lba_solve_batch(windows, **kw):
+    keeps = [lba_desc(w, **kw) for w in windows]
+    descs = (LbaDesc * len(windows))(*[k.desc for k in keeps])
+    ps = [np.ascontiguousarray(w.parameters, np.float64).copy() for w in windows]
+    pp = (dp * len(windows))(*[_d(p) for p in ps])
+    ss = (Summary * len(windows))()
+    _check(lib().slslam_lba_solve_batch(len(windows), descs, pp, ss))
+    return ps, [summary_dict(s) for s in ss]
+
+
+class LbaBatch:
+    """Device-resident batch: plan + upload once, solve many times (slslam_lba_batch_*)."""
+
+    def __init__(self, windows, device=-1, cluster_size=0, **kw):
+        self.windows = list(windows)
+        self.n = len(self.windows)
+        self._keeps = [lba_desc(w, **kw) for w in self.windows]
+        self._descs = (LbaDesc * self.n)(*[k.desc for k in self._keeps])
+        self._p0 = [np.ascontiguousarray(w.parameters, np.float64) for w in self.windows]
+        pp = (dp * self.n)(*[_d(p) for p in self._p0])
+        self._h = C.c_void_p()
+        _check(lib().slslam_lba_batch_create(self.n, self._descs, pp, device, cluster_size, C.byref(self._h)))
+        self.max_iters = [k.desc.max_iterations for k in self._keeps]
+
+    def info(self):
+        a, b, c, d = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        _check(lib().slslam_lba_batch_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(cluster_size=a.value, threads_per_cta=b.value, smem_bytes_per_cta=c.value, z_in_smem=d.value)
+
+    def upload(self, params=None, stream=None):
+        ps = self._p0 if params is None else [np.ascontiguousarray(p, np.float64) for p in params]
+        pp = (dp * self.n)(*[_d(p) for p in ps])
+        _check(lib().slslam_lba_batch_upload_params(self._h, pp, C.c_void_p(stream)))
+
+    def solve(self, stream=None):
+        _check(lib().slslam_lba_batch_solve(self._h, C.c_void_p(stream)))
+
+    def download(self, stream=None, trace=False):
+        ps = [np.zeros(6 * w.num_cameras + 4 * w.num_lines) for w in self.windows]
+        pp = (dp * self.n)(*[_d(p) for p in ps])
+        ss = (Summary * self.n)()
+        trs = [np.zeros((max(1, m), TRACE_WIDTH)) for m in self.max_iters]
+        tp = (dp * self.n)(*[_d(t) for t in trs]) if trace else None
+        _check(lib().slslam_lba_batch_download(self._h, C.c_void_p(stream), pp, ss, tp))
+        return ps, [summary_dict(s, trs[i] if trace else None) for i, s in enumerate(ss)]
+
+    def close(self):
+        if self._h:
+            lib().slslam_lba_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def lba_evaluate(w, params=None, robust=True):
+    k = lba_desc(w, robust=robust)
+    p = np.ascontiguousarray(w.parameters if params is None else params, np.float64)
+    N = w.num_observations
+    r, Jc, Jl = np.zeros((N, 4)), np.zeros((N, 4, 6)), np.zeros((N, 4, 4))
+    cost = C.c_double()
+    _check(lib().slslam_lba_evaluate(C.byref(k.desc), _d(p), _d(r), _d(Jc), _d(Jl), C.cast(C.byref(cost), dp)))
+    return r, Jc, Jl, cost.value
+
+
+def po_desc(g, max_iters=10, lm_opts=None) -> _Keep:
+    a = np.ascontiguousarray(g.pose_index_1, np.int32)
+    b = np.ascontiguousarray(g.pose_index_2, np.int32)
+    c = np.ascontiguousarray(g.constraints, np.float64)
+    o = [0.0, 0.0, 0.0, 0.0] if lm_opts is None else list(lm_opts)
+    return _Keep(PoDesc(g.num_poses, int(a.shape[0]), max_iters, _i(a), _i(b), _d(c), o[0], o[1], o[2], o[3]), (a, b, c))
+
+
+def po_solve(g, params=None, max_iters=10, lm_opts=None):
+    k = po_desc(g, max_iters, lm_opts)
+    p = np.ascontiguousarray(g.parameters if params is None else params, np.float64).copy()
+    s = Summary()
+    tr = np.zeros((max(1, max_iters), TRACE_WIDTH))
+    _check(lib().slslam_po_solve_trace(C.byref(k.desc), _d(p), C.byref(s), _d(tr)))
+    return p, summary_dict(s, tr)
+
+
+def po_evaluate(g, params=None):
+    k = po_desc(g)
+    p = np.ascontiguousarray(g.parameters if params is None else params, np.float64)
+    E = g.num_edges
+    r, J1, J2 = np.zeros((E, 6)), np.zeros((E, 6, 6)), np.zeros((E, 6, 6))
+    cost = C.c_double()
+    _check(lib().slslam_po_evaluate(C.byref(k.desc), _d(p), _d(r), _d(J1), _d(J2), C.cast(C.byref(cost), dp)))
+    return r, J1, J2, cost.value

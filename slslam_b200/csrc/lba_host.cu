@@ -1,0 +1,470 @@
+// Host side of the LBA path behind the C ABI (include/slslam_b200.h): validation, the per-solve "symbolic" plan
+// (observations grouped by line and packed into 32-lane tiles, lines partitioned over the CTAs of a cluster,
+// camera-pair list for the Schur blocks), upload, cluster launch, download.
+// Replaces what LBAProblem::build + ceres::Solve do on the host (reference src/lba_problem.cpp:54-93).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common_host.h"
+#include "lba_kernel.cuh"
+
+namespace slslam {
+
+struct WindowPlan {
+  int C = 0, Cf = 0, L = 0, N = 0, nkeys = 0;
+  int max_iters = 0, robust = 1;
+  double huber_a, baseline, ftol, gtol, ptol, radius0;
+  std::vector<double> obs;        // [slots*8]
+  std::vector<int2> meta;         // [slots]
+  std::vector<int> line_gid;      // device lines
+  std::vector<uint32_t> items;
+  std::vector<int> key_off;       // [CS*(nkeys+1)]
+  int cta_slot_off[MAX_CS + 1], cta_line_off[MAX_CS + 1];
+  signed char cam_free[MAX_CAMS];
+  int max_lines_cta = 0, max_slots_cta = 0;
+  bool has_unobserved_blocks = false;
+};
+
+static int validate_desc(const slslam_lba_desc& d) {
+  if (d.num_cameras < 0 || d.num_lines < 0 || d.num_observations < 0 || d.max_iterations < 0) return SLSLAM_ERR_INVALID;
+  if (d.num_observations > 0 && (!d.camera_index || !d.line_index || !d.fixed_index || !d.observations)) return SLSLAM_ERR_INVALID;
+  if (d.num_cameras > MAX_CAMS) return SLSLAM_ERR_UNSUPPORTED;
+  for (int i = 0; i < d.num_observations; ++i) {
+    if (d.camera_index[i] < 0 || d.camera_index[i] >= d.num_cameras) return SLSLAM_ERR_INVALID;
+    if (d.line_index[i] < 0 || d.line_index[i] >= d.num_lines) return SLSLAM_ERR_INVALID;
+  }
+  return SLSLAM_OK;
+}
+
+// Builds the device plan of one window for a cluster of CS CTAs.
+static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
+  const int C = d.num_cameras, L = d.num_lines, N = d.num_observations;
+  p.C = C; p.L = L; p.N = N; p.max_iters = d.max_iterations; p.robust = d.robust ? 1 : 0;
+  p.huber_a = d.huber_delta > 0 ? d.huber_delta : 1.0 / 406.05;     // reference lba_problem.cpp:78-80
+  p.baseline = d.baseline >= 0 ? d.baseline : 0.12;                 // reference lba_problem.h:101
+  p.ftol = d.function_tolerance > 0 ? d.function_tolerance : 1e-6;  // Ceres 1.7.0 defaults
+  p.gtol = d.gradient_tolerance > 0 ? d.gradient_tolerance : 1e-10;
+  p.ptol = d.parameter_tolerance > 0 ? d.parameter_tolerance : 1e-8;
+  p.radius0 = d.initial_trust_region_radius > 0 ? d.initial_trust_region_radius : 1e4;
+  // sticky constants per block (reference lba_problem.cpp:88-91); unobserved blocks are never touched
+  std::vector<char> cam_used(C, 0), cam_const(C, 0), line_const(L, 0);
+  std::vector<int> line_cnt(L, 0);
+  for (int i = 0; i < N; ++i) {
+    cam_used[d.camera_index[i]] = 1;
+    ++line_cnt[d.line_index[i]];
+    if (d.fixed_index[2 * i]) cam_const[d.camera_index[i]] = 1;
+    if (d.fixed_index[2 * i + 1]) line_const[d.line_index[i]] = 1;
+  }
+  p.Cf = 0;
+  for (int c = 0; c < MAX_CAMS; ++c) p.cam_free[c] = -1;
+  for (int c = 0; c < C; ++c) {
+    if (cam_used[c] && !cam_const[c]) p.cam_free[c] = (signed char)p.Cf++;
+    if (!cam_used[c]) p.has_unobserved_blocks = true;
+  }
+  if (p.Cf > MAX_FREE_CAMS) return SLSLAM_ERR_UNSUPPORTED;
+  p.nkeys = p.Cf * (p.Cf + 1) / 2;
+  // group observations by line (stable counting sort: keeps the caller's order inside a line)
+  std::vector<int> line_start(L + 1, 0);
+  for (int l = 0; l < L; ++l) {
+    line_start[l + 1] = line_start[l] + line_cnt[l];
+    if (line_cnt[l] > 32) return SLSLAM_ERR_UNSUPPORTED;
+    if (line_cnt[l] == 0) p.has_unobserved_blocks = true;
+  }
+  std::vector<int> order(N), fill(line_start.begin(), line_start.end() - 1);
+  for (int i = 0; i < N; ++i) order[fill[d.line_index[i]]++] = i;
+  std::vector<int> dl;   // device lines in increasing id
+  dl.reserve(L);
+  for (int l = 0; l < L; ++l) if (line_cnt[l] > 0) dl.push_back(l);
+  // partition the device lines over the CTAs, balancing observation counts
+  const int nd = (int)dl.size();
+  p.cta_line_off[0] = 0;
+  {
+    int li = 0; long long seen = 0;
+    for (int r = 0; r < CS; ++r) {
+      const long long target = ((long long)N * (r + 1) + CS - 1) / CS;
+      while (li < nd && (seen < target || r == CS - 1)) { seen += line_cnt[dl[li]]; ++li; }
+      p.cta_line_off[r + 1] = li;
+    }
+    for (int r = CS + 1; r <= MAX_CS; ++r) p.cta_line_off[r] = nd;
+  }
+  p.line_gid = dl;
+  p.key_off.assign((size_t)CS * (p.nkeys + 1), 0);
+  p.obs.clear(); p.meta.clear(); p.items.clear();
+  p.max_lines_cta = 1; p.max_slots_cta = 32;
+  p.cta_slot_off[0] = 0;
+  std::vector<std::vector<uint32_t> > buckets(p.nkeys);
+  for (int r = 0; r < CS; ++r) {
+    const int lb = p.cta_line_off[r], le = p.cta_line_off[r + 1];
+    p.max_lines_cta = std::max(p.max_lines_cta, le - lb);
+    const size_t slot_base = p.meta.size();
+    int lane = 0;
+    std::vector<int> round_cam_count;   // per (round, camera) occupancy inside the current tile
+    int tile_rounds[MAX_CAMS];          // next free round per camera in the current tile
+    for (int c = 0; c < MAX_CAMS; ++c) tile_rounds[c] = 0;
+    auto pad_tile = [&]() {
+      while (lane != 0 && lane < 32) {
+        int2 m; m.x = 0 | (lane << 8) | (1 << 14); m.y = 0;
+        p.meta.push_back(m);
+        for (int k = 0; k < 8; ++k) p.obs.push_back(0.0);
+        ++lane;
+      }
+      lane = 0;
+      for (int c = 0; c < MAX_CAMS; ++c) tile_rounds[c] = 0;
+    };
+    for (auto& b : buckets) b.clear();
+    for (int li = lb; li < le; ++li) {
+      const int l = dl[li], k = line_cnt[l];
+      if (lane + k > 32) pad_tile();
+      const int seg_start = lane;
+      const size_t first_slot = p.meta.size() - slot_base;
+      for (int a = 0; a < k; ++a) {
+        const int i = order[line_start[l] + a];
+        const int cam = d.camera_index[i];
+        int flags = F_VALID;
+        if (cam_const[cam]) flags |= F_CAM_FIXED;
+        if (line_const[l]) flags |= F_LINE_FIXED;
+        if (a == 0) flags |= F_HEAD;
+        const int round = tile_rounds[cam]++;   // lanes sharing a camera inside a tile get distinct rounds
+        int2 m;
+        m.x = cam | (seg_start << 8) | (k << 14) | (flags << 24);
+        m.y = (li - lb) | (round << 20);
+        p.meta.push_back(m);
+        for (int q = 0; q < 8; ++q) p.obs.push_back(d.observations[8 * (size_t)i + q]);
+        ++lane;
+      }
+      if (lane == 32) { lane = 0; for (int c = 0; c < MAX_CAMS; ++c) tile_rounds[c] = 0; }
+      // Schur pair list of this line: ordered pairs (i,j) of its free-camera observations with cf_i >= cf_j
+      if (!line_const[l]) {
+        for (int a = 0; a < k; ++a) {
+          const int ca = p.cam_free[d.camera_index[order[line_start[l] + a]]];
+          if (ca < 0) continue;
+          for (int b = 0; b < k; ++b) {
+            const int cb = p.cam_free[d.camera_index[order[line_start[l] + b]]];
+            if (cb < 0 || cb > ca) continue;
+            const uint32_t si = (uint32_t)(first_slot + a), sj = (uint32_t)(first_slot + b);
+            buckets[ca * (ca + 1) / 2 + cb].push_back(si | (sj << 16));
+          }
+        }
+      }
+    }
+    pad_tile();
+    const int nslots = (int)(p.meta.size() - slot_base);
+    if (nslots > 65535) return SLSLAM_ERR_UNSUPPORTED;
+    p.max_slots_cta = std::max(p.max_slots_cta, nslots);
+    p.cta_slot_off[r + 1] = (int)p.meta.size();
+    int* ko = &p.key_off[(size_t)r * (p.nkeys + 1)];
+    for (int key = 0; key < p.nkeys; ++key) {
+      ko[key] = (int)p.items.size();
+      p.items.insert(p.items.end(), buckets[key].begin(), buckets[key].end());
+    }
+    if (p.nkeys >= 0) ko[p.nkeys] = (int)p.items.size();
+  }
+  for (int r = CS + 1; r <= MAX_CS; ++r) p.cta_slot_off[r] = (int)p.meta.size();
+  return SLSLAM_OK;
+}
+
+}  // namespace slslam
+
+using namespace slslam;
+
+struct slslam_lba_batch {
+  int n = 0, device = 0, CS = 1;
+  std::vector<WindowPlan> plans;
+  std::vector<size_t> param_off, trace_off;   // in doubles
+  std::vector<int> nparams;
+  size_t total_params = 0, total_trace = 0;
+  SmemLayout lay;
+  size_t smem_bytes = 0;
+  // device
+  char* d_pool = nullptr;
+  WinHdr* d_hdrs = nullptr;
+  double *d_params_in = nullptr, *d_params_out = nullptr, *d_trace = nullptr;
+  slslam_summary* d_summ = nullptr;
+  // pinned host staging
+  double* h_params = nullptr;
+};
+
+namespace slslam {
+
+static int pick_cluster_size(int nwin, long long max_obs, int requested) {
+  if (requested > 0) {
+    int cs = 1;
+    while (cs * 2 <= requested && cs * 2 <= MAX_CS) cs *= 2;
+    return cs;
+  }
+  // at least ~8 tiles (one per warp) per CTA, and all clusters of the batch co-resident on the 148 SMs
+  int cs = MAX_CS;
+  const long long tiles = (max_obs + 27) / 28;
+  while (cs > 1 && tiles / cs < 8) cs >>= 1;
+  while (cs > 1 && (long long)nwin * cs > 148) cs >>= 1;
+  return cs;
+}
+
+static int launch_config(slslam_lba_batch* b, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, cudaStream_t st) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->gridDim = dim3((unsigned)(b->n * b->CS), 1, 1);
+  cfg->blockDim = dim3(LBA_NT, 1, 1);
+  cfg->dynamicSmemBytes = b->smem_bytes;
+  cfg->stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)b->CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg->attrs = attr; cfg->numAttrs = 1;
+  return 0;
+}
+
+}  // namespace slslam
+
+extern "C" {
+
+void slslam_lba_get_limits(slslam_lba_limits* out) {
+  if (!out) return;
+  out->max_cameras = MAX_CAMS; out->max_free_cameras = MAX_FREE_CAMS; out->max_observations_per_line = 32;
+  out->max_cluster_size = MAX_CS;
+}
+
+int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,
+                            int32_t cluster_size, slslam_lba_batch** out) {
+  if (!out) return SLSLAM_ERR_INVALID;
+  *out = nullptr;
+  if (n <= 0 || !descs || !params) return SLSLAM_ERR_INVALID;
+  for (int i = 0; i < n; ++i) {
+    const int rc = validate_desc(descs[i]);
+    if (rc != SLSLAM_OK) return rc;
+    if (!params[i]) return SLSLAM_ERR_INVALID;
+    const int np = 6 * descs[i].num_cameras + 4 * descs[i].num_lines;
+    for (int k = 0; k < np; ++k) if (!std::isfinite(params[i][k])) return SLSLAM_ERR_NUMERICAL;
+  }
+  int rc = ensure_device(device);
+  if (rc != SLSLAM_OK) return rc;
+  slslam_lba_batch* b = new (std::nothrow) slslam_lba_batch();
+  if (!b) return SLSLAM_ERR_INVALID;
+  cudaGetDevice(&b->device);
+  b->n = n;
+  long long max_obs = 0;
+  for (int i = 0; i < n; ++i) max_obs = std::max<long long>(max_obs, descs[i].num_observations);
+  int CS = pick_cluster_size(n, max_obs, cluster_size);
+
+  int smem_optin = 0;
+  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device);
+  for (int attempt = 0;; ++attempt) {
+    if (attempt > 8) { delete b; return SLSLAM_ERR_UNSUPPORTED; }
+    b->plans.assign(n, WindowPlan());
+    int Cmax = 1, Cfmax = 0, mlines = 1, mslots = 32;
+    for (int i = 0; i < n; ++i) {
+      rc = build_plan(descs[i], CS, b->plans[i]);
+      if (rc != SLSLAM_OK) { delete b; return rc; }
+      Cmax = std::max(Cmax, b->plans[i].C); Cfmax = std::max(Cfmax, b->plans[i].Cf);
+      mlines = std::max(mlines, b->plans[i].max_lines_cta); mslots = std::max(mslots, b->plans[i].max_slots_cta);
+    }
+    b->lay = lba_layout(Cmax, Cfmax, mlines, mslots, CS, (size_t)smem_optin);
+    b->smem_bytes = (size_t)b->lay.total * 8;
+    b->CS = CS;
+    if (b->smem_bytes > (size_t)smem_optin) {
+      // the fixed part alone does not fit: too many lines per CTA for this cluster size
+      if (CS < MAX_CS && cluster_size <= 0) { CS *= 2; continue; }
+      delete b; return SLSLAM_ERR_UNSUPPORTED;
+    }
+    // check that the cluster shape can be scheduled at all; fall back to smaller clusters otherwise
+    CUDA_TRY_OR(cudaFuncSetAttribute(lba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes), { delete b; return SLSLAM_ERR_CUDA; });
+    CUDA_TRY_OR(cudaFuncSetAttribute(lba_solve_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), { delete b; return SLSLAM_ERR_CUDA; });
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    launch_config(b, &cfg, attr, nullptr);
+    int nclusters = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, lba_solve_kernel, &cfg);
+    if (e != cudaSuccess || nclusters < 1) {
+      cudaGetLastError();
+      if (CS > 1 && cluster_size <= 0) { CS >>= 1; continue; }
+      set_last_error("cluster shape cannot be scheduled");
+      delete b; return SLSLAM_ERR_CUDA;
+    }
+    break;
+  }
+
+  // ---- pooled device allocation ----
+  size_t off = 0;
+  auto reserve = [&](size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; };
+  const size_t o_hdr = reserve(sizeof(WinHdr) * n);
+  b->param_off.resize(n); b->trace_off.resize(n); b->nparams.resize(n);
+  size_t tp = 0, tt = 0;
+  for (int i = 0; i < n; ++i) {
+    b->nparams[i] = 6 * b->plans[i].C + 4 * b->plans[i].L;
+    b->param_off[i] = tp; tp += (size_t)((b->nparams[i] + 1) & ~1);
+    b->trace_off[i] = tt; tt += (size_t)std::max(1, b->plans[i].max_iters) * SLSLAM_TRACE_WIDTH;
+  }
+  b->total_params = tp; b->total_trace = tt;
+  const size_t o_pin = reserve(tp * 8), o_pout = reserve(tp * 8), o_trace = reserve(tt * 8), o_summ = reserve(sizeof(slslam_summary) * n);
+  std::vector<size_t> o_obs(n), o_meta(n), o_gid(n), o_items(n), o_koff(n), o_z(n);
+  for (int i = 0; i < n; ++i) {
+    const WindowPlan& p = b->plans[i];
+    o_obs[i] = reserve(p.obs.size() * 8); o_meta[i] = reserve(p.meta.size() * sizeof(int2));
+    o_gid[i] = reserve(p.line_gid.size() * 4 + 4); o_items[i] = reserve(p.items.size() * 4 + 4);
+    o_koff[i] = reserve(p.key_off.size() * 4 + 4);
+    o_z[i] = b->lay.z_in_smem ? 0 : reserve(p.meta.size() * ZS * 8);
+  }
+  CUDA_TRY_OR(cudaMalloc((void**)&b->d_pool, off), { delete b; return SLSLAM_ERR_CUDA; });
+  std::vector<char> host(off, 0);
+  b->d_hdrs = (WinHdr*)(b->d_pool + o_hdr);
+  b->d_params_in = (double*)(b->d_pool + o_pin); b->d_params_out = (double*)(b->d_pool + o_pout);
+  b->d_trace = (double*)(b->d_pool + o_trace); b->d_summ = (slslam_summary*)(b->d_pool + o_summ);
+  for (int i = 0; i < n; ++i) {
+    const WindowPlan& p = b->plans[i];
+    WinHdr h; memset(&h, 0, sizeof(h));
+    h.C = p.C; h.Cf = p.Cf; h.L = p.L; h.n = 6 * p.Cf; h.nkeys = p.nkeys; h.vlen = lba_vlen(p.Cf);
+    h.max_iters = p.max_iters; h.robust = p.robust;
+    h.huber_a = p.huber_a; h.baseline = p.baseline; h.ftol = p.ftol; h.gtol = p.gtol; h.ptol = p.ptol; h.radius0 = p.radius0;
+    h.obs = (const double*)(b->d_pool + o_obs[i]); h.meta = (const int2*)(b->d_pool + o_meta[i]);
+    h.line_gid = (const int*)(b->d_pool + o_gid[i]); h.items = (const uint32_t*)(b->d_pool + o_items[i]);
+    h.key_off = (const int*)(b->d_pool + o_koff[i]);
+    h.params_in = b->d_params_in + b->param_off[i]; h.params_out = b->d_params_out + b->param_off[i];
+    h.Zg = b->lay.z_in_smem ? nullptr : (double*)(b->d_pool + o_z[i]);
+    h.summary = b->d_summ + i; h.trace = b->d_trace + b->trace_off[i];
+    memcpy(h.cta_slot_off, p.cta_slot_off, sizeof(h.cta_slot_off));
+    memcpy(h.cta_line_off, p.cta_line_off, sizeof(h.cta_line_off));
+    memcpy(h.cam_free, p.cam_free, sizeof(h.cam_free));
+    memcpy(host.data() + o_hdr + sizeof(WinHdr) * i, &h, sizeof(h));
+    memcpy(host.data() + o_obs[i], p.obs.data(), p.obs.size() * 8);
+    memcpy(host.data() + o_meta[i], p.meta.data(), p.meta.size() * sizeof(int2));
+    memcpy(host.data() + o_gid[i], p.line_gid.data(), p.line_gid.size() * 4);
+    memcpy(host.data() + o_items[i], p.items.data(), p.items.size() * 4);
+    memcpy(host.data() + o_koff[i], p.key_off.data(), p.key_off.size() * 4);
+    memcpy(host.data() + o_pin + b->param_off[i] * 8, params[i], (size_t)b->nparams[i] * 8);
+  }
+  // only the plan + params region needs uploading (Z staging at the tail is scratch)
+  CUDA_TRY_OR(cudaMemcpy(b->d_pool, host.data(), off, cudaMemcpyHostToDevice), { slslam_lba_batch_destroy(b); return SLSLAM_ERR_CUDA; });
+  CUDA_TRY_OR(cudaMallocHost((void**)&b->h_params, std::max<size_t>(tp, 1) * 8), { slslam_lba_batch_destroy(b); return SLSLAM_ERR_CUDA; });
+  *out = b;
+  return SLSLAM_OK;
+}
+
+int slslam_lba_batch_upload_params(slslam_lba_batch* b, const double* const* params, void* cuda_stream) {
+  if (!b || !params) return SLSLAM_ERR_INVALID;
+  cudaSetDevice(b->device);
+  for (int i = 0; i < b->n; ++i) {
+    if (!params[i]) return SLSLAM_ERR_INVALID;
+    memcpy(b->h_params + b->param_off[i], params[i], (size_t)b->nparams[i] * 8);
+  }
+  CUDA_TRY(cudaMemcpyAsync(b->d_params_in, b->h_params, b->total_params * 8, cudaMemcpyHostToDevice, (cudaStream_t)cuda_stream));
+  return SLSLAM_OK;
+}
+
+int slslam_lba_batch_solve(slslam_lba_batch* b, void* cuda_stream) {
+  if (!b) return SLSLAM_ERR_INVALID;
+  cudaSetDevice(b->device);
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  bool need_copy = false;
+  for (const auto& p : b->plans) need_copy = need_copy || p.has_unobserved_blocks;
+  if (need_copy) CUDA_TRY(cudaMemcpyAsync(b->d_params_out, b->d_params_in, b->total_params * 8, cudaMemcpyDeviceToDevice, st));
+  cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+  launch_config(b, &cfg, attr, st);
+  const WinHdr* hdrs = b->d_hdrs;
+  SmemLayout lay = b->lay;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, lba_solve_kernel, hdrs, lay));
+  return SLSLAM_OK;
+}
+
+int slslam_lba_batch_download(slslam_lba_batch* b, void* cuda_stream, double* const* params_out,
+                              slslam_summary* summaries_out, double* const* trace_out) {
+  if (!b) return SLSLAM_ERR_INVALID;
+  cudaSetDevice(b->device);
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (params_out) CUDA_TRY(cudaMemcpyAsync(b->h_params, b->d_params_out, b->total_params * 8, cudaMemcpyDeviceToHost, st));
+  std::vector<double> tr;
+  if (trace_out) { tr.resize(b->total_trace); CUDA_TRY(cudaMemcpyAsync(tr.data(), b->d_trace, b->total_trace * 8, cudaMemcpyDeviceToHost, st)); }
+  if (summaries_out) CUDA_TRY(cudaMemcpyAsync(summaries_out, b->d_summ, sizeof(slslam_summary) * b->n, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (int i = 0; i < b->n; ++i) {
+    if (params_out && params_out[i]) memcpy(params_out[i], b->h_params + b->param_off[i], (size_t)b->nparams[i] * 8);
+    if (trace_out && trace_out[i]) memcpy(trace_out[i], tr.data() + b->trace_off[i], (size_t)b->plans[i].max_iters * SLSLAM_TRACE_WIDTH * 8);
+  }
+  return SLSLAM_OK;
+}
+
+int slslam_lba_batch_info(const slslam_lba_batch* b, int32_t* cluster_size, int32_t* threads_per_cta,
+                          int32_t* smem_bytes_per_cta, int32_t* z_in_smem) {
+  if (!b) return SLSLAM_ERR_INVALID;
+  if (cluster_size) *cluster_size = b->CS;
+  if (threads_per_cta) *threads_per_cta = LBA_NT;
+  if (smem_bytes_per_cta) *smem_bytes_per_cta = (int32_t)b->smem_bytes;
+  if (z_in_smem) *z_in_smem = b->lay.z_in_smem;
+  return SLSLAM_OK;
+}
+
+void slslam_lba_batch_destroy(slslam_lba_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->d_pool) cudaFree(b->d_pool);
+  if (b->h_params) cudaFreeHost(b->h_params);
+  delete b;
+}
+
+int slslam_lba_solve_batch(int32_t n, const slslam_lba_desc* descs, double* const* params_inout, slslam_summary* summaries_out) {
+  if (n <= 0 || !descs || !params_inout) return SLSLAM_ERR_INVALID;
+  slslam_lba_batch* b = nullptr;
+  int rc = slslam_lba_batch_create(n, descs, (const double* const*)params_inout, -1, 0, &b);
+  if (rc != SLSLAM_OK) return rc;
+  rc = slslam_lba_batch_solve(b, nullptr);
+  std::vector<slslam_summary> summ(n);
+  std::vector<std::vector<double> > tmp(n);
+  std::vector<double*> ptrs(n);
+  for (int i = 0; i < n; ++i) { tmp[i].resize((size_t)b->nparams[i] + 1); ptrs[i] = tmp[i].data(); }
+  if (rc == SLSLAM_OK) rc = slslam_lba_batch_download(b, nullptr, ptrs.data(), summ.data(), nullptr);
+  if (rc == SLSLAM_OK) {
+    // parameters are only overwritten once the whole batch has succeeded
+    for (int i = 0; i < n; ++i) {
+      memcpy(params_inout[i], tmp[i].data(), (size_t)b->nparams[i] * 8);
+      if (summaries_out) summaries_out[i] = summ[i];
+    }
+  }
+  slslam_lba_batch_destroy(b);
+  return rc;
+}
+
+int slslam_lba_solve(const slslam_lba_desc* desc, double* params_inout, slslam_summary* summary_out) {
+  if (!desc || !params_inout) return SLSLAM_ERR_INVALID;
+  double* pp[1] = {params_inout};
+  return slslam_lba_solve_batch(1, desc, pp, summary_out);
+}
+
+int slslam_lba_evaluate(const slslam_lba_desc* desc, const double* params, double* residuals, double* jac_camera,
+                        double* jac_line, double* cost_out) {
+  if (!desc || !params || !residuals) return SLSLAM_ERR_INVALID;
+  int rc = validate_desc(*desc);
+  if (rc != SLSLAM_OK) return rc;
+  rc = ensure_device(-1);
+  if (rc != SLSLAM_OK) return rc;
+  const int N = desc->num_observations, C = desc->num_cameras, L = desc->num_lines;
+  if (N == 0) { if (cost_out) *cost_out = 0.0; return SLSLAM_OK; }
+  const size_t np = (size_t)6 * C + 4 * L;
+  char* pool = nullptr;
+  size_t off = 0;
+  auto reserve = [&](size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; };
+  const size_t o_ci = reserve(4 * (size_t)N), o_li = reserve(4 * (size_t)N), o_ob = reserve(64 * (size_t)N), o_p = reserve(8 * np);
+  const size_t o_r = reserve(32 * (size_t)N), o_jc = reserve(192 * (size_t)N), o_jl = reserve(128 * (size_t)N), o_c = reserve(8);
+  CUDA_TRY(cudaMalloc((void**)&pool, off));
+  rc = SLSLAM_OK;
+#define EV_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_last_error(cudaGetErrorString(e_)); rc = SLSLAM_ERR_CUDA; goto done; } } while (0)
+  EV_TRY(cudaMemcpy(pool + o_ci, desc->camera_index, 4 * (size_t)N, cudaMemcpyHostToDevice));
+  EV_TRY(cudaMemcpy(pool + o_li, desc->line_index, 4 * (size_t)N, cudaMemcpyHostToDevice));
+  EV_TRY(cudaMemcpy(pool + o_ob, desc->observations, 64 * (size_t)N, cudaMemcpyHostToDevice));
+  EV_TRY(cudaMemcpy(pool + o_p, params, 8 * np, cudaMemcpyHostToDevice));
+  EV_TRY(cudaMemset(pool + o_c, 0, 8));
+  lba_evaluate_kernel<<<(N + 127) / 128, 128>>>(N, C, (const int*)(pool + o_ci), (const int*)(pool + o_li), (const double*)(pool + o_ob),
+                                               (const double*)(pool + o_p), desc->baseline >= 0 ? desc->baseline : 0.12,
+                                               desc->huber_delta > 0 ? desc->huber_delta : 1.0 / 406.05, desc->robust,
+                                               (double*)(pool + o_r), (double*)(pool + o_jc), (double*)(pool + o_jl), (double*)(pool + o_c));
+  EV_TRY(cudaGetLastError());
+  EV_TRY(cudaMemcpy(residuals, pool + o_r, 32 * (size_t)N, cudaMemcpyDeviceToHost));
+  if (jac_camera) EV_TRY(cudaMemcpy(jac_camera, pool + o_jc, 192 * (size_t)N, cudaMemcpyDeviceToHost));
+  if (jac_line) EV_TRY(cudaMemcpy(jac_line, pool + o_jl, 128 * (size_t)N, cudaMemcpyDeviceToHost));
+  if (cost_out) EV_TRY(cudaMemcpy(cost_out, pool + o_c, 8, cudaMemcpyDeviceToHost));
+done:
+#undef EV_TRY
+  cudaFree(pool);
+  return rc;
+}
+
+}  // extern "C"

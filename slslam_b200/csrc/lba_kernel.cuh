@@ -1,0 +1,848 @@
+// The LBA solve kernel: one thread-block cluster per window, the whole Levenberg-Marquardt loop on device.
+// Replaces what ceres::Solve does for an LBAProblem (reference src/slam.cpp:663, 944; semantics restated in
+// SURVEY.md Appendix A3).  Phases of one LM iteration (K1..K4 of SURVEY.md §2):
+//   K1  linearise: lane = observation, whole lines packed in 32-lane tiles; analytic residual + Jacobian,
+//       Huber corrector, Jacobi scaling; per-line H_ll / g_l by segmented warp shuffles.
+//   K2  Schur assembly: per-line 4x4 Cholesky in registers, Z_i = (Jc_i^T Jl_i) L^-T staged in shared memory
+//       (or L2 when it does not fit), per-camera H_cc / g_c in warp-private accumulators, camera-pair blocks
+//       S_(ci,cj) -= sum_l Z_i Z_j^T from a host-built pair list (warp per block, lanes over lines, shuffle
+//       reduce: deterministic, no atomics), cluster reduce-scatter + all-gather over DSMEM.
+//   K3  blocked Cholesky + substitution of the reduced camera system (<= 6*MAX_FREE_CAMS), line back-substitution.
+//   K4  trial-cost sweep, step acceptance, trust-region radius, termination tests: identical on every CTA.
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/slslam_b200.h"
+#include "lba_math.cuh"
+
+namespace slslam {
+namespace cg = cooperative_groups;
+
+constexpr int LBA_NT = 256;          // threads per CTA (fp64 Jacobian code wants ~200 registers per thread)
+constexpr int LBA_NW = LBA_NT / 32;
+constexpr int MAX_CAMS = 32;
+constexpr int MAX_FREE_CAMS = 24;
+constexpr int MAX_CS = 16;
+constexpr int ZS = 24;               // doubles per Z block (6 x 4, row-major)
+constexpr int ACC = 33;              // per-camera accumulators: H_cc (21, lower) | g_c (6) | sum Z u (6)
+constexpr int LLU = 18;              // per-line: L (10, lower) | u = L^-1 g_l (4) | D_l (4)
+constexpr int NSCAL = 8;
+
+// slot flags (meta.x bits 24..)
+constexpr int F_VALID = 1, F_CAM_FIXED = 2, F_LINE_FIXED = 4, F_HEAD = 8;
+
+struct WinHdr {
+  int C, Cf, L, n, nkeys, vlen, max_iters, robust;
+  double huber_a, baseline, ftol, gtol, ptol, radius0;
+  const double* obs;        // [slots][8], slot order
+  const int2* meta;         // [slots] x: cam | seg_start<<8 | seg_len<<14 | flags<<24 ; y: line_local | round<<20
+  const int* line_gid;      // [device lines] global line id, CTA-contiguous
+  const uint32_t* items;    // pair list: slot_i | slot_j << 16 (slot indices local to the CTA)
+  const int* key_off;       // [CS][nkeys+1] offsets into items
+  const double* params_in;
+  double* params_out;
+  double* Zg;               // global Z staging when it does not fit in shared memory (else nullptr)
+  slslam_summary* summary;
+  double* trace;            // [max_iters][SLSLAM_TRACE_WIDTH] or nullptr
+  int cta_slot_off[MAX_CS + 1];
+  int cta_line_off[MAX_CS + 1];
+  signed char cam_free[MAX_CAMS];   // reduced block index of each camera or -1
+};
+
+// Shared-memory layout in doubles, identical for every CTA of a launch (sized by the largest window).
+struct SmemLayout {
+  int camx, camxt, camR, camRt, cscale, linex, linext, lscale, lineLU, V, Vred, wacc, yc, misc, Z, total;
+  int z_in_smem;
+};
+
+__host__ __device__ inline int lba_vlen(int Cf) {
+  const int n = 6 * Cf, nkeys = Cf * (Cf + 1) / 2;
+  return nkeys * 36 + 3 * n + NSCAL;   // S blocks | g_c | sum Z u | diag H_cc | scalars
+}
+
+__host__ inline SmemLayout lba_layout(int C, int Cf, int max_lines_cta, int max_slots_cta, int CS, size_t smem_limit_bytes) {
+  SmemLayout l;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
+  const int vlen = lba_vlen(Cf);
+  l.camx = take(6 * C); l.camxt = take(6 * C);
+  l.camR = take(CAM_STRIDE * C); l.camRt = take(CAM_STRIDE * C);
+  l.cscale = take(6 * (Cf > 0 ? Cf : 1));
+  l.linex = take(4 * max_lines_cta); l.linext = take(4 * max_lines_cta); l.lscale = take(4 * max_lines_cta);
+  l.lineLU = take(LLU * max_lines_cta);
+  l.V = take(vlen); l.Vred = take((vlen + CS - 1) / CS + 2);
+  l.wacc = take(LBA_NW * ACC * (Cf > 0 ? Cf : 1));
+  l.yc = take(6 * (Cf > 0 ? Cf : 1) + 8);
+  l.misc = take(64 + LBA_NW * NSCAL);
+  l.Z = o;
+  const size_t zbytes = (size_t)ZS * max_slots_cta * 8;
+  l.z_in_smem = ((size_t)o * 8 + zbytes <= smem_limit_bytes) ? 1 : 0;
+  if (l.z_in_smem) o += ZS * max_slots_cta;
+  l.total = o;
+  return l;
+}
+
+// symmetric 4x4 lower index: (p,q), p >= q
+__device__ __forceinline__ constexpr int L4(int p, int q) { return p * (p + 1) / 2 + q; }
+__device__ __forceinline__ constexpr int L6(int p, int q) { return p * (p + 1) / 2 + q; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Sum over the lanes [seg_start, seg_start+seg_len) of this lane's segment; every lane of the segment gets the total.
+// Fixed order (inclusive up-scan then broadcast from the last lane): deterministic.
+template <int NV>
+__device__ __forceinline__ void seg_allsum(double* v, int lane, int seg_start, int seg_len) {
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const bool take = (lane - off) >= seg_start;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const double t = __shfl_up_sync(0xffffffffu, v[k], off);
+      if (take) v[k] += t;
+    }
+  }
+  const int last = seg_start + seg_len - 1;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = __shfl_sync(0xffffffffu, v[k], last);
+}
+
+struct Ctx {
+  const WinHdr* h;
+  double* sm;
+  SmemLayout lay;
+  int tid, lane, warp, rank, CS;
+  int slot0, nslots, ntiles, line0, nlines;
+  double* Zbuf;   // this CTA's Z blocks (shared or global)
+};
+
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1 + first half of K2.  MODE 0: column norms only (Jacobi scale at x0).  MODE 1: full.
+// Outputs (MODE 1): Z blocks, lineLU, wacc (warp-private H_cc | g_c | sum Z u), partial scalars in misc.
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, double* out_fixed_cost, double* out_gmax,
+                                double* out_fail) {
+  const WinHdr& h = *c.h;
+  double* sm = c.sm;
+  const double* camR = sm + c.lay.camR;
+  const double* linex = sm + c.lay.linex;
+  const double* cscale = sm + c.lay.cscale;
+  double* lscale = sm + c.lay.lscale;
+  double* lineLU = sm + c.lay.lineLU;
+  const int Cf = h.Cf;
+  double* wacc = sm + c.lay.wacc + c.warp * ACC * (Cf > 0 ? Cf : 1);
+  constexpr int NACC = (MODE == 0) ? 6 : ACC;
+  // clear the warp-private camera accumulators
+  for (int i = c.lane; i < ACC * Cf; i += 32) wacc[i] = 0.0;
+  __syncwarp();
+  double cost = 0.0, fixed_cost = 0.0, gmax = 0.0, fail = 0.0;
+  const bool robust = h.robust != 0;
+  for (int tile = c.warp; tile < c.ntiles; tile += LBA_NW) {
+    const int ls = tile * 32 + c.lane;               // CTA-local slot
+    const int2 mt = h.meta[c.slot0 + ls];
+    const int flags = (mt.x >> 24) & 0xff;
+    const bool valid = flags & F_VALID;
+    const int cam = mt.x & 0xff, seg_start = (mt.x >> 8) & 0x3f, seg_len = (mt.x >> 14) & 0x3f;
+    const int ll = mt.y & 0xfffff, round = (mt.y >> 20) & 0xff;
+    const bool cam_free = valid && !(flags & F_CAM_FIXED), line_free = valid && !(flags & F_LINE_FIXED);
+    const int cf = valid ? h.cam_free[cam] : -1;
+    double r[4], Jc[24], Jl[16];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 24; ++k) Jc[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) Jl[k] = 0.0;
+    if (valid) {
+      double ob[8];
+      const double2* op = reinterpret_cast<const double2*>(h.obs + (size_t)(c.slot0 + ls) * 8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const double2 t = __ldg(op + k); ob[2 * k] = t.x; ob[2 * k + 1] = t.y; }
+      LineTrig lt;
+      line_trig(linex + 4 * ll, lt);
+      obs_eval<true>(camR + CAM_STRIDE * cam, lt, ob, h.baseline, r, Jc, Jl);
+      const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
+      double w;
+      const double rho = huber_rho(s, h.huber_a, robust, w);
+      if (cam_free || line_free) cost += 0.5 * rho; else fixed_cost += 0.5 * rho;
+      // corrector (rho'' <= 0): scale residual and Jacobian rows by sqrt(rho'); constant blocks drop out
+      const double wc = cam_free ? w : 0.0, wl = line_free ? w : 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) r[k] *= w;
+      if constexpr (MODE == 1) {
+        const double* cs = cscale + 6 * (cf >= 0 ? cf : 0);
+        const double* lsc = lscale + 4 * ll;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+          for (int j = 0; j < 6; ++j) Jc[6 * k + j] *= wc * cs[j];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) Jl[4 * k + j] *= wl * lsc[j];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 24; ++k) Jc[k] *= wc;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) Jl[k] *= wl;
+      }
+    }
+    double acc[NACC];
+    if constexpr (MODE == 0) {
+      // squared column norms: lines by segment, cameras by accumulator rounds
+      double ln[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ln[j] = Jl[j] * Jl[j] + Jl[4 + j] * Jl[4 + j] + Jl[8 + j] * Jl[8 + j] + Jl[12 + j] * Jl[12 + j];
+      seg_allsum<4>(ln, c.lane, seg_start, seg_len);
+      if (valid && (flags & F_HEAD)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) lscale[4 * ll + j] = 1.0 / (1.0 + sqrt(ln[j]));
+      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) acc[j] = Jc[j] * Jc[j] + Jc[6 + j] * Jc[6 + j] + Jc[12 + j] * Jc[12 + j] + Jc[18 + j] * Jc[18 + j];
+    } else {
+      // H_ll (10) and g_l (4) over the line's observations
+      double hg[14];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q <= p; ++q)
+          hg[L4(p, q)] = Jl[p] * Jl[q] + Jl[4 + p] * Jl[4 + q] + Jl[8 + p] * Jl[8 + q] + Jl[12 + p] * Jl[12 + q];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) hg[10 + p] = Jl[p] * r[0] + Jl[4 + p] * r[1] + Jl[8 + p] * r[2] + Jl[12 + p] * r[3];
+      seg_allsum<14>(hg, c.lane, seg_start, seg_len);
+      // LM diagonal of the line block and its Cholesky factor (every lane of the segment computes the same values)
+      double D[4], Lm[10], u[4], inv[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) D[p] = clampd(hg[L4(p, p)], 1e-6, 1e32) / radius;
+      bool ok = true;
+      {
+        double a00 = hg[0] + D[0];
+        ok = ok && (a00 > 0.0); inv[0] = rsqrt(a00); Lm[0] = a00 * inv[0];
+        Lm[1] = hg[1] * inv[0]; Lm[3] = hg[3] * inv[0]; Lm[6] = hg[6] * inv[0];
+        double a11 = hg[2] + D[1] - Lm[1] * Lm[1];
+        ok = ok && (a11 > 0.0); inv[1] = rsqrt(a11); Lm[2] = a11 * inv[1];
+        Lm[4] = (hg[4] - Lm[3] * Lm[1]) * inv[1]; Lm[7] = (hg[7] - Lm[6] * Lm[1]) * inv[1];
+        double a22 = hg[5] + D[2] - Lm[3] * Lm[3] - Lm[4] * Lm[4];
+        ok = ok && (a22 > 0.0); inv[2] = rsqrt(a22); Lm[5] = a22 * inv[2];
+        Lm[8] = (hg[8] - Lm[6] * Lm[3] - Lm[7] * Lm[4]) * inv[2];
+        double a33 = hg[9] + D[3] - Lm[6] * Lm[6] - Lm[7] * Lm[7] - Lm[8] * Lm[8];
+        ok = ok && (a33 > 0.0); inv[3] = rsqrt(a33); Lm[9] = a33 * inv[3];
+      }
+      if (valid && !ok) fail = 1.0;
+      u[0] = hg[10] * inv[0];
+      u[1] = (hg[11] - Lm[1] * u[0]) * inv[1];
+      u[2] = (hg[12] - Lm[3] * u[0] - Lm[4] * u[1]) * inv[2];
+      u[3] = (hg[13] - Lm[6] * u[0] - Lm[7] * u[1] - Lm[8] * u[2]) * inv[3];
+      if (valid && (flags & F_HEAD)) {
+        double* o = lineLU + LLU * ll;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) o[k] = Lm[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { o[10 + k] = u[k]; o[14 + k] = D[k]; }
+        if (line_free) {
+          const double* lsc = lscale + 4 * ll;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) gmax = fmax(gmax, fabs(hg[10 + k] / lsc[k]));
+        }
+      }
+      // Z = (Jc^T Jl) L^-T, row p of Z solves z L^T = W_p
+      double Z[24];
+#pragma unroll
+      for (int p = 0; p < 6; ++p) {
+        double W[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) W[q] = Jc[p] * Jl[q] + Jc[6 + p] * Jl[4 + q] + Jc[12 + p] * Jl[8 + q] + Jc[18 + p] * Jl[12 + q];
+        const double z0 = W[0] * inv[0];
+        const double z1 = (W[1] - z0 * Lm[1]) * inv[1];
+        const double z2 = (W[2] - z0 * Lm[3] - z1 * Lm[4]) * inv[2];
+        const double z3 = (W[3] - z0 * Lm[6] - z1 * Lm[7] - z2 * Lm[8]) * inv[3];
+        Z[4 * p] = z0; Z[4 * p + 1] = z1; Z[4 * p + 2] = z2; Z[4 * p + 3] = z3;
+      }
+      if (valid) {
+        double2* zp = reinterpret_cast<double2*>(c.Zbuf + (size_t)ls * ZS);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) zp[k] = make_double2(Z[2 * k], Z[2 * k + 1]);
+      }
+      // per-camera accumulators: H_cc lower (21), g_c (6), Z u (6)
+#pragma unroll
+      for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = 0; q <= p; ++q)
+          acc[L6(p, q)] = Jc[p] * Jc[q] + Jc[6 + p] * Jc[6 + q] + Jc[12 + p] * Jc[12 + q] + Jc[18 + p] * Jc[18 + q];
+#pragma unroll
+      for (int p = 0; p < 6; ++p) {
+        acc[21 + p] = Jc[p] * r[0] + Jc[6 + p] * r[1] + Jc[12 + p] * r[2] + Jc[18 + p] * r[3];
+        acc[27 + p] = Z[4 * p] * u[0] + Z[4 * p + 1] * u[1] + Z[4 * p + 2] * u[2] + Z[4 * p + 3] * u[3];
+      }
+    }
+    // rounds: lanes of one line have distinct cameras, so within a round no two lanes touch the same accumulator
+    const int nrounds = __reduce_max_sync(0xffffffffu, valid ? round + 1 : 0);
+    for (int rd = 0; rd < nrounds; ++rd) {
+      if (cam_free && round == rd && cf >= 0) {
+        double* a = wacc + ACC * cf;
+        if constexpr (MODE == 0) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) a[k] += acc[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < ACC; ++k) a[k] += acc[k];
+        }
+      }
+      __syncwarp();
+    }
+  }
+  *out_cost = cost; *out_fixed_cost = fixed_cost; *out_gmax = gmax; *out_fail = fail;
+}
+
+// Second half of K2: camera-pair blocks from the pair list.  Warp per block, lanes over the lines seeing both cameras.
+__device__ void schur_pairs(const Ctx& c) {
+  const WinHdr& h = *c.h;
+  double* V = c.sm + c.lay.V;
+  const int* koff = h.key_off + (size_t)c.rank * (h.nkeys + 1);
+  for (int key = c.warp; key < h.nkeys; key += LBA_NW) {
+    const int beg = koff[key], end = koff[key + 1];
+    double acc[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+    for (int it = beg + c.lane; it < end; it += 32) {
+      const uint32_t item = __ldg(h.items + it);
+      const double2* zi = reinterpret_cast<const double2*>(c.Zbuf + (size_t)(item & 0xffffu) * ZS);
+      const double2* zj = reinterpret_cast<const double2*>(c.Zbuf + (size_t)(item >> 16) * ZS);
+      double Zi[24], Zj[24];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) { const double2 a = zi[k], b = zj[k]; Zi[2 * k] = a.x; Zi[2 * k + 1] = a.y; Zj[2 * k] = b.x; Zj[2 * k + 1] = b.y; }
+#pragma unroll
+      for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+          acc[6 * p + q] += Zi[4 * p] * Zj[4 * q] + Zi[4 * p + 1] * Zj[4 * q + 1] + Zi[4 * p + 2] * Zj[4 * q + 2] + Zi[4 * p + 3] * Zj[4 * q + 3];
+    }
+    double mine = 0.0, mine2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 36; ++k) {
+      const double s = warp_sum(acc[k]);
+      if ((k & 31) == c.lane) { if (k < 32) mine = s; else mine2 = s; }
+    }
+    V[key * 36 + c.lane] = -mine;
+    if (c.lane < 4) V[key * 36 + 32 + c.lane] = -mine2;
+  }
+}
+
+// Fold the warp-private camera accumulators into V: H_cc onto the diagonal blocks, g_c, sum Z u, diag H_cc.
+__device__ void fold_cameras(const Ctx& c, bool norms_only) {
+  const WinHdr& h = *c.h;
+  double* V = c.sm + c.lay.V;
+  const double* wacc = c.sm + c.lay.wacc;
+  const int Cf = h.Cf, n = h.n;
+  const int g_off = h.nkeys * 36, zu_off = g_off + n, hd_off = zu_off + n;
+  const int nacc = norms_only ? 6 : ACC;
+  for (int i = c.tid; i < Cf * nacc; i += LBA_NT) {
+    const int f = i / nacc, e = i % nacc;
+    double s = 0.0;
+    for (int w = 0; w < LBA_NW; ++w) s += wacc[(w * Cf + f) * ACC + e];
+    if (norms_only) { V[hd_off + 6 * f + e] = s; continue; }
+    if (e < 21) {
+      int p = 0; while ((p + 1) * (p + 2) / 2 <= e) ++p;
+      const int q = e - p * (p + 1) / 2;
+      const int key = f * (f + 1) / 2 + f;
+      V[key * 36 + 6 * p + q] += s;
+      if (p != q) V[key * 36 + 6 * q + p] += s; else V[hd_off + 6 * f + p] = s;
+    } else if (e < 27) {
+      V[g_off + 6 * f + (e - 21)] = s;
+    } else {
+      V[zu_off + 6 * f + (e - 27)] = s;
+    }
+  }
+}
+
+// Sum V over the cluster: reduce-scatter then all-gather through distributed shared memory, fixed rank order.
+// The entry at max_idx is combined with max instead of +.
+__device__ void cluster_allreduce(cg::cluster_group& cl, const Ctx& c, int vlen, int max_idx) {
+  double* V = c.sm + c.lay.V;
+  double* Vred = c.sm + c.lay.Vred;
+  if (c.CS == 1) { __syncthreads(); return; }
+  cl.sync();
+  const int per = (vlen + c.CS - 1) / c.CS;
+  const int beg = c.rank * per, end = min(vlen, beg + per);
+  for (int i = beg + c.tid; i < end; i += LBA_NT) {
+    double s = 0.0;
+    for (int r = 0; r < c.CS; ++r) {
+      const double v = cl.map_shared_rank(V, r)[i];
+      s = (i == max_idx) ? fmax(s, v) : s + v;
+    }
+    Vred[i - beg] = s;
+  }
+  cl.sync();
+  for (int i = c.tid; i < vlen; i += LBA_NT) {
+    const int r = i / per;
+    V[i] = cl.map_shared_rank(Vred, r)[i - r * per];
+  }
+  __syncthreads();
+}
+
+// K3: blocked (6x6) right-looking Cholesky of the reduced camera system held block-packed in V, with the right-hand
+// side carried along (forward substitution folded in), then block back-substitution.  Every CTA of the cluster
+// solves the same system redundantly (same data, same order => same bits), which saves a broadcast.
+// On exit yc = (S + D_c)^-1 (g_c - sum Z u).  Returns false (uniformly) if a pivot is not positive.
+__device__ bool reduced_solve(const Ctx& c, double radius) {
+  const WinHdr& h = *c.h;
+  double* V = c.sm + c.lay.V;
+  double* yc = c.sm + c.lay.yc;
+  double* misc = c.sm + c.lay.misc;    // misc[0..5] 1/l_kk of the current diagonal block, misc[6] failure flag
+  const int Cf = h.Cf, n = h.n;
+  const int g_off = h.nkeys * 36, zu_off = g_off + n, hd_off = zu_off + n;
+  // right-hand side and LM diagonal of the camera blocks
+  for (int i = c.tid; i < n; i += LBA_NT) {
+    yc[i] = V[g_off + i] - V[zu_off + i];
+    const int f = i / 6, p = i % 6;
+    V[(f * (f + 1) / 2 + f) * 36 + 7 * p] += clampd(V[hd_off + i], 1e-6, 1e32) / radius;
+  }
+  if (c.tid == 0) misc[6] = 0.0;
+  __syncthreads();
+  for (int J = 0; J < Cf; ++J) {
+    double* AJJ = V + (J * (J + 1) / 2 + J) * 36;
+    // every participating thread factors the 6x6 diagonal block itself in registers (no shuffles on the pivot chain)
+    const int nrows = 6 * (Cf - J - 1) + 1;    // panel rows below + one thread for the rhs/diag write-back
+    double Lr[21], inv[6];
+    bool ok = true;
+    if (c.tid < nrows) {
+#pragma unroll
+      for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = 0; q <= p; ++q) Lr[L6(p, q)] = AJJ[6 * p + q];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        double d = Lr[L6(k, k)];
+#pragma unroll
+        for (int m = 0; m < k; ++m) d -= Lr[L6(k, m)] * Lr[L6(k, m)];
+        ok = ok && (d > 0.0);
+        inv[k] = rsqrt(d);
+        Lr[L6(k, k)] = d * inv[k];
+#pragma unroll
+        for (int p = k + 1; p < 6; ++p) {
+          double s = Lr[L6(p, k)];
+#pragma unroll
+          for (int m = 0; m < k; ++m) s -= Lr[L6(p, m)] * Lr[L6(k, m)];
+          Lr[L6(p, k)] = s * inv[k];
+        }
+      }
+    }
+    __syncthreads();   // everyone has read A_JJ before it is overwritten with L_JJ
+    if (c.tid < nrows - 1) {
+      // panel: row p of block (I,J):  x L_JJ^T = a
+      const int I = J + 1 + c.tid / 6, p = c.tid % 6;
+      double* a = V + (I * (I + 1) / 2 + J) * 36 + 6 * p;
+      double x[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        double s = a[q];
+#pragma unroll
+        for (int m = 0; m < q; ++m) s -= x[m] * Lr[L6(q, m)];
+        x[q] = s * inv[q];
+      }
+#pragma unroll
+      for (int q = 0; q < 6; ++q) a[q] = x[q];
+    } else if (c.tid == nrows - 1) {
+      // write L_JJ back, forward-substitute the rhs block: z_J = L_JJ^-1 b_J
+      if (!ok) misc[6] = 1.0;
+#pragma unroll
+      for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) AJJ[6 * p + q] = (q <= p) ? Lr[L6(p, q)] : 0.0;
+      double z[6];
+#pragma unroll
+      for (int p = 0; p < 6; ++p) {
+        double s = yc[6 * J + p];
+#pragma unroll
+        for (int m = 0; m < p; ++m) s -= Lr[L6(p, m)] * z[m];
+        z[p] = s * inv[p];
+      }
+#pragma unroll
+      for (int p = 0; p < 6; ++p) { yc[6 * J + p] = z[p]; misc[p] = inv[p]; }
+    }
+    __syncthreads();
+    // trailing update: A_IK -= L_IJ L_KJ^T for I >= K > J (entry per thread), and b_I -= L_IJ z_J
+    const int nb = Cf - J - 1;
+    const int nent = nb * (nb + 1) / 2 * 36;
+    for (int e = c.tid; e < nent + 6 * nb; e += LBA_NT) {
+      if (e < nent) {
+        const int blk = e / 36, pq = e % 36, p = pq / 6, q = pq % 6;
+        int bi = 0; while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
+        const int bk = blk - bi * (bi + 1) / 2;
+        const int I = J + 1 + bi, K = J + 1 + bk;
+        const double* li = V + (I * (I + 1) / 2 + J) * 36 + 6 * p;
+        const double* lk = V + (K * (K + 1) / 2 + J) * 36 + 6 * q;
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < 6; ++m) s += li[m] * lk[m];
+        V[(I * (I + 1) / 2 + K) * 36 + pq] -= s;
+      } else {
+        const int rI = e - nent, I = J + 1 + rI / 6, p = rI % 6;
+        const double* li = V + (I * (I + 1) / 2 + J) * 36 + 6 * p;
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < 6; ++m) s += li[m] * yc[6 * J + m];
+        yc[6 * I + p] -= s;
+      }
+    }
+    __syncthreads();
+  }
+  const bool failed = misc[6] != 0.0;
+  // back substitution L^T y = z by warp 0: after y_J is known, every lane removes its contribution from the rows above
+  if (c.warp == 0 && !failed) {
+    for (int J = Cf - 1; J >= 0; --J) {
+      const double* LJJ = V + (J * (J + 1) / 2 + J) * 36;
+      double y[6];
+#pragma unroll
+      for (int p = 5; p >= 0; --p) {
+        double s = yc[6 * J + p];
+#pragma unroll
+        for (int m = p + 1; m < 6; ++m) s -= LJJ[6 * m + p] * y[m];
+        y[p] = s / LJJ[7 * p];
+      }
+      __syncwarp();
+      if (c.lane < 6) yc[6 * J + c.lane] = y[c.lane];
+      for (int e = c.lane; e < 6 * J; e += 32) {
+        const int K = e / 6, q = e % 6;
+        const double* ljk = V + (J * (J + 1) / 2 + K) * 36;    // block (J,K): rows of J, columns of K
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < 6; ++m) s += ljk[6 * m + q] * y[m];
+        yc[6 * K + q] -= s;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  return !failed;
+}
+
+// Line back-substitution y_l = L^-T (u - sum_i Z_i^T y_c(i)), trial point, residual-only sweep at the trial point.
+// Partial scalars (this CTA): trial cost, line part of the model decrease, |delta|^2, |x|^2 of the line blocks.
+__device__ void trial_sweep(const Ctx& c, double* out4) {
+  const WinHdr& h = *c.h;
+  double* sm = c.sm;
+  const double* camRt = sm + c.lay.camRt;
+  const double* linex = sm + c.lay.linex;
+  double* linext = sm + c.lay.linext;
+  const double* lscale = sm + c.lay.lscale;
+  const double* lineLU = sm + c.lay.lineLU;
+  const double* yc = sm + c.lay.yc;
+  const bool robust = h.robust != 0;
+  double cost = 0.0, model = 0.0, dn2 = 0.0, xn2 = 0.0;
+  for (int tile = c.warp; tile < c.ntiles; tile += LBA_NW) {
+    const int ls = tile * 32 + c.lane;
+    const int2 mt = h.meta[c.slot0 + ls];
+    const int flags = (mt.x >> 24) & 0xff;
+    const bool valid = flags & F_VALID;
+    const int cam = mt.x & 0xff, seg_start = (mt.x >> 8) & 0x3f, seg_len = (mt.x >> 14) & 0x3f;
+    const int ll = mt.y & 0xfffff;
+    const bool cam_free = valid && !(flags & F_CAM_FIXED), line_free = valid && !(flags & F_LINE_FIXED);
+    const int cf = valid ? h.cam_free[cam] : -1;
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    if (cam_free && cf >= 0 && line_free) {
+      const double2* zp = reinterpret_cast<const double2*>(c.Zbuf + (size_t)ls * ZS);
+      const double* y = yc + 6 * cf;
+#pragma unroll
+      for (int p = 0; p < 6; ++p) {
+        const double2 a = zp[2 * p], b = zp[2 * p + 1];
+        v[0] += a.x * y[p]; v[1] += a.y * y[p]; v[2] += b.x * y[p]; v[3] += b.y * y[p];
+      }
+    }
+    seg_allsum<4>(v, c.lane, seg_start, seg_len);
+    if (valid) {
+      const double* lu = lineLU + LLU * ll;
+      double xl[4];
+      if (line_free) {
+        double yl[4];
+        const double w3 = lu[10 + 3] - v[3], w2 = lu[10 + 2] - v[2], w1 = lu[10 + 1] - v[1], w0 = lu[10] - v[0];
+        yl[3] = w3 / lu[9];
+        yl[2] = (w2 - lu[8] * yl[3]) / lu[5];
+        yl[1] = (w1 - lu[4] * yl[2] - lu[7] * yl[3]) / lu[2];
+        yl[0] = (w0 - lu[1] * yl[1] - lu[3] * yl[2] - lu[6] * yl[3]) / lu[0];
+        const double* lsc = lscale + 4 * ll;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xl[k] = linex[4 * ll + k] - yl[k] * lsc[k];
+        if (flags & F_HEAD) {
+          // g_l = L u ; model decrease = 1/2 (y.g + y.D y)   (equals -(m.(r + m/2)), m = J step, for an exact solve)
+          const double u0 = lu[10], u1 = lu[11], u2 = lu[12], u3 = lu[13];
+          const double g0 = lu[0] * u0, g1 = lu[1] * u0 + lu[2] * u1, g2 = lu[3] * u0 + lu[4] * u1 + lu[5] * u2,
+                       g3 = lu[6] * u0 + lu[7] * u1 + lu[8] * u2 + lu[9] * u3;
+          model += 0.5 * (yl[0] * (g0 + lu[14] * yl[0]) + yl[1] * (g1 + lu[15] * yl[1]) + yl[2] * (g2 + lu[16] * yl[2]) +
+                          yl[3] * (g3 + lu[17] * yl[3]));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const double d = yl[k] * lsc[k];
+            dn2 += d * d; xn2 += linex[4 * ll + k] * linex[4 * ll + k];
+            linext[4 * ll + k] = xl[k];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xl[k] = linex[4 * ll + k];
+        if (flags & F_HEAD) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) linext[4 * ll + k] = xl[k];
+        }
+      }
+      if (cam_free || line_free) {
+        double ob[8], r[4];
+        const double2* op = reinterpret_cast<const double2*>(h.obs + (size_t)(c.slot0 + ls) * 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const double2 t = __ldg(op + k); ob[2 * k] = t.x; ob[2 * k + 1] = t.y; }
+        LineTrig lt;
+        line_trig(xl, lt);
+        obs_eval<false>(camRt + CAM_STRIDE * cam, lt, ob, h.baseline, r, nullptr, nullptr);
+        const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
+        double w;
+        cost += 0.5 * huber_rho(s, h.huber_a, robust, w);
+      }
+    }
+  }
+  out4[0] = cost; out4[1] = model; out4[2] = dn2; out4[3] = xn2;
+}
+
+// CTA-level sum of per-thread partials (fixed order: lanes by butterfly, warps 0..7 in order) into dst[0..nv).
+template <int NV>
+__device__ void cta_sum(const Ctx& c, const double* vals, double* dst, bool is_max_last = false) {
+  double* wsc = c.sm + c.lay.misc + 64;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double s = (is_max_last && k == NV - 1) ? warp_max(vals[k]) : warp_sum(vals[k]);
+    if (c.lane == 0) wsc[c.warp * NSCAL + k] = s;
+  }
+  __syncthreads();
+  if (c.tid < NV) {
+    double s = 0.0;
+    for (int w = 0; w < LBA_NW; ++w) {
+      const double v = wsc[w * NSCAL + c.tid];
+      s = (is_max_last && c.tid == NV - 1) ? fmax(s, v) : s + v;
+    }
+    dst[c.tid] = s;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __restrict__ hdrs, SmemLayout lay) {
+  extern __shared__ __align__(16) double sm[];
+  cg::cluster_group cl = cg::this_cluster();
+  Ctx c;
+  c.CS = (int)cl.num_blocks();
+  c.rank = (int)cl.block_rank();
+  const int win = blockIdx.x / c.CS;
+  const WinHdr& h = hdrs[win];
+  c.h = &h; c.sm = sm; c.lay = lay;
+  c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
+  c.slot0 = h.cta_slot_off[c.rank]; c.nslots = h.cta_slot_off[c.rank + 1] - c.slot0; c.ntiles = c.nslots / 32;
+  c.line0 = h.cta_line_off[c.rank]; c.nlines = h.cta_line_off[c.rank + 1] - c.line0;
+  c.Zbuf = lay.z_in_smem ? (sm + lay.Z) : (h.Zg + (size_t)c.slot0 * ZS);
+  const int C = h.C, Cf = h.Cf, n = h.n, vlen = h.vlen;
+  const int g_off = h.nkeys * 36, zu_off = g_off + n, hd_off = zu_off + n, sc_off = hd_off + n;
+  double* camx = sm + lay.camx; double* camxt = sm + lay.camxt;
+  double* camR = sm + lay.camR; double* camRt = sm + lay.camRt;
+  double* cscale = sm + lay.cscale;
+  double* linex = sm + lay.linex; double* linext = sm + lay.linext;
+  double* V = sm + lay.V; double* yc = sm + lay.yc;
+  double* scal = sm + lay.misc + 8;     // [8] this CTA's partial scalars for the all-read exchange
+  double* red = sm + lay.misc + 16;     // [8] CTA-local reduction results
+
+  // ---- load parameters: cameras replicated, the CTA's lines gathered by global id ----
+  for (int i = c.tid; i < 6 * C; i += LBA_NT) camx[i] = h.params_in[i];
+  for (int i = c.tid; i < 4 * c.nlines; i += LBA_NT) linex[i] = h.params_in[6 * C + 4 * h.line_gid[c.line0 + i / 4] + (i & 3)];
+  __syncthreads();
+  if (c.tid < C) cam_precompute(camx + 6 * c.tid, camR + CAM_STRIDE * c.tid, true);
+  __syncthreads();
+
+  // ---- Jacobi scaling from the column norms at x0; initial and fixed cost ----
+  double p_cost, p_fixed, p_gmax, p_fail;
+  linearize_sweep<0>(c, 1.0, &p_cost, &p_fixed, &p_gmax, &p_fail);
+  __syncthreads();
+  for (int i = c.tid; i < vlen; i += LBA_NT) V[i] = 0.0;
+  __syncthreads();
+  fold_cameras(c, true);
+  {
+    double vals[2] = {p_cost, p_fixed};
+    cta_sum<2>(c, vals, V + sc_off);
+  }
+  cluster_allreduce(cl, c, vlen, -1);
+  for (int i = c.tid; i < n; i += LBA_NT) cscale[i] = 1.0 / (1.0 + sqrt(V[hd_off + i]));
+  const double fixed_cost = V[sc_off + 1];
+  double cost = V[sc_off + 0];
+  const double initial_cost = cost + fixed_cost;
+  __syncthreads();
+
+  // ---- LM state (identical on every thread of every CTA) ----
+  double radius = h.radius0, decrease_factor = 2.0;
+  double gmax = 0.0, gtol_abs = 0.0, x_norm2_cams = 0.0;
+  int successful = 0, unsuccessful = 0, invalid = 0, term = SLSLAM_NO_CONVERGENCE, iters = 0;
+  bool first_lin = true;
+
+  for (int it = 0; it < h.max_iters; ++it) {
+    // -- K1/K2: linearise at x with the current radius --
+    linearize_sweep<1>(c, radius, &p_cost, &p_fixed, &p_gmax, &p_fail);
+    __syncthreads();
+    schur_pairs(c);
+    for (int i = g_off + c.tid; i < vlen; i += LBA_NT) V[i] = 0.0;
+    __syncthreads();
+    fold_cameras(c, false);
+    {
+      double vals[3] = {p_cost, p_fail, p_gmax};
+      cta_sum<3>(c, vals, V + sc_off, true);
+    }
+    cluster_allreduce(cl, c, vlen, sc_off + 2);
+    cost = V[sc_off + 0];
+    const bool line_fail = V[sc_off + 1] != 0.0;
+    // gradient max norm (unscaled Jacobian): lines from the sweep, cameras from g_c / scale; |x|^2 of the free cameras
+    {
+      double part[2] = {0.0, 0.0};
+      if (c.tid < 6 * C && h.cam_free[c.tid / 6] >= 0) part[0] = camx[c.tid] * camx[c.tid];
+      if (c.tid < n) part[1] = fabs(V[g_off + c.tid] / cscale[c.tid]);
+      cta_sum<2>(c, part, red, true);
+      x_norm2_cams = red[0];
+      gmax = fmax(V[sc_off + 2], red[1]);
+    }
+    if (first_lin) {
+      gtol_abs = h.gtol * fmax(gmax, 2.220446049250313e-16);
+      first_lin = false;
+    }
+    if (gmax <= gtol_abs) { term = SLSLAM_GRADIENT_TOLERANCE; break; }
+    iters = it + 1;
+    double* tr = (h.trace && c.rank == 0 && c.tid == 0) ? h.trace + (size_t)it * SLSLAM_TRACE_WIDTH : nullptr;
+    if (tr) { tr[0] = cost; tr[1] = 0; tr[2] = 0; tr[3] = radius; tr[4] = 0; tr[5] = 0; tr[6] = gmax; tr[7] = 0; }
+    // camera part of the model decrease needs g_c and D_c before the solve overwrites V
+    bool ok = !line_fail;
+    double model_c = 0.0;
+    if (Cf > 0) ok = reduced_solve(c, radius) && ok;
+    double dn2c = 0.0;
+    if (ok && Cf > 0) {
+      double part[3] = {0.0, 0.0, 0.0};
+      if (c.tid < n) {
+        const double y = yc[c.tid];
+        part[0] = 0.5 * y * (V[g_off + c.tid] + clampd(V[hd_off + c.tid], 1e-6, 1e32) / radius * y);
+        const double d = y * cscale[c.tid];
+        part[1] = d * d;
+        part[2] = isfinite(y) ? 0.0 : 1.0;
+      }
+      cta_sum<3>(c, part, red);
+      model_c = red[0]; dn2c = red[1];
+      if (red[2] != 0.0) ok = false;
+    }
+    double trial[4] = {0, 0, 0, 0};
+    if (ok) {
+      // trial cameras
+      for (int i = c.tid; i < 6 * C; i += LBA_NT) {
+        const int cf = h.cam_free[i / 6];
+        camxt[i] = camx[i] - (cf >= 0 ? yc[6 * cf + i % 6] * cscale[6 * cf + i % 6] : 0.0);
+      }
+      __syncthreads();
+      if (c.tid < C) cam_precompute(camxt + 6 * c.tid, camRt + CAM_STRIDE * c.tid, false);
+      __syncthreads();
+      double part[4];
+      trial_sweep(c, part);
+      cta_sum<4>(c, part, scal);
+      if (c.CS > 1) {
+        cl.sync();
+        for (int r = 0; r < c.CS; ++r) {
+          const double* rs = cl.map_shared_rank(scal, r);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) trial[k] += rs[k];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) trial[k] = scal[k];
+      }
+    }
+    const double model = trial[1] + model_c;
+    if (tr) tr[2] = model;
+    if (!ok || !(model > 0.0)) {
+      // LevenbergMarquardtStrategy::StepIsInvalid
+      ++unsuccessful;
+      if (tr) tr[5] = -1.0;
+      if (++invalid >= 5) { term = SLSLAM_NUMERICAL_FAILURE; break; }
+      radius *= 0.5;
+      if (radius < 1e-32) { term = SLSLAM_PARAMETER_TOLERANCE; break; }
+      continue;
+    }
+    invalid = 0;
+    const double new_cost = trial[0];
+    const double step_norm = sqrt(trial[2] + dn2c);
+    const double x_norm = sqrt(trial[3] + x_norm2_cams);
+    if (tr) { tr[1] = new_cost; tr[4] = step_norm; }
+    if (step_norm <= h.ptol * (x_norm + h.ptol)) { term = SLSLAM_PARAMETER_TOLERANCE; break; }
+    const double cost_change = cost - new_cost;
+    if (fabs(cost_change) < h.ftol * cost) { term = SLSLAM_FUNCTION_TOLERANCE; break; }
+    const double rel = cost_change / model;
+    if (tr) tr[7] = rel;
+    if (rel > 1e-3) {
+      ++successful;
+      if (tr) tr[5] = 1.0;
+      __syncthreads();
+      // adopt the trial point
+      for (int i = c.tid; i < 6 * C; i += LBA_NT) camx[i] = camxt[i];
+      for (int i = c.tid; i < 4 * c.nlines; i += LBA_NT) linex[i] = linext[i];
+      __syncthreads();
+      if (c.tid < C) cam_precompute(camx + 6 * c.tid, camR + CAM_STRIDE * c.tid, true);
+      __syncthreads();
+      cost = new_cost;
+      const double t = 2.0 * rel - 1.0;
+      radius = fmin(1e16, radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+      decrease_factor = 2.0;
+    } else {
+      ++unsuccessful;
+      radius /= decrease_factor;
+      decrease_factor *= 2.0;
+    }
+    if (radius < 1e-32) { term = SLSLAM_PARAMETER_TOLERANCE; break; }
+  }
+
+  // ---- write back: cameras by rank 0, each CTA its own lines ----
+  __syncthreads();
+  if (c.rank == 0) for (int i = c.tid; i < 6 * C; i += LBA_NT) h.params_out[i] = camx[i];
+  for (int i = c.tid; i < 4 * c.nlines; i += LBA_NT) h.params_out[6 * C + 4 * h.line_gid[c.line0 + i / 4] + (i & 3)] = linex[i];
+  if (c.rank == 0 && c.tid == 0) {
+    slslam_summary s;
+    s.initial_cost = initial_cost; s.final_cost = cost + fixed_cost; s.fixed_cost = fixed_cost; s.gradient_max_norm = gmax;
+    s.num_successful_steps = successful; s.num_unsuccessful_steps = unsuccessful; s.termination_type = term; s.iterations = iters;
+    *h.summary = s;
+  }
+  if (c.CS > 1) cl.sync();   // no CTA may exit while a peer can still read its shared memory
+}
+
+// K1 alone, one thread per observation, for parity tests of the residual and the analytic Jacobian.
+__global__ void lba_evaluate_kernel(int N, int C, const int* __restrict__ cam_idx, const int* __restrict__ line_idx,
+                                    const double* __restrict__ obs, const double* __restrict__ params, double baseline,
+                                    double huber_a, int robust, double* __restrict__ res, double* __restrict__ Jc,
+                                    double* __restrict__ Jl, double* __restrict__ cost) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double rho = 0.0;
+  if (i < N) {
+    double cpre[CAM_STRIDE];
+    cam_precompute(params + 6 * cam_idx[i], cpre, true);
+    LineTrig lt;
+    line_trig(params + 6 * C + 4 * line_idx[i], lt);
+    double r[4], jc[24], jl[16];
+    obs_eval<true>(cpre, lt, obs + 8 * (size_t)i, baseline, r, jc, jl);
+    for (int k = 0; k < 4; ++k) res[4 * (size_t)i + k] = r[k];
+    if (Jc) for (int k = 0; k < 24; ++k) Jc[24 * (size_t)i + k] = jc[k];
+    if (Jl) for (int k = 0; k < 16; ++k) Jl[16 * (size_t)i + k] = jl[k];
+    double w;
+    rho = 0.5 * huber_rho(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3], huber_a, robust != 0, w);
+  }
+  rho = warp_sum(rho);
+  if ((threadIdx.x & 31) == 0 && rho != 0.0) atomicAdd(cost, rho);
+}
+
+}  // namespace slslam
