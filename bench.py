@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Benchmark of the LBA hot path: LM iterations / s on 10-keyframe windows (BASELINE.json metric).
+
+A step = one batched solve (max 10 LM iterations per window, Ceres-default tolerances) of WINDOWS_PER_GPU independent
+M windows (10 KF / 2 k lines / 10 k observations, BASELINE.json configs[1]; 8 per GPU so that 8 GPUs solve the 64 windows
+of configs[3]).  Weak scaling: every rank owns its own windows, no data-path collective.
+
+  value     LM iterations / s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e       the same through the host-buffer C-ABI call slslam_lba_solve_batch (plan + H2D + solve + D2H in the timed region)
+  roofline  algorithmic bytes of the solve kernel / its event-timed duration against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference   the CPU oracle (a restatement of the reference's Ceres path; Ceres itself cannot be
+            built here) timed on the host cores
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from slslam_b200 import synth  # noqa: E402
+
+WINDOWS_PER_GPU = 8
+MAX_ITERS = 10
+SIGMA_PX = 1.0
+START = "far"
+METRIC = "lba_lm_iterations_per_s"
+UNIT = "LM iterations/s"
+
+
+def make_windows(rank, count=WINDOWS_PER_GPU):
+    return [synth.window_M(rank * count + i, sigma_px=SIGMA_PX, start=START) for i in range(count)]
+
+
+def algorithmic_bytes_per_iteration(w):
+    """two sweeps over the observations (64 B + 8 B of indices each), parameters read twice, written once."""
+    return 2 * 72 * w.num_observations + 3 * 8 * (6 * w.num_cameras + 4 * w.num_lines)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region (pynvml)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.sm_max = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def result(self):
+        self.stop_flag = True
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+def oracle_solve_windows(windows, threads):
+    """The CPU oracle on `threads` host threads, one window per thread (ctypes releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle
+    oracle.lib()
+    t0 = time.perf_counter()
+    if threads <= 1:
+        res = [oracle.lba_solve(w, max_iters=MAX_ITERS, solver=1) for w in windows]
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            res = list(ex.map(lambda w: oracle.lba_solve(w, max_iters=MAX_ITERS, solver=1), windows))
+    dt = time.perf_counter() - t0
+    return sum(s["iterations"] for _, s in res), dt, res
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference itself cannot be compiled in this
+    image (Ceres 1.7.0 / Eigen / gflags / glog absent), so this is the oracle port, with every host thread it can use."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    windows = make_windows(0)
+    threads = min(cores, len(windows))
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        oracle_solve_windows(windows[:threads], threads)
+    iters, secs = 0, 0.0
+    for _ in range(args.steps):
+        it, dt, _ = oracle_solve_windows(windows, threads)
+        iters += it; secs += dt
+    value = iters / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(windows),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} x ({len(windows)} M windows x <= {MAX_ITERS} LM iterations), one window per thread"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle port of the reference's Ceres path (reference not buildable here: Ceres 1.7.0 absent)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(windows):
+    w = windows[0]
+    return {"workload": f"{len(windows)} independent M windows per GPU (10 KF / {w.num_lines} lines / {w.num_observations} obs each), "
+                        f"max {MAX_ITERS} LM iterations, Huber 1/406.05, sigma {SIGMA_PX} px, '{START}' start, gauge-anchored",
+            "windows_per_gpu": len(windows), "max_iterations": MAX_ITERS,
+            "l2": "flushed between timed steps (256 MiB write)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--windows-per-gpu", type=int, default=WINDOWS_PER_GPU)
+    ap.add_argument("--cluster-size", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps = 20
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from slslam_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available() or capi.lib().slslam_device_count() < 1:
+        raise SystemExit("bench.py: no sm_100 GPU; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W = max(3, args.warmup)
+    K = args.steps
+
+    windows = make_windows(rank, args.windows_per_gpu)
+    batch = capi.LbaBatch(windows, device=local_rank, cluster_size=args.cluster_size, max_iters=MAX_ITERS)
+    info = batch.info()
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        flush.zero_()
+        batch.solve(sptr)
+    torch.cuda.synchronize()
+    _, summ = batch.download(sptr)
+    iters_per_step = sum(s["iterations"] for s in summ)
+
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    for k in range(K):
+        flush.zero_()                 # evict the windows from L2 (not timed)
+        starts[k].record(stream)
+        batch.solve(sptr)             # ONE kernel launch: the whole LM loop of every window
+        ends[k].record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.result()
+    ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = float(sum(ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    it = torch.tensor([float(iters_per_step)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(it, op=dist.ReduceOp.SUM)
+    total_ms_max = float(t.item())
+    iters_all = float(it.item())
+    value = iters_all * K / (total_ms_max * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI, every step plans, uploads, solves and downloads ----
+    Ke = max(3, min(K, 20))
+    capi.lba_solve_batch(windows, max_iters=MAX_ITERS)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        ps, ss = capi.lba_solve_batch(windows, max_iters=MAX_ITERS)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_iters = sum(s["iterations"] for s in ss)
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = iters_all * Ke / float(te.item())
+    h2d, d2h = batch.transfer_bytes()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        alg_bytes = sum(algorithmic_bytes_per_iteration(w) * s["iterations"] for w, s in zip(windows, summ))
+        kernel_ms = float(np.mean(ms))
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(windows), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": Ke, "api": "slslam_lba_solve_batch (host buffers; plan + H2D + solve + D2H per step)"},
+            "gpu_launches": K,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "lba_solve_kernel", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src,
+                         "note": "fp64-issue / latency bound by construction (SURVEY.md §7): the whole LM loop runs "
+                                 "out of shared memory, DRAM traffic is far below the algorithmic bytes"},
+            "lm_iterations_per_step": iters_per_step, "kernel_config": info, "wall_s_timed_region": wall,
+            "final_cost_window0": summ[0]["final_cost"],
+        }
+        if not args.no_extras:
+            # configs[1] alone: one M window, latency bound
+            b1 = capi.LbaBatch(windows[:1], device=local_rank, max_iters=MAX_ITERS)
+            for _ in range(3):
+                b1.solve(sptr)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(20):
+                b1.solve(sptr)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            _, s1 = b1.download(sptr)
+            line["single_window"] = {"value": s1[0]["iterations"] * 20 / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT,
+                                     "cluster_size": b1.info()["cluster_size"], "l2": "warm"}
+            b1.close()
+        if world == 1 and not args.no_cpu_baseline:
+            reps = 2
+            iters_c, secs_c = 0, 0.0
+            for _ in range(reps):
+                a, b_, _ = oracle_solve_windows(windows, 1)
+                iters_c += a; secs_c += b_
+            line["cpu_baseline"] = {"value": iters_c / secs_c, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"{reps} x ({len(windows)} M windows x <= {MAX_ITERS} LM iterations), 1 thread "
+                                              "(the reference runs Ceres with num_threads = 1, lba_problem.cpp:103,127)",
+                                    "host_cpus": os.cpu_count()}
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

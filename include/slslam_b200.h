@@ -119,6 +119,11 @@ int slslam_lba_batch_download(slslam_lba_batch* b, void* cuda_stream, double* co
                               slslam_summary* summaries_out, double* const* trace_out);
 int slslam_lba_batch_info(const slslam_lba_batch* b, int32_t* cluster_size, int32_t* threads_per_cta,
                           int32_t* smem_bytes_per_cta, int32_t* z_in_smem);
+/* Diagnostics: SM cycles CTA 0 of `window` spent per phase in the last solve
+ * (init, linearise, pairs, fold, allreduce, gradient, reduced solve, trial, decide, total); n <= 10. */
+int slslam_lba_batch_phase_cycles(slslam_lba_batch* b, void* cuda_stream, int32_t window, int64_t* cycles_out, int32_t n);
+/* Bytes one host-buffer solve of this batch moves: plan + parameters up, parameters + summaries down. */
+int slslam_lba_batch_transfer_bytes(const slslam_lba_batch* b, int64_t* h2d_bytes, int64_t* d2h_bytes);
 void slslam_lba_batch_destroy(slslam_lba_batch* b);
 
 /* ---- K1 alone: residuals (Huber-unscaled) and analytic Jacobians of every observation, for parity tests ----

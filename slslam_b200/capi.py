@@ -21,7 +21,7 @@ TERMINATION = {0: "NO_CONVERGENCE", 1: "GRADIENT_TOLERANCE", 2: "FUNCTION_TOLERA
 EXPORTS = [
     "slslam_version", "slslam_strerror", "slslam_last_error", "slslam_device_count", "slslam_lba_get_limits",
     "slslam_lba_solve", "slslam_lba_solve_batch", "slslam_lba_batch_create", "slslam_lba_batch_solve",
-    "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_destroy",
+    "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_transfer_bytes", "slslam_lba_batch_phase_cycles", "slslam_lba_batch_destroy",
     "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate",
 ]
 
@@ -92,6 +92,8 @@ def lib():
         L.slslam_lba_batch_upload_params.argtypes = [C.c_void_p, C.POINTER(dp), C.c_void_p]
         L.slslam_lba_batch_download.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(dp), C.POINTER(Summary), C.POINTER(dp)]
         L.slslam_lba_batch_info.argtypes = [C.c_void_p, ip, ip, ip, ip]
+        L.slslam_lba_batch_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.slslam_lba_batch_phase_cycles.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.c_int32]
         L.slslam_lba_batch_destroy.argtypes = [C.c_void_p]
         L.slslam_lba_batch_destroy.restype = None
         L.slslam_lba_evaluate.argtypes = [C.POINTER(LbaDesc), dp, dp, dp, dp, dp]
@@ -181,6 +183,18 @@ class LbaBatch:
         a, b, c, d = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         _check(lib().slslam_lba_batch_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return dict(cluster_size=a.value, threads_per_cta=b.value, smem_bytes_per_cta=c.value, z_in_smem=d.value)
+
+    def transfer_bytes(self):
+        a, b = C.c_int64(), C.c_int64()
+        _check(lib().slslam_lba_batch_transfer_bytes(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    PHASES = ("init", "linearise", "pairs", "fold", "allreduce", "gradient", "reduced_solve", "trial", "decide", "total")
+
+    def phase_cycles(self, window=0, stream=None):
+        buf = (C.c_int64 * 10)()
+        _check(lib().slslam_lba_batch_phase_cycles(self._h, C.c_void_p(stream), window, buf, 10))
+        return dict(zip(self.PHASES, list(buf)))
 
     def upload(self, params=None, stream=None):
         ps = self._p0 if params is None else [np.ascontiguousarray(p, np.float64) for p in params]

@@ -184,8 +184,10 @@ struct slslam_lba_batch {
   WinHdr* d_hdrs = nullptr;
   double *d_params_in = nullptr, *d_params_out = nullptr, *d_trace = nullptr;
   slslam_summary* d_summ = nullptr;
+  long long* d_phase = nullptr;
   // pinned host staging
   double* h_params = nullptr;
+  size_t upload_bytes = 0;
 };
 
 namespace slslam {
@@ -296,7 +298,7 @@ int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const doubl
     b->trace_off[i] = tt; tt += (size_t)std::max(1, b->plans[i].max_iters) * SLSLAM_TRACE_WIDTH;
   }
   b->total_params = tp; b->total_trace = tt;
-  const size_t o_pin = reserve(tp * 8), o_pout = reserve(tp * 8), o_trace = reserve(tt * 8), o_summ = reserve(sizeof(slslam_summary) * n);
+  const size_t o_pin = reserve(tp * 8), o_pout = reserve(tp * 8), o_trace = reserve(tt * 8), o_summ = reserve(sizeof(slslam_summary) * n), o_phase = reserve(sizeof(long long) * NPHASE * n);
   std::vector<size_t> o_obs(n), o_meta(n), o_gid(n), o_items(n), o_koff(n), o_z(n);
   for (int i = 0; i < n; ++i) {
     const WindowPlan& p = b->plans[i];
@@ -310,6 +312,7 @@ int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const doubl
   b->d_hdrs = (WinHdr*)(b->d_pool + o_hdr);
   b->d_params_in = (double*)(b->d_pool + o_pin); b->d_params_out = (double*)(b->d_pool + o_pout);
   b->d_trace = (double*)(b->d_pool + o_trace); b->d_summ = (slslam_summary*)(b->d_pool + o_summ);
+  b->d_phase = (long long*)(b->d_pool + o_phase);
   for (int i = 0; i < n; ++i) {
     const WindowPlan& p = b->plans[i];
     WinHdr h; memset(&h, 0, sizeof(h));
@@ -321,7 +324,7 @@ int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const doubl
     h.key_off = (const int*)(b->d_pool + o_koff[i]);
     h.params_in = b->d_params_in + b->param_off[i]; h.params_out = b->d_params_out + b->param_off[i];
     h.Zg = b->lay.z_in_smem ? nullptr : (double*)(b->d_pool + o_z[i]);
-    h.summary = b->d_summ + i; h.trace = b->d_trace + b->trace_off[i];
+    h.summary = b->d_summ + i; h.trace = b->d_trace + b->trace_off[i]; h.phase_cycles = b->d_phase + (size_t)NPHASE * i;
     memcpy(h.cta_slot_off, p.cta_slot_off, sizeof(h.cta_slot_off));
     memcpy(h.cta_line_off, p.cta_line_off, sizeof(h.cta_line_off));
     memcpy(h.cam_free, p.cam_free, sizeof(h.cam_free));
@@ -335,6 +338,7 @@ int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const doubl
   }
   // only the plan + params region needs uploading (Z staging at the tail is scratch)
   CUDA_TRY_OR(cudaMemcpy(b->d_pool, host.data(), off, cudaMemcpyHostToDevice), { slslam_lba_batch_destroy(b); return SLSLAM_ERR_CUDA; });
+  b->upload_bytes = off;
   CUDA_TRY_OR(cudaMallocHost((void**)&b->h_params, std::max<size_t>(tp, 1) * 8), { slslam_lba_batch_destroy(b); return SLSLAM_ERR_CUDA; });
   *out = b;
   return SLSLAM_OK;
@@ -390,6 +394,23 @@ int slslam_lba_batch_info(const slslam_lba_batch* b, int32_t* cluster_size, int3
   if (threads_per_cta) *threads_per_cta = LBA_NT;
   if (smem_bytes_per_cta) *smem_bytes_per_cta = (int32_t)b->smem_bytes;
   if (z_in_smem) *z_in_smem = b->lay.z_in_smem;
+  return SLSLAM_OK;
+}
+
+int slslam_lba_batch_phase_cycles(slslam_lba_batch* b, void* cuda_stream, int32_t window, int64_t* cycles_out, int32_t n) {
+  if (!b || !cycles_out || window < 0 || window >= b->n) return SLSLAM_ERR_INVALID;
+  cudaSetDevice(b->device);
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  long long tmp[NPHASE];
+  CUDA_TRY(cudaMemcpy(tmp, b->d_phase + (size_t)NPHASE * window, sizeof(tmp), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < n && k < NPHASE; ++k) cycles_out[k] = tmp[k];
+  return SLSLAM_OK;
+}
+
+int slslam_lba_batch_transfer_bytes(const slslam_lba_batch* b, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+  if (!b) return SLSLAM_ERR_INVALID;
+  if (h2d_bytes) *h2d_bytes = (int64_t)b->upload_bytes;
+  if (d2h_bytes) *d2h_bytes = (int64_t)(b->total_params * 8 + sizeof(slslam_summary) * (size_t)b->n);
   return SLSLAM_OK;
 }
 

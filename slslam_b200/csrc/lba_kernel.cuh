@@ -29,6 +29,7 @@ constexpr int ZS = 24;               // doubles per Z block (6 x 4, row-major)
 constexpr int ACC = 33;              // per-camera accumulators: H_cc (21, lower) | g_c (6) | sum Z u (6)
 constexpr int LLU = 18;              // per-line: L (10, lower) | u = L^-1 g_l (4) | D_l (4)
 constexpr int NSCAL = 8;
+constexpr int NPHASE = 10;         // init | linearise | pairs | fold | allreduce | gradient | reduced solve | trial | decide | total
 
 // slot flags (meta.x bits 24..)
 constexpr int F_VALID = 1, F_CAM_FIXED = 2, F_LINE_FIXED = 4, F_HEAD = 8;
@@ -46,6 +47,7 @@ struct WinHdr {
   double* Zg;               // global Z staging when it does not fit in shared memory (else nullptr)
   slslam_summary* summary;
   double* trace;            // [max_iters][SLSLAM_TRACE_WIDTH] or nullptr
+  long long* phase_cycles;  // [NPHASE] SM cycles spent per phase by CTA 0 (diagnostics) or nullptr
   int cta_slot_off[MAX_CS + 1];
   int cta_line_off[MAX_CS + 1];
   signed char cam_free[MAX_CAMS];   // reduced block index of each camera or -1
@@ -639,6 +641,7 @@ __device__ void cta_sum(const Ctx& c, const double* vals, double* dst, bool is_m
 __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __restrict__ hdrs, SmemLayout lay) {
   extern __shared__ __align__(16) double sm[];
   cg::cluster_group cl = cg::this_cluster();
+  const long long t0k = clock64();
   Ctx c;
   c.CS = (int)cl.num_blocks();
   c.rank = (int)cl.block_rank();
@@ -690,19 +693,30 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
   int successful = 0, unsuccessful = 0, invalid = 0, term = SLSLAM_NO_CONVERGENCE, iters = 0;
   bool first_lin = true;
 
+  long long ph[NPHASE];
+#pragma unroll
+  for (int k = 0; k < NPHASE; ++k) ph[k] = 0;
+  long long tk = clock64();
+  const long long t_begin = t0k;
+#define PHASE(i) { const long long now_ = clock64(); ph[i] += now_ - tk; tk = now_; }
+  PHASE(0)
   for (int it = 0; it < h.max_iters; ++it) {
     // -- K1/K2: linearise at x with the current radius --
     linearize_sweep<1>(c, radius, &p_cost, &p_fixed, &p_gmax, &p_fail);
     __syncthreads();
+    PHASE(1)
     schur_pairs(c);
     for (int i = g_off + c.tid; i < vlen; i += LBA_NT) V[i] = 0.0;
     __syncthreads();
+    PHASE(2)
     fold_cameras(c, false);
     {
       double vals[3] = {p_cost, p_fail, p_gmax};
       cta_sum<3>(c, vals, V + sc_off, true);
     }
+    PHASE(3)
     cluster_allreduce(cl, c, vlen, sc_off + 2);
+    PHASE(4)
     cost = V[sc_off + 0];
     const bool line_fail = V[sc_off + 1] != 0.0;
     // gradient max norm (unscaled Jacobian): lines from the sweep, cameras from g_c / scale; |x|^2 of the free cameras
@@ -718,6 +732,7 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
       gtol_abs = h.gtol * fmax(gmax, 2.220446049250313e-16);
       first_lin = false;
     }
+    PHASE(5)
     if (gmax <= gtol_abs) { term = SLSLAM_GRADIENT_TOLERANCE; break; }
     iters = it + 1;
     double* tr = (h.trace && c.rank == 0 && c.tid == 0) ? h.trace + (size_t)it * SLSLAM_TRACE_WIDTH : nullptr;
@@ -726,6 +741,7 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
     bool ok = !line_fail;
     double model_c = 0.0;
     if (Cf > 0) ok = reduced_solve(c, radius) && ok;
+    PHASE(6)
     double dn2c = 0.0;
     if (ok && Cf > 0) {
       double part[3] = {0.0, 0.0, 0.0};
@@ -765,6 +781,7 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
         for (int k = 0; k < 4; ++k) trial[k] = scal[k];
       }
     }
+    PHASE(7)
     const double model = trial[1] + model_c;
     if (tr) tr[2] = model;
     if (!ok || !(model > 0.0)) {
@@ -806,6 +823,7 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
       decrease_factor *= 2.0;
     }
     if (radius < 1e-32) { term = SLSLAM_PARAMETER_TOLERANCE; break; }
+    PHASE(8)
   }
 
   // ---- write back: cameras by rank 0, each CTA its own lines ----
@@ -817,7 +835,13 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
     s.initial_cost = initial_cost; s.final_cost = cost + fixed_cost; s.fixed_cost = fixed_cost; s.gradient_max_norm = gmax;
     s.num_successful_steps = successful; s.num_unsuccessful_steps = unsuccessful; s.termination_type = term; s.iterations = iters;
     *h.summary = s;
+    if (h.phase_cycles) {
+      ph[NPHASE - 1] = clock64() - t_begin;
+#pragma unroll
+      for (int k = 0; k < NPHASE; ++k) h.phase_cycles[k] = ph[k];
+    }
   }
+#undef PHASE
   if (c.CS > 1) cl.sync();   // no CTA may exit while a peer can still read its shared memory
 }
 
