@@ -119,6 +119,8 @@ int slslam_lba_batch_download(slslam_lba_batch* b, void* cuda_stream, double* co
                               slslam_summary* summaries_out, double* const* trace_out);
 int slslam_lba_batch_info(const slslam_lba_batch* b, int32_t* cluster_size, int32_t* threads_per_cta,
                           int32_t* smem_bytes_per_cta, int32_t* z_in_smem);
+/* How many clusters of this batch's shape the device keeps resident at once (a batch larger than this runs in waves). */
+int slslam_lba_batch_max_active_clusters(const slslam_lba_batch* b, int32_t* max_active);
 /* Diagnostics: SM cycles CTA 0 of `window` spent per phase in the last solve
  * (init, linearise, pairs, fold, allreduce, gradient, reduced solve, trial, decide, total); n <= 10. */
 int slslam_lba_batch_phase_cycles(slslam_lba_batch* b, void* cuda_stream, int32_t window, int64_t* cycles_out, int32_t n);
@@ -135,6 +137,8 @@ int slslam_lba_evaluate(const slslam_lba_desc* desc, const double* params, doubl
 int slslam_po_solve(const slslam_po_desc* desc, double* poses_inout, slslam_summary* summary_out);
 int slslam_po_solve_trace(const slslam_po_desc* desc, double* poses_inout, slslam_summary* summary_out,
                           double* trace_out);
+/* Device time (CUDA events, ms) of the LM loop of this thread's last slslam_po_solve*, transfers excluded. */
+float slslam_po_last_solve_ms(void);
 /* residuals [6E], jac_pose1 / jac_pose2 [36E] row-major 6x6 */
 int slslam_po_evaluate(const slslam_po_desc* desc, const double* poses, double* residuals, double* jac_pose1,
                        double* jac_pose2, double* cost_out);

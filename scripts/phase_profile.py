@@ -6,7 +6,11 @@ import torch
 from slslam_b200 import capi, synth
 
 def run(windows, cs, reps=10):
-    b = capi.LbaBatch(windows, cluster_size=cs, max_iters=10)
+    try:
+        b = capi.LbaBatch(windows, cluster_size=cs, max_iters=10)
+    except capi.SlslamError as e:
+        print(f"nwin={len(windows)} CS={cs}: {e}")
+        return
     st = torch.cuda.current_stream(); sp = st.cuda_stream
     for _ in range(3): b.solve(sp)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -19,20 +23,20 @@ def run(windows, cs, reps=10):
     ph = b.phase_cycles(0, sp)
     info = b.info(); b.close()
     n0 = ss[0]["iterations"]
-    print(f"nwin={len(windows)} CS={info['cluster_size']} zsm={info['z_in_smem']} smem={info['smem_bytes_per_cta']} ms={ms:.3f} iters={it} "
+    print(f"nwin={len(windows)} CS={info['cluster_size']} act={info['max_active_clusters']} zsm={info['z_in_smem']} smem={info['smem_bytes_per_cta']} ms={ms:.3f} iters={it} "
           f"-> {it/ms*1e3:.0f} it/s, {ms*1e3/ n0:.1f} us/iter(win0)")
-    print("   cycles/iter: " + " ".join(f"{k}={v/(n0 if k not in ('init','total') else 1):.0f}" for k, v in ph.items()))
+    print("   cycles/iter: " + " ".join(f"{k}={v/(n0 if k not in ('init','total') else 1):.0f}" for k, v in ph.items()), flush=True)
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     ws = [synth.window_M(i, sigma_px=1.0, start="far") for i in range(8)]
     if which in ("all", "single"):
-        for cs in (16, 8, 4, 2, 1):
+        for cs in (16, 12, 8, 4):
             run(ws[:1], cs)
     if which in ("all", "batch"):
-        for cs in (16, 8, 4):
+        for cs in (0, 16, 14, 12, 10, 8, 4):
             run(ws, cs)
     if which in ("all", "small"):
         s = [synth.window_S(i, sigma_px=1.0, start="far") for i in range(8)]
-        for cs in (8, 4, 2, 1):
+        for cs in (0, 8, 4, 2, 1):
             run(s[:1], cs)

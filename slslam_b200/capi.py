@@ -13,7 +13,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libslslam_b200.so")
+LIB_PATH = os.environ.get("SLSLAM_B200_LIB", os.path.join(_HERE, "libslslam_b200.so"))
 TRACE_WIDTH = 8
 TERMINATION = {0: "NO_CONVERGENCE", 1: "GRADIENT_TOLERANCE", 2: "FUNCTION_TOLERANCE", 3: "PARAMETER_TOLERANCE",
                4: "NUMERICAL_FAILURE"}
@@ -21,8 +21,8 @@ TERMINATION = {0: "NO_CONVERGENCE", 1: "GRADIENT_TOLERANCE", 2: "FUNCTION_TOLERA
 EXPORTS = [
     "slslam_version", "slslam_strerror", "slslam_last_error", "slslam_device_count", "slslam_lba_get_limits",
     "slslam_lba_solve", "slslam_lba_solve_batch", "slslam_lba_batch_create", "slslam_lba_batch_solve",
-    "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_transfer_bytes", "slslam_lba_batch_phase_cycles", "slslam_lba_batch_destroy",
-    "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate",
+    "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_max_active_clusters", "slslam_lba_batch_transfer_bytes", "slslam_lba_batch_phase_cycles", "slslam_lba_batch_destroy",
+    "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate", "slslam_po_last_solve_ms",
 ]
 
 dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
@@ -92,6 +92,7 @@ def lib():
         L.slslam_lba_batch_upload_params.argtypes = [C.c_void_p, C.POINTER(dp), C.c_void_p]
         L.slslam_lba_batch_download.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(dp), C.POINTER(Summary), C.POINTER(dp)]
         L.slslam_lba_batch_info.argtypes = [C.c_void_p, ip, ip, ip, ip]
+        L.slslam_lba_batch_max_active_clusters.argtypes = [C.c_void_p, ip]
         L.slslam_lba_batch_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.slslam_lba_batch_phase_cycles.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.c_int32]
         L.slslam_lba_batch_destroy.argtypes = [C.c_void_p]
@@ -100,6 +101,7 @@ def lib():
         L.slslam_po_solve.argtypes = [C.POINTER(PoDesc), dp, C.POINTER(Summary)]
         L.slslam_po_solve_trace.argtypes = [C.POINTER(PoDesc), dp, C.POINTER(Summary), dp]
         L.slslam_po_evaluate.argtypes = [C.POINTER(PoDesc), dp, dp, dp, dp, dp]
+        L.slslam_po_last_solve_ms.restype = C.c_float
         _LIB = L
     return _LIB
 
@@ -182,7 +184,10 @@ class LbaBatch:
     def info(self):
         a, b, c, d = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         _check(lib().slslam_lba_batch_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
-        return dict(cluster_size=a.value, threads_per_cta=b.value, smem_bytes_per_cta=c.value, z_in_smem=d.value)
+        m = C.c_int32()
+        _check(lib().slslam_lba_batch_max_active_clusters(self._h, C.byref(m)))
+        return dict(cluster_size=a.value, threads_per_cta=b.value, smem_bytes_per_cta=c.value, z_in_smem=d.value,
+                    max_active_clusters=m.value)
 
     def transfer_bytes(self):
         a, b = C.c_int64(), C.c_int64()

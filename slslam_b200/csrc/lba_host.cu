@@ -188,22 +188,50 @@ struct slslam_lba_batch {
   // pinned host staging
   double* h_params = nullptr;
   size_t upload_bytes = 0;
+  int max_active = 0;   // co-resident clusters of this shape on the device
 };
 
 namespace slslam {
 
-static int pick_cluster_size(int nwin, long long max_obs, int requested) {
-  if (requested > 0) {
-    int cs = 1;
-    while (cs * 2 <= requested && cs * 2 <= MAX_CS) cs *= 2;
-    return cs;
+// Co-resident clusters of each size (1 CTA per SM: the kernel uses 255 registers x 256 threads), cached per device.
+// On B200 a 16-CTA cluster must sit inside one GPC, so fewer than 148/16 fit.
+static int max_active_clusters(int device, int cs) {
+  static int table[16][MAX_CS + 1];
+  static bool known[16][MAX_CS + 1];
+  if (device < 0 || device >= 16 || cs < 1 || cs > MAX_CS) return 0;
+  if (!known[device][cs]) {
+    cudaFuncSetAttribute(lba_solve_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = dim3((unsigned)cs, 1, 1); cfg.blockDim = dim3(LBA_NT, 1, 1); cfg.dynamicSmemBytes = 0;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, lba_solve_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    table[device][cs] = n; known[device][cs] = true;
   }
-  // at least ~8 tiles (one per warp) per CTA, and all clusters of the batch co-resident on the 148 SMs
-  int cs = MAX_CS;
-  const long long tiles = (max_obs + 27) / 28;
-  while (cs > 1 && tiles / cs < 8) cs >>= 1;
-  while (cs > 1 && (long long)nwin * cs > 148) cs >>= 1;
-  return cs;
+  return table[device][cs];
+}
+
+// Cluster sizes to try, best first.  Model of one LM iteration of a window on a cluster of cs CTAs (measured on B200,
+// profiles/): t(cs) = fixed + per_obs * N / cs; a batch runs ceil(nwin / co-resident clusters) waves.
+static void rank_cluster_sizes(int device, int nwin, long long max_obs, int requested, std::vector<int>& out) {
+  out.clear();
+  if (requested > 0) { out.push_back(std::min(requested, (int)MAX_CS)); return; }
+  std::vector<std::pair<double, int> > cand;
+  for (int cs = 1; cs <= MAX_CS; ++cs) {
+    const int act = max_active_clusters(device, cs);
+    if (act < 1) continue;
+    const long long tiles = (max_obs + 27) / 28;
+    if (cs > 1 && tiles / cs < 2) continue;                 // not even two tiles per CTA: the syncs would dominate
+    const double waves = std::ceil((double)nwin / act);
+    const double t = waves * (60.0 + 0.081 * (double)max_obs / cs);
+    cand.push_back(std::make_pair(t, -cs));                  // ties: larger cluster first
+  }
+  std::sort(cand.begin(), cand.end());
+  for (auto& c : cand) out.push_back(-c.second);
+  if (out.empty()) out.push_back(1);
 }
 
 static int launch_config(slslam_lba_batch* b, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, cudaStream_t st) {
@@ -248,12 +276,14 @@ int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const doubl
   b->n = n;
   long long max_obs = 0;
   for (int i = 0; i < n; ++i) max_obs = std::max<long long>(max_obs, descs[i].num_observations);
-  int CS = pick_cluster_size(n, max_obs, cluster_size);
+  std::vector<int> cs_order;
+  rank_cluster_sizes(b->device, n, max_obs, cluster_size, cs_order);
 
   int smem_optin = 0;
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device);
-  for (int attempt = 0;; ++attempt) {
-    if (attempt > 8) { delete b; return SLSLAM_ERR_UNSUPPORTED; }
+  bool placed = false;
+  for (size_t attempt = 0; attempt < cs_order.size() && !placed; ++attempt) {
+    const int CS = cs_order[attempt];
     b->plans.assign(n, WindowPlan());
     int Cmax = 1, Cfmax = 0, mlines = 1, mslots = 32;
     for (int i = 0; i < n; ++i) {
@@ -265,25 +295,22 @@ int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const doubl
     b->lay = lba_layout(Cmax, Cfmax, mlines, mslots, CS, (size_t)smem_optin);
     b->smem_bytes = (size_t)b->lay.total * 8;
     b->CS = CS;
-    if (b->smem_bytes > (size_t)smem_optin) {
-      // the fixed part alone does not fit: too many lines per CTA for this cluster size
-      if (CS < MAX_CS && cluster_size <= 0) { CS *= 2; continue; }
-      delete b; return SLSLAM_ERR_UNSUPPORTED;
-    }
-    // check that the cluster shape can be scheduled at all; fall back to smaller clusters otherwise
+    if (b->smem_bytes > (size_t)smem_optin) continue;   // the fixed part alone does not fit: too many lines per CTA
     CUDA_TRY_OR(cudaFuncSetAttribute(lba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes), { delete b; return SLSLAM_ERR_CUDA; });
     CUDA_TRY_OR(cudaFuncSetAttribute(lba_solve_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), { delete b; return SLSLAM_ERR_CUDA; });
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
     launch_config(b, &cfg, attr, nullptr);
     int nclusters = 0;
     cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, lba_solve_kernel, &cfg);
-    if (e != cudaSuccess || nclusters < 1) {
-      cudaGetLastError();
-      if (CS > 1 && cluster_size <= 0) { CS >>= 1; continue; }
-      set_last_error("cluster shape cannot be scheduled");
-      delete b; return SLSLAM_ERR_CUDA;
-    }
-    break;
+    if (e != cudaSuccess || nclusters < 1) { cudaGetLastError(); continue; }
+    b->max_active = nclusters;
+    placed = true;
+  }
+  if (!placed) {
+    set_last_error("no cluster shape fits this batch (shared memory / scheduling)");
+    const bool cuda_side = cluster_size > 0 && cs_order.size() == 1 && b->smem_bytes <= (size_t)smem_optin;
+    delete b;
+    return cuda_side ? SLSLAM_ERR_CUDA : SLSLAM_ERR_UNSUPPORTED;
   }
 
   // ---- pooled device allocation ----
@@ -305,7 +332,7 @@ int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const doubl
     o_obs[i] = reserve(p.obs.size() * 8); o_meta[i] = reserve(p.meta.size() * sizeof(int2));
     o_gid[i] = reserve(p.line_gid.size() * 4 + 4); o_items[i] = reserve(p.items.size() * 4 + 4);
     o_koff[i] = reserve(p.key_off.size() * 4 + 4);
-    o_z[i] = b->lay.z_in_smem ? 0 : reserve(p.meta.size() * ZS * 8);
+    o_z[i] = b->lay.z_in_smem ? 0 : reserve(p.meta.size() * ZST * 8);
   }
   CUDA_TRY_OR(cudaMalloc((void**)&b->d_pool, off), { delete b; return SLSLAM_ERR_CUDA; });
   std::vector<char> host(off, 0);
@@ -384,6 +411,12 @@ int slslam_lba_batch_download(slslam_lba_batch* b, void* cuda_stream, double* co
     if (params_out && params_out[i]) memcpy(params_out[i], b->h_params + b->param_off[i], (size_t)b->nparams[i] * 8);
     if (trace_out && trace_out[i]) memcpy(trace_out[i], tr.data() + b->trace_off[i], (size_t)b->plans[i].max_iters * SLSLAM_TRACE_WIDTH * 8);
   }
+  return SLSLAM_OK;
+}
+
+int slslam_lba_batch_max_active_clusters(const slslam_lba_batch* b, int32_t* max_active) {
+  if (!b || !max_active) return SLSLAM_ERR_INVALID;
+  *max_active = b->max_active;
   return SLSLAM_OK;
 }
 

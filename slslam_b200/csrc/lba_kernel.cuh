@@ -26,6 +26,7 @@ constexpr int MAX_CAMS = 32;
 constexpr int MAX_FREE_CAMS = 24;
 constexpr int MAX_CS = 16;
 constexpr int ZS = 24;               // doubles per Z block (6 x 4, row-major)
+constexpr int ZST = 26;              // row stride of the Z staging: 13 x 16 B, so 8 consecutive rows cover all 32 banks
 constexpr int ACC = 33;              // per-camera accumulators: H_cc (21, lower) | g_c (6) | sum Z u (6)
 constexpr int LLU = 18;              // per-line: L (10, lower) | u = L^-1 g_l (4) | D_l (4)
 constexpr int NSCAL = 8;
@@ -79,9 +80,9 @@ __host__ inline SmemLayout lba_layout(int C, int Cf, int max_lines_cta, int max_
   l.yc = take(6 * (Cf > 0 ? Cf : 1) + 8);
   l.misc = take(64 + LBA_NW * NSCAL);
   l.Z = o;
-  const size_t zbytes = (size_t)ZS * max_slots_cta * 8;
+  const size_t zbytes = (size_t)ZST * max_slots_cta * 8;
   l.z_in_smem = ((size_t)o * 8 + zbytes <= smem_limit_bytes) ? 1 : 0;
-  if (l.z_in_smem) o += ZS * max_slots_cta;
+  if (l.z_in_smem) o += ZST * max_slots_cta;
   l.total = o;
   return l;
 }
@@ -274,7 +275,7 @@ __device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, d
         Z[4 * p] = z0; Z[4 * p + 1] = z1; Z[4 * p + 2] = z2; Z[4 * p + 3] = z3;
       }
       if (valid) {
-        double2* zp = reinterpret_cast<double2*>(c.Zbuf + (size_t)ls * ZS);
+        double2* zp = reinterpret_cast<double2*>(c.Zbuf + (size_t)ls * ZST);
 #pragma unroll
         for (int k = 0; k < 12; ++k) zp[k] = make_double2(Z[2 * k], Z[2 * k + 1]);
       }
@@ -309,20 +310,46 @@ __device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, d
   *out_cost = cost; *out_fixed_cost = fixed_cost; *out_gmax = gmax; *out_fail = fail;
 }
 
+// Transposing warp reduction: every lane holds v[0..31]; on exit lane l holds sum over lanes of v[l] in v[0].
+// 31 shuffles instead of 160, fixed summation order (deterministic).
+__device__ __forceinline__ void warp_reduce_scatter32(double* v, int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int k = 0; k < half; ++k) {
+      const double send = upper ? v[k] : v[k + half];
+      const double keep = upper ? v[k + half] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+}
+
 // Second half of K2: camera-pair blocks from the pair list.  Warp per block, lanes over the lines seeing both cameras.
 __device__ void schur_pairs(const Ctx& c) {
   const WinHdr& h = *c.h;
   double* V = c.sm + c.lay.V;
   const int* koff = h.key_off + (size_t)c.rank * (h.nkeys + 1);
-  for (int key = c.warp; key < h.nkeys; key += LBA_NW) {
-    const int beg = koff[key], end = koff[key + 1];
+  int key = c.warp;
+  int beg = 0, end = 0;
+  uint32_t item = 0;
+  if (key < h.nkeys) {
+    beg = __ldg(koff + key); end = __ldg(koff + key + 1);
+    if (beg + c.lane < end) item = __ldg(h.items + beg + c.lane);
+  }
+  for (; key < h.nkeys; key += LBA_NW) {
+    // prefetch the next key's range and first items while this key is being accumulated
+    const int nkey = key + LBA_NW;
+    int nbeg = 0, nend = 0;
+    if (nkey < h.nkeys) { nbeg = __ldg(koff + nkey); nend = __ldg(koff + nkey + 1); }
     double acc[36];
 #pragma unroll
     for (int k = 0; k < 36; ++k) acc[k] = 0.0;
     for (int it = beg + c.lane; it < end; it += 32) {
-      const uint32_t item = __ldg(h.items + it);
-      const double2* zi = reinterpret_cast<const double2*>(c.Zbuf + (size_t)(item & 0xffffu) * ZS);
-      const double2* zj = reinterpret_cast<const double2*>(c.Zbuf + (size_t)(item >> 16) * ZS);
+      const uint32_t cur = item;
+      if (it + 32 < end) item = __ldg(h.items + it + 32);
+      const double2* zi = reinterpret_cast<const double2*>(c.Zbuf + (size_t)(cur & 0xffffu) * ZST);
+      const double2* zj = reinterpret_cast<const double2*>(c.Zbuf + (size_t)(cur >> 16) * ZST);
       double Zi[24], Zj[24];
 #pragma unroll
       for (int k = 0; k < 12; ++k) { const double2 a = zi[k], b = zj[k]; Zi[2 * k] = a.x; Zi[2 * k + 1] = a.y; Zj[2 * k] = b.x; Zj[2 * k + 1] = b.y; }
@@ -332,14 +359,14 @@ __device__ void schur_pairs(const Ctx& c) {
         for (int q = 0; q < 6; ++q)
           acc[6 * p + q] += Zi[4 * p] * Zj[4 * q] + Zi[4 * p + 1] * Zj[4 * q + 1] + Zi[4 * p + 2] * Zj[4 * q + 2] + Zi[4 * p + 3] * Zj[4 * q + 3];
     }
-    double mine = 0.0, mine2 = 0.0;
+    if (nkey < h.nkeys && nbeg + c.lane < nend) item = __ldg(h.items + nbeg + c.lane);
+    double tail[4];
 #pragma unroll
-    for (int k = 0; k < 36; ++k) {
-      const double s = warp_sum(acc[k]);
-      if ((k & 31) == c.lane) { if (k < 32) mine = s; else mine2 = s; }
-    }
-    V[key * 36 + c.lane] = -mine;
-    if (c.lane < 4) V[key * 36 + 32 + c.lane] = -mine2;
+    for (int k = 0; k < 4; ++k) tail[k] = warp_sum(acc[32 + k]);
+    warp_reduce_scatter32(acc, c.lane);
+    V[key * 36 + c.lane] = -acc[0];
+    if (c.lane < 4) V[key * 36 + 32 + c.lane] = -(c.lane == 0 ? tail[0] : c.lane == 1 ? tail[1] : c.lane == 2 ? tail[2] : tail[3]);
+    beg = nbeg; end = nend;
   }
 }
 
@@ -556,7 +583,7 @@ __device__ void trial_sweep(const Ctx& c, double* out4) {
     const int cf = valid ? h.cam_free[cam] : -1;
     double v[4] = {0.0, 0.0, 0.0, 0.0};
     if (cam_free && cf >= 0 && line_free) {
-      const double2* zp = reinterpret_cast<const double2*>(c.Zbuf + (size_t)ls * ZS);
+      const double2* zp = reinterpret_cast<const double2*>(c.Zbuf + (size_t)ls * ZST);
       const double* y = yc + 6 * cf;
 #pragma unroll
       for (int p = 0; p < 6; ++p) {
@@ -651,7 +678,7 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
   c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
   c.slot0 = h.cta_slot_off[c.rank]; c.nslots = h.cta_slot_off[c.rank + 1] - c.slot0; c.ntiles = c.nslots / 32;
   c.line0 = h.cta_line_off[c.rank]; c.nlines = h.cta_line_off[c.rank + 1] - c.line0;
-  c.Zbuf = lay.z_in_smem ? (sm + lay.Z) : (h.Zg + (size_t)c.slot0 * ZS);
+  c.Zbuf = lay.z_in_smem ? (sm + lay.Z) : (h.Zg + (size_t)c.slot0 * ZST);
   const int C = h.C, Cf = h.Cf, n = h.n, vlen = h.vlen;
   const int g_off = h.nkeys * 36, zu_off = g_off + n, hd_off = zu_off + n, sc_off = hd_off + n;
   double* camx = sm + lay.camx; double* camxt = sm + lay.camxt;

@@ -1,0 +1,452 @@
+// Pose-graph optimisation on device: what ceres::Solve does for a POProblem (reference src/slam.cpp:1283-1293,
+// src/po_problem.cpp:40-77; LM semantics restated in SURVEY.md App. A3).
+//
+// The whole Levenberg-Marquardt loop is enqueued on one stream with NO host round trip: the trust-region state lives
+// in a PoState record in HBM, the accept / reject / terminate decision is a one-CTA kernel, and every other kernel
+// starts by reading `done` and returns at once after termination.
+//   K5  po_linearize      thread per edge: residual + dual-number Jacobians (two 6x6 per edge)
+//       po_colnorm_grad   thread per unknown: column norms and gradient over the pose's incident edges (CSR, fixed order)
+//   K6  po_assemble       thread per entry of each non-zero 6x6 block of J^T J (+ LM diagonal), dense lower storage,
+//                         right-hand side appended as row n so that the factorisation also forward-substitutes it
+//       po_chol_panel     32-wide panel: diagonal block factorised in shared memory by every CTA, rows below solved
+//       po_chol_syrk      trailing update, 64x64 register-tiled
+//       po_backsolve      L^T y = z, right-looking, one CTA
+//       po_step / po_decide / po_accept / po_refresh   trial point, model decrease, step acceptance, termination
+// Every reduction has a fixed order (no atomics): results are bit-reproducible.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/slslam_b200.h"
+#include "po_math.cuh"
+
+namespace slslam {
+
+constexpr int PO_NB = 32;      // panel width of the dense factorisation
+constexpr int PO_TR = 128;     // rows per CTA in the panel solve
+constexpr int PO_TS = 64;      // trailing-update tile
+
+struct PoState {
+  double cost, new_cost, fixed_cost, initial_cost, radius, decrease_factor, gmax, gtol_abs, x_norm;
+  double ftol, gtol, ptol;
+  int done, term, successful, unsuccessful, invalid, iters, it, max_iters, cur, chol_fail, accepted, first;
+};
+
+struct PoDev {
+  int K, E, n, M, ld, nblk;       // poses, edges, unknowns (6*free poses), M = n+1 rows, leading dimension, H blocks
+  const int *idx1, *idx2;         // [E]
+  const double* cons;             // [6E]
+  const int* slot;                // [K] reduced block index or -1
+  const int* slot_pose;           // [n/6] pose of each reduced block
+  const unsigned char* active;    // [E] edge has a free pose
+  const int* inc_off;             // [n/6 + 1] CSR of incident edges per reduced block
+  const int* inc;                 // edge << 1 | (1 if the block is pose2 of the edge)
+  const int *blk_i, *blk_j;       // [nblk] block coordinates, blk_i >= blk_j
+  const int* blk_off;             // [nblk + 1]
+  const int* contrib;             // edge << 1 | (1 if blk_i is pose2 of the edge)
+  double *x, *xt;                 // [6K]
+  double *r, *J1, *J2, *cost_e;   // two sets each: [2][6E], [2][36E], [2][36E], [2][E]
+  double *scale, *cn, *g, *y, *mval;   // [n], [n], [n], [n], [E]
+  double *H, *Ld;                 // [M][ld] dense lower + rhs row; [ceil(n/32)][32][32] factored diagonal blocks
+  PoState* st;
+  double* trace;                  // [max_iters][SLSLAM_TRACE_WIDTH]
+  slslam_summary* summary;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// K5: residual and Jacobians of every edge at x (which_x = 0) or at the trial point (1), into buffer set `use_cur ?
+// cur : 1 - cur`.  all_free = 1 ignores the constant pose (evaluate-only entry point).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void po_linearize(PoDev d, int which_x, int use_cur, int all_free) {
+  if (d.st->done) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.E) return;
+  const int set = use_cur ? d.st->cur : 1 - d.st->cur;
+  const double* x = which_x ? d.xt : d.x;
+  const int a = d.idx1[e], b = d.idx2[e];
+  const bool f1 = all_free || d.slot[a] >= 0, f2 = all_free || d.slot[b] >= 0;
+  double* r = d.r + ((size_t)set * d.E + e) * 6;
+  double* J1 = d.J1 + ((size_t)set * d.E + e) * 36;
+  double* J2 = d.J2 + ((size_t)set * d.E + e) * 36;
+  double p1[6], p2[6], c[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { p1[k] = x[6 * a + k]; p2[k] = x[6 * b + k]; c[k] = d.cons[6 * (size_t)e + k]; }
+  typedef Dual<6> D6;
+  D6 A[6], B[6], res[6];
+  // derivatives with respect to pose1 (a self edge aliases one block for both arguments: directions coincide)
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { A[k] = dvar<6>(p1[k], k); B[k] = (a == b) ? dvar<6>(p2[k], k) : dconst<6>(p2[k]); }
+  pose_constraint_residual<6>(A, B, c, res);
+  double cost = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    r[k] = res[k].a;
+    cost += 0.5 * res[k].a * res[k].a;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) J1[6 * k + j] = f1 ? res[k].v[j] : 0.0;
+  }
+  d.cost_e[(size_t)set * d.E + e] = cost;
+  if (a == b || !f2) {
+#pragma unroll
+    for (int k = 0; k < 36; ++k) J2[k] = 0.0;
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { A[k] = dconst<6>(p1[k]); B[k] = dvar<6>(p2[k], k); }
+  pose_constraint_residual<6>(A, B, c, res);
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) J2[6 * k + j] = res[k].v[j];
+}
+
+// squared column norms and gradient of the unscaled Jacobian (current set), thread per unknown
+__global__ void po_colnorm_grad(PoDev d, int only_if_accepted) {
+  if (d.st->done || (only_if_accepted && !d.st->accepted)) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.n) return;
+  const int s = i / 6, j = i % 6, set = d.st->cur;
+  double cn = 0.0, g = 0.0;
+  for (int t = d.inc_off[s]; t < d.inc_off[s + 1]; ++t) {
+    const int code = d.inc[t], e = code >> 1;
+    const double* J = ((code & 1) ? d.J2 : d.J1) + ((size_t)set * d.E + e) * 36;
+    const double* r = d.r + ((size_t)set * d.E + e) * 6;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { const double v = J[6 * k + j]; cn += v * v; g += v * r[k]; }
+  }
+  d.cn[i] = cn; d.g[i] = g;
+}
+
+// block-wide sum / max in a fixed order; result valid on every thread
+template <bool MAX>
+__device__ double po_block_reduce(double v, double* sh) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  sh[tid] = v;
+  __syncthreads();
+  for (int s = nt >> 1; s > 0; s >>= 1) {
+    if (tid < s) sh[tid] = MAX ? fmax(sh[tid], sh[tid + s]) : sh[tid] + sh[tid + s];
+    __syncthreads();
+  }
+  const double out = sh[0];
+  __syncthreads();
+  return out;
+}
+
+// After a (re-)linearisation: cost sums, Jacobi scaling (first call), gradient max norm, |x|, gradient test.
+__global__ void po_refresh(PoDev d, int first) {
+  __shared__ double sh[256];
+  PoState* st = d.st;
+  if (st->done || (!first && !st->accepted)) return;
+  const int tid = threadIdx.x, set = st->cur;
+  double c_act = 0.0, c_fix = 0.0, gm = 0.0, xn = 0.0;
+  if (first) {
+    for (int e = tid; e < d.E; e += 256) { if (d.active[e]) c_act += d.cost_e[(size_t)set * d.E + e]; else c_fix += d.cost_e[(size_t)set * d.E + e]; }
+    for (int i = tid; i < d.n; i += 256) d.scale[i] = 1.0 / (1.0 + sqrt(d.cn[i]));
+  }
+  for (int i = tid; i < d.n; i += 256) {
+    gm = fmax(gm, fabs(d.g[i]));
+    const double xv = d.x[6 * d.slot_pose[i / 6] + i % 6];
+    xn += xv * xv;
+  }
+  gm = po_block_reduce<true>(gm, sh);
+  xn = po_block_reduce<false>(xn, sh);
+  if (first) { c_act = po_block_reduce<false>(c_act, sh); c_fix = po_block_reduce<false>(c_fix, sh); }
+  if (tid == 0) {
+    st->gmax = gm; st->x_norm = sqrt(xn);
+    if (first) {
+      st->cost = c_act; st->fixed_cost = c_fix; st->initial_cost = c_act + c_fix;
+      st->gtol_abs = st->gtol * fmax(gm, 2.220446049250313e-16);
+      if (d.n == 0 || gm <= st->gtol_abs) { st->term = SLSLAM_GRADIENT_TOLERANCE; st->done = 1; }
+    } else if (gm <= st->gtol_abs) {
+      st->term = SLSLAM_GRADIENT_TOLERANCE; st->done = 1;
+    }
+    st->accepted = 0;
+  }
+}
+
+// K6a: scaled normal equations.  One thread per entry of every structurally non-zero block; the right-hand side
+// J^T r goes to row n.  H must have been zeroed.
+__global__ void po_assemble(PoDev d) {
+  const PoState* st = d.st;
+  if (st->done) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int set = st->cur;
+  if (t < d.nblk * 36) {
+    const int b = t / 36, p = (t % 36) / 6, q = t % 6;
+    const int bi = d.blk_i[b], bj = d.blk_j[b];
+    double s = 0.0;
+    for (int u = d.blk_off[b]; u < d.blk_off[b + 1]; ++u) {
+      const int code = d.contrib[u], e = code >> 1;
+      const double* Ja = ((code & 1) ? d.J2 : d.J1) + ((size_t)set * d.E + e) * 36;
+      const double* Jb = (bi == bj) ? Ja : (((code & 1) ? d.J1 : d.J2) + ((size_t)set * d.E + e) * 36);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s += Ja[6 * k + p] * Jb[6 * k + q];
+    }
+    const int row = 6 * bi + p, col = 6 * bj + q;
+    s *= d.scale[row] * d.scale[col];
+    if (row == col) {
+      const double sc = d.scale[row];
+      s += fmin(fmax(d.cn[row] * sc * sc, 1e-6), 1e32) / st->radius;
+    }
+    if (col <= row) d.H[(size_t)row * d.ld + col] = s;
+  } else {
+    const int i = t - d.nblk * 36;
+    if (i < d.n) d.H[(size_t)d.n * d.ld + i] = d.g[i] * d.scale[i];
+  }
+}
+
+// K6b: panel [k0, k0+nb).  Every CTA factors the diagonal block in shared memory (same data, same order, same bits);
+// CTA 0 stores it to Ld, CTA b >= 1 solves PO_TR rows below it: X L_kk^T = A.
+__global__ void __launch_bounds__(PO_TR) po_chol_panel(PoDev d, int k0) {
+  if (d.st->done) return;
+  __shared__ double Ls[PO_NB][PO_NB + 1];
+  __shared__ double inv[PO_NB];
+  __shared__ int bad;
+  const int tid = threadIdx.x;
+  const int nb = min(PO_NB, d.n - k0);
+  if (tid == 0) bad = 0;
+  for (int t = tid; t < PO_NB * PO_NB; t += PO_TR) {
+    const int i = t / PO_NB, j = t % PO_NB;
+    double v = (i == j) ? 1.0 : 0.0;                      // identity padding beyond nb
+    if (i < nb && j < nb && j <= i) v = d.H[(size_t)(k0 + i) * d.ld + k0 + j];
+    Ls[i][j] = v;
+  }
+  __syncthreads();
+  for (int k = 0; k < nb; ++k) {
+    // column k: l_kk, then the column below, then the rank-1 update of the trailing block
+    const double dkk = Ls[k][k];
+    const bool ok = dkk > 0.0 && isfinite(dkk);
+    const double lkk = sqrt(dkk), ik = 1.0 / lkk;
+    __syncthreads();
+    if (tid == 0) { Ls[k][k] = lkk; inv[k] = ik; if (!ok) bad = 1; }
+    if (tid > k && tid < nb) Ls[tid][k] *= ik;
+    __syncthreads();
+    for (int t = tid; t < (nb - k - 1) * (nb - k - 1); t += PO_TR) {
+      const int i = k + 1 + t / (nb - k - 1), j = k + 1 + t % (nb - k - 1);
+      if (j <= i) Ls[i][j] -= Ls[i][k] * Ls[j][k];
+    }
+    __syncthreads();
+  }
+  if (tid >= nb && tid < PO_NB) inv[tid] = 1.0;
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    double* out = d.Ld + (size_t)(k0 / PO_NB) * PO_NB * PO_NB;
+    for (int t = tid; t < PO_NB * PO_NB; t += PO_TR) out[t] = Ls[t / PO_NB][t % PO_NB];
+    if (tid == 0 && bad) d.st->chol_fail = 1;
+    return;
+  }
+  const int row = k0 + nb + (blockIdx.x - 1) * PO_TR + tid;
+  if (row >= d.M) return;
+  double* a = d.H + (size_t)row * d.ld + k0;
+  double x[PO_NB];
+#pragma unroll
+  for (int q = 0; q < PO_NB; ++q) x[q] = (q < nb) ? a[q] : 0.0;
+#pragma unroll
+  for (int q = 0; q < PO_NB; ++q) {
+    x[q] *= inv[q];
+#pragma unroll
+    for (int m = q + 1; m < PO_NB; ++m) x[m] -= x[q] * Ls[m][q];
+  }
+#pragma unroll
+  for (int q = 0; q < PO_NB; ++q) if (q < nb) a[q] = x[q];
+}
+
+// K6c: trailing update A_ij -= sum_k L_ik L_jk over the panel columns, lower tiles only, rhs row included.
+__global__ void __launch_bounds__(256) po_chol_syrk(PoDev d, int k0, int nb, int t0, int ntile) {
+  if (d.st->done) return;
+  __shared__ double Pi[PO_NB][PO_TS + 2];
+  __shared__ double Pj[PO_NB][PO_TS + 2];
+  // tile (ti, tj), tj <= ti, from the linear block index
+  int ti = 0, rem = blockIdx.x;
+  while (rem > ti) { rem -= ti + 1; ++ti; }
+  const int tj = rem;
+  (void)ntile;
+  const int tid = threadIdx.x;
+  const int r0 = t0 + ti * PO_TS, c0 = t0 + tj * PO_TS;
+  for (int t = tid; t < PO_TS * PO_NB; t += 256) {
+    const int rr = t / PO_NB, k = t % PO_NB;
+    const int gi = r0 + rr, gj = c0 + rr;
+    Pi[k][rr] = (gi < d.M && k < nb) ? d.H[(size_t)gi * d.ld + k0 + k] : 0.0;
+    Pj[k][rr] = (gj < d.M && k < nb) ? d.H[(size_t)gj * d.ld + k0 + k] : 0.0;
+  }
+  __syncthreads();
+  const int ty = tid / 16, tx = tid % 16;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+#pragma unroll 8
+  for (int k = 0; k < PO_NB; ++k) {
+    double ai[4], bj[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ai[i] = Pi[k][ty * 4 + i]; bj[i] = Pj[k][tx * 4 + i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += ai[i] * bj[j];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gi = r0 + ty * 4 + i;
+    if (gi >= d.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gj = c0 + tx * 4 + j;
+      if (gj <= gi && gj < d.n) d.H[(size_t)gi * d.ld + gj] -= acc[i][j];
+    }
+  }
+}
+
+// L^T y = z with z = row n of H (the forward-substituted right-hand side).  Right-looking over 32-blocks from the
+// last: warp 0 solves the diagonal block from Ld, then every thread removes the block's contribution from the
+// unknowns before it (independent, coalesced reads of the block's rows).
+__global__ void __launch_bounds__(1024) po_backsolve(PoDev d) {
+  if (d.st->done) return;
+  __shared__ double yk[PO_NB];
+  const int tid = threadIdx.x, n = d.n;
+  double* w = d.y;
+  for (int i = tid; i < n; i += 1024) w[i] = d.H[(size_t)n * d.ld + i];
+  __syncthreads();
+  const int nblocks = (n + PO_NB - 1) / PO_NB;
+  for (int kb = nblocks - 1; kb >= 0; --kb) {
+    const int k0 = kb * PO_NB, nb = min(PO_NB, n - k0);
+    const double* L = d.Ld + (size_t)kb * PO_NB * PO_NB;
+    if (tid < 32) {
+      double wv = (tid < nb) ? w[k0 + tid] : 0.0;
+      for (int q = nb - 1; q >= 0; --q) {
+        const double yq = __shfl_sync(0xffffffffu, wv, q) / L[q * PO_NB + q];
+        if (tid == q) wv = yq;
+        else if (tid < q) wv -= L[q * PO_NB + tid] * yq;
+      }
+      if (tid < nb) { w[k0 + tid] = wv; }
+      yk[tid] = (tid < nb) ? wv : 0.0;
+    }
+    __syncthreads();
+    for (int j = tid; j < k0; j += 1024) {
+      double s = 0.0;
+#pragma unroll 8
+      for (int q = 0; q < PO_NB; ++q) if (q < nb) s += d.H[(size_t)(k0 + q) * d.ld + j] * yk[q];
+      w[j] -= s;
+    }
+    __syncthreads();
+  }
+}
+
+// trial point x' = x - scale*y on the free poses, and the per-edge part of the model decrease -(m.(r + m/2)), m = J delta
+__global__ void po_step(PoDev d) {
+  if (d.st->done) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 6 * d.K) {
+    const int s = d.slot[t / 6];
+    double v = d.x[t];
+    if (s >= 0) v -= d.y[6 * s + t % 6] * d.scale[6 * s + t % 6];
+    d.xt[t] = v;
+  } else {
+    const int e = t - 6 * d.K;
+    if (e >= d.E) return;
+    double acc = 0.0;
+    if (d.active[e]) {
+      const int set = d.st->cur;
+      const int s1 = d.slot[d.idx1[e]], s2 = d.slot[d.idx2[e]];
+      const double* J1 = d.J1 + ((size_t)set * d.E + e) * 36;
+      const double* J2 = d.J2 + ((size_t)set * d.E + e) * 36;
+      const double* r = d.r + ((size_t)set * d.E + e) * 6;
+      double d1[6], d2[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        d1[j] = s1 >= 0 ? -d.y[6 * s1 + j] * d.scale[6 * s1 + j] : 0.0;
+        d2[j] = s2 >= 0 ? -d.y[6 * s2 + j] * d.scale[6 * s2 + j] : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        double m = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) m += J1[6 * k + j] * d1[j] + J2[6 * k + j] * d2[j];
+        acc += m * (r[k] + 0.5 * m);
+      }
+    }
+    d.mval[e] = acc;
+  }
+}
+
+// Step acceptance and trust-region update (TrustRegionMinimizer / LevenbergMarquardtStrategy semantics).
+__global__ void po_decide(PoDev d) {
+  __shared__ double sh[256];
+  PoState* st = d.st;
+  if (st->done) return;
+  const int tid = threadIdx.x, tset = 1 - st->cur;
+  double nc = 0.0, mv = 0.0, dn = 0.0, bad = 0.0;
+  for (int e = tid; e < d.E; e += 256) if (d.active[e]) { nc += d.cost_e[(size_t)tset * d.E + e]; mv += d.mval[e]; }
+  for (int i = tid; i < d.n; i += 256) {
+    const double y = d.y[i], dl = y * d.scale[i];
+    dn += dl * dl;
+    if (!isfinite(y)) bad = 1.0;
+  }
+  nc = po_block_reduce<false>(nc, sh);
+  mv = po_block_reduce<false>(mv, sh);
+  dn = po_block_reduce<false>(dn, sh);
+  bad = po_block_reduce<true>(bad, sh);
+  if (tid != 0) return;
+  const int it = st->it;
+  st->it = it + 1;
+  st->iters = it + 1;
+  double* tr = d.trace ? d.trace + (size_t)it * SLSLAM_TRACE_WIDTH : nullptr;
+  if (tr) { tr[0] = st->cost; tr[1] = 0; tr[2] = 0; tr[3] = st->radius; tr[4] = 0; tr[5] = 0; tr[6] = st->gmax; tr[7] = 0; }
+  const bool ok = !st->chol_fail && bad == 0.0;
+  st->chol_fail = 0;
+  st->accepted = 0;
+  const double model = ok ? -mv : 0.0;
+  if (tr) tr[2] = model;
+  if (!ok || !(model > 0.0)) {
+    ++st->unsuccessful;
+    if (tr) tr[5] = -1.0;
+    if (++st->invalid >= 5) { st->term = SLSLAM_NUMERICAL_FAILURE; st->done = 1; return; }
+    st->radius *= 0.5;
+    if (st->radius < 1e-32) { st->term = SLSLAM_PARAMETER_TOLERANCE; st->done = 1; }
+    if (it + 1 >= st->max_iters) st->done = 1;
+    return;
+  }
+  st->invalid = 0;
+  const double step_norm = sqrt(dn);
+  if (tr) { tr[1] = nc; tr[4] = step_norm; }
+  if (step_norm <= st->ptol * (st->x_norm + st->ptol)) { st->term = SLSLAM_PARAMETER_TOLERANCE; st->done = 1; return; }
+  const double change = st->cost - nc;
+  if (fabs(change) < st->ftol * st->cost) { st->term = SLSLAM_FUNCTION_TOLERANCE; st->done = 1; return; }
+  const double rel = change / model;
+  if (tr) tr[7] = rel;
+  if (rel > 1e-3) {
+    ++st->successful;
+    if (tr) tr[5] = 1.0;
+    st->cost = nc;
+    st->cur = tset;            // the trial linearisation becomes the current one
+    st->accepted = 1;
+    const double q = 2.0 * rel - 1.0;
+    st->radius = fmin(1e16, st->radius / fmax(1.0 / 3.0, 1.0 - q * q * q));
+    st->decrease_factor = 2.0;
+  } else {
+    ++st->unsuccessful;
+    st->radius /= st->decrease_factor;
+    st->decrease_factor *= 2.0;
+  }
+  if (st->radius < 1e-32) { st->term = SLSLAM_PARAMETER_TOLERANCE; st->done = 1; return; }
+  if (it + 1 >= st->max_iters && !st->accepted) st->done = 1;
+}
+
+__global__ void po_accept(PoDev d) {
+  const PoState* st = d.st;
+  if (st->done || !st->accepted) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 6 * d.K) d.x[t] = d.xt[t];
+}
+
+__global__ void po_finish(PoDev d) {
+  const PoState* st = d.st;
+  slslam_summary s;
+  s.initial_cost = st->initial_cost; s.final_cost = st->cost + st->fixed_cost; s.fixed_cost = st->fixed_cost;
+  s.gradient_max_norm = st->gmax; s.num_successful_steps = st->successful; s.num_unsuccessful_steps = st->unsuccessful;
+  s.termination_type = st->term; s.iterations = st->iters;
+  *d.summary = s;
+}
+
+}  // namespace slslam
