@@ -43,11 +43,17 @@ def algorithmic_bytes_per_iteration(w):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU during the timed region (pynvml)."""
+    """Samples SM clock and throttle reasons of one GPU during the timed region: pynvml when it works, and an
+    `nvidia-smi -lms` subprocess beside it as the fallback (the profiling recipe's clocks line)."""
+
+    SMI_FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                  "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    SMI_NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.sm_max = index, [], set(), False, None
+        self.smi = None
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -56,6 +62,16 @@ class ClockSampler(threading.Thread):
             self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
             self.nv = None
+
+    def start(self):
+        import subprocess
+        try:
+            self.smi = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.SMI_FIELDS}",
+                                         "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
+                                        stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.smi = None
+        super().start()
 
     def run(self):
         if self.nv is None:
@@ -77,10 +93,27 @@ class ClockSampler(threading.Thread):
 
     def result(self):
         self.stop_flag = True
-        if self.nv is None or not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"]}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+        smi_samples, smi_reasons, smi_max = [], set(), None
+        if self.smi is not None:
+            try:
+                self.smi.terminate()
+                out, _ = self.smi.communicate(timeout=5)
+                for ln in out.splitlines():
+                    f = [x.strip() for x in ln.split(",")]
+                    if len(f) >= 6 and f[0].isdigit():
+                        smi_samples.append(int(f[0])); smi_max = int(f[1]) if f[1].isdigit() else smi_max
+                        for name, v in zip(self.SMI_NAMES, f[2:6]):
+                            if v.lower().startswith("active"):
+                                smi_reasons.add(name)
+            except Exception:
+                pass
+        if self.samples:
+            return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons | smi_reasons),
+                    "samples": len(self.samples), "source": "nvml"}
+        if smi_samples:
+            return {"sm_mhz": float(np.median(smi_samples)), "sm_max_mhz": smi_max or self.sm_max, "reasons": sorted(smi_reasons),
+                    "samples": len(smi_samples), "source": "nvidia-smi"}
+        return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"]}
 
 
 def physical_gpu_index(local_rank):
@@ -235,6 +268,7 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = iters_all * Ke / float(te.item())
+    e2e_split = capi.last_timings()
     h2d, d2h = batch.transfer_bytes()
 
     if rank == 0:
@@ -253,7 +287,8 @@ def main():
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(windows), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": Ke, "api": "slslam_lba_solve_batch (host buffers; plan + H2D + solve + D2H per step)"},
+                    "steps": Ke, "api": "slslam_lba_solve_batch (host buffers; plan + H2D + solve + D2H per step)",
+                    "host_split_ms_last_step": e2e_split},
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "lba_solve_kernel", "kernel_ms": kernel_ms,

@@ -104,6 +104,11 @@ int slslam_lba_solve(const slslam_lba_desc* desc, double* params_inout, slslam_s
 int slslam_lba_solve_batch(int32_t n, const slslam_lba_desc* descs, double* const* params_inout,
                            slslam_summary* summaries_out);
 
+/* Host wall-clock split (ms) of this thread's last slslam_lba_solve / slslam_lba_solve_batch:
+ * plan | staging + H2D enqueue | launch + device solve + D2H | copy-out | total, then device time by CUDA events:
+ * H2D | kernel | D2H.  ms8 receives 8 doubles. */
+void slslam_lba_last_timings(double* ms8);
+
 /* ---- device-resident form: plan + upload once, solve any number of times from the uploaded initial guess ---- */
 typedef struct slslam_lba_batch slslam_lba_batch;
 /* cluster_size 0 = choose automatically; device < 0 = current device. */

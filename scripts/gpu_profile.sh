@@ -1,0 +1,15 @@
+#!/bin/bash
+# Run under gpurun: parity tests, bench line, ncu launch list and one full capture of the LBA solve kernel.
+# usage: scripts/gpu_profile.sh <tag>
+tag=${1:-r1}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python bench.py --steps 50 --warmup 5 > gpurun_out/bench_${tag}.json 2> gpurun_out/bench_${tag}.err; tail -c 3000 gpurun_out/bench_${tag}.json
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_${tag}.json 2>> gpurun_out/bench_${tag}.err; cat gpurun_out/bench_ref_${tag}.json
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_${tag}.csv \
+    python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_a_${tag}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:lba_solve -s 3 -c 1 -f -o gpurun_out/prof_lba_${tag} \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_b_${tag}.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_po_${tag}.csv \
+    python scripts/po_profile.py 1 > gpurun_out/ncu_po_${tag}.log 2>&1
+python scripts/po_profile.py 3 2>&1 | tee gpurun_out/po_${tag}.txt

@@ -20,7 +20,7 @@ TERMINATION = {0: "NO_CONVERGENCE", 1: "GRADIENT_TOLERANCE", 2: "FUNCTION_TOLERA
 
 EXPORTS = [
     "slslam_version", "slslam_strerror", "slslam_last_error", "slslam_device_count", "slslam_lba_get_limits",
-    "slslam_lba_solve", "slslam_lba_solve_batch", "slslam_lba_batch_create", "slslam_lba_batch_solve",
+    "slslam_lba_solve", "slslam_lba_solve_batch", "slslam_lba_last_timings", "slslam_lba_batch_create", "slslam_lba_batch_solve",
     "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_max_active_clusters", "slslam_lba_batch_transfer_bytes", "slslam_lba_batch_phase_cycles", "slslam_lba_batch_destroy",
     "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate", "slslam_po_last_solve_ms",
 ]
@@ -92,6 +92,8 @@ def lib():
         L.slslam_lba_batch_upload_params.argtypes = [C.c_void_p, C.POINTER(dp), C.c_void_p]
         L.slslam_lba_batch_download.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(dp), C.POINTER(Summary), C.POINTER(dp)]
         L.slslam_lba_batch_info.argtypes = [C.c_void_p, ip, ip, ip, ip]
+        L.slslam_lba_last_timings.argtypes = [dp]
+        L.slslam_lba_last_timings.restype = None
         L.slslam_lba_batch_max_active_clusters.argtypes = [C.c_void_p, ip]
         L.slslam_lba_batch_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.slslam_lba_batch_phase_cycles.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.c_int32]
@@ -155,6 +157,14 @@ def lba_solve(w, params=None, **kw):
     s = Summary()
     _check(lib().slslam_lba_solve(C.byref(k.desc), _d(p), C.byref(s)))
     return p, summary_dict(s)
+
+
+def last_timings():
+    """plan | stage + H2D enqueue | launch + solve + D2H | copy-out | total (ms) of the last one-shot solve."""
+    t = np.zeros(8)
+    lib().slslam_lba_last_timings(_d(t))
+    return dict(zip(("plan_ms", "stage_ms", "solve_ms", "copy_out_ms", "total_ms", "dev_h2d_ms", "dev_kernel_ms", "dev_d2h_ms"),
+                    t.tolist()))
 
 
 def lba_solve_batch(windows, **kw):

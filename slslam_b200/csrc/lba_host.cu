@@ -3,10 +3,12 @@
 // camera-pair list for the Schur blocks), upload, cluster launch, download.
 // Replaces what LBAProblem::build + ceres::Solve do on the host (reference src/lba_problem.cpp:54-93).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common_host.h"
@@ -18,7 +20,7 @@ struct WindowPlan {
   int C = 0, Cf = 0, L = 0, N = 0, nkeys = 0;
   int max_iters = 0, robust = 1;
   double huber_a, baseline, ftol, gtol, ptol, radius0;
-  std::vector<double> obs;        // [slots*8]
+  std::vector<int> slot_src;      // [slots] index of the caller's observation in this slot, or -1 (padding)
   std::vector<int2> meta;         // [slots]
   std::vector<int> line_gid;      // device lines
   std::vector<uint32_t> items;
@@ -93,7 +95,8 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
   }
   p.line_gid = dl;
   p.key_off.assign((size_t)CS * (p.nkeys + 1), 0);
-  p.obs.clear(); p.meta.clear(); p.items.clear();
+  p.slot_src.clear(); p.meta.clear(); p.items.clear();
+  p.slot_src.reserve((size_t)N + 32 * (size_t)CS + N / 4); p.meta.reserve((size_t)N + 32 * (size_t)CS + N / 4);
   p.max_lines_cta = 1; p.max_slots_cta = 32;
   p.cta_slot_off[0] = 0;
   std::vector<std::vector<uint32_t> > buckets(p.nkeys);
@@ -109,7 +112,7 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
       while (lane != 0 && lane < 32) {
         int2 m; m.x = 0 | (lane << 8) | (1 << 14); m.y = 0;
         p.meta.push_back(m);
-        for (int k = 0; k < 8; ++k) p.obs.push_back(0.0);
+        p.slot_src.push_back(-1);
         ++lane;
       }
       lane = 0;
@@ -133,7 +136,7 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
         m.x = cam | (seg_start << 8) | (k << 14) | (flags << 24);
         m.y = (li - lb) | (round << 20);
         p.meta.push_back(m);
-        for (int q = 0; q < 8; ++q) p.obs.push_back(d.observations[8 * (size_t)i + q]);
+        p.slot_src.push_back(i);
         ++lane;
       }
       if (lane == 32) { lane = 0; for (int c = 0; c < MAX_CAMS; ++c) tile_rounds[c] = 0; }
@@ -189,7 +192,49 @@ struct slslam_lba_batch {
   double* h_params = nullptr;
   size_t upload_bytes = 0;
   int max_active = 0;   // co-resident clusters of this shape on the device
+  bool borrowed = false;   // device pool and pinned staging belong to the calling thread's Workspace
 };
+
+namespace slslam {
+// Grow-only device pool + pinned staging cached per host thread, so that the one-shot entry points
+// (slslam_lba_solve / slslam_lba_solve_batch: plan + H2D + solve + D2H per call, the way the reference calls
+// ceres::Solve once per keyframe) do not pay cudaMalloc / cudaMallocHost / cudaFree on every call.
+struct Workspace {
+  int device = -1;
+  char* d_pool = nullptr; size_t d_cap = 0;
+  char* h_pin = nullptr; size_t h_cap = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int ensure(int dev, size_t d_bytes, size_t h_bytes) {
+    if (device != dev) { release(); device = dev; }
+    for (int k = 0; k < 4; ++k) if (!ev[k]) CUDA_TRY(cudaEventCreate(&ev[k]));
+    if (d_bytes > d_cap) {
+      if (d_pool) cudaFree(d_pool);
+      d_pool = nullptr; d_cap = 0;
+      const size_t want = d_bytes + d_bytes / 4;
+      CUDA_TRY(cudaMalloc((void**)&d_pool, want));
+      d_cap = want;
+    }
+    if (h_bytes > h_cap) {
+      if (h_pin) cudaFreeHost(h_pin);
+      h_pin = nullptr; h_cap = 0;
+      const size_t want = h_bytes + h_bytes / 4;
+      CUDA_TRY(cudaMallocHost((void**)&h_pin, want));
+      h_cap = want;
+    }
+    return SLSLAM_OK;
+  }
+  void release() {
+    if (d_pool) cudaFree(d_pool);
+    if (h_pin) cudaFreeHost(h_pin);
+    d_pool = nullptr; h_pin = nullptr; d_cap = h_cap = 0;
+    for (int k = 0; k < 4; ++k) { if (ev[k]) cudaEventDestroy(ev[k]); ev[k] = nullptr; }
+  }
+};
+static thread_local Workspace g_ws;
+// host wall-clock split of this thread's last one-shot solve, ms: plan | stage + H2D enqueue | launch + wait + D2H | copy-out | total
+static thread_local double g_timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // + device ms: H2D | kernel | D2H
+static inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace slslam
 
 namespace slslam {
 
@@ -246,18 +291,26 @@ static int launch_config(slslam_lba_batch* b, cudaLaunchConfig_t* cfg, cudaLaunc
   return 0;
 }
 
-}  // namespace slslam
-
-extern "C" {
-
-void slslam_lba_get_limits(slslam_lba_limits* out) {
-  if (!out) return;
-  out->max_cameras = MAX_CAMS; out->max_free_cameras = MAX_FREE_CAMS; out->max_observations_per_line = 32;
-  out->max_cluster_size = MAX_CS;
+// fn(i) for i in [0, n) on up to 8 host threads (planning and staging of different windows are independent work)
+template <class F>
+static void parallel_for(int n, F fn) {
+  const int nthreads = std::min(n, 8);
+  if (nthreads <= 1) { for (int i = 0; i < n; ++i) fn(i); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t) th.emplace_back([&fn, t, n, nthreads]() { for (int i = t; i < n; i += nthreads) fn(i); });
+  for (auto& t : th) t.join();
 }
 
-int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,
-                            int32_t cluster_size, slslam_lba_batch** out) {
+static int build_plans(int n, const slslam_lba_desc* descs, int CS, std::vector<WindowPlan>& plans) {
+  plans.assign(n, WindowPlan());
+  std::vector<int> rcs(n, SLSLAM_OK);
+  parallel_for(n, [&](int i) { rcs[i] = build_plan(descs[i], CS, plans[i]); });
+  for (int i = 0; i < n; ++i) if (rcs[i] != SLSLAM_OK) return rcs[i];
+  return SLSLAM_OK;
+}
+
+static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,
+                             int32_t cluster_size, Workspace* ws, cudaStream_t stream, slslam_lba_batch** out) {
   if (!out) return SLSLAM_ERR_INVALID;
   *out = nullptr;
   if (n <= 0 || !descs || !params) return SLSLAM_ERR_INVALID;
@@ -268,12 +321,14 @@ int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const doubl
     const int np = 6 * descs[i].num_cameras + 4 * descs[i].num_lines;
     for (int k = 0; k < np; ++k) if (!std::isfinite(params[i][k])) return SLSLAM_ERR_NUMERICAL;
   }
+  const double t_begin = now_ms();
   int rc = ensure_device(device);
   if (rc != SLSLAM_OK) return rc;
   slslam_lba_batch* b = new (std::nothrow) slslam_lba_batch();
   if (!b) return SLSLAM_ERR_INVALID;
   cudaGetDevice(&b->device);
   b->n = n;
+  b->borrowed = ws != nullptr;
   long long max_obs = 0;
   for (int i = 0; i < n; ++i) max_obs = std::max<long long>(max_obs, descs[i].num_observations);
   std::vector<int> cs_order;
@@ -284,11 +339,10 @@ int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const doubl
   bool placed = false;
   for (size_t attempt = 0; attempt < cs_order.size() && !placed; ++attempt) {
     const int CS = cs_order[attempt];
-    b->plans.assign(n, WindowPlan());
+    rc = build_plans(n, descs, CS, b->plans);
+    if (rc != SLSLAM_OK) { delete b; return rc; }
     int Cmax = 1, Cfmax = 0, mlines = 1, mslots = 32;
     for (int i = 0; i < n; ++i) {
-      rc = build_plan(descs[i], CS, b->plans[i]);
-      if (rc != SLSLAM_OK) { delete b; return rc; }
       Cmax = std::max(Cmax, b->plans[i].C); Cfmax = std::max(Cfmax, b->plans[i].Cf);
       mlines = std::max(mlines, b->plans[i].max_lines_cta); mslots = std::max(mslots, b->plans[i].max_slots_cta);
     }
@@ -313,7 +367,8 @@ int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const doubl
     return cuda_side ? SLSLAM_ERR_CUDA : SLSLAM_ERR_UNSUPPORTED;
   }
 
-  // ---- pooled device allocation ----
+  const double t_planned = now_ms();
+  // ---- pooled device allocation: [uploaded: headers | initial parameters | plans] [device only: results | Z staging] ----
   size_t off = 0;
   auto reserve = [&](size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; };
   const size_t o_hdr = reserve(sizeof(WinHdr) * n);
@@ -325,22 +380,38 @@ int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const doubl
     b->trace_off[i] = tt; tt += (size_t)std::max(1, b->plans[i].max_iters) * SLSLAM_TRACE_WIDTH;
   }
   b->total_params = tp; b->total_trace = tt;
-  const size_t o_pin = reserve(tp * 8), o_pout = reserve(tp * 8), o_trace = reserve(tt * 8), o_summ = reserve(sizeof(slslam_summary) * n), o_phase = reserve(sizeof(long long) * NPHASE * n);
+  const size_t o_pin = reserve(tp * 8);
   std::vector<size_t> o_obs(n), o_meta(n), o_gid(n), o_items(n), o_koff(n), o_z(n);
   for (int i = 0; i < n; ++i) {
     const WindowPlan& p = b->plans[i];
-    o_obs[i] = reserve(p.obs.size() * 8); o_meta[i] = reserve(p.meta.size() * sizeof(int2));
+    o_obs[i] = reserve(p.slot_src.size() * 64); o_meta[i] = reserve(p.meta.size() * sizeof(int2));
     o_gid[i] = reserve(p.line_gid.size() * 4 + 4); o_items[i] = reserve(p.items.size() * 4 + 4);
     o_koff[i] = reserve(p.key_off.size() * 4 + 4);
-    o_z[i] = b->lay.z_in_smem ? 0 : reserve(p.meta.size() * ZST * 8);
   }
-  CUDA_TRY_OR(cudaMalloc((void**)&b->d_pool, off), { delete b; return SLSLAM_ERR_CUDA; });
-  std::vector<char> host(off, 0);
+  const size_t upload = off;
+  const size_t o_pout = reserve(tp * 8), o_summ = reserve(sizeof(slslam_summary) * n), o_trace = reserve(tt * 8),
+               o_phase = reserve(sizeof(long long) * NPHASE * n);
+  for (int i = 0; i < n; ++i) o_z[i] = b->lay.z_in_smem ? 0 : reserve(b->plans[i].meta.size() * ZST * 8);
+  const size_t result_bytes = tp * 8 + sizeof(slslam_summary) * n + 256;
+  char* host = nullptr;
+  std::vector<char> host_vec;
+  if (ws) {
+    rc = ws->ensure(b->device, off, upload + result_bytes);
+    if (rc != SLSLAM_OK) { delete b; return rc; }
+    b->d_pool = ws->d_pool;
+    host = ws->h_pin;
+    b->h_params = (double*)(ws->h_pin + upload);
+  } else {
+    CUDA_TRY_OR(cudaMalloc((void**)&b->d_pool, off), { delete b; return SLSLAM_ERR_CUDA; });
+    host_vec.resize(upload);
+    host = host_vec.data();
+    CUDA_TRY_OR(cudaMallocHost((void**)&b->h_params, std::max<size_t>(tp, 1) * 8), { slslam_lba_batch_destroy(b); return SLSLAM_ERR_CUDA; });
+  }
   b->d_hdrs = (WinHdr*)(b->d_pool + o_hdr);
   b->d_params_in = (double*)(b->d_pool + o_pin); b->d_params_out = (double*)(b->d_pool + o_pout);
   b->d_trace = (double*)(b->d_pool + o_trace); b->d_summ = (slslam_summary*)(b->d_pool + o_summ);
   b->d_phase = (long long*)(b->d_pool + o_phase);
-  for (int i = 0; i < n; ++i) {
+  parallel_for(n, [&](int i) {
     const WindowPlan& p = b->plans[i];
     WinHdr h; memset(&h, 0, sizeof(h));
     h.C = p.C; h.Cf = p.Cf; h.L = p.L; h.n = 6 * p.Cf; h.nkeys = p.nkeys; h.vlen = lba_vlen(p.Cf);
@@ -351,24 +422,52 @@ int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const doubl
     h.key_off = (const int*)(b->d_pool + o_koff[i]);
     h.params_in = b->d_params_in + b->param_off[i]; h.params_out = b->d_params_out + b->param_off[i];
     h.Zg = b->lay.z_in_smem ? nullptr : (double*)(b->d_pool + o_z[i]);
-    h.summary = b->d_summ + i; h.trace = b->d_trace + b->trace_off[i]; h.phase_cycles = b->d_phase + (size_t)NPHASE * i;
+    h.summary = b->d_summ + i;
+    h.trace = ws ? nullptr : b->d_trace + b->trace_off[i];          // the one-shot path never reads the trace back
+    h.phase_cycles = ws ? nullptr : b->d_phase + (size_t)NPHASE * i;
     memcpy(h.cta_slot_off, p.cta_slot_off, sizeof(h.cta_slot_off));
     memcpy(h.cta_line_off, p.cta_line_off, sizeof(h.cta_line_off));
     memcpy(h.cam_free, p.cam_free, sizeof(h.cam_free));
-    memcpy(host.data() + o_hdr + sizeof(WinHdr) * i, &h, sizeof(h));
-    memcpy(host.data() + o_obs[i], p.obs.data(), p.obs.size() * 8);
-    memcpy(host.data() + o_meta[i], p.meta.data(), p.meta.size() * sizeof(int2));
-    memcpy(host.data() + o_gid[i], p.line_gid.data(), p.line_gid.size() * 4);
-    memcpy(host.data() + o_items[i], p.items.data(), p.items.size() * 4);
-    memcpy(host.data() + o_koff[i], p.key_off.data(), p.key_off.size() * 4);
-    memcpy(host.data() + o_pin + b->param_off[i] * 8, params[i], (size_t)b->nparams[i] * 8);
+    memcpy(host + o_hdr + sizeof(WinHdr) * i, &h, sizeof(h));
+    // observations are gathered from the caller's array straight into the (pinned) staging buffer, slot order
+    double* so = (double*)(host + o_obs[i]);
+    const double* src = descs[i].observations;
+    const size_t ns = p.slot_src.size();
+    for (size_t k = 0; k < ns; ++k) {
+      const int j = p.slot_src[k];
+      if (j >= 0) memcpy(so + 8 * k, src + 8 * (size_t)j, 64); else memset(so + 8 * k, 0, 64);
+    }
+    memcpy(host + o_meta[i], p.meta.data(), p.meta.size() * sizeof(int2));
+    memcpy(host + o_gid[i], p.line_gid.data(), p.line_gid.size() * 4);
+    memcpy(host + o_items[i], p.items.data(), p.items.size() * 4);
+    memcpy(host + o_koff[i], p.key_off.data(), p.key_off.size() * 4);
+    memcpy(host + o_pin + b->param_off[i] * 8, params[i], (size_t)b->nparams[i] * 8);
+  });
+  b->upload_bytes = upload;
+  if (ws) {
+    cudaEventRecord(ws->ev[0], stream);
+    CUDA_TRY_OR(cudaMemcpyAsync(b->d_pool, host, upload, cudaMemcpyHostToDevice, stream), { slslam_lba_batch_destroy(b); return SLSLAM_ERR_CUDA; });
+  } else {
+    CUDA_TRY_OR(cudaMemcpy(b->d_pool, host, upload, cudaMemcpyHostToDevice), { slslam_lba_batch_destroy(b); return SLSLAM_ERR_CUDA; });
   }
-  // only the plan + params region needs uploading (Z staging at the tail is scratch)
-  CUDA_TRY_OR(cudaMemcpy(b->d_pool, host.data(), off, cudaMemcpyHostToDevice), { slslam_lba_batch_destroy(b); return SLSLAM_ERR_CUDA; });
-  b->upload_bytes = off;
-  CUDA_TRY_OR(cudaMallocHost((void**)&b->h_params, std::max<size_t>(tp, 1) * 8), { slslam_lba_batch_destroy(b); return SLSLAM_ERR_CUDA; });
+  if (ws) { g_timing[0] = t_planned - t_begin; g_timing[1] = now_ms() - t_planned; }
   *out = b;
   return SLSLAM_OK;
+}
+
+}  // namespace slslam
+
+extern "C" {
+
+void slslam_lba_get_limits(slslam_lba_limits* out) {
+  if (!out) return;
+  out->max_cameras = MAX_CAMS; out->max_free_cameras = MAX_FREE_CAMS; out->max_observations_per_line = 32;
+  out->max_cluster_size = MAX_CS;
+}
+
+int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,
+                            int32_t cluster_size, slslam_lba_batch** out) {
+  return batch_create_impl(n, descs, params, device, cluster_size, nullptr, nullptr, out);
 }
 
 int slslam_lba_batch_upload_params(slslam_lba_batch* b, const double* const* params, void* cuda_stream) {
@@ -450,31 +549,53 @@ int slslam_lba_batch_transfer_bytes(const slslam_lba_batch* b, int64_t* h2d_byte
 void slslam_lba_batch_destroy(slslam_lba_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
-  if (b->d_pool) cudaFree(b->d_pool);
-  if (b->h_params) cudaFreeHost(b->h_params);
+  if (!b->borrowed) {
+    if (b->d_pool) cudaFree(b->d_pool);
+    if (b->h_params) cudaFreeHost(b->h_params);
+  }
   delete b;
 }
 
 int slslam_lba_solve_batch(int32_t n, const slslam_lba_desc* descs, double* const* params_inout, slslam_summary* summaries_out) {
   if (n <= 0 || !descs || !params_inout) return SLSLAM_ERR_INVALID;
+  // plan -> pinned staging -> H2D -> one cluster launch -> D2H, all on the calling thread's cached workspace
   slslam_lba_batch* b = nullptr;
-  int rc = slslam_lba_batch_create(n, descs, (const double* const*)params_inout, -1, 0, &b);
+  const double t0 = now_ms();
+  int rc = batch_create_impl(n, descs, (const double* const*)params_inout, -1, 0, &g_ws, nullptr, &b);
   if (rc != SLSLAM_OK) return rc;
+  const double t1 = now_ms();
+  double t2 = t1;
+  cudaEventRecord(g_ws.ev[1], nullptr);
   rc = slslam_lba_batch_solve(b, nullptr);
-  std::vector<slslam_summary> summ(n);
-  std::vector<std::vector<double> > tmp(n);
-  std::vector<double*> ptrs(n);
-  for (int i = 0; i < n; ++i) { tmp[i].resize((size_t)b->nparams[i] + 1); ptrs[i] = tmp[i].data(); }
-  if (rc == SLSLAM_OK) rc = slslam_lba_batch_download(b, nullptr, ptrs.data(), summ.data(), nullptr);
   if (rc == SLSLAM_OK) {
-    // parameters are only overwritten once the whole batch has succeeded
-    for (int i = 0; i < n; ++i) {
-      memcpy(params_inout[i], tmp[i].data(), (size_t)b->nparams[i] * 8);
-      if (summaries_out) summaries_out[i] = summ[i];
+    slslam_summary* h_summ = (slslam_summary*)(b->h_params + b->total_params);
+    cudaEventRecord(g_ws.ev[2], nullptr);
+    cudaError_t e = cudaMemcpyAsync(b->h_params, b->d_params_out, b->total_params * 8, cudaMemcpyDeviceToHost, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_summ, b->d_summ, sizeof(slslam_summary) * n, cudaMemcpyDeviceToHost, nullptr);
+    if (e == cudaSuccess) e = cudaEventRecord(g_ws.ev[3], nullptr);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); cudaGetLastError(); rc = SLSLAM_ERR_CUDA; }
+    t2 = now_ms();
+    if (rc == SLSLAM_OK) {
+      float ms = 0.f;
+      for (int k = 0; k < 3; ++k) { cudaEventElapsedTime(&ms, g_ws.ev[k], g_ws.ev[k + 1]); g_timing[5 + k] = ms; }
+    }
+    if (rc == SLSLAM_OK) {
+      // parameters are only overwritten once the whole batch has succeeded
+      for (int i = 0; i < n; ++i) {
+        memcpy(params_inout[i], b->h_params + b->param_off[i], (size_t)b->nparams[i] * 8);
+        if (summaries_out) summaries_out[i] = h_summ[i];
+      }
     }
   }
   slslam_lba_batch_destroy(b);
+  const double t3 = now_ms();
+  g_timing[2] = t2 - t1; g_timing[3] = t3 - t2; g_timing[4] = t3 - t0;
   return rc;
+}
+
+void slslam_lba_last_timings(double* ms5) {   // 8 values, see the header
+  if (ms5) for (int k = 0; k < 8; ++k) ms5[k] = g_timing[k];
 }
 
 int slslam_lba_solve(const slslam_lba_desc* desc, double* params_inout, slslam_summary* summary_out) {

@@ -56,8 +56,8 @@ struct WinHdr {
 
 // Shared-memory layout in doubles, identical for every CTA of a launch (sized by the largest window).
 struct SmemLayout {
-  int camx, camxt, camR, camRt, cscale, linex, linext, lscale, lineLU, V, Vred, wacc, yc, misc, Z, total;
-  int z_in_smem;
+  int camx, camxt, camR, camRt, cscale, linex, linext, lscale, lineLU, V, Vred, wacc, yc, misc, tri, Z, obs, meta, total;
+  int z_in_smem, obs_in_smem;
 };
 
 __host__ __device__ inline int lba_vlen(int Cf) {
@@ -79,10 +79,18 @@ __host__ inline SmemLayout lba_layout(int C, int Cf, int max_lines_cta, int max_
   l.wacc = take(LBA_NW * ACC * (Cf > 0 ? Cf : 1));
   l.yc = take(6 * (Cf > 0 ? Cf : 1) + 8);
   l.misc = take(64 + LBA_NW * NSCAL);
+  l.tri = take((Cf * (Cf + 1) / 2 + 2) / 2 + 1);   // int table: key -> (I, K)
   l.Z = o;
   const size_t zbytes = (size_t)ZST * max_slots_cta * 8;
   l.z_in_smem = ((size_t)o * 8 + zbytes <= smem_limit_bytes) ? 1 : 0;
   if (l.z_in_smem) o += ZST * max_slots_cta;
+  // second priority: the CTA's observations + slot metadata (read by both sweeps of every LM iteration)
+  l.obs = o; l.meta = o + 8 * max_slots_cta;
+  // Only when Z is already SMEM-resident: with Z in L2 the unified L1 is what caches the Z rows of the pair pass, and
+  // growing the SMEM carve-out by 80 KB for the observations cost more there than it saved here (measured on B200:
+  // pairs 46 k -> 62 k cycles per iteration).
+  l.obs_in_smem = (l.z_in_smem && (size_t)(o + 9 * max_slots_cta) * 8 <= smem_limit_bytes) ? 1 : 0;
+  if (l.obs_in_smem) o += 9 * max_slots_cta;
   l.total = o;
   return l;
 }
@@ -127,6 +135,8 @@ struct Ctx {
   int tid, lane, warp, rank, CS;
   int slot0, nslots, ntiles, line0, nlines;
   double* Zbuf;   // this CTA's Z blocks (shared or global)
+  const double* obs;   // this CTA's observations [nslots][8] (shared or global)
+  const int2* meta;    // this CTA's slot metadata (shared or global)
 };
 
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
@@ -155,7 +165,7 @@ __device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, d
   const bool robust = h.robust != 0;
   for (int tile = c.warp; tile < c.ntiles; tile += LBA_NW) {
     const int ls = tile * 32 + c.lane;               // CTA-local slot
-    const int2 mt = h.meta[c.slot0 + ls];
+    const int2 mt = c.meta[ls];
     const int flags = (mt.x >> 24) & 0xff;
     const bool valid = flags & F_VALID;
     const int cam = mt.x & 0xff, seg_start = (mt.x >> 8) & 0x3f, seg_len = (mt.x >> 14) & 0x3f;
@@ -171,9 +181,9 @@ __device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, d
     for (int k = 0; k < 16; ++k) Jl[k] = 0.0;
     if (valid) {
       double ob[8];
-      const double2* op = reinterpret_cast<const double2*>(h.obs + (size_t)(c.slot0 + ls) * 8);
+      const double2* op = reinterpret_cast<const double2*>(c.obs + (size_t)ls * 8);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const double2 t = __ldg(op + k); ob[2 * k] = t.x; ob[2 * k + 1] = t.y; }
+      for (int k = 0; k < 4; ++k) { const double2 t = op[k]; ob[2 * k] = t.x; ob[2 * k + 1] = t.y; }
       LineTrig lt;
       line_trig(linex + 4 * ll, lt);
       obs_eval<true>(camR + CAM_STRIDE * cam, lt, ob, h.baseline, r, Jc, Jl);
@@ -425,29 +435,35 @@ __device__ void cluster_allreduce(cg::cluster_group& cl, const Ctx& c, int vlen,
 // K3: blocked (6x6) right-looking Cholesky of the reduced camera system held block-packed in V, with the right-hand
 // side carried along (forward substitution folded in), then block back-substitution.  Every CTA of the cluster
 // solves the same system redundantly (same data, same order => same bits), which saves a broadcast.
-// On exit yc = (S + D_c)^-1 (g_c - sum Z u).  Returns false (uniformly) if a pivot is not positive.
+// Two barriers per block column: [diagonal factor in registers by every participating thread + panel rows + rhs] |
+// [trailing update + write-back of the factored diagonal block].  A factored diagonal block stores L strictly below
+// the diagonal, 1/l_kk on it and the strict part of L^-1 transposed above it, so the back-substitution of a block is
+// six independent dot products.  On exit yc = (S + D_c)^-1 (g_c - sum Z u).  Returns false (uniformly) if a pivot
+// is not positive.
 __device__ bool reduced_solve(const Ctx& c, double radius) {
   const WinHdr& h = *c.h;
   double* V = c.sm + c.lay.V;
   double* yc = c.sm + c.lay.yc;
-  double* misc = c.sm + c.lay.misc;    // misc[0..5] 1/l_kk of the current diagonal block, misc[6] failure flag
+  double* misc = c.sm + c.lay.misc;    // misc[6] failure flag
+  const int* tri = reinterpret_cast<const int*>(c.sm + c.lay.tri);   // key -> I << 8 | K
   const int Cf = h.Cf, n = h.n;
   const int g_off = h.nkeys * 36, zu_off = g_off + n, hd_off = zu_off + n;
   // right-hand side and LM diagonal of the camera blocks
   for (int i = c.tid; i < n; i += LBA_NT) {
     yc[i] = V[g_off + i] - V[zu_off + i];
-    const int f = i / 6, p = i % 6;
+    const int f = i / 6, p = i - 6 * f;
     V[(f * (f + 1) / 2 + f) * 36 + 7 * p] += clampd(V[hd_off + i], 1e-6, 1e32) / radius;
   }
   if (c.tid == 0) misc[6] = 0.0;
   __syncthreads();
   for (int J = 0; J < Cf; ++J) {
     double* AJJ = V + (J * (J + 1) / 2 + J) * 36;
-    // every participating thread factors the 6x6 diagonal block itself in registers (no shuffles on the pivot chain)
-    const int nrows = 6 * (Cf - J - 1) + 1;    // panel rows below + one thread for the rhs/diag write-back
+    const int nb = Cf - J - 1;
+    const int npanel = 6 * nb;            // threads [0, npanel): panel rows; npanel: rhs; npanel + 1: block write-back
     double Lr[21], inv[6];
     bool ok = true;
-    if (c.tid < nrows) {
+    const bool part = c.tid < npanel + 2;
+    if (part) {
 #pragma unroll
       for (int p = 0; p < 6; ++p)
 #pragma unroll
@@ -468,50 +484,64 @@ __device__ bool reduced_solve(const Ctx& c, double radius) {
           Lr[L6(p, k)] = s * inv[k];
         }
       }
+      if (c.tid < npanel) {
+        // panel: row p of block (I,J):  x L_JJ^T = a
+        const int bI = c.tid / 6, p = c.tid - 6 * bI, I = J + 1 + bI;
+        double* a = V + (I * (I + 1) / 2 + J) * 36 + 6 * p;
+        double x[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) x[q] = a[q];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          x[q] *= inv[q];
+#pragma unroll
+          for (int m = q + 1; m < 6; ++m) x[m] -= x[q] * Lr[L6(m, q)];
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) a[q] = x[q];
+      } else if (c.tid == npanel) {
+        // forward-substitute the rhs block: z_J = L_JJ^-1 b_J
+        if (!ok) misc[6] = 1.0;
+        double z[6];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) z[p] = yc[6 * J + p];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+          z[p] *= inv[p];
+#pragma unroll
+          for (int m = p + 1; m < 6; ++m) z[m] -= z[p] * Lr[L6(m, p)];
+        }
+#pragma unroll
+        for (int p = 0; p < 6; ++p) yc[6 * J + p] = z[p];
+      }
     }
-    __syncthreads();   // everyone has read A_JJ before it is overwritten with L_JJ
-    if (c.tid < nrows - 1) {
-      // panel: row p of block (I,J):  x L_JJ^T = a
-      const int I = J + 1 + c.tid / 6, p = c.tid % 6;
-      double* a = V + (I * (I + 1) / 2 + J) * 36 + 6 * p;
-      double x[6];
+    __syncthreads();
+    if (c.tid == npanel + 1) {
+      // M = L_JJ^-1 (lower): m_pp = 1/l_pp, m_pq = -m_pp sum_{k=q}^{p-1} l_pk m_kq
+      double Mi[21];
 #pragma unroll
       for (int q = 0; q < 6; ++q) {
-        double s = a[q];
+        Mi[L6(q, q)] = inv[q];
 #pragma unroll
-        for (int m = 0; m < q; ++m) s -= x[m] * Lr[L6(q, m)];
-        x[q] = s * inv[q];
+        for (int p = q + 1; p < 6; ++p) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = q; k < p; ++k) s += Lr[L6(p, k)] * Mi[L6(k, q)];
+          Mi[L6(p, q)] = -s * inv[p];
+        }
       }
-#pragma unroll
-      for (int q = 0; q < 6; ++q) a[q] = x[q];
-    } else if (c.tid == nrows - 1) {
-      // write L_JJ back, forward-substitute the rhs block: z_J = L_JJ^-1 b_J
-      if (!ok) misc[6] = 1.0;
 #pragma unroll
       for (int p = 0; p < 6; ++p)
 #pragma unroll
-        for (int q = 0; q < 6; ++q) AJJ[6 * p + q] = (q <= p) ? Lr[L6(p, q)] : 0.0;
-      double z[6];
-#pragma unroll
-      for (int p = 0; p < 6; ++p) {
-        double s = yc[6 * J + p];
-#pragma unroll
-        for (int m = 0; m < p; ++m) s -= Lr[L6(p, m)] * z[m];
-        z[p] = s * inv[p];
-      }
-#pragma unroll
-      for (int p = 0; p < 6; ++p) { yc[6 * J + p] = z[p]; misc[p] = inv[p]; }
+        for (int q = 0; q < 6; ++q) AJJ[6 * p + q] = (q < p) ? Lr[L6(p, q)] : (q == p ? inv[p] : Mi[L6(q, p)]);
     }
-    __syncthreads();
     // trailing update: A_IK -= L_IJ L_KJ^T for I >= K > J (entry per thread), and b_I -= L_IJ z_J
-    const int nb = Cf - J - 1;
     const int nent = nb * (nb + 1) / 2 * 36;
-    for (int e = c.tid; e < nent + 6 * nb; e += LBA_NT) {
+    for (int e = c.tid; e < nent + npanel; e += LBA_NT) {
       if (e < nent) {
-        const int blk = e / 36, pq = e % 36, p = pq / 6, q = pq % 6;
-        int bi = 0; while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
-        const int bk = blk - bi * (bi + 1) / 2;
-        const int I = J + 1 + bi, K = J + 1 + bk;
+        const int blk = e / 36, pq = e - 36 * blk, p = pq / 6, q = pq - 6 * p;
+        const int t = tri[blk];
+        const int I = J + 1 + (t >> 8), K = J + 1 + (t & 0xff);
         const double* li = V + (I * (I + 1) / 2 + J) * 36 + 6 * p;
         const double* lk = V + (K * (K + 1) / 2 + J) * 36 + 6 * q;
         double s = 0.0;
@@ -519,7 +549,7 @@ __device__ bool reduced_solve(const Ctx& c, double radius) {
         for (int m = 0; m < 6; ++m) s += li[m] * lk[m];
         V[(I * (I + 1) / 2 + K) * 36 + pq] -= s;
       } else {
-        const int rI = e - nent, I = J + 1 + rI / 6, p = rI % 6;
+        const int rI = e - nent, bI = rI / 6, I = J + 1 + bI, p = rI - 6 * bI;
         const double* li = V + (I * (I + 1) / 2 + J) * 36 + 6 * p;
         double s = 0.0;
 #pragma unroll
@@ -530,26 +560,26 @@ __device__ bool reduced_solve(const Ctx& c, double radius) {
     __syncthreads();
   }
   const bool failed = misc[6] != 0.0;
-  // back substitution L^T y = z by warp 0: after y_J is known, every lane removes its contribution from the rows above
+  // back substitution L^T y = z by warp 0: y_J = L_JJ^-T w_J as six dot products with the stored inverse, then every
+  // lane removes the block's contribution from the rows above
   if (c.warp == 0 && !failed) {
     for (int J = Cf - 1; J >= 0; --J) {
-      const double* LJJ = V + (J * (J + 1) / 2 + J) * 36;
-      double y[6];
+      const double* DJ = V + (J * (J + 1) / 2 + J) * 36;
+      double yp = 0.0;
+      if (c.lane < 6) {
+        // (L^-T)[p][m] = M[m][p], m >= p: diagonal holds 1/l_pp, strict part of M sits transposed above the diagonal
 #pragma unroll
-      for (int p = 5; p >= 0; --p) {
-        double s = yc[6 * J + p];
-#pragma unroll
-        for (int m = p + 1; m < 6; ++m) s -= LJJ[6 * m + p] * y[m];
-        y[p] = s / LJJ[7 * p];
+        for (int m = 0; m < 6; ++m) if (m >= c.lane) yp += DJ[6 * c.lane + m] * yc[6 * J + m];
       }
       __syncwarp();
-      if (c.lane < 6) yc[6 * J + c.lane] = y[c.lane];
+      if (c.lane < 6) yc[6 * J + c.lane] = yp;
+      __syncwarp();
       for (int e = c.lane; e < 6 * J; e += 32) {
-        const int K = e / 6, q = e % 6;
+        const int K = e / 6, q = e - 6 * K;
         const double* ljk = V + (J * (J + 1) / 2 + K) * 36;    // block (J,K): rows of J, columns of K
         double s = 0.0;
 #pragma unroll
-        for (int m = 0; m < 6; ++m) s += ljk[6 * m + q] * y[m];
+        for (int m = 0; m < 6; ++m) s += ljk[6 * m + q] * yc[6 * J + m];
         yc[6 * K + q] -= s;
       }
       __syncwarp();
@@ -574,7 +604,7 @@ __device__ void trial_sweep(const Ctx& c, double* out4) {
   double cost = 0.0, model = 0.0, dn2 = 0.0, xn2 = 0.0;
   for (int tile = c.warp; tile < c.ntiles; tile += LBA_NW) {
     const int ls = tile * 32 + c.lane;
-    const int2 mt = h.meta[c.slot0 + ls];
+    const int2 mt = c.meta[ls];
     const int flags = (mt.x >> 24) & 0xff;
     const bool valid = flags & F_VALID;
     const int cam = mt.x & 0xff, seg_start = (mt.x >> 8) & 0x3f, seg_len = (mt.x >> 14) & 0x3f;
@@ -629,9 +659,9 @@ __device__ void trial_sweep(const Ctx& c, double* out4) {
       }
       if (cam_free || line_free) {
         double ob[8], r[4];
-        const double2* op = reinterpret_cast<const double2*>(h.obs + (size_t)(c.slot0 + ls) * 8);
+        const double2* op = reinterpret_cast<const double2*>(c.obs + (size_t)ls * 8);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { const double2 t = __ldg(op + k); ob[2 * k] = t.x; ob[2 * k + 1] = t.y; }
+        for (int k = 0; k < 4; ++k) { const double2 t = op[k]; ob[2 * k] = t.x; ob[2 * k + 1] = t.y; }
         LineTrig lt;
         line_trig(xl, lt);
         obs_eval<false>(camRt + CAM_STRIDE * cam, lt, ob, h.baseline, r, nullptr, nullptr);
@@ -679,6 +709,17 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
   c.slot0 = h.cta_slot_off[c.rank]; c.nslots = h.cta_slot_off[c.rank + 1] - c.slot0; c.ntiles = c.nslots / 32;
   c.line0 = h.cta_line_off[c.rank]; c.nlines = h.cta_line_off[c.rank + 1] - c.line0;
   c.Zbuf = lay.z_in_smem ? (sm + lay.Z) : (h.Zg + (size_t)c.slot0 * ZST);
+  if (lay.obs_in_smem) {
+    // stage the CTA's observations and slot metadata once per solve (coalesced 16-byte loads)
+    double2* so = reinterpret_cast<double2*>(sm + lay.obs);
+    const double2* go = reinterpret_cast<const double2*>(h.obs + (size_t)c.slot0 * 8);
+    for (int i = c.tid; i < 4 * c.nslots; i += LBA_NT) so[i] = __ldg(go + i);
+    int2* smeta = reinterpret_cast<int2*>(sm + lay.meta);
+    for (int i = c.tid; i < c.nslots; i += LBA_NT) smeta[i] = __ldg(h.meta + c.slot0 + i);
+    c.obs = sm + lay.obs; c.meta = smeta;
+  } else {
+    c.obs = h.obs + (size_t)c.slot0 * 8; c.meta = h.meta + c.slot0;
+  }
   const int C = h.C, Cf = h.Cf, n = h.n, vlen = h.vlen;
   const int g_off = h.nkeys * 36, zu_off = g_off + n, hd_off = zu_off + n, sc_off = hd_off + n;
   double* camx = sm + lay.camx; double* camxt = sm + lay.camxt;
@@ -689,6 +730,15 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
   double* scal = sm + lay.misc + 8;     // [8] this CTA's partial scalars for the all-read exchange
   double* red = sm + lay.misc + 16;     // [8] CTA-local reduction results
 
+  // key -> (I, K) decode table of the lower-triangular block enumeration key = I (I + 1) / 2 + K
+  {
+    int* tri = reinterpret_cast<int*>(sm + lay.tri);
+    for (int k = c.tid; k < h.nkeys; k += LBA_NT) {
+      int I = 0;
+      while ((I + 1) * (I + 2) / 2 <= k) ++I;
+      tri[k] = (I << 8) | (k - I * (I + 1) / 2);
+    }
+  }
   // ---- load parameters: cameras replicated, the CTA's lines gathered by global id ----
   for (int i = c.tid; i < 6 * C; i += LBA_NT) camx[i] = h.params_in[i];
   for (int i = c.tid; i < 4 * c.nlines; i += LBA_NT) linex[i] = h.params_in[6 * C + 4 * h.line_gid[c.line0 + i / 4] + (i & 3)];

@@ -204,30 +204,38 @@ __global__ void __launch_bounds__(PO_TR) po_chol_panel(PoDev d, int k0) {
   __shared__ int bad;
   const int tid = threadIdx.x;
   const int nb = min(PO_NB, d.n - k0);
-  if (tid == 0) bad = 0;
-  for (int t = tid; t < PO_NB * PO_NB; t += PO_TR) {
-    const int i = t / PO_NB, j = t % PO_NB;
-    double v = (i == j) ? 1.0 : 0.0;                      // identity padding beyond nb
-    if (i < nb && j < nb && j <= i) v = d.H[(size_t)(k0 + i) * d.ld + k0 + j];
-    Ls[i][j] = v;
-  }
-  __syncthreads();
-  for (int k = 0; k < nb; ++k) {
-    // column k: l_kk, then the column below, then the rank-1 update of the trailing block
-    const double dkk = Ls[k][k];
-    const bool ok = dkk > 0.0 && isfinite(dkk);
-    const double lkk = sqrt(dkk), ik = 1.0 / lkk;
-    __syncthreads();
-    if (tid == 0) { Ls[k][k] = lkk; inv[k] = ik; if (!ok) bad = 1; }
-    if (tid > k && tid < nb) Ls[tid][k] *= ik;
-    __syncthreads();
-    for (int t = tid; t < (nb - k - 1) * (nb - k - 1); t += PO_TR) {
-      const int i = k + 1 + t / (nb - k - 1), j = k + 1 + t % (nb - k - 1);
-      if (j <= i) Ls[i][j] -= Ls[i][k] * Ls[j][k];
+  if (tid < 32) {
+    // warp 0 factors the block in registers: lane i holds row i; column k needs one broadcast of a_kk and one shuffle
+    // per trailing column, no block-wide barrier on the pivot chain
+    const int i = tid;
+    double a[PO_NB];
+#pragma unroll
+    for (int j = 0; j < PO_NB; ++j) {
+      double v = (i == j) ? 1.0 : 0.0;                     // identity padding beyond nb
+      if (i < nb && j < nb && j <= i) v = d.H[(size_t)(k0 + i) * d.ld + k0 + j];
+      a[j] = v;
     }
-    __syncthreads();
+    bool notpd = false;
+    double myinv = 1.0;
+#pragma unroll
+    for (int k = 0; k < PO_NB; ++k) {
+      const double dkk = __shfl_sync(0xffffffffu, a[k], k);
+      notpd = notpd || !(dkk > 0.0) || !isfinite(dkk);
+      const double ik = rsqrt(dkk);
+      const double lik = a[k] * ik;                        // lane k: l_kk = d_kk / sqrt(d_kk)
+      a[k] = lik;
+      if (i == k) myinv = ik;
+#pragma unroll
+      for (int j = k + 1; j < PO_NB; ++j) {
+        const double ljk = __shfl_sync(0xffffffffu, lik, j);
+        a[j] -= lik * ljk;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PO_NB; ++j) Ls[i][j] = (j <= i) ? a[j] : 0.0;
+    inv[i] = myinv;
+    if (i == 0) bad = notpd ? 1 : 0;
   }
-  if (tid >= nb && tid < PO_NB) inv[tid] = 1.0;
   __syncthreads();
   if (blockIdx.x == 0) {
     double* out = d.Ld + (size_t)(k0 / PO_NB) * PO_NB * PO_NB;
@@ -304,6 +312,8 @@ __global__ void __launch_bounds__(256) po_chol_syrk(PoDev d, int k0, int nb, int
 __global__ void __launch_bounds__(1024) po_backsolve(PoDev d) {
   if (d.st->done) return;
   __shared__ double yk[PO_NB];
+  __shared__ double Lsm[PO_NB][PO_NB + 1];
+  __shared__ double invd[PO_NB];
   const int tid = threadIdx.x, n = d.n;
   double* w = d.y;
   for (int i = tid; i < n; i += 1024) w[i] = d.H[(size_t)n * d.ld + i];
@@ -312,12 +322,16 @@ __global__ void __launch_bounds__(1024) po_backsolve(PoDev d) {
   for (int kb = nblocks - 1; kb >= 0; --kb) {
     const int k0 = kb * PO_NB, nb = min(PO_NB, n - k0);
     const double* L = d.Ld + (size_t)kb * PO_NB * PO_NB;
+    Lsm[tid / PO_NB][tid % PO_NB] = L[tid];              // 1024 threads = one entry each, coalesced
+    __syncthreads();
+    if (tid < 32) invd[tid] = 1.0 / Lsm[tid][tid];
+    __syncthreads();
     if (tid < 32) {
       double wv = (tid < nb) ? w[k0 + tid] : 0.0;
       for (int q = nb - 1; q >= 0; --q) {
-        const double yq = __shfl_sync(0xffffffffu, wv, q) / L[q * PO_NB + q];
+        const double yq = __shfl_sync(0xffffffffu, wv, q) * invd[q];
         if (tid == q) wv = yq;
-        else if (tid < q) wv -= L[q * PO_NB + tid] * yq;
+        else if (tid < q) wv -= Lsm[q][tid] * yq;
       }
       if (tid < nb) { w[k0 + tid] = wv; }
       yk[tid] = (tid < nb) ? wv : 0.0;

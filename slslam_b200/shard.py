@@ -1,0 +1,187 @@
+"""Sharding independent LBA windows over the GPUs of one node (BASELINE.json configs[3]).
+
+Only whole windows shard: inside the live pipeline consecutive windows depend on each other (reference
+src/slam.cpp:957-972 -> :1317-1366), but a batch of independent windows partitions trivially.  Window w goes to rank
+w mod G.  Rank 0 holds the packed windows; the exchange is one grouped point-to-point scatter of the packed byte
+buffers (NCCL grouped ncclSend/ncclRecv under `torch.distributed.batch_isend_irecv`; gloo on CPU for the tests) and
+one gather of parameters + summaries.  There is no collective inside the LM loop.
+
+The solver is injected (`solve_fn(windows, max_iters) -> (params_list, summaries)`): the product passes
+`capi.lba_solve_batch`; this module never imports a CPU solver.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .synth import Window
+
+_MAGIC = 0x534C4241  # 'SLBA'
+SUMMARY_WIDTH = 8    # initial_cost final_cost fixed_cost gradient_max_norm successful unsuccessful termination iterations
+_TERM = ["NO_CONVERGENCE", "GRADIENT_TOLERANCE", "FUNCTION_TOLERANCE", "PARAMETER_TOLERANCE", "NUMERICAL_FAILURE"]
+
+
+def owner(window: int, world: int) -> int:
+    return window % world
+
+
+def local_indices(num_windows: int, rank: int, world: int) -> list[int]:
+    return [w for w in range(num_windows) if owner(w, world) == rank]
+
+
+def packed_size(C: int, L: int, N: int) -> int:
+    """Bytes of one packed window: 4 int32 header, 4N int32 indices/flags, 8N observations, 6C+4L parameters."""
+    return 16 + 4 * 4 * N + 8 * (8 * N + 6 * C + 4 * L)
+
+
+def pack_window(w: Window) -> np.ndarray:
+    """Window -> flat uint8 buffer in the reference's array layout (reference src/lba_problem.h:188-196)."""
+    N = w.num_observations
+    head = np.array([_MAGIC, w.num_cameras, w.num_lines, N], np.int32)
+    parts = [head, np.ascontiguousarray(w.camera_index, np.int32), np.ascontiguousarray(w.line_index, np.int32),
+             np.ascontiguousarray(w.fixed_index, np.int32), np.ascontiguousarray(w.observations, np.float64),
+             np.ascontiguousarray(w.parameters, np.float64)]
+    buf = np.concatenate([p.view(np.uint8).ravel() for p in parts])
+    assert buf.size == packed_size(w.num_cameras, w.num_lines, N)
+    return buf
+
+
+def unpack_window(buf: np.ndarray) -> Window:
+    buf = np.ascontiguousarray(buf, np.uint8)
+    head = buf[:16].view(np.int32)
+    if int(head[0]) != _MAGIC:
+        raise ValueError("not a packed LBA window")
+    C, L, N = int(head[1]), int(head[2]), int(head[3])
+    if buf.size != packed_size(C, L, N):
+        raise ValueError("packed LBA window has the wrong length")
+    o = 16
+    ci = buf[o:o + 4 * N].view(np.int32).copy(); o += 4 * N
+    li = buf[o:o + 4 * N].view(np.int32).copy(); o += 4 * N
+    fi = buf[o:o + 8 * N].view(np.int32).copy(); o += 8 * N
+    ob = buf[o:o + 64 * N].view(np.float64).copy(); o += 64 * N
+    pr = buf[o:].view(np.float64).copy()
+    return Window(C, L, ci, li, fi, ob, pr, pr.copy(), {})
+
+
+def summary_to_row(s: dict) -> np.ndarray:
+    t = s["termination"]
+    return np.array([s["initial_cost"], s["final_cost"], s.get("fixed_cost", 0.0), s.get("gradient_max_norm", 0.0),
+                     s["num_successful_steps"], s["num_unsuccessful_steps"], _TERM.index(t) if t in _TERM else -1,
+                     s["iterations"]], np.float64)
+
+
+def row_to_summary(r: np.ndarray) -> dict:
+    return dict(initial_cost=float(r[0]), final_cost=float(r[1]), fixed_cost=float(r[2]), gradient_max_norm=float(r[3]),
+                num_successful_steps=int(r[4]), num_unsuccessful_steps=int(r[5]),
+                termination=_TERM[int(r[6])] if 0 <= int(r[6]) < len(_TERM) else "?", iterations=int(r[7]))
+
+
+def _exchange(ops, dist):
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+def scatter_windows(windows, device=None, group=None):
+    """Rank 0 passes the full list (other ranks pass None); every rank returns (its windows, their global indices).
+    One broadcast of the per-window byte counts, then one grouped send/recv of the packed buffers."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cpu") if device is None else torch.device(device)
+    meta = torch.zeros(1, dtype=torch.int64, device=dev)
+    packed = None
+    if rank == 0:
+        packed = [pack_window(w) for w in windows]
+        meta[0] = len(packed)
+    dist.broadcast(meta, 0, group=group)
+    n = int(meta.item())
+    sizes = torch.zeros(max(n, 1), dtype=torch.int64, device=dev)
+    if rank == 0 and n:
+        sizes[:n] = torch.tensor([p.size for p in packed], dtype=torch.int64)
+    dist.broadcast(sizes, 0, group=group)
+    sizes = sizes.cpu().numpy()
+    mine = local_indices(n, rank, world)
+    ops, recv, keep = [], {}, []
+    if rank == 0:
+        for w in range(n):
+            r = owner(w, world)
+            if r != 0:
+                t = torch.from_numpy(packed[w]).to(dev)
+                keep.append(t)
+                ops.append(dist.P2POp(dist.isend, t, r, group=group))
+    else:
+        for w in mine:
+            recv[w] = torch.empty(int(sizes[w]), dtype=torch.uint8, device=dev)
+            ops.append(dist.P2POp(dist.irecv, recv[w], 0, group=group))
+    _exchange(ops, dist)
+    if rank == 0:
+        local = [windows[w] for w in mine]
+    else:
+        local = [unpack_window(recv[w].cpu().numpy()) for w in mine]
+    return local, mine
+
+
+def gather_results(params, summaries, indices, num_windows, device=None, group=None):
+    """Every rank passes the parameters / summaries of its windows (global `indices`); rank 0 returns the full lists in
+    window order, other ranks return (None, None).  Parameter lengths travel in the summary row."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cpu") if device is None else torch.device(device)
+    # fixed-size rows first (they carry the parameter counts), then the parameter vectors
+    rows = torch.zeros((max(num_windows, 1), SUMMARY_WIDTH + 1), dtype=torch.float64, device=dev)
+    for p, s, w in zip(params, summaries, indices):
+        rows[w, :SUMMARY_WIDTH] = torch.from_numpy(summary_to_row(s))
+        rows[w, SUMMARY_WIDTH] = float(len(p))
+    ops, keep = [], []
+    if rank == 0:
+        for w in range(num_windows):
+            r = owner(w, world)
+            if r != 0:
+                ops.append(dist.P2POp(dist.irecv, rows[w], r, group=group))
+    else:
+        for w in indices:
+            t = rows[w].clone()
+            keep.append(t)
+            ops.append(dist.P2POp(dist.isend, t, 0, group=group))
+    _exchange(ops, dist)
+    ops, bufs = [], {}
+    if rank == 0:
+        for w in range(num_windows):
+            r = owner(w, world)
+            if r != 0:
+                bufs[w] = torch.empty(int(rows[w, SUMMARY_WIDTH].item()), dtype=torch.float64, device=dev)
+                ops.append(dist.P2POp(dist.irecv, bufs[w], r, group=group))
+    else:
+        for p, w in zip(params, indices):
+            t = torch.from_numpy(np.ascontiguousarray(p, np.float64)).to(dev)
+            keep.append(t)
+            ops.append(dist.P2POp(dist.isend, t, 0, group=group))
+    _exchange(ops, dist)
+    if rank != 0:
+        return None, None
+    out_p, out_s = [None] * num_windows, [None] * num_windows
+    for p, s, w in zip(params, summaries, indices):
+        out_p[w], out_s[w] = np.asarray(p, np.float64), s
+    rows_h = rows.cpu().numpy()
+    for w, t in bufs.items():
+        out_p[w] = t.cpu().numpy()
+        out_s[w] = row_to_summary(rows_h[w])
+    return out_p, out_s
+
+
+def solve_sharded(windows, solve_fn, max_iters=10, device=None, group=None):
+    """Scatter -> every rank solves its windows with `solve_fn` -> gather.  Rank 0 returns (params, summaries) for
+    all windows in order; other ranks (None, None)."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    local, idx = scatter_windows(windows if rank == 0 else None, device=device, group=group)
+    n = len(windows) if rank == 0 else None
+    import torch
+    cnt = torch.tensor([n if rank == 0 else 0], dtype=torch.int64, device=torch.device("cpu") if device is None else torch.device(device))
+    dist.broadcast(cnt, 0, group=group)
+    if local:
+        ps, ss = solve_fn(local, max_iters)
+    else:
+        ps, ss = [], []
+    return gather_results(ps, ss, idx, int(cnt.item()), device=device, group=group)

@@ -1,0 +1,74 @@
+"""Multi-GPU host logic on CPU: world_size-2 gloo runs of the window scatter / gather.  The solver is
+injected; here it is the CPU oracle (tests may use it), on the GPU box it is capi.lba_solve_batch."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from slslam_b200 import shard, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_partition_and_pack_round_trip():
+    assert shard.local_indices(7, 1, 3) == [1, 4]
+    assert sorted(sum((shard.local_indices(64, r, 8) for r in range(8)), [])) == list(range(64))
+    w = synth.make_window(3, 4, 30, 100, num_fixed_cameras=2)
+    b = shard.pack_window(w)
+    assert b.dtype == np.uint8 and b.size == shard.packed_size(w.num_cameras, w.num_lines, w.num_observations)
+    u = shard.unpack_window(b)
+    for k in ("camera_index", "line_index", "fixed_index", "observations", "parameters"):
+        assert np.array_equal(getattr(u, k), getattr(w, k))
+    with pytest.raises(ValueError):
+        shard.unpack_window(b[:-8])
+    m = synth.window_M(0)
+    # ~0.87 MB per M window
+    assert abs(shard.pack_window(m).size - 864_560) < 4000
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from oracle import oracle
+    from slslam_b200 import shard as sh, synth as sy
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def solve(ws, max_iters):
+        res = [oracle.lba_solve(w, max_iters=max_iters, solver=1) for w in ws]
+        return [p for p, _ in res], [s for _, s in res]
+
+    windows = [sy.make_window(40 + i, 4, 30 + 3 * i, 110 + 7 * i, sigma_px=0.5) for i in range(5)] if rank == 0 else None
+    local, idx = sh.scatter_windows(windows)
+    np.save(os.path.join(out_dir, f"idx{rank}.npy"), np.array(idx))
+    ps, ss = sh.solve_sharded(windows, solve, max_iters=6)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "cost.npy"), np.array([s["final_cost"] for s in ss]))
+        np.save(os.path.join(out_dir, "iters.npy"), np.array([s["iterations"] for s in ss]))
+        np.savez(os.path.join(out_dir, "params.npz"), *ps)
+    else:
+        assert ps is None and ss is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_scatter_solve_gather_world2(tmp_path):
+    import torch.multiprocessing as mp
+    from oracle import oracle
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert list(np.load(tmp_path / "idx0.npy")) == [0, 2, 4] and list(np.load(tmp_path / "idx1.npy")) == [1, 3]
+    cost, iters = np.load(tmp_path / "cost.npy"), np.load(tmp_path / "iters.npy")
+    params = np.load(tmp_path / "params.npz")
+    for i in range(5):
+        w = synth.make_window(40 + i, 4, 30 + 3 * i, 110 + 7 * i, sigma_px=0.5)
+        p, s = oracle.lba_solve(w, max_iters=6, solver=1)
+        assert cost[i] == s["final_cost"] and iters[i] == s["iterations"]
+        assert np.array_equal(params[f"arr_{i}"], p)
