@@ -271,6 +271,41 @@ def main():
     e2e_split = capi.last_timings()
     h2d, d2h = batch.transfer_bytes()
 
+    # ---- N > 1: what the NCCL scatter / gather of whole windows around the batch costs ----
+    sg = None
+    if world > 1:
+        from slslam_b200 import shard
+        dev = torch.device("cuda", local_rank)
+        allw = [windows[j % len(windows)] for j in range(len(windows) * world)] if rank == 0 else None
+        results = {}
+
+        def solve_fn(ws, max_iters):
+            ps_, ss_ = capi.lba_solve_batch(ws, max_iters=max_iters)
+            return ps_, ss_
+
+        for rep in range(2):           # first repetition warms NCCL's point-to-point channels
+            barrier()
+            t0 = time.perf_counter()
+            local, idx = shard.scatter_windows(allw, device=dev)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            ps_, ss_ = solve_fn(local, MAX_ITERS)
+            t2 = time.perf_counter()
+            outp, outs = shard.gather_results(ps_, ss_, idx, len(windows) * world, device=dev)
+            torch.cuda.synchronize()
+            barrier()
+            t3 = time.perf_counter()
+            results = {"scatter_ms": 1e3 * (t1 - t0), "solve_ms": 1e3 * (t2 - t1), "gather_ms": 1e3 * (t3 - t2)}
+        tt = torch.tensor([results["scatter_ms"], results["solve_ms"], results["gather_ms"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            nbytes = sum(shard.packed_size(w.num_cameras, w.num_lines, w.num_observations) for w in allw)
+            it_all = sum(s_["iterations"] for s_ in outs)
+            sg = {"windows": len(allw), "scatter_bytes": int(nbytes * (world - 1) / world), "scatter_ms": float(tt[0]),
+                  "solve_ms": float(tt[1]), "gather_ms": float(tt[2]),
+                  "lm_iterations_per_s_including_transfer": it_all / (1e-3 * float(tt.sum())),
+                  "note": "rank 0 packs, grouped NCCL send/recv of whole windows, host-buffer solve per rank, gather of parameters + summaries"}
+
     if rank == 0:
         peaks = {}
         try:
@@ -298,6 +333,8 @@ def main():
             "lm_iterations_per_step": iters_per_step, "kernel_config": info, "wall_s_timed_region": wall,
             "final_cost_window0": summ[0]["final_cost"],
         }
+        if sg is not None:
+            line["scatter_gather"] = sg
         if not args.no_extras:
             # configs[1] alone: one M window, latency bound
             b1 = capi.LbaBatch(windows[:1], device=local_rank, max_iters=MAX_ITERS)

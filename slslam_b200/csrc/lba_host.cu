@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -99,14 +100,20 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
   p.slot_src.reserve((size_t)N + 32 * (size_t)CS + N / 4); p.meta.reserve((size_t)N + 32 * (size_t)CS + N / 4);
   p.max_lines_cta = 1; p.max_slots_cta = 32;
   p.cta_slot_off[0] = 0;
-  std::vector<std::vector<uint32_t> > buckets(p.nkeys);
+  // reduced camera index of every observation in line-grouped order (-1: constant camera or constant line => no pair)
+  std::vector<signed char> ocf(N);
+  for (int l = 0; l < L; ++l)
+    for (int a = line_start[l]; a < line_start[l + 1]; ++a)
+      ocf[a] = line_const[l] ? (signed char)-1 : p.cam_free[d.camera_index[order[a]]];
+  std::vector<int> first_slot(nd, 0), kcount(p.nkeys + 1, 0), sorted_off(nd, 0);
+  std::vector<unsigned char> sorted_pos((size_t)N + 1), sorted_cnt(nd, 0);
+  int pos_off = 0;
   for (int r = 0; r < CS; ++r) {
     const int lb = p.cta_line_off[r], le = p.cta_line_off[r + 1];
     p.max_lines_cta = std::max(p.max_lines_cta, le - lb);
     const size_t slot_base = p.meta.size();
     int lane = 0;
-    std::vector<int> round_cam_count;   // per (round, camera) occupancy inside the current tile
-    int tile_rounds[MAX_CAMS];          // next free round per camera in the current tile
+    int tile_rounds[MAX_CAMS];          // next free accumulator round per camera in the current tile
     for (int c = 0; c < MAX_CAMS; ++c) tile_rounds[c] = 0;
     auto pad_tile = [&]() {
       while (lane != 0 && lane < 32) {
@@ -116,20 +123,20 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
         ++lane;
       }
       lane = 0;
-      for (int c = 0; c < MAX_CAMS; ++c) tile_rounds[c] = 0;
+      for (int c = 0; c < C; ++c) tile_rounds[c] = 0;
     };
-    for (auto& b : buckets) b.clear();
+    std::fill(kcount.begin(), kcount.end(), 0);
     for (int li = lb; li < le; ++li) {
-      const int l = dl[li], k = line_cnt[l];
+      const int l = dl[li], k = line_cnt[l], ls0 = line_start[l];
       if (lane + k > 32) pad_tile();
       const int seg_start = lane;
-      const size_t first_slot = p.meta.size() - slot_base;
+      first_slot[li] = (int)(p.meta.size() - slot_base);
+      const int lflag = line_const[l] ? F_LINE_FIXED : 0;
       for (int a = 0; a < k; ++a) {
-        const int i = order[line_start[l] + a];
+        const int i = order[ls0 + a];
         const int cam = d.camera_index[i];
-        int flags = F_VALID;
+        int flags = F_VALID | lflag;
         if (cam_const[cam]) flags |= F_CAM_FIXED;
-        if (line_const[l]) flags |= F_LINE_FIXED;
         if (a == 0) flags |= F_HEAD;
         const int round = tile_rounds[cam]++;   // lanes sharing a camera inside a tile get distinct rounds
         int2 m;
@@ -139,19 +146,26 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
         p.slot_src.push_back(i);
         ++lane;
       }
-      if (lane == 32) { lane = 0; for (int c = 0; c < MAX_CAMS; ++c) tile_rounds[c] = 0; }
-      // Schur pair list of this line: ordered pairs (i,j) of its free-camera observations with cf_i >= cf_j
-      if (!line_const[l]) {
+      if (lane == 32) { lane = 0; for (int c = 0; c < C; ++c) tile_rounds[c] = 0; }
+      // count the Schur pairs of this line: ordered pairs (a,b) of free-camera observations with cf_a >= cf_b
+      // (cameras are distinct within a line).  The line's free observations are sorted by reduced camera index first
+      // (insertion sort; the reference packs them in keyframe order, so they usually are already), which makes the
+      // pair loops branch-free: every (i, j <= i) of the sorted list is a pair.
+      {
+        int m = 0;
         for (int a = 0; a < k; ++a) {
-          const int ca = p.cam_free[d.camera_index[order[line_start[l] + a]]];
+          const int ca = ocf[ls0 + a];
           if (ca < 0) continue;
-          for (int b = 0; b < k; ++b) {
-            const int cb = p.cam_free[d.camera_index[order[line_start[l] + b]]];
-            if (cb < 0 || cb > ca) continue;
-            const uint32_t si = (uint32_t)(first_slot + a), sj = (uint32_t)(first_slot + b);
-            buckets[ca * (ca + 1) / 2 + cb].push_back(si | (sj << 16));
-          }
+          int q = m++;
+          while (q > 0 && ocf[ls0 + sorted_pos[pos_off + q - 1]] > ca) { sorted_pos[pos_off + q] = sorted_pos[pos_off + q - 1]; --q; }
+          sorted_pos[pos_off + q] = (unsigned char)a;
         }
+        sorted_cnt[li] = (unsigned char)m; sorted_off[li] = pos_off;
+        for (int i = 0; i < m; ++i) {
+          const int ca = ocf[ls0 + sorted_pos[pos_off + i]], base = ca * (ca + 1) / 2;
+          for (int j = 0; j <= i; ++j) ++kcount[base + ocf[ls0 + sorted_pos[pos_off + j]]];
+        }
+        pos_off += m;
       }
     }
     pad_tile();
@@ -159,12 +173,24 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
     if (nslots > 65535) return SLSLAM_ERR_UNSUPPORTED;
     p.max_slots_cta = std::max(p.max_slots_cta, nslots);
     p.cta_slot_off[r + 1] = (int)p.meta.size();
+    // offsets of this CTA's pair blocks, then the fill pass (same loop order => lines ascending inside a block)
     int* ko = &p.key_off[(size_t)r * (p.nkeys + 1)];
-    for (int key = 0; key < p.nkeys; ++key) {
-      ko[key] = (int)p.items.size();
-      p.items.insert(p.items.end(), buckets[key].begin(), buckets[key].end());
+    int run = (int)p.items.size();
+    for (int key = 0; key < p.nkeys; ++key) { ko[key] = run; run += kcount[key]; kcount[key] = ko[key]; }
+    ko[p.nkeys] = run;
+    p.items.resize((size_t)run);
+    for (int li = lb; li < le; ++li) {
+      const int l = dl[li], k = line_cnt[l], ls0 = line_start[l];
+      const uint32_t fs = (uint32_t)first_slot[li];
+      const int m = sorted_cnt[li];
+      const unsigned char* sp = &sorted_pos[sorted_off[li]];
+      (void)k;
+      for (int i = 0; i < m; ++i) {
+        const int ca = ocf[ls0 + sp[i]], base = ca * (ca + 1) / 2;
+        const uint32_t si = fs + sp[i];
+        for (int j = 0; j <= i; ++j) p.items[(size_t)kcount[base + ocf[ls0 + sp[j]]]++] = si | ((fs + sp[j]) << 16);
+      }
     }
-    if (p.nkeys >= 0) ko[p.nkeys] = (int)p.items.size();
   }
   for (int r = CS + 1; r <= MAX_CS; ++r) p.cta_slot_off[r] = (int)p.meta.size();
   return SLSLAM_OK;
@@ -202,9 +228,10 @@ namespace slslam {
 struct Workspace {
   int device = -1;
   char* d_pool = nullptr; size_t d_cap = 0;
-  char* h_pin = nullptr; size_t h_cap = 0;
+  char* h_pin = nullptr; size_t h_cap = 0;     // upload staging: write-combined, written once by one thread, read only by the DMA engine
+  char* h_res = nullptr; size_t r_cap = 0;     // results: ordinary pinned memory (the CPU reads it)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  int ensure(int dev, size_t d_bytes, size_t h_bytes) {
+  int ensure(int dev, size_t d_bytes, size_t h_bytes, size_t r_bytes) {
     if (device != dev) { release(); device = dev; }
     for (int k = 0; k < 4; ++k) if (!ev[k]) CUDA_TRY(cudaEventCreate(&ev[k]));
     if (d_bytes > d_cap) {
@@ -218,15 +245,23 @@ struct Workspace {
       if (h_pin) cudaFreeHost(h_pin);
       h_pin = nullptr; h_cap = 0;
       const size_t want = h_bytes + h_bytes / 4;
-      CUDA_TRY(cudaMallocHost((void**)&h_pin, want));
+      CUDA_TRY(cudaHostAlloc((void**)&h_pin, want, getenv("SLSLAM_NO_WC_STAGING") ? cudaHostAllocDefault : cudaHostAllocWriteCombined));
       h_cap = want;
+    }
+    if (r_bytes > r_cap) {
+      if (h_res) cudaFreeHost(h_res);
+      h_res = nullptr; r_cap = 0;
+      const size_t want = r_bytes + r_bytes / 4;
+      CUDA_TRY(cudaMallocHost((void**)&h_res, want));
+      r_cap = want;
     }
     return SLSLAM_OK;
   }
   void release() {
     if (d_pool) cudaFree(d_pool);
     if (h_pin) cudaFreeHost(h_pin);
-    d_pool = nullptr; h_pin = nullptr; d_cap = h_cap = 0;
+    if (h_res) cudaFreeHost(h_res);
+    d_pool = nullptr; h_pin = nullptr; h_res = nullptr; d_cap = h_cap = r_cap = 0;
     for (int k = 0; k < 4; ++k) { if (ev[k]) cudaEventDestroy(ev[k]); ev[k] = nullptr; }
   }
 };
@@ -294,7 +329,8 @@ static int launch_config(slslam_lba_batch* b, cudaLaunchConfig_t* cfg, cudaLaunc
 // fn(i) for i in [0, n) on up to 8 host threads (planning and staging of different windows are independent work)
 template <class F>
 static void parallel_for(int n, F fn) {
-  const int nthreads = std::min(n, 8);
+  static const int max_threads = []() { const char* e = getenv("SLSLAM_HOST_THREADS"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 64 ? 64 : v); }();
+  const int nthreads = std::min(n, max_threads);
   if (nthreads <= 1) { for (int i = 0; i < n; ++i) fn(i); return; }
   std::vector<std::thread> th;
   for (int t = 0; t < nthreads; ++t) th.emplace_back([&fn, t, n, nthreads]() { for (int i = t; i < n; i += nthreads) fn(i); });
@@ -396,11 +432,11 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
   char* host = nullptr;
   std::vector<char> host_vec;
   if (ws) {
-    rc = ws->ensure(b->device, off, upload + result_bytes);
+    rc = ws->ensure(b->device, off, upload, result_bytes);
     if (rc != SLSLAM_OK) { delete b; return rc; }
     b->d_pool = ws->d_pool;
     host = ws->h_pin;
-    b->h_params = (double*)(ws->h_pin + upload);
+    b->h_params = (double*)ws->h_res;
   } else {
     CUDA_TRY_OR(cudaMalloc((void**)&b->d_pool, off), { delete b; return SLSLAM_ERR_CUDA; });
     host_vec.resize(upload);
@@ -411,7 +447,10 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
   b->d_params_in = (double*)(b->d_pool + o_pin); b->d_params_out = (double*)(b->d_pool + o_pout);
   b->d_trace = (double*)(b->d_pool + o_trace); b->d_summ = (slslam_summary*)(b->d_pool + o_summ);
   b->d_phase = (long long*)(b->d_pool + o_phase);
-  parallel_for(n, [&](int i) {
+  // Staging is done by ONE thread and sent as ONE copy: a pinned buffer written by several cores is read by the DMA
+  // engine at 8.5 GB/s instead of 48 GB/s (measured on the B200 host, scripts/h2d_test.py), and interleaving
+  // per-window copies with the staging of the next window slowed the staging more than the overlap saved.
+  for (int i = 0; i < n; ++i) {
     const WindowPlan& p = b->plans[i];
     WinHdr h; memset(&h, 0, sizeof(h));
     h.C = p.C; h.Cf = p.Cf; h.L = p.L; h.n = 6 * p.Cf; h.nkeys = p.nkeys; h.vlen = lba_vlen(p.Cf);
@@ -442,7 +481,7 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
     memcpy(host + o_items[i], p.items.data(), p.items.size() * 4);
     memcpy(host + o_koff[i], p.key_off.data(), p.key_off.size() * 4);
     memcpy(host + o_pin + b->param_off[i] * 8, params[i], (size_t)b->nparams[i] * 8);
-  });
+  }
   b->upload_bytes = upload;
   if (ws) {
     cudaEventRecord(ws->ev[0], stream);

@@ -56,7 +56,7 @@ struct WinHdr {
 
 // Shared-memory layout in doubles, identical for every CTA of a launch (sized by the largest window).
 struct SmemLayout {
-  int camx, camxt, camR, camRt, cscale, linex, linext, lscale, lineLU, V, Vred, wacc, yc, misc, tri, Z, obs, meta, total;
+  int camx, camxt, camR, camRt, cscale, linex, linext, lscale, lineLU, ltrig, ltrigt, V, Vred, wacc, yc, misc, tri, Z, obs, meta, total;
   int z_in_smem, obs_in_smem;
 };
 
@@ -75,6 +75,7 @@ __host__ inline SmemLayout lba_layout(int C, int Cf, int max_lines_cta, int max_
   l.cscale = take(6 * (Cf > 0 ? Cf : 1));
   l.linex = take(4 * max_lines_cta); l.linext = take(4 * max_lines_cta); l.lscale = take(4 * max_lines_cta);
   l.lineLU = take(LLU * max_lines_cta);
+  l.ltrig = take(8 * max_lines_cta); l.ltrigt = take(8 * max_lines_cta);   // sin/cos of the line angles at x and at x'
   l.V = take(vlen); l.Vred = take((vlen + CS - 1) / CS + 2);
   l.wacc = take(LBA_NW * ACC * (Cf > 0 ? Cf : 1));
   l.yc = take(6 * (Cf > 0 ? Cf : 1) + 8);
@@ -114,8 +115,11 @@ __device__ __forceinline__ double warp_max(double v) {
 // Fixed order (inclusive up-scan then broadcast from the last lane): deterministic.
 template <int NV>
 __device__ __forceinline__ void seg_allsum(double* v, int lane, int seg_start, int seg_len) {
+  // levels needed = ceil(log2(longest segment of this tile)); warp-uniform, so the early exit does not diverge
+  const int maxlen = __reduce_max_sync(0xffffffffu, seg_len);
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
+    if (off >= maxlen) break;
     const bool take = (lane - off) >= seg_start;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -126,6 +130,27 @@ __device__ __forceinline__ void seg_allsum(double* v, int lane, int seg_start, i
   const int last = seg_start + seg_len - 1;
 #pragma unroll
   for (int k = 0; k < NV; ++k) v[k] = __shfl_sync(0xffffffffu, v[k], last);
+}
+
+// sin/cos of the four line angles, computed once per line: the lane at position p of a segment evaluates parameter
+// p (+ seg_len, ...) and the segment shares the results by shuffle.  ln[4] must be identical on the lanes of a segment.
+__device__ __forceinline__ void seg_sincos4(const double* ln, bool valid, int lane, int seg_start, int seg_len, double* sc) {
+  const int pos = lane - seg_start;
+  const int nr = valid ? (4 + seg_len - 1) / seg_len : 0;
+  const int maxr = __reduce_max_sync(0xffffffffu, nr);
+  for (int r = 0; r < maxr; ++r) {
+    const int j = pos + r * seg_len;
+    double s = 0.0, cs = 0.0;
+    if (valid && j < 4) sincos(j == 0 ? ln[0] : j == 1 ? ln[1] : j == 2 ? ln[2] : ln[3], &s, &cs);
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      const int rel = jp - r * seg_len;
+      const bool here = rel >= 0 && rel < seg_len;
+      const int src = (seg_start + (here ? rel : 0)) & 31;
+      const double ts = __shfl_sync(0xffffffffu, s, src), tc = __shfl_sync(0xffffffffu, cs, src);
+      if (here) { sc[2 * jp] = ts; sc[2 * jp + 1] = tc; }
+    }
+  }
 }
 
 struct Ctx {
@@ -185,7 +210,7 @@ __device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, d
 #pragma unroll
       for (int k = 0; k < 4; ++k) { const double2 t = op[k]; ob[2 * k] = t.x; ob[2 * k + 1] = t.y; }
       LineTrig lt;
-      line_trig(linex + 4 * ll, lt);
+      line_trig_sc(sm + c.lay.ltrig + 8 * ll, lt);     // sines / cosines cached per line (no sincos in this sweep)
       obs_eval<true>(camR + CAM_STRIDE * cam, lt, ob, h.baseline, r, Jc, Jl);
       const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
       double w;
@@ -336,9 +361,12 @@ __device__ __forceinline__ void warp_reduce_scatter32(double* v, int lane) {
 }
 
 // Second half of K2: camera-pair blocks from the pair list.  Warp per block, lanes over the lines seeing both cameras.
+// Blocks are handed out dynamically (shared counter, first LBA_NW statically): which warp sums a block does not change
+// its value, so the result stays bit-reproducible while the warps finish together.
 __device__ void schur_pairs(const Ctx& c) {
   const WinHdr& h = *c.h;
   double* V = c.sm + c.lay.V;
+  int* next_key = reinterpret_cast<int*>(c.sm + c.lay.misc + 7);
   const int* koff = h.key_off + (size_t)c.rank * (h.nkeys + 1);
   int key = c.warp;
   int beg = 0, end = 0;
@@ -347,9 +375,11 @@ __device__ void schur_pairs(const Ctx& c) {
     beg = __ldg(koff + key); end = __ldg(koff + key + 1);
     if (beg + c.lane < end) item = __ldg(h.items + beg + c.lane);
   }
-  for (; key < h.nkeys; key += LBA_NW) {
-    // prefetch the next key's range and first items while this key is being accumulated
-    const int nkey = key + LBA_NW;
+  while (key < h.nkeys) {
+    // claim the next block and prefetch its range and first items while this one is being accumulated
+    int nkey = 0;
+    if (c.lane == 0) nkey = atomicAdd(next_key, 1);
+    nkey = __shfl_sync(0xffffffffu, nkey, 0);
     int nbeg = 0, nend = 0;
     if (nkey < h.nkeys) { nbeg = __ldg(koff + nkey); nend = __ldg(koff + nkey + 1); }
     double acc[36];
@@ -376,7 +406,7 @@ __device__ void schur_pairs(const Ctx& c) {
     warp_reduce_scatter32(acc, c.lane);
     V[key * 36 + c.lane] = -acc[0];
     if (c.lane < 4) V[key * 36 + 32 + c.lane] = -(c.lane == 0 ? tail[0] : c.lane == 1 ? tail[1] : c.lane == 2 ? tail[2] : tail[3]);
-    beg = nbeg; end = nend;
+    key = nkey; beg = nbeg; end = nend;
   }
 }
 
@@ -622,6 +652,7 @@ __device__ void trial_sweep(const Ctx& c, double* out4) {
       }
     }
     seg_allsum<4>(v, c.lane, seg_start, seg_len);
+    double xlv[4] = {0.0, 0.0, 0.0, 0.0};
     if (valid) {
       const double* lu = lineLU + LLU * ll;
       double xl[4];
@@ -657,13 +688,24 @@ __device__ void trial_sweep(const Ctx& c, double* out4) {
           for (int k = 0; k < 4; ++k) linext[4 * ll + k] = xl[k];
         }
       }
+      xlv[0] = xl[0]; xlv[1] = xl[1]; xlv[2] = xl[2]; xlv[3] = xl[3];
+    }
+    // sin/cos of the trial line, shared over the segment and cached for the linearisation that follows an accepted step
+    double sc[8] = {0.0, 1.0, 0.0, 1.0, 0.0, 1.0, 1.0, 0.0};
+    seg_sincos4(xlv, valid, c.lane, seg_start, seg_len, sc);
+    if (valid) {
+      if (flags & F_HEAD) {
+        double* o = sm + c.lay.ltrigt + 8 * ll;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = sc[k];
+      }
       if (cam_free || line_free) {
         double ob[8], r[4];
         const double2* op = reinterpret_cast<const double2*>(c.obs + (size_t)ls * 8);
 #pragma unroll
         for (int k = 0; k < 4; ++k) { const double2 t = op[k]; ob[2 * k] = t.x; ob[2 * k + 1] = t.y; }
         LineTrig lt;
-        line_trig(xl, lt);
+        line_trig_sc(sc, lt);
         obs_eval<false>(camRt + CAM_STRIDE * cam, lt, ob, h.baseline, r, nullptr, nullptr);
         const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
         double w;
@@ -744,6 +786,12 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
   for (int i = c.tid; i < 4 * c.nlines; i += LBA_NT) linex[i] = h.params_in[6 * C + 4 * h.line_gid[c.line0 + i / 4] + (i & 3)];
   __syncthreads();
   if (c.tid < C) cam_precompute(camx + 6 * c.tid, camR + CAM_STRIDE * c.tid, true);
+  // sin/cos of every line angle at x0 (afterwards the trial sweep refreshes them, so the linearisation never calls sincos)
+  for (int i = c.tid; i < 4 * c.nlines; i += LBA_NT) {
+    double sv, cv;
+    sincos(linex[i], &sv, &cv);
+    sm[lay.ltrig + 2 * i] = sv; sm[lay.ltrig + 2 * i + 1] = cv;
+  }
   __syncthreads();
 
   // ---- Jacobi scaling from the column norms at x0; initial and fixed cost ----
@@ -779,6 +827,7 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
   PHASE(0)
   for (int it = 0; it < h.max_iters; ++it) {
     // -- K1/K2: linearise at x with the current radius --
+    if (c.tid == 0) *reinterpret_cast<int*>(sm + lay.misc + 7) = LBA_NW;   // pair blocks beyond the first LBA_NW are claimed dynamically
     linearize_sweep<1>(c, radius, &p_cost, &p_fixed, &p_gmax, &p_fail);
     __syncthreads();
     PHASE(1)
@@ -887,6 +936,7 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
       // adopt the trial point
       for (int i = c.tid; i < 6 * C; i += LBA_NT) camx[i] = camxt[i];
       for (int i = c.tid; i < 4 * c.nlines; i += LBA_NT) linex[i] = linext[i];
+      for (int i = c.tid; i < 8 * c.nlines; i += LBA_NT) sm[lay.ltrig + i] = sm[lay.ltrigt + i];
       __syncthreads();
       if (c.tid < C) cam_precompute(camx + 6 * c.tid, camR + CAM_STRIDE * c.tid, true);
       __syncthreads();

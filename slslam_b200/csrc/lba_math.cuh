@@ -89,12 +89,9 @@ struct LineTrig {
   double s1;
 };
 
-__device__ __forceinline__ void line_trig(const double* __restrict__ ln, LineTrig& lt) {
-  double s1, c1, s2, c2, s3, c3, st, ct;
-  sincos(ln[0], &s1, &c1);
-  sincos(ln[1], &s2, &c2);
-  sincos(ln[2], &s3, &c3);
-  sincos(ln[3], &st, &ct);
+// from the eight sines / cosines sc = {s1, c1, s2, c2, s3, c3, st, ct} of (a, b, g, t)
+__device__ __forceinline__ void line_trig_sc(const double* sc, LineTrig& lt) {
+  const double s1 = sc[0], c1 = sc[1], s2 = sc[2], c2 = sc[3], s3 = sc[4], c3 = sc[5], st = sc[6], ct = sc[7];
   lt.xh[0] = c2 * c3; lt.xh[1] = c2 * s3; lt.xh[2] = -s2;
   lt.yh[0] = s1 * s2 * c3 - c1 * s3; lt.yh[1] = s1 * s2 * s3 + c1 * c3; lt.yh[2] = s1 * c2;
   lt.zh[0] = c1 * s2 * c3 + s1 * s3; lt.zh[1] = c1 * s2 * s3 - s1 * c3; lt.zh[2] = c1 * c2;
@@ -103,6 +100,15 @@ __device__ __forceinline__ void line_trig(const double* __restrict__ ln, LineTri
   lt.d = ct * ist;
   lt.ist2 = ist * ist;
   lt.s1 = s1;
+}
+
+__device__ __forceinline__ void line_trig(const double* __restrict__ ln, LineTrig& lt) {
+  double sc[8];
+  sincos(ln[0], &sc[0], &sc[1]);
+  sincos(ln[1], &sc[2], &sc[3]);
+  sincos(ln[2], &sc[4], &sc[5]);
+  sincos(ln[3], &sc[6], &sc[7]);
+  line_trig_sc(sc, lt);
 }
 
 __device__ __forceinline__ void mv3(const double* __restrict__ M, const double* v, double* o) {

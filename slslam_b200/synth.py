@@ -330,3 +330,45 @@ def make_pose_graph(seed: int, num_poses: int = 261, neighbours: int = 3, num_lo
         p0[k] = _compose(C, p0[k - 1])
     return PoseGraph(K, e1, e2, np.ascontiguousarray(cons.ravel()), np.ascontiguousarray(p0.ravel()),
                      np.ascontiguousarray(truth.ravel()), dict(seed=seed))
+
+
+def pose_graph_from_trajectory(poses_wc: np.ndarray, seed: int = 0, neighbours: int = 2, num_loops: int = 10,
+                               noise_rot: float = 2e-3, noise_tr: float = 1e-2, drift: float = 1.0) -> PoseGraph:
+    """Pose graph around a given keyframe trajectory (camera->world rows of (angle-axis, t), e.g. the fixture derived
+    from the reference's myungdong output): odometry + neighbour edges with measurement noise, `num_loops`
+    loop-closure edges between keyframes that are far apart in time but closest in space, and a drifted
+    dead-reckoning initial guess.  Substitute for BASELINE.json configs[4]."""
+    rng = np.random.default_rng(seed)
+    K = len(poses_wc)
+    truth = np.stack([_inverse(T) for T in poses_wc])          # world -> camera
+    T0inv = _inverse(truth[0])
+    truth = np.stack([_compose(truth[k], T0inv) for k in range(K)])
+    truth[0] = 0.0
+    centres = np.stack([-rodrigues(T[:3]).T @ T[3:] for T in truth])
+    e1, e2, cons = [], [], []
+
+    def add(n1, n2):
+        C = _compose(truth[n2], _inverse(truth[n1]))
+        C = C + np.concatenate([rng.normal(0, noise_rot, 3), rng.normal(0, noise_tr, 3)])
+        e1.append(n1); e2.append(n2); cons.append(C)
+
+    for k in range(K):
+        for d in range(1, neighbours + 1):
+            if k + d < K:
+                add(k, k + d)
+    # loop closures: spatially closest pairs at least K/4 keyframes apart, one per anchor spread along the path
+    anchors = np.linspace(0, K - 1, num_loops + 2).astype(int)[1:-1]
+    for a in anchors:
+        far = [j for j in range(K) if abs(j - a) >= K // 4]
+        j = min(far, key=lambda j: np.linalg.norm(centres[j] - centres[a]))
+        add(min(a, j), max(a, j))
+    orderv = sorted(range(len(e1)), key=lambda i: (e1[i], e2[i]))
+    e1a = np.asarray([e1[i] for i in orderv], np.int32); e2a = np.asarray([e2[i] for i in orderv], np.int32)
+    consa = np.asarray([cons[i] for i in orderv], np.float64)
+    p0 = np.zeros((K, 6))
+    for k in range(1, K):
+        C = _compose(truth[k], _inverse(truth[k - 1]))
+        C = C + drift * np.concatenate([rng.normal(0, noise_rot, 3), rng.normal(0, noise_tr, 3)])
+        p0[k] = _compose(C, p0[k - 1])
+    return PoseGraph(K, e1a, e2a, np.ascontiguousarray(consa.ravel()), np.ascontiguousarray(p0.ravel()),
+                     np.ascontiguousarray(truth.ravel()), dict(seed=seed, source="trajectory"))
