@@ -31,12 +31,12 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     ws = [synth.window_M(i, sigma_px=1.0, start="far") for i in range(8)]
     if which in ("all", "single"):
-        for cs in (16, 12, 8, 4):
+        for cs in (0, 64, 48, 32, 24, 16, 8):
             run(ws[:1], cs)
     if which in ("all", "batch"):
-        for cs in (0, 16, 14, 12, 10, 8, 4):
+        for cs in (0, 18, 16, 12, 10, 8):
             run(ws, cs)
     if which in ("all", "small"):
         s = [synth.window_S(i, sigma_px=1.0, start="far") for i in range(8)]
-        for cs in (0, 8, 4, 2, 1):
+        for cs in (0, 16, 8, 4, 1):
             run(s[:1], cs)

@@ -26,7 +26,7 @@ struct WindowPlan {
   std::vector<int> line_gid;      // device lines
   std::vector<uint32_t> items;
   std::vector<int> key_off;       // [CS*(nkeys+1)]
-  int cta_slot_off[MAX_CS + 1], cta_line_off[MAX_CS + 1];
+  int cta_slot_off[MAX_G + 1], cta_line_off[MAX_G + 1];
   signed char cam_free[MAX_CAMS];
   int max_lines_cta = 0, max_slots_cta = 0;
   bool has_unobserved_blocks = false;
@@ -92,7 +92,7 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
       while (li < nd && (seen < target || r == CS - 1)) { seen += line_cnt[dl[li]]; ++li; }
       p.cta_line_off[r + 1] = li;
     }
-    for (int r = CS + 1; r <= MAX_CS; ++r) p.cta_line_off[r] = nd;
+    for (int r = CS + 1; r <= MAX_G; ++r) p.cta_line_off[r] = nd;
   }
   p.line_gid = dl;
   p.key_off.assign((size_t)CS * (p.nkeys + 1), 0);
@@ -192,7 +192,7 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
       }
     }
   }
-  for (int r = CS + 1; r <= MAX_CS; ++r) p.cta_slot_off[r] = (int)p.meta.size();
+  for (int r = CS + 1; r <= MAX_G; ++r) p.cta_slot_off[r] = (int)p.meta.size();
   return SLSLAM_OK;
 }
 
@@ -217,7 +217,8 @@ struct slslam_lba_batch {
   // pinned host staging
   double* h_params = nullptr;
   size_t upload_bytes = 0;
-  int max_active = 0;   // co-resident clusters of this shape on the device
+  int max_active = 0;   // windows of this shape the device keeps resident at once (a larger batch runs in waves)
+  unsigned int* d_bar = nullptr; size_t bar_bytes = 0;   // group barrier counters, zeroed before every launch
   bool borrowed = false;   // device pool and pinned staging belong to the calling thread's Workspace
 };
 
@@ -273,57 +274,31 @@ static inline double now_ms() { return std::chrono::duration<double, std::milli>
 
 namespace slslam {
 
-// Co-resident clusters of each size (1 CTA per SM: the kernel uses 255 registers x 256 threads), cached per device.
-// On B200 a 16-CTA cluster must sit inside one GPC, so fewer than 148/16 fit.
-static int max_active_clusters(int device, int cs) {
-  static int table[16][MAX_CS + 1];
-  static bool known[16][MAX_CS + 1];
-  if (device < 0 || device >= 16 || cs < 1 || cs > MAX_CS) return 0;
-  if (!known[device][cs]) {
-    cudaFuncSetAttribute(lba_solve_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-    cudaLaunchAttribute attr[1];
-    cfg.gridDim = dim3((unsigned)cs, 1, 1); cfg.blockDim = dim3(LBA_NT, 1, 1); cfg.dynamicSmemBytes = 0;
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, lba_solve_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
-    table[device][cs] = n; known[device][cs] = true;
+// CTAs of the solve kernel that can be resident at once on `device` (1 per SM: 255 registers x 256 threads).
+static int resident_ctas(int device) {
+  static int table[16];
+  static bool known[16];
+  if (device < 0 || device >= 16) return 0;
+  if (!known[device]) {
+    int sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lba_solve_kernel, LBA_NT, 0) != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
+    table[device] = sms * std::max(per_sm, 0); known[device] = true;
   }
-  return table[device][cs];
+  return table[device];
 }
 
-// Cluster sizes to try, best first.  Model of one LM iteration of a window on a cluster of cs CTAs (measured on B200,
-// profiles/): t(cs) = fixed + per_obs * N / cs; a batch runs ceil(nwin / co-resident clusters) waves.
-static void rank_cluster_sizes(int device, int nwin, long long max_obs, int requested, std::vector<int>& out) {
-  out.clear();
-  if (requested > 0) { out.push_back(std::min(requested, (int)MAX_CS)); return; }
-  std::vector<std::pair<double, int> > cand;
-  for (int cs = 1; cs <= MAX_CS; ++cs) {
-    const int act = max_active_clusters(device, cs);
-    if (act < 1) continue;
-    const long long tiles = (max_obs + 27) / 28;
-    if (cs > 1 && tiles / cs < 2) continue;                 // not even two tiles per CTA: the syncs would dominate
-    const double waves = std::ceil((double)nwin / act);
-    const double t = waves * (60.0 + 0.081 * (double)max_obs / cs);
-    cand.push_back(std::make_pair(t, -cs));                  // ties: larger cluster first
-  }
-  std::sort(cand.begin(), cand.end());
-  for (auto& c : cand) out.push_back(-c.second);
-  if (out.empty()) out.push_back(1);
-}
-
-static int launch_config(slslam_lba_batch* b, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, cudaStream_t st) {
-  memset(cfg, 0, sizeof(*cfg));
-  cfg->gridDim = dim3((unsigned)(b->n * b->CS), 1, 1);
-  cfg->blockDim = dim3(LBA_NT, 1, 1);
-  cfg->dynamicSmemBytes = b->smem_bytes;
-  cfg->stream = st;
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)b->CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg->attrs = attr; cfg->numAttrs = 1;
-  return 0;
+// CTAs per window.  One LM iteration of a window on G CTAs costs about fixed + per_obs * N / G (profiles/: ~55 k +
+// 156 N / G cycles on B200), all CTAs of a launch must be co-resident, so: spread the batch over the whole GPU, but keep
+// at least three 32-lane tiles per CTA, and fall back to several launches (waves) of G = 1 when there are more
+// windows than SMs.
+static int pick_group_size(int device, int nwin, long long max_obs, int requested) {
+  if (requested > 0) return std::min(requested, (int)MAX_G);
+  const int cap = std::max(1, resident_ctas(device));
+  int g = std::max(1, cap / std::max(1, nwin));
+  const long long tiles = (max_obs + 27) / 28;
+  g = (int)std::min<long long>(g, std::max<long long>(1, tiles / 3));
+  return std::min(g, (int)MAX_G);
 }
 
 // fn(i) for i in [0, n) on up to 8 host threads (planning and staging of different windows are independent work)
@@ -367,14 +342,12 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
   b->borrowed = ws != nullptr;
   long long max_obs = 0;
   for (int i = 0; i < n; ++i) max_obs = std::max<long long>(max_obs, descs[i].num_observations);
-  std::vector<int> cs_order;
-  rank_cluster_sizes(b->device, n, max_obs, cluster_size, cs_order);
-
+  const int cap = resident_ctas(b->device);
   int smem_optin = 0;
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device);
   bool placed = false;
-  for (size_t attempt = 0; attempt < cs_order.size() && !placed; ++attempt) {
-    const int CS = cs_order[attempt];
+  int CS = pick_group_size(b->device, n, max_obs, cluster_size);
+  for (int attempt = 0; attempt < 8 && !placed; ++attempt) {
     rc = build_plans(n, descs, CS, b->plans);
     if (rc != SLSLAM_OK) { delete b; return rc; }
     int Cmax = 1, Cfmax = 0, mlines = 1, mslots = 32;
@@ -385,22 +358,21 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
     b->lay = lba_layout(Cmax, Cfmax, mlines, mslots, CS, (size_t)smem_optin);
     b->smem_bytes = (size_t)b->lay.total * 8;
     b->CS = CS;
-    if (b->smem_bytes > (size_t)smem_optin) continue;   // the fixed part alone does not fit: too many lines per CTA
+    if (b->smem_bytes > (size_t)smem_optin) {
+      // the fixed part alone does not fit: too many lines per CTA.  More CTAs per window (fewer windows per wave).
+      if (cluster_size > 0 || CS >= MAX_G) break;
+      CS = std::min((int)MAX_G, CS * 2);
+      continue;
+    }
     CUDA_TRY_OR(cudaFuncSetAttribute(lba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes), { delete b; return SLSLAM_ERR_CUDA; });
-    CUDA_TRY_OR(cudaFuncSetAttribute(lba_solve_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), { delete b; return SLSLAM_ERR_CUDA; });
-    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
-    launch_config(b, &cfg, attr, nullptr);
-    int nclusters = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, lba_solve_kernel, &cfg);
-    if (e != cudaSuccess || nclusters < 1) { cudaGetLastError(); continue; }
-    b->max_active = nclusters;
+    if (CS > cap) { set_last_error("more CTAs per window than the device keeps resident"); delete b; return SLSLAM_ERR_CUDA; }
+    b->max_active = std::max(1, cap / CS);
     placed = true;
   }
   if (!placed) {
-    set_last_error("no cluster shape fits this batch (shared memory / scheduling)");
-    const bool cuda_side = cluster_size > 0 && cs_order.size() == 1 && b->smem_bytes <= (size_t)smem_optin;
+    set_last_error("no CTA group shape fits this batch in shared memory");
     delete b;
-    return cuda_side ? SLSLAM_ERR_CUDA : SLSLAM_ERR_UNSUPPORTED;
+    return SLSLAM_ERR_UNSUPPORTED;
   }
 
   const double t_planned = now_ms();
@@ -427,6 +399,13 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
   const size_t upload = off;
   const size_t o_pout = reserve(tp * 8), o_summ = reserve(sizeof(slslam_summary) * n), o_trace = reserve(tt * 8),
                o_phase = reserve(sizeof(long long) * NPHASE * n);
+  std::vector<size_t> o_vg(n), o_vr(n), o_sg(n);
+  for (int i = 0; i < n; ++i) {
+    const int vpad = (lba_vlen(b->plans[i].Cf) + 31) & ~31;
+    o_vg[i] = reserve((size_t)b->CS * vpad * 8); o_vr[i] = reserve((size_t)vpad * 8); o_sg[i] = reserve((size_t)b->CS * 8 * 8);
+  }
+  const size_t o_bar = reserve((size_t)n * 128);   // one counter per window, 128 B apart
+  b->bar_bytes = (size_t)n * 128;
   for (int i = 0; i < n; ++i) o_z[i] = b->lay.z_in_smem ? 0 : reserve(b->plans[i].meta.size() * ZST * 8);
   const size_t result_bytes = tp * 8 + sizeof(slslam_summary) * n + 256;
   char* host = nullptr;
@@ -447,6 +426,7 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
   b->d_params_in = (double*)(b->d_pool + o_pin); b->d_params_out = (double*)(b->d_pool + o_pout);
   b->d_trace = (double*)(b->d_pool + o_trace); b->d_summ = (slslam_summary*)(b->d_pool + o_summ);
   b->d_phase = (long long*)(b->d_pool + o_phase);
+  b->d_bar = (unsigned int*)(b->d_pool + o_bar);
   // Staging is done by ONE thread and sent as ONE copy: a pinned buffer written by several cores is read by the DMA
   // engine at 8.5 GB/s instead of 48 GB/s (measured on the B200 host, scripts/h2d_test.py), and interleaving
   // per-window copies with the staging of the next window slowed the staging more than the overlap saved.
@@ -461,6 +441,8 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
     h.key_off = (const int*)(b->d_pool + o_koff[i]);
     h.params_in = b->d_params_in + b->param_off[i]; h.params_out = b->d_params_out + b->param_off[i];
     h.Zg = b->lay.z_in_smem ? nullptr : (double*)(b->d_pool + o_z[i]);
+    h.Vg = (double*)(b->d_pool + o_vg[i]); h.Vr = (double*)(b->d_pool + o_vr[i]); h.scalg = (double*)(b->d_pool + o_sg[i]);
+    h.bar = (unsigned int*)(b->d_pool + o_bar + (size_t)i * 128); h.vpad = (lba_vlen(p.Cf) + 31) & ~31;
     h.summary = b->d_summ + i;
     h.trace = ws ? nullptr : b->d_trace + b->trace_off[i];          // the one-shot path never reads the trace back
     h.phase_cycles = ws ? nullptr : b->d_phase + (size_t)NPHASE * i;
@@ -501,7 +483,7 @@ extern "C" {
 void slslam_lba_get_limits(slslam_lba_limits* out) {
   if (!out) return;
   out->max_cameras = MAX_CAMS; out->max_free_cameras = MAX_FREE_CAMS; out->max_observations_per_line = 32;
-  out->max_cluster_size = MAX_CS;
+  out->max_cluster_size = MAX_G;
 }
 
 int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,
@@ -527,11 +509,15 @@ int slslam_lba_batch_solve(slslam_lba_batch* b, void* cuda_stream) {
   bool need_copy = false;
   for (const auto& p : b->plans) need_copy = need_copy || p.has_unobserved_blocks;
   if (need_copy) CUDA_TRY(cudaMemcpyAsync(b->d_params_out, b->d_params_in, b->total_params * 8, cudaMemcpyDeviceToDevice, st));
-  cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
-  launch_config(b, &cfg, attr, st);
-  const WinHdr* hdrs = b->d_hdrs;
+  CUDA_TRY(cudaMemsetAsync(b->d_bar, 0, b->bar_bytes, st));
+  // cooperative launches (every CTA of a group must be resident: the group barrier spins), `max_active` windows per wave
   SmemLayout lay = b->lay;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, lba_solve_kernel, hdrs, lay));
+  for (int w0 = 0; w0 < b->n; w0 += b->max_active) {
+    const int nw = std::min(b->max_active, b->n - w0);
+    const WinHdr* hdrs = b->d_hdrs + w0;
+    void* args[2] = {(void*)&hdrs, (void*)&lay};
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)lba_solve_kernel, dim3((unsigned)(nw * b->CS)), dim3(LBA_NT), args, b->smem_bytes, st));
+  }
   return SLSLAM_OK;
 }
 

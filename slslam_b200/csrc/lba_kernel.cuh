@@ -1,4 +1,7 @@
-// The LBA solve kernel: one thread-block cluster per window, the whole Levenberg-Marquardt loop on device.
+// The LBA solve kernel: one group of G co-resident CTAs per window (cooperative launch, 1 CTA per SM), the whole
+// Levenberg-Marquardt loop on device.  The CTAs of a group exchange their partial reduced systems and scalars through
+// L2-resident scratch and a per-window arrive/spin barrier, so G is not limited by the 16-CTA hardware cluster (a
+// 16-cluster must sit in one GPC: only 7 fit on a B200) and a batch can be spread over all 148 SMs.
 // Replaces what ceres::Solve does for an LBAProblem (reference src/slam.cpp:663, 944; semantics restated in
 // SURVEY.md Appendix A3).  Phases of one LM iteration (K1..K4 of SURVEY.md §2):
 //   K1  linearise: lane = observation, whole lines packed in 32-lane tiles; analytic residual + Jacobian,
@@ -6,11 +9,10 @@
 //   K2  Schur assembly: per-line 4x4 Cholesky in registers, Z_i = (Jc_i^T Jl_i) L^-T staged in shared memory
 //       (or L2 when it does not fit), per-camera H_cc / g_c in warp-private accumulators, camera-pair blocks
 //       S_(ci,cj) -= sum_l Z_i Z_j^T from a host-built pair list (warp per block, lanes over lines, shuffle
-//       reduce: deterministic, no atomics), cluster reduce-scatter + all-gather over DSMEM.
+//       reduce: deterministic, no atomics), group reduce-scatter + all-gather through L2 scratch.
 //   K3  blocked Cholesky + substitution of the reduced camera system (<= 6*MAX_FREE_CAMS), line back-substitution.
 //   K4  trial-cost sweep, step acceptance, trust-region radius, termination tests: identical on every CTA.
 #pragma once
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -18,17 +20,16 @@
 #include "lba_math.cuh"
 
 namespace slslam {
-namespace cg = cooperative_groups;
 
 constexpr int LBA_NT = 256;          // threads per CTA (fp64 Jacobian code wants ~200 registers per thread)
 constexpr int LBA_NW = LBA_NT / 32;
 constexpr int MAX_CAMS = 32;
 constexpr int MAX_FREE_CAMS = 24;
-constexpr int MAX_CS = 16;
+constexpr int MAX_G = 64;              // CTAs cooperating on one window (a CTA group; exchanges go through L2)
 constexpr int ZS = 24;               // doubles per Z block (6 x 4, row-major)
 constexpr int ZST = 26;              // row stride of the Z staging: 13 x 16 B, so 8 consecutive rows cover all 32 banks
 constexpr int ACC = 33;              // per-camera accumulators: H_cc (21, lower) | g_c (6) | sum Z u (6)
-constexpr int LLU = 18;              // per-line: L (10, lower) | u = L^-1 g_l (4) | D_l (4)
+constexpr int LLU = 22;              // per-line: L (10, lower) | u = L^-1 g_l (4) | D_l (4) | 1 / l_kk (4)
 constexpr int NSCAL = 8;
 constexpr int NPHASE = 10;         // init | linearise | pairs | fold | allreduce | gradient | reduced solve | trial | decide | total
 
@@ -49,8 +50,13 @@ struct WinHdr {
   slslam_summary* summary;
   double* trace;            // [max_iters][SLSLAM_TRACE_WIDTH] or nullptr
   long long* phase_cycles;  // [NPHASE] SM cycles spent per phase by CTA 0 (diagnostics) or nullptr
-  int cta_slot_off[MAX_CS + 1];
-  int cta_line_off[MAX_CS + 1];
+  double* Vg;               // [G][vpad] partial reduced systems of the group's CTAs (L2 scratch)
+  double* Vr;               // [vpad] the reduced (summed) system
+  double* scalg;            // [G][8] per-CTA partial scalars of the trial sweep
+  unsigned int* bar;        // arrive counter of the group barrier (zeroed by the host before every launch)
+  int vpad;
+  int cta_slot_off[MAX_G + 1];
+  int cta_line_off[MAX_G + 1];
   signed char cam_free[MAX_CAMS];   // reduced block index of each camera or -1
 };
 
@@ -58,6 +64,7 @@ struct WinHdr {
 struct SmemLayout {
   int camx, camxt, camR, camRt, cscale, linex, linext, lscale, lineLU, ltrig, ltrigt, V, Vred, wacc, yc, misc, tri, Z, obs, meta, total;
   int z_in_smem, obs_in_smem;
+  int G;   // CTAs per window of this launch
 };
 
 __host__ __device__ inline int lba_vlen(int Cf) {
@@ -76,7 +83,7 @@ __host__ inline SmemLayout lba_layout(int C, int Cf, int max_lines_cta, int max_
   l.linex = take(4 * max_lines_cta); l.linext = take(4 * max_lines_cta); l.lscale = take(4 * max_lines_cta);
   l.lineLU = take(LLU * max_lines_cta);
   l.ltrig = take(8 * max_lines_cta); l.ltrigt = take(8 * max_lines_cta);   // sin/cos of the line angles at x and at x'
-  l.V = take(vlen); l.Vred = take((vlen + CS - 1) / CS + 2);
+  l.V = take(vlen); l.Vred = l.V; l.G = CS;
   l.wacc = take(LBA_NW * ACC * (Cf > 0 ? Cf : 1));
   l.yc = take(6 * (Cf > 0 ? Cf : 1) + 8);
   l.misc = take(64 + LBA_NW * NSCAL);
@@ -157,7 +164,7 @@ struct Ctx {
   const WinHdr* h;
   double* sm;
   SmemLayout lay;
-  int tid, lane, warp, rank, CS;
+  int tid, lane, warp, rank, G;
   int slot0, nslots, ntiles, line0, nlines;
   double* Zbuf;   // this CTA's Z blocks (shared or global)
   const double* obs;   // this CTA's observations [nslots][8] (shared or global)
@@ -289,7 +296,7 @@ __device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, d
 #pragma unroll
         for (int k = 0; k < 10; ++k) o[k] = Lm[k];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { o[10 + k] = u[k]; o[14 + k] = D[k]; }
+        for (int k = 0; k < 4; ++k) { o[10 + k] = u[k]; o[14 + k] = D[k]; o[18 + k] = inv[k]; }
         if (line_free) {
           const double* lsc = lscale + 4 * ll;
 #pragma unroll
@@ -437,33 +444,57 @@ __device__ void fold_cameras(const Ctx& c, bool norms_only) {
   }
 }
 
-// Sum V over the cluster: reduce-scatter then all-gather through distributed shared memory, fixed rank order.
-// The entry at max_idx is combined with max instead of +.
-__device__ void cluster_allreduce(cg::cluster_group& cl, const Ctx& c, int vlen, int max_idx) {
-  double* V = c.sm + c.lay.V;
-  double* Vred = c.sm + c.lay.Vred;
-  if (c.CS == 1) { __syncthreads(); return; }
-  cl.sync();
-  const int per = (vlen + c.CS - 1) / c.CS;
-  const int beg = c.rank * per, end = min(vlen, beg + per);
-  for (int i = beg + c.tid; i < end; i += LBA_NT) {
-    double s = 0.0;
-    for (int r = 0; r < c.CS; ++r) {
-      const double v = cl.map_shared_rank(V, r)[i];
-      s = (i == max_idx) ? fmax(s, v) : s + v;
-    }
-    Vred[i - beg] = s;
-  }
-  cl.sync();
-  for (int i = c.tid; i < vlen; i += LBA_NT) {
-    const int r = i / per;
-    V[i] = cl.map_shared_rank(Vred, r)[i - r * per];
+// Barrier over the G CTAs of a window: one arrive (release) + spin (acquire) by thread 0 on a counter in L2.
+// `target` advances by G per barrier; the host zeroes the counter before every launch.  All CTAs of a group are
+// co-resident (cooperative launch), so the spin cannot deadlock.
+__device__ __forceinline__ void group_barrier(const Ctx& c, unsigned int& target) {
+  target += (unsigned int)c.G;
+  __syncthreads();
+  if (c.tid == 0) {
+    unsigned int* bar = c.h->bar;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+    } while ((int)(seen - target) < 0);
+    __threadfence();
   }
   __syncthreads();
 }
 
+// Sum V over the group: every CTA publishes its partial vector, CTA r reduces slice r in fixed rank order
+// (deterministic), every CTA reads the reduced vector back.  The entry at max_idx is combined with max instead of +.
+// Reads of peer data bypass L1 (ld.cg): the scratch is rewritten every iteration.
+__device__ void group_allreduce(const Ctx& c, int vlen, int max_idx, unsigned int& target) {
+  double* V = c.sm + c.lay.V;
+  if (c.G == 1) { __syncthreads(); return; }
+  const WinHdr& h = *c.h;
+  double* mine = h.Vg + (size_t)c.rank * h.vpad;
+  __syncthreads();
+  for (int i = c.tid; i < vlen; i += LBA_NT) mine[i] = V[i];
+  group_barrier(c, target);
+  const int per = (vlen + c.G - 1) / c.G;
+  const int beg = c.rank * per, end = min(vlen, beg + per);
+  for (int i = beg + c.tid; i < end; i += LBA_NT) {
+    // eight peer loads in flight at a time (each is an L2 round trip), combined in rank order
+    double s = 0.0;
+    for (int r0 = 0; r0 < c.G; r0 += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (r0 + u < c.G) ? __ldcg(h.Vg + (size_t)(r0 + u) * h.vpad + i) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) if (r0 + u < c.G) s = (i == max_idx) ? fmax(s, v[u]) : s + v[u];
+    }
+    h.Vr[i] = s;
+  }
+  group_barrier(c, target);
+  for (int i = c.tid; i < vlen; i += LBA_NT) V[i] = __ldcg(h.Vr + i);
+  __syncthreads();
+}
+
 // K3: blocked (6x6) right-looking Cholesky of the reduced camera system held block-packed in V, with the right-hand
-// side carried along (forward substitution folded in), then block back-substitution.  Every CTA of the cluster
+// side carried along (forward substitution folded in), then block back-substitution.  Every CTA of the group
 // solves the same system redundantly (same data, same order => same bits), which saves a broadcast.
 // Two barriers per block column: [diagonal factor in registers by every participating thread + panel rows + rhs] |
 // [trailing update + write-back of the factored diagonal block].  A factored diagonal block stores L strictly below
@@ -565,21 +596,30 @@ __device__ bool reduced_solve(const Ctx& c, double radius) {
 #pragma unroll
         for (int q = 0; q < 6; ++q) AJJ[6 * p + q] = (q < p) ? Lr[L6(p, q)] : (q == p ? inv[p] : Mi[L6(q, p)]);
     }
-    // trailing update: A_IK -= L_IJ L_KJ^T for I >= K > J (entry per thread), and b_I -= L_IJ z_J
-    const int nent = nb * (nb + 1) / 2 * 36;
-    for (int e = c.tid; e < nent + npanel; e += LBA_NT) {
-      if (e < nent) {
-        const int blk = e / 36, pq = e - 36 * blk, p = pq / 6, q = pq - 6 * p;
+    // trailing update: A_IK -= L_IJ L_KJ^T for I >= K > J, one ROW of a 6x6 block per thread (six independent
+    // 6-term dot products, so a block column is usually a single pass of the CTA), and b_I -= L_IJ z_J
+    const int nitem = nb * (nb + 1) / 2 * 6;
+    for (int e = c.tid; e < nitem + npanel; e += LBA_NT) {
+      if (e < nitem) {
+        const int blk = e / 6, p = e - 6 * blk;
         const int t = tri[blk];
         const int I = J + 1 + (t >> 8), K = J + 1 + (t & 0xff);
         const double* li = V + (I * (I + 1) / 2 + J) * 36 + 6 * p;
-        const double* lk = V + (K * (K + 1) / 2 + J) * 36 + 6 * q;
-        double s = 0.0;
+        const double* lk = V + (K * (K + 1) / 2 + J) * 36;
+        double* dst = V + (I * (I + 1) / 2 + K) * 36 + 6 * p;
+        double a[6], o[6];
 #pragma unroll
-        for (int m = 0; m < 6; ++m) s += li[m] * lk[m];
-        V[(I * (I + 1) / 2 + K) * 36 + pq] -= s;
+        for (int m = 0; m < 6; ++m) { a[m] = li[m]; o[m] = dst[m]; }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          double s0 = a[0] * lk[6 * q] + a[1] * lk[6 * q + 1] + a[2] * lk[6 * q + 2];
+          double s1 = a[3] * lk[6 * q + 3] + a[4] * lk[6 * q + 4] + a[5] * lk[6 * q + 5];
+          o[q] -= s0 + s1;
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) dst[q] = o[q];
       } else {
-        const int rI = e - nent, bI = rI / 6, I = J + 1 + bI, p = rI - 6 * bI;
+        const int rI = e - nitem, bI = rI / 6, I = J + 1 + bI, p = rI - 6 * bI;
         const double* li = V + (I * (I + 1) / 2 + J) * 36 + 6 * p;
         double s = 0.0;
 #pragma unroll
@@ -659,10 +699,10 @@ __device__ void trial_sweep(const Ctx& c, double* out4) {
       if (line_free) {
         double yl[4];
         const double w3 = lu[10 + 3] - v[3], w2 = lu[10 + 2] - v[2], w1 = lu[10 + 1] - v[1], w0 = lu[10] - v[0];
-        yl[3] = w3 / lu[9];
-        yl[2] = (w2 - lu[8] * yl[3]) / lu[5];
-        yl[1] = (w1 - lu[4] * yl[2] - lu[7] * yl[3]) / lu[2];
-        yl[0] = (w0 - lu[1] * yl[1] - lu[3] * yl[2] - lu[6] * yl[3]) / lu[0];
+        yl[3] = w3 * lu[21];
+        yl[2] = (w2 - lu[8] * yl[3]) * lu[20];
+        yl[1] = (w1 - lu[4] * yl[2] - lu[7] * yl[3]) * lu[19];
+        yl[0] = (w0 - lu[1] * yl[1] - lu[3] * yl[2] - lu[6] * yl[3]) * lu[18];
         const double* lsc = lscale + 4 * ll;
 #pragma unroll
         for (int k = 0; k < 4; ++k) xl[k] = linex[4 * ll + k] - yl[k] * lsc[k];
@@ -739,12 +779,12 @@ __device__ void cta_sum(const Ctx& c, const double* vals, double* dst, bool is_m
 
 __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __restrict__ hdrs, SmemLayout lay) {
   extern __shared__ __align__(16) double sm[];
-  cg::cluster_group cl = cg::this_cluster();
   const long long t0k = clock64();
   Ctx c;
-  c.CS = (int)cl.num_blocks();
-  c.rank = (int)cl.block_rank();
-  const int win = blockIdx.x / c.CS;
+  c.G = lay.G;
+  c.rank = (int)(blockIdx.x % (unsigned)lay.G);
+  const int win = (int)(blockIdx.x / (unsigned)lay.G);
+  unsigned int bar_target = 0;
   const WinHdr& h = hdrs[win];
   c.h = &h; c.sm = sm; c.lay = lay;
   c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
@@ -805,7 +845,7 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
     double vals[2] = {p_cost, p_fixed};
     cta_sum<2>(c, vals, V + sc_off);
   }
-  cluster_allreduce(cl, c, vlen, -1);
+  group_allreduce(c, vlen, -1, bar_target);
   for (int i = c.tid; i < n; i += LBA_NT) cscale[i] = 1.0 / (1.0 + sqrt(V[hd_off + i]));
   const double fixed_cost = V[sc_off + 1];
   double cost = V[sc_off + 0];
@@ -841,7 +881,7 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
       cta_sum<3>(c, vals, V + sc_off, true);
     }
     PHASE(3)
-    cluster_allreduce(cl, c, vlen, sc_off + 2);
+    group_allreduce(c, vlen, sc_off + 2, bar_target);
     PHASE(4)
     cost = V[sc_off + 0];
     const bool line_fail = V[sc_off + 1] != 0.0;
@@ -895,12 +935,19 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
       double part[4];
       trial_sweep(c, part);
       cta_sum<4>(c, part, scal);
-      if (c.CS > 1) {
-        cl.sync();
-        for (int r = 0; r < c.CS; ++r) {
-          const double* rs = cl.map_shared_rank(scal, r);
+      if (c.G > 1) {
+        if (c.tid < 4) h.scalg[c.rank * 8 + c.tid] = scal[c.tid];
+        group_barrier(c, bar_target);
+        for (int r0 = 0; r0 < c.G; r0 += 4) {
+          double v[4][4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) trial[k] += rs[k];
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[u][k] = (r0 + u < c.G) ? __ldcg(h.scalg + (r0 + u) * 8 + k) : 0.0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) trial[k] += v[u][k];
         }
       } else {
 #pragma unroll
@@ -969,7 +1016,6 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
     }
   }
 #undef PHASE
-  if (c.CS > 1) cl.sync();   // no CTA may exit while a peer can still read its shared memory
 }
 
 // K1 alone, one thread per observation, for parity tests of the residual and the analytic Jacobian.

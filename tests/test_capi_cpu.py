@@ -42,7 +42,7 @@ def test_struct_layouts_match_header(lib):
     assert C.sizeof(capi.LbaDesc) == 16 + 4 * 8 + 8 + 6 * 8
     lim = capi.Limits()
     lib.slslam_lba_get_limits(C.byref(lim))
-    assert lim.max_cameras >= 20 and lim.max_free_cameras >= 10 and lim.max_cluster_size == 16
+    assert lim.max_cameras >= 20 and lim.max_free_cameras >= 10 and lim.max_cluster_size >= 16
 
 
 def test_no_cpu_fallback_without_gpu(lib):
