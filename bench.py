@@ -185,7 +185,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--windows-per-gpu", type=int, default=WINDOWS_PER_GPU)
-    ap.add_argument("--cluster-size", type=int, default=0)
+    ap.add_argument("--ctas-per-window", type=int, default=0, help="0 = chosen by the planner")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
@@ -211,7 +211,7 @@ def main():
     K = args.steps
 
     windows = make_windows(rank, args.windows_per_gpu)
-    batch = capi.LbaBatch(windows, device=local_rank, cluster_size=args.cluster_size, max_iters=MAX_ITERS)
+    batch = capi.LbaBatch(windows, device=local_rank, cluster_size=args.ctas_per_window, max_iters=MAX_ITERS)
     info = batch.info()
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
@@ -348,7 +348,7 @@ def main():
             torch.cuda.synchronize()
             _, s1 = b1.download(sptr)
             line["single_window"] = {"value": s1[0]["iterations"] * 20 / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT,
-                                     "cluster_size": b1.info()["cluster_size"], "l2": "warm"}
+                                     "ctas_per_window": b1.info()["ctas_per_window"], "l2": "warm"}
             b1.close()
         if world == 1 and not args.no_cpu_baseline:
             reps = 2

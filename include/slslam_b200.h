@@ -127,7 +127,8 @@ int slslam_lba_batch_info(const slslam_lba_batch* b, int32_t* cluster_size, int3
 /* How many clusters of this batch's shape the device keeps resident at once (a batch larger than this runs in waves). */
 int slslam_lba_batch_max_active_clusters(const slslam_lba_batch* b, int32_t* max_active);
 /* Diagnostics: SM cycles CTA 0 of `window` spent per phase in the last solve
- * (init, linearise, pairs, fold, allreduce, gradient, reduced solve, trial, decide, total); n <= 10. */
+ * (init, linearise, pairs, fold, allreduce, gradient, reduced solve, trial, decide, total, then the reduced solve split:
+ * prep, factor + panel, trailing update, back-substitution); n <= 14. */
 int slslam_lba_batch_phase_cycles(slslam_lba_batch* b, void* cuda_stream, int32_t window, int64_t* cycles_out, int32_t n);
 /* Bytes one host-buffer solve of this batch moves: plan + parameters up, parameters + summaries down. */
 int slslam_lba_batch_transfer_bytes(const slslam_lba_batch* b, int64_t* h2d_bytes, int64_t* d2h_bytes);

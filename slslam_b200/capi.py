@@ -196,19 +196,20 @@ class LbaBatch:
         _check(lib().slslam_lba_batch_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         m = C.c_int32()
         _check(lib().slslam_lba_batch_max_active_clusters(self._h, C.byref(m)))
-        return dict(cluster_size=a.value, threads_per_cta=b.value, smem_bytes_per_cta=c.value, z_in_smem=d.value,
-                    max_active_clusters=m.value)
+        return dict(cluster_size=a.value, ctas_per_window=a.value, threads_per_cta=b.value, smem_bytes_per_cta=c.value,
+                    z_in_smem=d.value, max_active_clusters=m.value, windows_per_wave=m.value)
 
     def transfer_bytes(self):
         a, b = C.c_int64(), C.c_int64()
         _check(lib().slslam_lba_batch_transfer_bytes(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    PHASES = ("init", "linearise", "pairs", "fold", "allreduce", "gradient", "reduced_solve", "trial", "decide", "total")
+    PHASES = ("init", "linearise", "pairs", "fold", "allreduce", "gradient", "reduced_solve", "trial", "decide", "total",
+              "rs_prep", "rs_factor_panel", "rs_trailing", "rs_backsub")
 
     def phase_cycles(self, window=0, stream=None):
-        buf = (C.c_int64 * 10)()
-        _check(lib().slslam_lba_batch_phase_cycles(self._h, C.c_void_p(stream), window, buf, 10))
+        buf = (C.c_int64 * 14)()
+        _check(lib().slslam_lba_batch_phase_cycles(self._h, C.c_void_p(stream), window, buf, 14))
         return dict(zip(self.PHASES, list(buf)))
 
     def upload(self, params=None, stream=None):

@@ -31,7 +31,7 @@ constexpr int ZST = 26;              // row stride of the Z staging: 13 x 16 B, 
 constexpr int ACC = 33;              // per-camera accumulators: H_cc (21, lower) | g_c (6) | sum Z u (6)
 constexpr int LLU = 22;              // per-line: L (10, lower) | u = L^-1 g_l (4) | D_l (4) | 1 / l_kk (4)
 constexpr int NSCAL = 8;
-constexpr int NPHASE = 10;         // init | linearise | pairs | fold | allreduce | gradient | reduced solve | trial | decide | total
+constexpr int NPHASE = 14;         // init | linearise | pairs | fold | allreduce | gradient | reduced solve | trial | decide | total | solve: prep, factor+panel, trailing, back-substitution
 
 // slot flags (meta.x bits 24..)
 constexpr int F_VALID = 1, F_CAM_FIXED = 2, F_LINE_FIXED = 4, F_HEAD = 8;
@@ -501,7 +501,9 @@ __device__ void group_allreduce(const Ctx& c, int vlen, int max_idx, unsigned in
 // the diagonal, 1/l_kk on it and the strict part of L^-1 transposed above it, so the back-substitution of a block is
 // six independent dot products.  On exit yc = (S + D_c)^-1 (g_c - sum Z u).  Returns false (uniformly) if a pivot
 // is not positive.
-__device__ bool reduced_solve(const Ctx& c, double radius) {
+__device__ bool reduced_solve(const Ctx& c, double radius, long long* ph) {
+  long long tq = clock64();
+#define RSPHASE(i) { const long long now_ = clock64(); ph[i] += now_ - tq; tq = now_; }
   const WinHdr& h = *c.h;
   double* V = c.sm + c.lay.V;
   double* yc = c.sm + c.lay.yc;
@@ -517,6 +519,7 @@ __device__ bool reduced_solve(const Ctx& c, double radius) {
   }
   if (c.tid == 0) misc[6] = 0.0;
   __syncthreads();
+  RSPHASE(10)
   for (int J = 0; J < Cf; ++J) {
     double* AJJ = V + (J * (J + 1) / 2 + J) * 36;
     const int nb = Cf - J - 1;
@@ -577,6 +580,7 @@ __device__ bool reduced_solve(const Ctx& c, double radius) {
       }
     }
     __syncthreads();
+    RSPHASE(11)
     if (c.tid == npanel + 1) {
       // M = L_JJ^-1 (lower): m_pp = 1/l_pp, m_pq = -m_pp sum_{k=q}^{p-1} l_pk m_kq
       double Mi[21];
@@ -628,6 +632,7 @@ __device__ bool reduced_solve(const Ctx& c, double radius) {
       }
     }
     __syncthreads();
+    RSPHASE(12)
   }
   const bool failed = misc[6] != 0.0;
   // back substitution L^T y = z by warp 0: y_J = L_JJ^-T w_J as six dot products with the stored inverse, then every
@@ -656,6 +661,8 @@ __device__ bool reduced_solve(const Ctx& c, double radius) {
     }
   }
   __syncthreads();
+  RSPHASE(13)
+#undef RSPHASE
   return !failed;
 }
 
@@ -906,7 +913,7 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
     // camera part of the model decrease needs g_c and D_c before the solve overwrites V
     bool ok = !line_fail;
     double model_c = 0.0;
-    if (Cf > 0) ok = reduced_solve(c, radius) && ok;
+    if (Cf > 0) ok = reduced_solve(c, radius, ph) && ok;
     PHASE(6)
     double dn2c = 0.0;
     if (ok && Cf > 0) {
@@ -1010,7 +1017,7 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
     s.num_successful_steps = successful; s.num_unsuccessful_steps = unsuccessful; s.termination_type = term; s.iterations = iters;
     *h.summary = s;
     if (h.phase_cycles) {
-      ph[NPHASE - 1] = clock64() - t_begin;
+      ph[9] = clock64() - t_begin;
 #pragma unroll
       for (int k = 0; k < NPHASE; ++k) h.phase_cycles[k] = ph[k];
     }
