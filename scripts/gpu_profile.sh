@@ -13,3 +13,6 @@ ncu --set full --clock-control none --import-source on -k regex:lba_solve -s 3 -
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_po_${tag}.csv \
     python scripts/po_profile.py 1 > gpurun_out/ncu_po_${tag}.log 2>&1
 python scripts/po_profile.py 3 2>&1 | tee gpurun_out/po_${tag}.txt
+python scripts/phase_profile.py all > gpurun_out/phase_${tag}.txt 2>&1
+python scripts/e2e_profile.py > gpurun_out/e2e_${tag}.txt 2>&1
+python scripts/h2d_test2.py > gpurun_out/h2d_${tag}.txt 2>&1

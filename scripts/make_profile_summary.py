@@ -54,7 +54,7 @@ if os.path.exists(rep):
 for src, dst in ((f"launches_{tag}.csv", f"{rnd}_launches_bench_lba.csv"), (f"launches_po_{tag}.csv", f"{rnd}_launches_po_solve.csv"),
                  (f"bench_{tag}.json", f"{rnd}_bench_ours.json"), (f"bench_ref_{tag}.json", f"{rnd}_bench_reference_arm.json"),
                  (f"po_{tag}.txt", f"{rnd}_po_solve_timing.txt"), (f"phase_{tag}.txt", f"{rnd}_lba_phase_cycles.txt"),
-                 (f"e2e_{tag}.txt", f"{rnd}_lba_e2e_split.txt")):
+                 (f"e2e_{tag}.txt", f"{rnd}_lba_e2e_split.txt"), (f"h2d_{tag}.txt", f"{rnd}_h2d_staging.txt")):
     if os.path.exists(os.path.join(G, src)):
         shutil.copy(os.path.join(G, src), os.path.join(P, dst))
 

@@ -9,6 +9,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -30,6 +34,11 @@ struct WindowPlan {
   signed char cam_free[MAX_CAMS];
   int max_lines_cta = 0, max_slots_cta = 0;
   bool has_unobserved_blocks = false;
+  // planning scratch, kept so that a cached plan object does not allocate on reuse
+  std::vector<char> s_cam_used, s_cam_const, s_line_const;
+  std::vector<int> s_line_cnt, s_line_start, s_order, s_fill, s_first_slot, s_kcount, s_sorted_off;
+  std::vector<signed char> s_ocf;
+  std::vector<unsigned char> s_sorted_pos, s_sorted_cnt;
 };
 
 static int validate_desc(const slslam_lba_desc& d) {
@@ -54,8 +63,11 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
   p.ptol = d.parameter_tolerance > 0 ? d.parameter_tolerance : 1e-8;
   p.radius0 = d.initial_trust_region_radius > 0 ? d.initial_trust_region_radius : 1e4;
   // sticky constants per block (reference lba_problem.cpp:88-91); unobserved blocks are never touched
-  std::vector<char> cam_used(C, 0), cam_const(C, 0), line_const(L, 0);
-  std::vector<int> line_cnt(L, 0);
+  p.has_unobserved_blocks = false;
+  std::vector<char>&cam_used = p.s_cam_used, &cam_const = p.s_cam_const, &line_const = p.s_line_const;
+  cam_used.assign(C, 0); cam_const.assign(C, 0); line_const.assign(L, 0);
+  std::vector<int>& line_cnt = p.s_line_cnt;
+  line_cnt.assign(L, 0);
   for (int i = 0; i < N; ++i) {
     cam_used[d.camera_index[i]] = 1;
     ++line_cnt[d.line_index[i]];
@@ -71,16 +83,18 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
   if (p.Cf > MAX_FREE_CAMS) return SLSLAM_ERR_UNSUPPORTED;
   p.nkeys = p.Cf * (p.Cf + 1) / 2;
   // group observations by line (stable counting sort: keeps the caller's order inside a line)
-  std::vector<int> line_start(L + 1, 0);
+  std::vector<int>& line_start = p.s_line_start;
+  line_start.assign(L + 1, 0);
   for (int l = 0; l < L; ++l) {
     line_start[l + 1] = line_start[l] + line_cnt[l];
     if (line_cnt[l] > 32) return SLSLAM_ERR_UNSUPPORTED;
     if (line_cnt[l] == 0) p.has_unobserved_blocks = true;
   }
-  std::vector<int> order(N), fill(line_start.begin(), line_start.end() - 1);
+  std::vector<int>&order = p.s_order, &fill = p.s_fill;
+  order.resize(N); fill.assign(line_start.begin(), line_start.end() - 1);
   for (int i = 0; i < N; ++i) order[fill[d.line_index[i]]++] = i;
-  std::vector<int> dl;   // device lines in increasing id
-  dl.reserve(L);
+  std::vector<int>& dl = p.line_gid;   // device lines in increasing id
+  dl.clear(); dl.reserve(L);
   for (int l = 0; l < L; ++l) if (line_cnt[l] > 0) dl.push_back(l);
   // partition the device lines over the CTAs, balancing observation counts
   const int nd = (int)dl.size();
@@ -94,19 +108,21 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
     }
     for (int r = CS + 1; r <= MAX_G; ++r) p.cta_line_off[r] = nd;
   }
-  p.line_gid = dl;
   p.key_off.assign((size_t)CS * (p.nkeys + 1), 0);
   p.slot_src.clear(); p.meta.clear(); p.items.clear();
   p.slot_src.reserve((size_t)N + 32 * (size_t)CS + N / 4); p.meta.reserve((size_t)N + 32 * (size_t)CS + N / 4);
   p.max_lines_cta = 1; p.max_slots_cta = 32;
   p.cta_slot_off[0] = 0;
   // reduced camera index of every observation in line-grouped order (-1: constant camera or constant line => no pair)
-  std::vector<signed char> ocf(N);
+  std::vector<signed char>& ocf = p.s_ocf;
+  ocf.resize(N);
   for (int l = 0; l < L; ++l)
     for (int a = line_start[l]; a < line_start[l + 1]; ++a)
       ocf[a] = line_const[l] ? (signed char)-1 : p.cam_free[d.camera_index[order[a]]];
-  std::vector<int> first_slot(nd, 0), kcount(p.nkeys + 1, 0), sorted_off(nd, 0);
-  std::vector<unsigned char> sorted_pos((size_t)N + 1), sorted_cnt(nd, 0);
+  std::vector<int>&first_slot = p.s_first_slot, &kcount = p.s_kcount, &sorted_off = p.s_sorted_off;
+  first_slot.assign(nd, 0); kcount.assign(p.nkeys + 1, 0); sorted_off.assign(nd, 0);
+  std::vector<unsigned char>&sorted_pos = p.s_sorted_pos, &sorted_cnt = p.s_sorted_cnt;
+  sorted_pos.resize((size_t)N + 1); sorted_cnt.assign(nd, 0);
   int pos_off = 0;
   for (int r = 0; r < CS; ++r) {
     const int lb = p.cta_line_off[r], le = p.cta_line_off[r + 1];
@@ -232,6 +248,7 @@ struct Workspace {
   char* h_pin = nullptr; size_t h_cap = 0;     // upload staging: write-combined, written once by one thread, read only by the DMA engine
   char* h_res = nullptr; size_t r_cap = 0;     // results: ordinary pinned memory (the CPU reads it)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<WindowPlan> plans;               // plan objects of the previous call, reused for their capacity
   int ensure(int dev, size_t d_bytes, size_t h_bytes, size_t r_bytes) {
     if (device != dev) { release(); device = dev; }
     for (int k = 0; k < 4; ++k) if (!ev[k]) CUDA_TRY(cudaEventCreate(&ev[k]));
@@ -298,22 +315,75 @@ static int pick_group_size(int device, int nwin, long long max_obs, int requeste
   int g = std::max(1, cap / std::max(1, nwin));
   const long long tiles = (max_obs + 27) / 28;
   g = (int)std::min<long long>(g, std::max<long long>(1, tiles / 3));
-  return std::min(g, (int)MAX_G);
+  return std::min(g, 48);   // beyond ~48 CTAs the exchange grows faster than the sweeps shrink (profiles/r1_cluster_vs_group.txt)
 }
 
-// fn(i) for i in [0, n) on up to 8 host threads (planning and staging of different windows are independent work)
+// fn(i) for i in [0, n) on up to 8 host threads (the plans of different windows are independent work).  The workers
+// are created once and parked on a condition variable: creating and joining 8 threads per solve cost ~0.1 ms of a
+// 2 ms call.  One job at a time (callers are serialised by a mutex); the calling thread takes a share of the work.
+class HostPool {
+ public:
+  static HostPool& get() { static HostPool* p = new HostPool(); return *p; }   // never destroyed: no join at exit
+  template <class F>
+  void run(int n, F& fn) {
+    const int nthreads = std::min(n, max_threads_);
+    if (nthreads <= 1) { for (int i = 0; i < n; ++i) fn(i); return; }
+    std::lock_guard<std::mutex> serial(job_mutex_);
+    ensure_workers(nthreads - 1);
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      call_ = [](void* f, int i) { (*static_cast<F*>(f))(i); };
+      fn_ = &fn; n_ = n; next_.store(0); pending_ = nthreads - 1; active_ = nthreads - 1; ++generation_;
+    }
+    cv_.notify_all();
+    for (int i = next_.fetch_add(1); i < n; i = next_.fetch_add(1)) fn(i);
+    std::unique_lock<std::mutex> lk(m_);
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+  }
+ private:
+  HostPool() {
+    const char* e = getenv("SLSLAM_HOST_THREADS");
+    const int v = e ? atoi(e) : 8;
+    max_threads_ = v < 1 ? 1 : (v > 64 ? 64 : v);
+  }
+  void ensure_workers(int k) {
+    while ((int)workers_.size() < k) {
+      const int id = (int)workers_.size();
+      workers_.emplace_back([this, id]() { worker(id); });
+      workers_.back().detach();
+    }
+  }
+  void worker(int id) {
+    unsigned long long seen = 0;
+    for (;;) {
+      void (*call)(void*, int); void* fn; int n;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return generation_ != seen && id < active_; });
+        seen = generation_; call = call_; fn = fn_; n = n_;
+      }
+      for (int i = next_.fetch_add(1); i < n; i = next_.fetch_add(1)) call(fn, i);
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        if (--pending_ == 0) done_cv_.notify_one();
+      }
+    }
+  }
+  std::mutex m_, job_mutex_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<std::thread> workers_;
+  void (*call_)(void*, int) = nullptr;
+  void* fn_ = nullptr;
+  int n_ = 0, pending_ = 0, active_ = 0, max_threads_ = 8;
+  std::atomic<int> next_{0};
+  unsigned long long generation_ = 0;
+};
+
 template <class F>
-static void parallel_for(int n, F fn) {
-  static const int max_threads = []() { const char* e = getenv("SLSLAM_HOST_THREADS"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 64 ? 64 : v); }();
-  const int nthreads = std::min(n, max_threads);
-  if (nthreads <= 1) { for (int i = 0; i < n; ++i) fn(i); return; }
-  std::vector<std::thread> th;
-  for (int t = 0; t < nthreads; ++t) th.emplace_back([&fn, t, n, nthreads]() { for (int i = t; i < n; i += nthreads) fn(i); });
-  for (auto& t : th) t.join();
-}
+static void parallel_for(int n, F fn) { HostPool::get().run(n, fn); }
 
 static int build_plans(int n, const slslam_lba_desc* descs, int CS, std::vector<WindowPlan>& plans) {
-  plans.assign(n, WindowPlan());
+  plans.resize(n);   // existing plan objects keep their vector capacity
   std::vector<int> rcs(n, SLSLAM_OK);
   parallel_for(n, [&](int i) { rcs[i] = build_plan(descs[i], CS, plans[i]); });
   for (int i = 0; i < n; ++i) if (rcs[i] != SLSLAM_OK) return rcs[i];
@@ -340,6 +410,7 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
   cudaGetDevice(&b->device);
   b->n = n;
   b->borrowed = ws != nullptr;
+  if (ws) b->plans.swap(ws->plans);
   long long max_obs = 0;
   for (int i = 0; i < n; ++i) max_obs = std::max<long long>(max_obs, descs[i].num_observations);
   const int cap = resident_ctas(b->device);
@@ -574,6 +645,7 @@ int slslam_lba_batch_transfer_bytes(const slslam_lba_batch* b, int64_t* h2d_byte
 void slslam_lba_batch_destroy(slslam_lba_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
+  if (b->borrowed) g_ws.plans.swap(b->plans);
   if (!b->borrowed) {
     if (b->d_pool) cudaFree(b->d_pool);
     if (b->h_params) cudaFreeHost(b->h_params);
