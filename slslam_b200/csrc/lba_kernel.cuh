@@ -275,16 +275,16 @@ __device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, d
       bool ok = true;
       {
         double a00 = hg[0] + D[0];
-        ok = ok && (a00 > 0.0); inv[0] = rsqrt(a00); Lm[0] = a00 * inv[0];
+        ok = ok && (a00 > 0.0); inv[0] = pivot_rsqrt(a00); Lm[0] = a00 * inv[0];
         Lm[1] = hg[1] * inv[0]; Lm[3] = hg[3] * inv[0]; Lm[6] = hg[6] * inv[0];
         double a11 = hg[2] + D[1] - Lm[1] * Lm[1];
-        ok = ok && (a11 > 0.0); inv[1] = rsqrt(a11); Lm[2] = a11 * inv[1];
+        ok = ok && (a11 > 0.0); inv[1] = pivot_rsqrt(a11); Lm[2] = a11 * inv[1];
         Lm[4] = (hg[4] - Lm[3] * Lm[1]) * inv[1]; Lm[7] = (hg[7] - Lm[6] * Lm[1]) * inv[1];
         double a22 = hg[5] + D[2] - Lm[3] * Lm[3] - Lm[4] * Lm[4];
-        ok = ok && (a22 > 0.0); inv[2] = rsqrt(a22); Lm[5] = a22 * inv[2];
+        ok = ok && (a22 > 0.0); inv[2] = pivot_rsqrt(a22); Lm[5] = a22 * inv[2];
         Lm[8] = (hg[8] - Lm[6] * Lm[3] - Lm[7] * Lm[4]) * inv[2];
         double a33 = hg[9] + D[3] - Lm[6] * Lm[6] - Lm[7] * Lm[7] - Lm[8] * Lm[8];
-        ok = ok && (a33 > 0.0); inv[3] = rsqrt(a33); Lm[9] = a33 * inv[3];
+        ok = ok && (a33 > 0.0); inv[3] = pivot_rsqrt(a33); Lm[9] = a33 * inv[3];
       }
       if (valid && !ok) fail = 1.0;
       u[0] = hg[10] * inv[0];
@@ -538,7 +538,7 @@ __device__ bool reduced_solve(const Ctx& c, double radius, long long* ph) {
 #pragma unroll
         for (int m = 0; m < k; ++m) d -= Lr[L6(k, m)] * Lr[L6(k, m)];
         ok = ok && (d > 0.0);
-        inv[k] = rsqrt(d);
+        inv[k] = pivot_rsqrt(d);
         Lr[L6(k, k)] = d * inv[k];
 #pragma unroll
         for (int p = k + 1; p < 6; ++p) {

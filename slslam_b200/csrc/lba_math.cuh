@@ -8,6 +8,19 @@
 
 namespace slslam {
 
+// 1 / sqrt(d) for the pivot chains of the block Choleskys: the hardware approximation (MUFU.RSQ64H, ~20 bits) and two
+// Newton steps y <- y (1.5 - 0.5 d y^2), accurate to a few ulp.  The library rsqrt() spends most of its ~200 cycles of
+// latency on special cases that cannot occur here (the callers test d > 0 separately; a non-positive or non-finite
+// pivot still yields NaN / inf, which the step-validity checks catch).
+__device__ __forceinline__ double pivot_rsqrt(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double h = 0.5 * d;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  return y;
+}
+
 // Per-camera block staged in shared memory: R (9, row-major), dR/dw_k (3 x 9), t (3), pad -> 40 doubles.
 constexpr int CAM_STRIDE = 40;
 
