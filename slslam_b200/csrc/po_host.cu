@@ -108,6 +108,7 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   const size_t o_summ = pool.reserve(sizeof(slslam_summary));
   const size_t o_trace = pool.reserve(8 * (size_t)SLSLAM_TRACE_WIDTH * std::max(max_iters, 1));
   const size_t o_Ld = pool.reserve(8 * (size_t)PO_NB * PO_NB * std::max(nb32, 1));
+  const size_t o_flags = pool.reserve(4 * (size_t)std::max(nb32, 1));
   const size_t o_H = evaluate_only ? pool.off : pool.reserve(8 * (size_t)M * ld);
   CUDA_TRY(cudaMalloc((void**)&pool.base, pool.off));
 
@@ -156,6 +157,8 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
 
   cudaStream_t s = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  unsigned int* d_flags = (unsigned int*)(B + o_flags);
+  int bs_ctas = 1;
   rc = SLSLAM_OK;
 #define PO_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_last_error(cudaGetErrorString(e_)); cudaGetLastError(); rc = SLSLAM_ERR_CUDA; goto done; } } while (0)
   PO_TRY(cudaMemcpyAsync(B, host.data(), upload_end, cudaMemcpyHostToDevice, s));
@@ -180,6 +183,17 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
     }
     goto done;
   }
+  if (!evaluate_only && n > 0) {
+    // back-substitution spreads its 32-column blocks over co-resident CTAs (cooperative launch)
+    int dev = 0, sms = 1, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, po_backsolve, 256, 0) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
+    bs_ctas = std::max(1, std::min(nb32, sms * std::max(per_sm, 1)));
+    bs_ctas = std::min(bs_ctas, 64);
+    if ((nb32 + bs_ctas - 1) / bs_ctas > PO_BS_MAXOWN) { set_last_error("pose graph too large for the back-substitution kernel"); rc = SLSLAM_ERR_UNSUPPORTED; goto done; }
+    PO_TRY(cudaMemsetAsync(d_flags, 0, 4 * (size_t)std::max(nb32, 1), s));
+  }
   if (n > 0) po_colnorm_grad<<<(n + 127) / 128, 128, 0, s>>>(d, 0);
   po_refresh<<<1, 256, 0, s>>>(d, 1);
   if (n > 0) {
@@ -194,7 +208,11 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
           po_chol_syrk<<<T * (T + 1) / 2, 256, 0, s>>>(d, k0, nb, t0, T);
         }
       }
-      po_backsolve<<<1, 1024, 0, s>>>(d);
+      {
+        unsigned int gen = (unsigned int)(it + 1);
+        void* args[3] = {(void*)&d, (void*)&d_flags, (void*)&gen};
+        PO_TRY(cudaLaunchCooperativeKernel((const void*)po_backsolve, dim3((unsigned)bs_ctas), dim3(256), args, 0, s));
+      }
       po_step<<<(6 * K + E + 255) / 256, 256, 0, s>>>(d);
       po_linearize<<<(E + 127) / 128, 128, 0, s>>>(d, 1, 0, 0);
       po_decide<<<1, 256, 0, s>>>(d);

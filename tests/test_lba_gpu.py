@@ -172,3 +172,95 @@ def test_errors(gpu):
     with pytest.raises(gpu.SlslamError) as e:
         gpu.lba_solve(w, params=nanp)
     assert e.value.code == -4
+
+
+def test_heterogeneous_batch_and_waves(gpu):
+    """One launch holds windows of different shapes (the group size and shared-memory layout are sized by the largest),
+    and a batch with more windows than the GPU has SMs runs as several cooperative launches."""
+    oracle = _oracle()
+    ws = [synth.make_window(100 + i, 3 + i % 6, 40 + 17 * i, 150 + 60 * i, sigma_px=0.5, num_fixed_cameras=i % 3, anchored=bool(i % 2))
+          for i in range(9)]
+    ps, ss = gpu.lba_solve_batch(ws, max_iters=6)
+    for w, p, s in zip(ws, ps, ss):
+        po, so = oracle.lba_solve(w, max_iters=6, solver=1)
+        assert _rel(s["final_cost"], so["final_cost"]) < 1e-6, (w.num_cameras, w.num_observations)
+        assert s["iterations"] == so["iterations"]
+        p1, s1 = gpu.lba_solve(w, max_iters=6)
+        assert _rel(s1["final_cost"], s["final_cost"]) < 1e-9      # group size differs between the two calls: same result
+    many = [synth.make_window(300 + i, 3, 20, 70, sigma_px=0.5) for i in range(12)]
+    many = [many[i % 12] for i in range(170)]                       # 170 windows > 148 SMs: two waves
+    b = gpu.LbaBatch(many, max_iters=5)
+    info = b.info()
+    assert info["windows_per_wave"] < len(many)
+    b.solve()
+    pm, sm = b.download()
+    b.close()
+    for i in range(12):
+        po, so = oracle.lba_solve(many[i], max_iters=5, solver=1)
+        assert _rel(sm[i]["final_cost"], so["final_cost"]) < 1e-6
+    for i in range(12, 170):
+        assert np.array_equal(pm[i], pm[i % 12]) and sm[i]["final_cost"] == sm[i % 12]["final_cost"]
+
+
+def test_large_group_sizes(gpu):
+    """Up to 64 CTAs per window (the hardware cluster limit of 16 does not apply to CTA groups)."""
+    w = synth.window_M(1, sigma_px=0.5)
+    ref = None
+    for g in (24, 48, 64):
+        b = gpu.LbaBatch([w], cluster_size=g, max_iters=6)
+        assert b.info()["ctas_per_window"] == g
+        b.solve()
+        (p,), (s,) = b.download()
+        b.close()
+        if ref is None:
+            po, so = _oracle().lba_solve(w, max_iters=6, solver=1)
+            assert _rel(s["final_cost"], so["final_cost"]) < 1e-6
+            ref = s["final_cost"]
+        assert _rel(s["final_cost"], ref) < 1e-9
+
+
+def test_edge_cases(gpu):
+    """Empty problems, blocks no observation touches (never written: reference SetParameterBlockConstant / AddResidualBlock
+    semantics), single-observation lines, and the kernel limits as clean errors."""
+    oracle = _oracle()
+    # no observations at all: nothing to do, parameters untouched, zero cost
+    w0 = synth.Window(2, 3, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0),
+                      np.arange(24, dtype=np.float64) * 0.01, np.zeros(24))
+    p, s = gpu.lba_solve(w0, max_iters=5)
+    assert np.array_equal(p, w0.parameters) and s["initial_cost"] == 0.0 and s["final_cost"] == 0.0
+    # unobserved camera and lines appended: their parameters must come back bit-identical
+    w = synth.window_S(12, sigma_px=0.5)
+    extra_cam, extra_lines = np.full(6, 0.123), np.full(8, 0.456)
+    params = np.concatenate([w.parameters[:6 * w.num_cameras], extra_cam, w.parameters[6 * w.num_cameras:], extra_lines])
+    # line indices are unchanged (the new camera is appended after the existing ones, the new lines after the existing lines)
+    w2 = synth.Window(w.num_cameras + 1, w.num_lines + 2, w.camera_index, w.line_index, w.fixed_index, w.observations,
+                      params, params.copy())
+    p2, s2 = gpu.lba_solve(w2, max_iters=6)
+    po, so = oracle.lba_solve(w2, max_iters=6, solver=1)
+    C = w.num_cameras
+    assert np.array_equal(p2[6 * C:6 * C + 6], extra_cam) and np.array_equal(p2[-8:], extra_lines)
+    assert _rel(s2["final_cost"], so["final_cost"]) < 1e-6
+    # lines seen once (no pair, Schur block from a single observation) mixed with ordinary lines
+    keep = np.ones(w.num_observations, bool)
+    first = {}
+    for i, l in enumerate(w.line_index):
+        if l % 3 == 0:
+            keep[i] = l not in first
+            first[l] = True
+    w3 = synth.Window(w.num_cameras, w.num_lines, w.camera_index[keep], w.line_index[keep],
+                      w.fixed_index.reshape(-1, 2)[keep].ravel(), w.observations.reshape(-1, 8)[keep].ravel(),
+                      w.parameters.copy(), w.truth)
+    p3, s3 = gpu.lba_solve(w3, max_iters=6)
+    po3, so3 = oracle.lba_solve(w3, max_iters=6, solver=1)
+    assert _rel(s3["final_cost"], so3["final_cost"]) < 1e-6 and s3["iterations"] == so3["iterations"]
+    # limits: more than 32 camera blocks, more than 32 observations of one line -> SLSLAM_ERR_UNSUPPORTED, inputs untouched
+    big = synth.Window(40, 1, np.arange(40, dtype=np.int32), np.zeros(40, np.int32), np.zeros(80, np.int32),
+                       np.zeros(320), np.full(244, 0.1), np.zeros(244))
+    with pytest.raises(gpu.SlslamError) as e:
+        gpu.lba_solve(big)
+    assert e.value.code == -2
+    many = synth.Window(2, 1, np.zeros(33, np.int32), np.zeros(33, np.int32), np.zeros(66, np.int32), np.zeros(264),
+                        np.full(16, 0.1), np.zeros(16))
+    with pytest.raises(gpu.SlslamError) as e:
+        gpu.lba_solve(many)
+    assert e.value.code == -2
