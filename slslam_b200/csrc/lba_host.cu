@@ -166,7 +166,8 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
       // count the Schur pairs of this line: ordered pairs (a,b) of free-camera observations with cf_a >= cf_b
       // (cameras are distinct within a line).  The line's free observations are sorted by reduced camera index first
       // (insertion sort; the reference packs them in keyframe order, so they usually are already), which makes the
-      // pair loops branch-free: every (i, j <= i) of the sorted list is a pair.
+      // pair loops branch-free: every (i, j < i) of the sorted list is a pair.  The same-observation term (i, i), the
+      // whole of a diagonal block, is folded into the camera accumulators by the linearisation sweep instead.
       {
         int m = 0;
         for (int a = 0; a < k; ++a) {
@@ -179,7 +180,7 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
         sorted_cnt[li] = (unsigned char)m; sorted_off[li] = pos_off;
         for (int i = 0; i < m; ++i) {
           const int ca = ocf[ls0 + sorted_pos[pos_off + i]], base = ca * (ca + 1) / 2;
-          for (int j = 0; j <= i; ++j) ++kcount[base + ocf[ls0 + sorted_pos[pos_off + j]]];
+          for (int j = 0; j < i; ++j) ++kcount[base + ocf[ls0 + sorted_pos[pos_off + j]]];
         }
         pos_off += m;
       }
@@ -204,7 +205,7 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
       for (int i = 0; i < m; ++i) {
         const int ca = ocf[ls0 + sp[i]], base = ca * (ca + 1) / 2;
         const uint32_t si = fs + sp[i];
-        for (int j = 0; j <= i; ++j) p.items[(size_t)kcount[base + ocf[ls0 + sp[j]]]++] = si | ((fs + sp[j]) << 16);
+        for (int j = 0; j < i; ++j) p.items[(size_t)kcount[base + ocf[ls0 + sp[j]]]++] = si | ((fs + sp[j]) << 16);
       }
     }
   }

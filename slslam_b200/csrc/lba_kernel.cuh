@@ -28,7 +28,7 @@ constexpr int MAX_FREE_CAMS = 24;
 constexpr int MAX_G = 64;              // CTAs cooperating on one window (a CTA group; exchanges go through L2)
 constexpr int ZS = 24;               // doubles per Z block (6 x 4, row-major)
 constexpr int ZST = 26;              // row stride of the Z staging: 13 x 16 B, so 8 consecutive rows cover all 32 banks
-constexpr int ACC = 33;              // per-camera accumulators: H_cc (21, lower) | g_c (6) | sum Z u (6)
+constexpr int ACC = 39;              // per-camera accumulators: H_cc - sum Z Z^T (21, lower) | g_c (6) | sum Z u (6) | diag H_cc (6)
 constexpr int LLU = 22;              // per-line: L (10, lower) | u = L^-1 g_l (4) | D_l (4) | 1 / l_kk (4)
 constexpr int NSCAL = 8;
 constexpr int NPHASE = 14;         // init | linearise | pairs | fold | allreduce | gradient | reduced solve | trial | decide | total | solve: prep, factor+panel, trailing, back-substitution
@@ -321,12 +321,17 @@ __device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, d
 #pragma unroll
         for (int k = 0; k < 12; ++k) zp[k] = make_double2(Z[2 * k], Z[2 * k + 1]);
       }
-      // per-camera accumulators: H_cc lower (21), g_c (6), Z u (6)
+      // per-camera accumulators: the observation's own Schur term folded into the diagonal block, H_cc - Z Z^T (21,
+      // lower; a line sees a camera at most once, so the (c,c) pair block is exactly these same-observation terms and
+      // the pair pass only handles c_i != c_j), g_c (6), Z u (6), and diag H_cc alone (6) for the LM diagonal
 #pragma unroll
       for (int p = 0; p < 6; ++p)
 #pragma unroll
-        for (int q = 0; q <= p; ++q)
-          acc[L6(p, q)] = Jc[p] * Jc[q] + Jc[6 + p] * Jc[6 + q] + Jc[12 + p] * Jc[12 + q] + Jc[18 + p] * Jc[18 + q];
+        for (int q = 0; q <= p; ++q) {
+          const double hpq = Jc[p] * Jc[q] + Jc[6 + p] * Jc[6 + q] + Jc[12 + p] * Jc[12 + q] + Jc[18 + p] * Jc[18 + q];
+          if (p == q) acc[33 + p] = hpq;
+          acc[L6(p, q)] = hpq - (Z[4 * p] * Z[4 * q] + Z[4 * p + 1] * Z[4 * q + 1] + Z[4 * p + 2] * Z[4 * q + 2] + Z[4 * p + 3] * Z[4 * q + 3]);
+        }
 #pragma unroll
       for (int p = 0; p < 6; ++p) {
         acc[21 + p] = Jc[p] * r[0] + Jc[6 + p] * r[1] + Jc[12 + p] * r[2] + Jc[18 + p] * r[3];
@@ -417,7 +422,7 @@ __device__ void schur_pairs(const Ctx& c) {
   }
 }
 
-// Fold the warp-private camera accumulators into V: H_cc onto the diagonal blocks, g_c, sum Z u, diag H_cc.
+// Fold the warp-private camera accumulators into V: H_cc - sum Z Z^T onto the diagonal blocks, g_c, sum Z u, diag H_cc.
 __device__ void fold_cameras(const Ctx& c, bool norms_only) {
   const WinHdr& h = *c.h;
   double* V = c.sm + c.lay.V;
@@ -435,11 +440,13 @@ __device__ void fold_cameras(const Ctx& c, bool norms_only) {
       const int q = e - p * (p + 1) / 2;
       const int key = f * (f + 1) / 2 + f;
       V[key * 36 + 6 * p + q] += s;
-      if (p != q) V[key * 36 + 6 * q + p] += s; else V[hd_off + 6 * f + p] = s;
+      if (p != q) V[key * 36 + 6 * q + p] += s;
     } else if (e < 27) {
       V[g_off + 6 * f + (e - 21)] = s;
-    } else {
+    } else if (e < 33) {
       V[zu_off + 6 * f + (e - 27)] = s;
+    } else {
+      V[hd_off + 6 * f + (e - 33)] = s;
     }
   }
 }
