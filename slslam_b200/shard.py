@@ -54,12 +54,13 @@ def unpack_window(buf: np.ndarray) -> Window:
     if buf.size != packed_size(C, L, N):
         raise ValueError("packed LBA window has the wrong length")
     o = 16
-    ci = buf[o:o + 4 * N].view(np.int32).copy(); o += 4 * N
-    li = buf[o:o + 4 * N].view(np.int32).copy(); o += 4 * N
-    fi = buf[o:o + 8 * N].view(np.int32).copy(); o += 8 * N
-    ob = buf[o:o + 64 * N].view(np.float64).copy(); o += 64 * N
-    pr = buf[o:].view(np.float64).copy()
-    return Window(C, L, ci, li, fi, ob, pr, pr.copy(), {})
+    # views into the received buffer (no copies; the solver entry points never write into a window's arrays)
+    ci = buf[o:o + 4 * N].view(np.int32); o += 4 * N
+    li = buf[o:o + 4 * N].view(np.int32); o += 4 * N
+    fi = buf[o:o + 8 * N].view(np.int32); o += 8 * N
+    ob = buf[o:o + 64 * N].view(np.float64); o += 64 * N
+    pr = buf[o:].view(np.float64)
+    return Window(C, L, ci, li, fi, ob, pr, pr, {})
 
 
 def summary_to_row(s: dict) -> np.ndarray:
@@ -81,104 +82,124 @@ def _exchange(ops, dist):
             req.wait()
 
 
+def pack_for_ranks(windows, world: int):
+    """Rank-0 side assembly: one contiguous byte buffer per destination rank, holding that rank's windows back to back
+    (int64 count, int64 byte sizes, then the packed windows).  Window w goes to rank w mod world."""
+    out = []
+    for r in range(world):
+        mine = [pack_window(windows[w]) for w in local_indices(len(windows), r, world)]
+        head = np.array([len(mine)] + [m.size for m in mine], np.int64).view(np.uint8)
+        out.append(np.concatenate([head] + mine) if mine else head.copy())
+    return out
+
+
+def unpack_many(buf: np.ndarray):
+    buf = np.ascontiguousarray(buf, np.uint8)
+    cnt = int(buf[:8].view(np.int64)[0])
+    sizes = buf[8:8 + 8 * cnt].view(np.int64)
+    o, ws = 8 + 8 * cnt, []
+    for sz in sizes:
+        ws.append(unpack_window(buf[o:o + int(sz)]))
+        o += int(sz)
+    return ws
+
+
+def scatter_packed(bufs, device=None, group=None):
+    """Rank 0 passes the per-rank buffers of `pack_for_ranks` (other ranks None); every rank returns its own buffer as a
+    host uint8 array.  One size broadcast, then ONE send per destination rank, grouped (`batch_isend_irecv` = grouped
+    ncclSend / ncclRecv on NCCL; gloo on CPU)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cpu") if device is None else torch.device(device)
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    if rank == 0:
+        sizes[:] = torch.tensor([b.size for b in bufs], dtype=torch.int64)
+    dist.broadcast(sizes, 0, group=group)
+    sizes = sizes.cpu().numpy()
+    ops, keep, recv = [], [], None
+    if rank == 0:
+        for r in range(1, world):
+            t = torch.from_numpy(bufs[r])
+            t = t.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else t
+            keep.append(t)
+            ops.append(dist.P2POp(dist.isend, t, r, group=group))
+    else:
+        recv = torch.empty(int(sizes[rank]), dtype=torch.uint8, device=dev)
+        ops.append(dist.P2POp(dist.irecv, recv, 0, group=group))
+    _exchange(ops, dist)
+    return bufs[0] if rank == 0 else recv.cpu().numpy()
+
+
 def scatter_windows(windows, device=None, group=None):
-    """Rank 0 passes the full list (other ranks pass None); every rank returns (its windows, their global indices).
-    One broadcast of the per-window byte counts, then one grouped send/recv of the packed buffers."""
+    """Rank 0 passes the full list (other ranks pass None); every rank returns (its windows, their global indices)."""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = torch.device("cpu") if device is None else torch.device(device)
     meta = torch.zeros(1, dtype=torch.int64, device=dev)
-    packed = None
     if rank == 0:
-        packed = [pack_window(w) for w in windows]
-        meta[0] = len(packed)
+        meta[0] = len(windows)
     dist.broadcast(meta, 0, group=group)
     n = int(meta.item())
-    sizes = torch.zeros(max(n, 1), dtype=torch.int64, device=dev)
-    if rank == 0 and n:
-        sizes[:n] = torch.tensor([p.size for p in packed], dtype=torch.int64)
-    dist.broadcast(sizes, 0, group=group)
-    sizes = sizes.cpu().numpy()
-    mine = local_indices(n, rank, world)
-    ops, recv, keep = [], {}, []
-    if rank == 0:
-        for w in range(n):
-            r = owner(w, world)
-            if r != 0:
-                t = torch.from_numpy(packed[w]).to(dev)
-                keep.append(t)
-                ops.append(dist.P2POp(dist.isend, t, r, group=group))
-    else:
-        for w in mine:
-            recv[w] = torch.empty(int(sizes[w]), dtype=torch.uint8, device=dev)
-            ops.append(dist.P2POp(dist.irecv, recv[w], 0, group=group))
-    _exchange(ops, dist)
-    if rank == 0:
-        local = [windows[w] for w in mine]
-    else:
-        local = [unpack_window(recv[w].cpu().numpy()) for w in mine]
-    return local, mine
+    bufs = pack_for_ranks(windows, world) if rank == 0 else None
+    mine = scatter_packed(bufs, device=device, group=group)
+    idx = local_indices(n, rank, world)
+    local = [windows[w] for w in idx] if rank == 0 else unpack_many(mine)
+    return local, idx
 
 
 def gather_results(params, summaries, indices, num_windows, device=None, group=None):
     """Every rank passes the parameters / summaries of its windows (global `indices`); rank 0 returns the full lists in
-    window order, other ranks return (None, None).  Parameter lengths travel in the summary row."""
+    window order, other ranks return (None, None).  One float64 buffer per rank: per window the summary row, the
+    parameter count and the parameters; one size all-gather, then one grouped send/recv per rank."""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = torch.device("cpu") if device is None else torch.device(device)
-    # fixed-size rows first (they carry the parameter counts), then the parameter vectors
-    rows = torch.zeros((max(num_windows, 1), SUMMARY_WIDTH + 1), dtype=torch.float64, device=dev)
-    for p, s, w in zip(params, summaries, indices):
-        rows[w, :SUMMARY_WIDTH] = torch.from_numpy(summary_to_row(s))
-        rows[w, SUMMARY_WIDTH] = float(len(p))
-    ops, keep = [], []
+    parts = []
+    for p, s in zip(params, summaries):
+        parts += [summary_to_row(s), np.array([float(len(p))]), np.ascontiguousarray(p, np.float64)]
+    mine = np.concatenate(parts) if parts else np.zeros(0)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([mine.size], dtype=torch.int64, device=dev), group=group)
+    sizes = [int(t.item()) for t in sizes]
+    ops, keep, bufs = [], [], {}
     if rank == 0:
-        for w in range(num_windows):
-            r = owner(w, world)
-            if r != 0:
-                ops.append(dist.P2POp(dist.irecv, rows[w], r, group=group))
-    else:
-        for w in indices:
-            t = rows[w].clone()
-            keep.append(t)
-            ops.append(dist.P2POp(dist.isend, t, 0, group=group))
-    _exchange(ops, dist)
-    ops, bufs = [], {}
-    if rank == 0:
-        for w in range(num_windows):
-            r = owner(w, world)
-            if r != 0:
-                bufs[w] = torch.empty(int(rows[w, SUMMARY_WIDTH].item()), dtype=torch.float64, device=dev)
-                ops.append(dist.P2POp(dist.irecv, bufs[w], r, group=group))
-    else:
-        for p, w in zip(params, indices):
-            t = torch.from_numpy(np.ascontiguousarray(p, np.float64)).to(dev)
-            keep.append(t)
-            ops.append(dist.P2POp(dist.isend, t, 0, group=group))
+        for r in range(1, world):
+            if sizes[r]:
+                bufs[r] = torch.empty(sizes[r], dtype=torch.float64, device=dev)
+                ops.append(dist.P2POp(dist.irecv, bufs[r], r, group=group))
+    elif mine.size:
+        t = torch.from_numpy(mine)
+        t = t.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else t
+        keep.append(t)
+        ops.append(dist.P2POp(dist.isend, t, 0, group=group))
     _exchange(ops, dist)
     if rank != 0:
         return None, None
     out_p, out_s = [None] * num_windows, [None] * num_windows
     for p, s, w in zip(params, summaries, indices):
         out_p[w], out_s[w] = np.asarray(p, np.float64), s
-    rows_h = rows.cpu().numpy()
-    for w, t in bufs.items():
-        out_p[w] = t.cpu().numpy()
-        out_s[w] = row_to_summary(rows_h[w])
+    for r, t in bufs.items():
+        a = t.cpu().numpy()
+        o = 0
+        for w in local_indices(num_windows, r, world):
+            row = a[o:o + SUMMARY_WIDTH]; npar = int(a[o + SUMMARY_WIDTH]); o += SUMMARY_WIDTH + 1
+            out_s[w] = row_to_summary(row)
+            out_p[w] = a[o:o + npar].copy(); o += npar
     return out_p, out_s
 
 
 def solve_sharded(windows, solve_fn, max_iters=10, device=None, group=None):
     """Scatter -> every rank solves its windows with `solve_fn` -> gather.  Rank 0 returns (params, summaries) for
     all windows in order; other ranks (None, None)."""
+    import torch
     import torch.distributed as dist
     rank = dist.get_rank(group)
     local, idx = scatter_windows(windows if rank == 0 else None, device=device, group=group)
-    n = len(windows) if rank == 0 else None
-    import torch
-    cnt = torch.tensor([n if rank == 0 else 0], dtype=torch.int64, device=torch.device("cpu") if device is None else torch.device(device))
+    cnt = torch.tensor([len(windows) if rank == 0 else 0], dtype=torch.int64,
+                       device=torch.device("cpu") if device is None else torch.device(device))
     dist.broadcast(cnt, 0, group=group)
     if local:
         ps, ss = solve_fn(local, max_iters)
