@@ -31,6 +31,7 @@ constexpr int ZST = 26;              // row stride of the Z staging: 13 x 16 B, 
 constexpr int ACC = 39;              // per-camera accumulators: H_cc - sum Z Z^T (21, lower) | g_c (6) | sum Z u (6) | diag H_cc (6)
 constexpr int LLU = 22;              // per-line: L (10, lower) | u = L^-1 g_l (4) | D_l (4) | 1 / l_kk (4)
 constexpr int NSCAL = 8;
+constexpr bool LBA_BLOCKINV_SOLVE = true;   // reduced camera system: explicit 6x6 pivot inverses (true) or block Cholesky (false)
 constexpr int NPHASE = 14;         // init | linearise | pairs | fold | allreduce | gradient | reduced solve | trial | decide | total | solve: prep, factor+panel, trailing, back-substitution
 
 // slot flags (meta.x bits 24..)
@@ -62,7 +63,7 @@ struct WinHdr {
 
 // Shared-memory layout in doubles, identical for every CTA of a launch (sized by the largest window).
 struct SmemLayout {
-  int camx, camxt, camR, camRt, cscale, linex, linext, lscale, lineLU, ltrig, ltrigt, V, Vred, wacc, yc, misc, tri, Z, obs, meta, total;
+  int camx, camxt, camR, camRt, cscale, linex, linext, lscale, lineLU, ltrig, ltrigt, V, Vred, wacc, yc, misc, tri, pbuf, Z, obs, meta, total;
   int z_in_smem, obs_in_smem;
   int G;   // CTAs per window of this launch
 };
@@ -88,6 +89,7 @@ __host__ inline SmemLayout lba_layout(int C, int Cf, int max_lines_cta, int max_
   l.yc = take(6 * (Cf > 0 ? Cf : 1) + 8);
   l.misc = take(64 + LBA_NW * NSCAL);
   l.tri = take((Cf * (Cf + 1) / 2 + 2) / 2 + 1);   // int table: key -> (I, K)
+  l.pbuf = l.wacc;   // reduced solve scratch (48 Cf doubles: original panel rows | u | acc) reuses the accumulators, dead by then
   l.Z = o;
   const size_t zbytes = (size_t)ZST * max_slots_cta * 8;
   l.z_in_smem = ((size_t)o * 8 + zbytes <= smem_limit_bytes) ? 1 : 0;
@@ -673,6 +675,181 @@ __device__ bool reduced_solve(const Ctx& c, double radius, long long* ph) {
   return !failed;
 }
 
+// K3, second form (the one in use): block elimination of the reduced camera system with EXPLICIT inverses of the 6x6
+// pivot blocks.  The Cholesky form above spends its time on a chain of 6 dependent reciprocal square roots per block
+// column (~215 cycles each); here a pivot block is inverted through two closed-form 3x3 cofactor inverses (one
+// reciprocal each) and a 3x3 Schur complement, W = A_JJ^-1.  Per block column J:
+//   phase 1  threads [0, 6 nb]: W in registers (all redundantly); panel rows P_I = A_IJ W (independent dot products,
+//            no substitution chain), the original rows saved to `pbuf`; one thread: u_J = W b_J
+//   phase 2  A_IK -= P_I A_KJ^T (row of a block per thread), b_I -= P_I b_J, W written over A_JJ
+// and the back-substitution needs no solve at all: y_J = u_J - sum_{I>J} P_IJ^T y_I.
+// The pivot blocks are LM-damped and Jacobi-scaled, so forming their inverses costs no accuracy that matters here
+// (parity with the oracle's plain Cholesky is unchanged: tests/test_lba_gpu.py).
+__device__ bool reduced_solve_blockinv(const Ctx& c, double radius, long long* ph) {
+  long long tq = clock64();
+#define RSPHASE(i) { const long long now_ = clock64(); ph[i] += now_ - tq; tq = now_; }
+  const WinHdr& h = *c.h;
+  double* V = c.sm + c.lay.V;
+  double* yc = c.sm + c.lay.yc;
+  double* misc = c.sm + c.lay.misc;    // misc[6] failure flag
+  double* pbuf = c.sm + c.lay.pbuf;    // [6 (Cf-1)][6] original panel rows of the current block column
+  const int* tri = reinterpret_cast<const int*>(c.sm + c.lay.tri);   // key -> I << 8 | K
+  const int Cf = h.Cf, n = h.n;
+  double* ub = pbuf + 36 * Cf;         // u_J = W_J b_J
+  double* ab = ub + 6 * Cf;            // acc_J = sum_{I>J} P_IJ^T y_I
+  const int g_off = h.nkeys * 36, zu_off = g_off + n, hd_off = zu_off + n;
+  for (int i = c.tid; i < n; i += LBA_NT) {
+    yc[i] = V[g_off + i] - V[zu_off + i];
+    ab[i] = 0.0;
+    const int f = i / 6, p = i - 6 * f;
+    V[(f * (f + 1) / 2 + f) * 36 + 7 * p] += clampd(V[hd_off + i], 1e-6, 1e32) / radius;
+  }
+  if (c.tid == 0) misc[6] = 0.0;
+  __syncthreads();
+  RSPHASE(10)
+  for (int J = 0; J < Cf; ++J) {
+    double* AJJ = V + (J * (J + 1) / 2 + J) * 36;
+    const int nb = Cf - J - 1, npanel = 6 * nb;
+    double W[21];                      // lower triangle of the symmetric inverse, W[L6(p,q)], p >= q
+    if (c.tid <= npanel) {
+      double A[21];
+#pragma unroll
+      for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = 0; q <= p; ++q) A[L6(p, q)] = AJJ[6 * p + q];
+      double Ai[6], Si[6], M[9], S[6];
+      bool ok = spd3_inverse(A[L6(0, 0)], A[L6(1, 0)], A[L6(2, 0)], A[L6(1, 1)], A[L6(2, 1)], A[L6(2, 2)], Ai);
+      // symmetric 3x3 stored as {00, 01, 02, 11, 12, 22}
+#define SY3(m, r, cc) m[(r) <= (cc) ? ((r) == 0 ? (cc) : (r) == 1 ? 2 + (cc) : 5) : ((cc) == 0 ? (r) : (cc) == 1 ? 2 + (r) : 5)]
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+          M[3 * r + cc] = A[L6(3 + r, 0)] * SY3(Ai, 0, cc) + A[L6(3 + r, 1)] * SY3(Ai, 1, cc) + A[L6(3 + r, 2)] * SY3(Ai, 2, cc);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = r; cc < 3; ++cc)
+          SY3(S, r, cc) = A[L6(3 + cc, 3 + r)] - (M[3 * r] * A[L6(3 + cc, 0)] + M[3 * r + 1] * A[L6(3 + cc, 1)] + M[3 * r + 2] * A[L6(3 + cc, 2)]);
+      ok = spd3_inverse(S[0], S[1], S[2], S[3], S[4], S[5], Si) && ok;
+      double W21[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+          W21[3 * r + cc] = -(SY3(Si, r, 0) * M[cc] + SY3(Si, r, 1) * M[3 + cc] + SY3(Si, r, 2) * M[6 + cc]);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc <= r; ++cc) {
+          W[L6(r, cc)] = SY3(Ai, r, cc) - (M[r] * W21[cc] + M[3 + r] * W21[3 + cc] + M[6 + r] * W21[6 + cc]);
+          W[L6(3 + r, 3 + cc)] = SY3(Si, r, cc);
+        }
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) W[L6(3 + r, cc)] = W21[3 * r + cc];
+#undef SY3
+      if (c.tid < npanel) {
+        // panel row: P = a W (W symmetric), the original row kept for the trailing update
+        const int bI = c.tid / 6, p = c.tid - 6 * bI, I = J + 1 + bI;
+        double* a = V + (I * (I + 1) / 2 + J) * 36 + 6 * p;
+        double av[6], pv[6];
+#pragma unroll
+        for (int m = 0; m < 6; ++m) av[m] = a[m];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int m = 0; m < 3; ++m) s0 += av[m] * W[m >= q ? L6(m, q) : L6(q, m)];
+#pragma unroll
+          for (int m = 3; m < 6; ++m) s1 += av[m] * W[m >= q ? L6(m, q) : L6(q, m)];
+          pv[q] = s0 + s1;
+        }
+#pragma unroll
+        for (int m = 0; m < 6; ++m) { pbuf[6 * c.tid + m] = av[m]; a[m] = pv[m]; }
+      } else {
+        // tid == npanel: u_J = W b_J
+        if (!ok) misc[6] = 1.0;
+        double bv[6];
+#pragma unroll
+        for (int m = 0; m < 6; ++m) bv[m] = yc[6 * J + m];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          double s = 0.0;
+#pragma unroll
+          for (int m = 0; m < 6; ++m) s += bv[m] * W[m >= q ? L6(m, q) : L6(q, m)];
+          ub[6 * J + q] = s;
+        }
+      }
+    }
+    __syncthreads();
+    RSPHASE(11)
+    if (c.tid == npanel) {
+#pragma unroll
+      for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) AJJ[6 * p + q] = W[p >= q ? L6(p, q) : L6(q, p)];
+    }
+    // trailing update: row p of block (I,K) -= P_I[p,:] A_KJ^T  (P in V, the original A_KJ rows in pbuf); rhs rows
+    const int nitem = nb * (nb + 1) / 2 * 6;
+    for (int e = c.tid; e < nitem + npanel; e += LBA_NT) {
+      if (e < nitem) {
+        const int blk = e / 6, p = e - 6 * blk;
+        const int t = tri[blk];
+        const int bi = t >> 8, bk = t & 0xff, I = J + 1 + bi, K = J + 1 + bk;
+        const double* pi = V + (I * (I + 1) / 2 + J) * 36 + 6 * p;
+        const double* ak = pbuf + 36 * bk;
+        double* dst = V + (I * (I + 1) / 2 + K) * 36 + 6 * p;
+        double a[6], o[6];
+#pragma unroll
+        for (int m = 0; m < 6; ++m) { a[m] = pi[m]; o[m] = dst[m]; }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const double s0 = a[0] * ak[6 * q] + a[1] * ak[6 * q + 1] + a[2] * ak[6 * q + 2];
+          const double s1 = a[3] * ak[6 * q + 3] + a[4] * ak[6 * q + 4] + a[5] * ak[6 * q + 5];
+          o[q] -= s0 + s1;
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) dst[q] = o[q];
+      } else {
+        const int rI = e - nitem, bI = rI / 6, I = J + 1 + bI, p = rI - 6 * bI;
+        const double* pi = V + (I * (I + 1) / 2 + J) * 36 + 6 * p;
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < 6; ++m) s += pi[m] * yc[6 * J + m];
+        yc[6 * I + p] -= s;
+      }
+    }
+    __syncthreads();
+    RSPHASE(12)
+  }
+  const bool failed = misc[6] != 0.0;
+  // back substitution by warp 0: y_J = u_J - acc_J, then acc_K += P_JK^T y_J for every K < J
+  if (c.warp == 0 && !failed) {
+    for (int J = Cf - 1; J >= 0; --J) {
+      double y[6];
+#pragma unroll
+      for (int m = 0; m < 6; ++m) y[m] = ub[6 * J + m] - ab[6 * J + m];
+      __syncwarp();
+      if (c.lane < 6) yc[6 * J + c.lane] = ub[6 * J + c.lane] - ab[6 * J + c.lane];
+      for (int e = c.lane; e < 6 * J; e += 32) {
+        const int K = e / 6, q = e - 6 * K;
+        const double* pjk = V + (J * (J + 1) / 2 + K) * 36;    // block (J,K): rows of J, columns of K
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < 6; ++m) s += pjk[6 * m + q] * y[m];
+        ab[6 * K + q] += s;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  RSPHASE(13)
+#undef RSPHASE
+  return !failed;
+}
+
 // Line back-substitution y_l = L^-T (u - sum_i Z_i^T y_c(i)), trial point, residual-only sweep at the trial point.
 // Partial scalars (this CTA): trial cost, line part of the model decrease, |delta|^2, |x|^2 of the line blocks.
 __device__ void trial_sweep(const Ctx& c, double* out4) {
@@ -920,7 +1097,7 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
     // camera part of the model decrease needs g_c and D_c before the solve overwrites V
     bool ok = !line_fail;
     double model_c = 0.0;
-    if (Cf > 0) ok = reduced_solve(c, radius, ph) && ok;
+    if (Cf > 0) ok = (LBA_BLOCKINV_SOLVE ? reduced_solve_blockinv(c, radius, ph) : reduced_solve(c, radius, ph)) && ok;
     PHASE(6)
     double dn2c = 0.0;
     if (ok && Cf > 0) {

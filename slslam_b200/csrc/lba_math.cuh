@@ -214,6 +214,28 @@ __device__ __forceinline__ void obs_eval(const double* __restrict__ cpre, const 
 #undef SLSLAM_COL
 }
 
+// 1 / d from the hardware approximation (MUFU.RCP64H) and two Newton steps; same remarks as pivot_rsqrt.
+__device__ __forceinline__ double pivot_rcp(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
+// Inverse of a symmetric positive definite 3x3 [a b c; b d e; c e f] by cofactors: one reciprocal instead of three
+// dependent square roots.  o = {i00, i01, i02, i11, i12, i22}.  Returns false if a leading minor is not positive.
+__device__ __forceinline__ bool spd3_inverse(double a, double b, double c, double d, double e, double f, double* o) {
+  const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+  const double c11 = a * f - c * c, c12 = b * c - a * e, c22 = a * d - b * b;
+  const double det = a * c00 + b * c01 + c * c02;
+  const double r = pivot_rcp(det);
+  o[0] = c00 * r; o[1] = c01 * r; o[2] = c02 * r; o[3] = c11 * r; o[4] = c12 * r; o[5] = c22 * r;
+  return a > 0.0 && c22 > 0.0 && det > 0.0;
+}
+
 // HuberLoss(a) on s = |r|^2 with the rho'' <= 0 corrector: returns rho, sets sqrt(rho').
 __device__ __forceinline__ double huber_rho(double s, double a, bool robust, double& sqrt_rho1) {
   if (!robust || s <= a * a) { sqrt_rho1 = 1.0; return s; }

@@ -76,6 +76,26 @@ def row_to_summary(r: np.ndarray) -> dict:
                 termination=_TERM[int(r[6])] if 0 <= int(r[6]) < len(_TERM) else "?", iterations=int(r[7]))
 
 
+_PINNED = {}
+
+
+def _to_device(arr: np.ndarray, dev):
+    """Host array -> tensor on `dev`.  For CUDA the bytes go through a cached pinned staging tensor (allocating pinned
+    memory per call costs more than the copy)."""
+    import torch
+    t = torch.from_numpy(arr)
+    if dev.type != "cuda":
+        return t
+    key = (t.dtype, dev.index)
+    stage = _PINNED.get(key)
+    if stage is None or stage.numel() < t.numel():
+        stage = torch.empty(max(t.numel(), 1 << 16), dtype=t.dtype).pin_memory()
+        _PINNED[key] = stage
+    view = stage[:t.numel()]
+    view.copy_(t)
+    return view.to(dev)          # blocking: the staging tensor is reused for the next buffer
+
+
 def _exchange(ops, dist):
     if ops:
         for req in dist.batch_isend_irecv(ops):
@@ -120,8 +140,7 @@ def scatter_packed(bufs, device=None, group=None):
     ops, keep, recv = [], [], None
     if rank == 0:
         for r in range(1, world):
-            t = torch.from_numpy(bufs[r])
-            t = t.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else t
+            t = _to_device(bufs[r], dev)
             keep.append(t)
             ops.append(dist.P2POp(dist.isend, t, r, group=group))
     else:
@@ -171,8 +190,7 @@ def gather_results(params, summaries, indices, num_windows, device=None, group=N
                 bufs[r] = torch.empty(sizes[r], dtype=torch.float64, device=dev)
                 ops.append(dist.P2POp(dist.irecv, bufs[r], r, group=group))
     elif mine.size:
-        t = torch.from_numpy(mine)
-        t = t.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else t
+        t = _to_device(mine, dev)
         keep.append(t)
         ops.append(dist.P2POp(dist.isend, t, 0, group=group))
     _exchange(ops, dist)
