@@ -134,6 +134,22 @@ int slslam_lba_batch_phase_cycles(slslam_lba_batch* b, void* cuda_stream, int32_
 int slslam_lba_batch_transfer_bytes(const slslam_lba_batch* b, int64_t* h2d_bytes, int64_t* d2h_bytes);
 void slslam_lba_batch_destroy(slslam_lba_batch* b);
 
+/* ---- pipelined host-buffer form (throughput over independent batches, BASELINE.json configs[3]) ----
+ * submit() validates, plans, stages and enqueues one batch (H2D, solve kernel, D2H) on one of `depth` slots, each with
+ * its own device pool, pinned staging and CUDA stream, and returns without waiting for the device; wait() blocks until
+ * that batch has finished and only then overwrites the `params_inout` / `summaries_out` given to submit() (they and
+ * the arrays the descs point to must stay valid and unmodified until then).  When every slot is in flight, submit()
+ * first waits for the oldest batch.  With depth 2 the host plans batch k+1, and its H2D copy runs, while the device
+ * solves batch k.  Not thread-safe: one pipeline per caller thread.  ticket < 0 in wait() drains every slot. */
+typedef struct slslam_lba_pipeline slslam_lba_pipeline;
+#define SLSLAM_PIPELINE_PARALLEL_STAGING 1   /* each window is staged by the host thread that planned it (faster host
+                                                stage, slower DMA: it hides behind the previous batch's kernel) */
+int slslam_lba_pipeline_create(int32_t device, int32_t depth, int32_t flags, slslam_lba_pipeline** out);
+int slslam_lba_pipeline_submit(slslam_lba_pipeline* p, int32_t n, const slslam_lba_desc* descs, double* const* params_inout,
+                               slslam_summary* summaries_out, int64_t* ticket_out);
+int slslam_lba_pipeline_wait(slslam_lba_pipeline* p, int64_t ticket);
+void slslam_lba_pipeline_destroy(slslam_lba_pipeline* p);
+
 /* ---- K1 alone: residuals (Huber-unscaled) and analytic Jacobians of every observation, for parity tests ----
  * residuals [4N]; jac_camera [24N] row-major 4x6; jac_line [16N] row-major 4x4; cost_out = 1/2 sum rho. */
 int slslam_lba_evaluate(const slslam_lba_desc* desc, const double* params, double* residuals, double* jac_camera,

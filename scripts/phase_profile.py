@@ -36,6 +36,11 @@ if __name__ == "__main__":
     if which in ("all", "batch"):
         for cs in (0, 18, 16, 12, 10, 8):
             run(ws, cs)
+    if which in ("scale",):
+        # throughput against windows per launch (smaller groups, more windows resident)
+        wl = [synth.window_M(i, sigma_px=1.0, start="far") for i in range(64)]
+        for n, cs in ((8, 0), (16, 0), (16, 8), (32, 0), (64, 0), (64, 1)):
+            run(wl[:n], cs, reps=5)
     if which in ("all", "small"):
         s = [synth.window_S(i, sigma_px=1.0, start="far") for i in range(8)]
         for cs in (0, 16, 8, 4, 1):

@@ -22,6 +22,7 @@ EXPORTS = [
     "slslam_version", "slslam_strerror", "slslam_last_error", "slslam_device_count", "slslam_lba_get_limits",
     "slslam_lba_solve", "slslam_lba_solve_batch", "slslam_lba_last_timings", "slslam_lba_batch_create", "slslam_lba_batch_solve",
     "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_max_active_clusters", "slslam_lba_batch_transfer_bytes", "slslam_lba_batch_phase_cycles", "slslam_lba_batch_destroy",
+    "slslam_lba_pipeline_create", "slslam_lba_pipeline_submit", "slslam_lba_pipeline_wait", "slslam_lba_pipeline_destroy",
     "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate", "slslam_po_last_solve_ms",
 ]
 
@@ -99,6 +100,12 @@ def lib():
         L.slslam_lba_batch_phase_cycles.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.c_int32]
         L.slslam_lba_batch_destroy.argtypes = [C.c_void_p]
         L.slslam_lba_batch_destroy.restype = None
+        L.slslam_lba_pipeline_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        L.slslam_lba_pipeline_submit.argtypes = [C.c_void_p, C.c_int32, C.POINTER(LbaDesc), C.POINTER(dp), C.POINTER(Summary),
+                                                 C.POINTER(C.c_int64)]
+        L.slslam_lba_pipeline_wait.argtypes = [C.c_void_p, C.c_int64]
+        L.slslam_lba_pipeline_destroy.argtypes = [C.c_void_p]
+        L.slslam_lba_pipeline_destroy.restype = None
         L.slslam_lba_evaluate.argtypes = [C.POINTER(LbaDesc), dp, dp, dp, dp, dp]
         L.slslam_po_solve.argtypes = [C.POINTER(PoDesc), dp, C.POINTER(Summary)]
         L.slslam_po_solve_trace.argtypes = [C.POINTER(PoDesc), dp, C.POINTER(Summary), dp]
@@ -233,6 +240,55 @@ class LbaBatch:
         if self._h:
             lib().slslam_lba_batch_destroy(self._h)
             self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PreparedBatch:
+    """Descs of a list of windows marshalled once (the numpy arrays stay referenced), for repeated submission."""
+
+    def __init__(self, windows, **kw):
+        self.windows = list(windows)
+        self.n = len(self.windows)
+        self.keeps = [lba_desc(w, **kw) for w in self.windows]
+        self.descs = (LbaDesc * self.n)(*[k.desc for k in self.keeps])
+        self.p0 = [np.ascontiguousarray(w.parameters, np.float64) for w in self.windows]
+
+
+class LbaPipeline:
+    """slslam_lba_pipeline_*: submit() returns a ticket at once, wait(ticket) returns (params, summaries)."""
+
+    PARALLEL_STAGING = 1
+
+    def __init__(self, device=-1, depth=2, flags=0):
+        self._h = C.c_void_p()
+        self._inflight = {}
+        _check(lib().slslam_lba_pipeline_create(device, depth, flags, C.byref(self._h)))
+
+    def submit(self, batch, **kw):
+        pb = batch if isinstance(batch, PreparedBatch) else PreparedBatch(batch, **kw)
+        ps = [p.copy() for p in pb.p0]
+        pp = (dp * pb.n)(*[_d(p) for p in ps])
+        ss = (Summary * pb.n)()
+        t = C.c_int64()
+        _check(lib().slslam_lba_pipeline_submit(self._h, pb.n, pb.descs, pp, ss, C.byref(t)))
+        self._inflight[t.value] = (pb, ps, pp, ss)
+        return t.value
+
+    def wait(self, ticket):
+        _check(lib().slslam_lba_pipeline_wait(self._h, ticket))
+        pb, ps, pp, ss = self._inflight.pop(ticket)
+        return ps, [summary_dict(s) for s in ss]
+
+    def close(self):
+        if self._h:
+            lib().slslam_lba_pipeline_destroy(self._h)
+            self._h = C.c_void_p()
+            self._inflight.clear()
 
     def __del__(self):
         try:

@@ -216,6 +216,7 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
 }  // namespace slslam
 
 using namespace slslam;
+namespace slslam { struct Workspace; }
 
 struct slslam_lba_batch {
   int n = 0, device = 0, CS = 1;
@@ -236,7 +237,8 @@ struct slslam_lba_batch {
   size_t upload_bytes = 0;
   int max_active = 0;   // windows of this shape the device keeps resident at once (a larger batch runs in waves)
   unsigned int* d_bar = nullptr; size_t bar_bytes = 0;   // group barrier counters, zeroed before every launch
-  bool borrowed = false;   // device pool and pinned staging belong to the calling thread's Workspace
+  bool borrowed = false;   // device pool and pinned staging belong to a Workspace (the calling thread's or a pipeline slot's)
+  slslam::Workspace* ws = nullptr;
 };
 
 namespace slslam {
@@ -392,7 +394,8 @@ static int build_plans(int n, const slslam_lba_desc* descs, int CS, std::vector<
 }
 
 static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,
-                             int32_t cluster_size, Workspace* ws, cudaStream_t stream, slslam_lba_batch** out) {
+                             int32_t cluster_size, Workspace* ws, cudaStream_t stream, slslam_lba_batch** out,
+                             bool parallel_stage = false) {
   if (!out) return SLSLAM_ERR_INVALID;
   *out = nullptr;
   if (n <= 0 || !descs || !params) return SLSLAM_ERR_INVALID;
@@ -411,6 +414,7 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
   cudaGetDevice(&b->device);
   b->n = n;
   b->borrowed = ws != nullptr;
+  b->ws = ws;
   if (ws) b->plans.swap(ws->plans);
   long long max_obs = 0;
   for (int i = 0; i < n; ++i) max_obs = std::max<long long>(max_obs, descs[i].num_observations);
@@ -502,7 +506,9 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
   // Staging is done by ONE thread and sent as ONE copy: a pinned buffer written by several cores is read by the DMA
   // engine at 8.5 GB/s instead of 48 GB/s (measured on the B200 host, scripts/h2d_test.py), and interleaving
   // per-window copies with the staging of the next window slowed the staging more than the overlap saved.
-  for (int i = 0; i < n; ++i) {
+  // (The pipelined entry points stage every window on the host thread that planned it instead: there the slower DMA
+  // hides behind the previous batch's kernel and the host is the stage to shorten.)
+  auto stage_window = [&](int i) {
     const WindowPlan& p = b->plans[i];
     WinHdr h; memset(&h, 0, sizeof(h));
     h.C = p.C; h.Cf = p.Cf; h.L = p.L; h.n = 6 * p.Cf; h.nkeys = p.nkeys; h.vlen = lba_vlen(p.Cf);
@@ -535,7 +541,9 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
     memcpy(host + o_items[i], p.items.data(), p.items.size() * 4);
     memcpy(host + o_koff[i], p.key_off.data(), p.key_off.size() * 4);
     memcpy(host + o_pin + b->param_off[i] * 8, params[i], (size_t)b->nparams[i] * 8);
-  }
+  };
+  if (parallel_stage) parallel_for(n, stage_window);
+  else for (int i = 0; i < n; ++i) stage_window(i);
   b->upload_bytes = upload;
   if (ws) {
     cudaEventRecord(ws->ev[0], stream);
@@ -646,7 +654,7 @@ int slslam_lba_batch_transfer_bytes(const slslam_lba_batch* b, int64_t* h2d_byte
 void slslam_lba_batch_destroy(slslam_lba_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
-  if (b->borrowed) g_ws.plans.swap(b->plans);
+  if (b->borrowed && b->ws) b->ws->plans.swap(b->plans);
   if (!b->borrowed) {
     if (b->d_pool) cudaFree(b->d_pool);
     if (b->h_params) cudaFreeHost(b->h_params);
@@ -690,6 +698,124 @@ int slslam_lba_solve_batch(int32_t n, const slslam_lba_desc* descs, double* cons
   const double t3 = now_ms();
   g_timing[2] = t2 - t1; g_timing[3] = t3 - t2; g_timing[4] = t3 - t0;
   return rc;
+}
+
+// ---- pipelined host-buffer entry points: submit() plans, stages and enqueues a batch on one of `depth` slots (own
+// device pool, pinned staging and stream) and returns; wait() blocks on that batch and writes the results back.  With
+// depth 2 the host plans batch k+1 and its H2D copy runs while the device solves batch k. ----
+struct slslam_lba_pipeline {
+  int device = 0, depth = 2, flags = 0;
+  struct Slot {
+    slslam::Workspace ws;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    slslam_lba_batch* b = nullptr;
+    std::vector<double*> params;
+    slslam_summary* summ = nullptr;
+    int64_t ticket = -1;
+  };
+  std::vector<Slot> slots;
+  int64_t next_ticket = 0;
+};
+
+static int pipeline_finish(slslam_lba_pipeline* p, slslam_lba_pipeline::Slot& s) {
+  if (!s.b) return SLSLAM_OK;
+  int rc = SLSLAM_OK;
+  cudaError_t e = cudaEventSynchronize(s.done);
+  if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); cudaGetLastError(); rc = SLSLAM_ERR_CUDA; }
+  slslam_lba_batch* b = s.b;
+  if (rc == SLSLAM_OK) {
+    const slslam_summary* h_summ = (const slslam_summary*)(b->h_params + b->total_params);
+    for (int i = 0; i < b->n; ++i) {
+      memcpy(s.params[i], b->h_params + b->param_off[i], (size_t)b->nparams[i] * 8);
+      if (s.summ) s.summ[i] = h_summ[i];
+    }
+  }
+  slslam_lba_batch_destroy(b);
+  s.b = nullptr; s.ticket = -1;
+  (void)p;
+  return rc;
+}
+
+int slslam_lba_pipeline_create(int32_t device, int32_t depth, int32_t flags, slslam_lba_pipeline** out) {
+  if (!out) return SLSLAM_ERR_INVALID;
+  *out = nullptr;
+  if (depth < 1 || depth > 8) return SLSLAM_ERR_INVALID;
+  int rc = ensure_device(device);
+  if (rc != SLSLAM_OK) return rc;
+  slslam_lba_pipeline* p = new (std::nothrow) slslam_lba_pipeline();
+  if (!p) return SLSLAM_ERR_INVALID;
+  cudaGetDevice(&p->device);
+  p->depth = depth; p->flags = flags;
+  p->slots.resize(depth);
+  for (auto& s : p->slots) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) {
+      set_last_error(cudaGetErrorString(cudaGetLastError()));
+      slslam_lba_pipeline_destroy(p);
+      return SLSLAM_ERR_CUDA;
+    }
+  }
+  *out = p;
+  return SLSLAM_OK;
+}
+
+int slslam_lba_pipeline_submit(slslam_lba_pipeline* p, int32_t n, const slslam_lba_desc* descs, double* const* params_inout,
+                               slslam_summary* summaries_out, int64_t* ticket_out) {
+  if (!p || n <= 0 || !descs || !params_inout) return SLSLAM_ERR_INVALID;
+  cudaSetDevice(p->device);
+  auto& s = p->slots[(size_t)(p->next_ticket % p->depth)];
+  int rc = pipeline_finish(p, s);        // the slot's previous batch (submitted `depth` calls ago) must have drained
+  if (rc != SLSLAM_OK) return rc;
+  slslam_lba_batch* b = nullptr;
+  rc = batch_create_impl(n, descs, (const double* const*)params_inout, -1, 0, &s.ws, s.stream, &b,
+                         (p->flags & SLSLAM_PIPELINE_PARALLEL_STAGING) != 0);
+  if (rc != SLSLAM_OK) return rc;
+  rc = slslam_lba_batch_solve(b, s.stream);
+  if (rc == SLSLAM_OK) {
+    slslam_summary* h_summ = (slslam_summary*)(b->h_params + b->total_params);
+    cudaError_t e = cudaMemcpyAsync(b->h_params, b->d_params_out, b->total_params * 8, cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_summ, b->d_summ, sizeof(slslam_summary) * n, cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaEventRecord(s.done, s.stream);
+    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); cudaGetLastError(); rc = SLSLAM_ERR_CUDA; }
+  }
+  if (rc != SLSLAM_OK) {
+    cudaStreamSynchronize(s.stream);
+    slslam_lba_batch_destroy(b);
+    return rc;
+  }
+  s.b = b;
+  s.params.assign(params_inout, params_inout + n);
+  s.summ = summaries_out;
+  s.ticket = p->next_ticket++;
+  if (ticket_out) *ticket_out = s.ticket;
+  return SLSLAM_OK;
+}
+
+int slslam_lba_pipeline_wait(slslam_lba_pipeline* p, int64_t ticket) {
+  if (!p) return SLSLAM_ERR_INVALID;
+  cudaSetDevice(p->device);
+  int rc = SLSLAM_OK;
+  for (auto& s : p->slots) {
+    if (!s.b) continue;
+    if (ticket < 0 || s.ticket == ticket) {
+      const int r = pipeline_finish(p, s);
+      if (r != SLSLAM_OK) rc = r;
+    }
+  }
+  return rc;
+}
+
+void slslam_lba_pipeline_destroy(slslam_lba_pipeline* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  for (auto& s : p->slots) {
+    if (s.b) { cudaStreamSynchronize(s.stream); slslam_lba_batch_destroy(s.b); s.b = nullptr; }   // abandoned: results dropped
+    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.done) cudaEventDestroy(s.done);
+    s.ws.release();
+  }
+  delete p;
 }
 
 void slslam_lba_last_timings(double* ms5) {   // 8 values, see the header

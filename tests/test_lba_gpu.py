@@ -146,6 +146,34 @@ def test_host_buffer_entry_point_and_batch(gpu):
     assert np.array_equal(p1, ps[0])          # deterministic: same bits from the single and the batched entry point
 
 
+@pytest.mark.parametrize("flags", [0, 1])
+def test_pipeline_matches_one_shot(gpu, flags):
+    """slslam_lba_pipeline_*: batches in flight on two slots give the same bits as the synchronous entry point, results
+    appear only at wait(), more submissions than slots drain in order, heterogeneous batch sizes reuse the slots."""
+    batches = [[synth.window_S(40 + 3 * b + i, sigma_px=0.5) for i in range(1 + (b % 3))] for b in range(5)]
+    ref = [gpu.lba_solve_batch(ws, max_iters=6) for ws in batches]
+    pipe = gpu.LbaPipeline(depth=2, flags=flags)
+    tickets = [pipe.submit(ws, max_iters=6) for ws in batches]          # submissions 2.. wait for the slot's previous batch
+    assert tickets == list(range(5))
+    for t in (4, 3):                                                      # out of order among the two still in flight
+        ps, ss = pipe.wait(t)
+        for p, s, pr, sr in zip(ps, ss, ref[t][0], ref[t][1]):
+            assert np.array_equal(p, pr) and s == sr
+    for t in (0, 1, 2):                                                   # already drained by later submissions
+        ps, ss = pipe.wait(t)
+        for p, s, pr, sr in zip(ps, ss, ref[t][0], ref[t][1]):
+            assert np.array_equal(p, pr) and s == sr
+    # an invalid batch is refused at submit and leaves the pipeline usable
+    bad = synth.window_S(1)
+    bad.line_index = bad.line_index.copy(); bad.line_index[0] = 10 ** 6
+    with pytest.raises(gpu.SlslamError):
+        pipe.submit([bad])
+    t = pipe.submit(batches[0], max_iters=6)
+    ps, ss = pipe.wait(t)
+    assert np.array_equal(ps[0], ref[0][0][0])
+    pipe.close()
+
+
 def test_determinism(gpu):
     w = synth.window_S(9, sigma_px=1.0, start="far")
     a, sa = gpu.lba_solve(w, max_iters=10)
