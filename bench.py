@@ -315,7 +315,7 @@ def main():
     Kp = max(20, K)
     prepared = capi.PreparedBatch(windows, max_iters=MAX_ITERS)
     pipe_runs = {}
-    for name, flags in (("serial_staging", 0), ("parallel_staging", capi.LbaPipeline.PARALLEL_STAGING)):
+    for name, flags in (("host_on_caller_thread", 0), ("host_thread_per_slot", capi.LbaPipeline.ASYNC_HOST)):
         pipe = capi.LbaPipeline(device=local_rank, depth=2, flags=flags)
         for _ in range(3):
             pipe.wait(pipe.submit(prepared))

@@ -135,15 +135,19 @@ int slslam_lba_batch_transfer_bytes(const slslam_lba_batch* b, int64_t* h2d_byte
 void slslam_lba_batch_destroy(slslam_lba_batch* b);
 
 /* ---- pipelined host-buffer form (throughput over independent batches, BASELINE.json configs[3]) ----
- * submit() validates, plans, stages and enqueues one batch (H2D, solve kernel, D2H) on one of `depth` slots, each with
- * its own device pool, pinned staging and CUDA stream, and returns without waiting for the device; wait() blocks until
- * that batch has finished and only then overwrites the `params_inout` / `summaries_out` given to submit() (they and
- * the arrays the descs point to must stay valid and unmodified until then).  When every slot is in flight, submit()
- * first waits for the oldest batch.  With depth 2 the host plans batch k+1, and its H2D copy runs, while the device
- * solves batch k.  Not thread-safe: one pipeline per caller thread.  ticket < 0 in wait() drains every slot. */
+ * submit() validates the arguments and hands the batch to one of `depth` slots, each with its own device pool, pinned
+ * staging and CUDA stream; the batch is planned, staged, copied H2D, solved and read back D2H on that slot.  wait()
+ * blocks until that batch has finished and only then overwrites the `params_inout` / `summaries_out` given to
+ * submit(): they, and the arrays the descs point to, must stay valid and unmodified until then (the desc structs
+ * themselves are copied).  When every slot is in flight, submit() first waits for the oldest batch.
+ *   flags 0: submit() plans, stages and enqueues on the calling thread and returns without waiting for the device:
+ *            the host work and the H2D copy of batch k+1 overlap the kernel of batch k.
+ *   SLSLAM_PIPELINE_ASYNC_HOST: every slot also has its own host thread that does the planning / staging / enqueue,
+ *            so submit() returns at once, two batches are prepared side by side, and an error found while planning
+ *            is reported by wait() (or by the submit() that reuses the slot).
+ * One pipeline per caller thread (submit / wait are not re-entrant).  ticket < 0 in wait() drains every slot. */
 typedef struct slslam_lba_pipeline slslam_lba_pipeline;
-#define SLSLAM_PIPELINE_PARALLEL_STAGING 1   /* each window is staged by the host thread that planned it (faster host
-                                                stage, slower DMA: it hides behind the previous batch's kernel) */
+#define SLSLAM_PIPELINE_ASYNC_HOST 2
 int slslam_lba_pipeline_create(int32_t device, int32_t depth, int32_t flags, slslam_lba_pipeline** out);
 int slslam_lba_pipeline_submit(slslam_lba_pipeline* p, int32_t n, const slslam_lba_desc* descs, double* const* params_inout,
                                slslam_summary* summaries_out, int64_t* ticket_out);

@@ -36,6 +36,8 @@ if __name__ == "__main__":
     if which in ("all", "batch"):
         for cs in (0, 18, 16, 12, 10, 8):
             run(ws, cs)
+    if which in ("batch0",):
+        run(ws, 0); run(ws, 0); run(ws[:1], 0)
     if which in ("scale",):
         # throughput against windows per launch (smaller groups, more windows resident)
         wl = [synth.window_M(i, sigma_px=1.0, start="far") for i in range(64)]

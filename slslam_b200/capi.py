@@ -262,7 +262,7 @@ class PreparedBatch:
 class LbaPipeline:
     """slslam_lba_pipeline_*: submit() returns a ticket at once, wait(ticket) returns (params, summaries)."""
 
-    PARALLEL_STAGING = 1
+    ASYNC_HOST = 2
 
     def __init__(self, device=-1, depth=2, flags=0):
         self._h = C.c_void_p()

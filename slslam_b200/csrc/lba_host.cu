@@ -12,6 +12,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -32,7 +33,7 @@ struct WindowPlan {
   std::vector<int> key_off;       // [CS*(nkeys+1)]
   int cta_slot_off[MAX_G + 1], cta_line_off[MAX_G + 1];
   signed char cam_free[MAX_CAMS];
-  int max_lines_cta = 0, max_slots_cta = 0;
+  int max_lines_cta = 0, max_slots_cta = 0, max_items_cta = 0;
   bool has_unobserved_blocks = false;
   // planning scratch, kept so that a cached plan object does not allocate on reuse
   std::vector<char> s_cam_used, s_cam_const, s_line_const;
@@ -111,7 +112,7 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
   p.key_off.assign((size_t)CS * (p.nkeys + 1), 0);
   p.slot_src.clear(); p.meta.clear(); p.items.clear();
   p.slot_src.reserve((size_t)N + 32 * (size_t)CS + N / 4); p.meta.reserve((size_t)N + 32 * (size_t)CS + N / 4);
-  p.max_lines_cta = 1; p.max_slots_cta = 32;
+  p.max_lines_cta = 1; p.max_slots_cta = 32; p.max_items_cta = 0;
   p.cta_slot_off[0] = 0;
   // reduced camera index of every observation in line-grouped order (-1: constant camera or constant line => no pair)
   std::vector<signed char>& ocf = p.s_ocf;
@@ -195,6 +196,7 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
     int run = (int)p.items.size();
     for (int key = 0; key < p.nkeys; ++key) { ko[key] = run; run += kcount[key]; kcount[key] = ko[key]; }
     ko[p.nkeys] = run;
+    p.max_items_cta = std::max(p.max_items_cta, run - ko[0]);
     p.items.resize((size_t)run);
     for (int li = lb; li < le; ++li) {
       const int l = dl[li], k = line_cnt[l], ls0 = line_start[l];
@@ -394,8 +396,7 @@ static int build_plans(int n, const slslam_lba_desc* descs, int CS, std::vector<
 }
 
 static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,
-                             int32_t cluster_size, Workspace* ws, cudaStream_t stream, slslam_lba_batch** out,
-                             bool parallel_stage = false) {
+                             int32_t cluster_size, Workspace* ws, cudaStream_t stream, slslam_lba_batch** out) {
   if (!out) return SLSLAM_ERR_INVALID;
   *out = nullptr;
   if (n <= 0 || !descs || !params) return SLSLAM_ERR_INVALID;
@@ -426,12 +427,13 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
   for (int attempt = 0; attempt < 8 && !placed; ++attempt) {
     rc = build_plans(n, descs, CS, b->plans);
     if (rc != SLSLAM_OK) { delete b; return rc; }
-    int Cmax = 1, Cfmax = 0, mlines = 1, mslots = 32;
+    int Cmax = 1, Cfmax = 0, mlines = 1, mslots = 32, mitems = 0;
     for (int i = 0; i < n; ++i) {
       Cmax = std::max(Cmax, b->plans[i].C); Cfmax = std::max(Cfmax, b->plans[i].Cf);
       mlines = std::max(mlines, b->plans[i].max_lines_cta); mslots = std::max(mslots, b->plans[i].max_slots_cta);
+      mitems = std::max(mitems, b->plans[i].max_items_cta);
     }
-    b->lay = lba_layout(Cmax, Cfmax, mlines, mslots, CS, (size_t)smem_optin);
+    b->lay = lba_layout(Cmax, Cfmax, mlines, mslots, CS, (size_t)smem_optin, mitems);
     b->smem_bytes = (size_t)b->lay.total * 8;
     b->CS = CS;
     if (b->smem_bytes > (size_t)smem_optin) {
@@ -506,8 +508,8 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
   // Staging is done by ONE thread and sent as ONE copy: a pinned buffer written by several cores is read by the DMA
   // engine at 8.5 GB/s instead of 48 GB/s (measured on the B200 host, scripts/h2d_test.py), and interleaving
   // per-window copies with the staging of the next window slowed the staging more than the overlap saved.
-  // (The pipelined entry points stage every window on the host thread that planned it instead: there the slower DMA
-  // hides behind the previous batch's kernel and the host is the stage to shorten.)
+  // (Measured again inside the pipeline, where the copy hides behind the previous kernel: parallel staging still lost,
+  // 48.7 k vs 65.7 k LM iterations/s.  Each pipeline slot therefore stages with one thread -- its own.)
   auto stage_window = [&](int i) {
     const WindowPlan& p = b->plans[i];
     WinHdr h; memset(&h, 0, sizeof(h));
@@ -542,8 +544,7 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
     memcpy(host + o_koff[i], p.key_off.data(), p.key_off.size() * 4);
     memcpy(host + o_pin + b->param_off[i] * 8, params[i], (size_t)b->nparams[i] * 8);
   };
-  if (parallel_stage) parallel_for(n, stage_window);
-  else for (int i = 0; i < n; ++i) stage_window(i);
+  for (int i = 0; i < n; ++i) stage_window(i);
   b->upload_bytes = upload;
   if (ws) {
     cudaEventRecord(ws->ev[0], stream);
@@ -700,9 +701,10 @@ int slslam_lba_solve_batch(int32_t n, const slslam_lba_desc* descs, double* cons
   return rc;
 }
 
-// ---- pipelined host-buffer entry points: submit() plans, stages and enqueues a batch on one of `depth` slots (own
-// device pool, pinned staging and stream) and returns; wait() blocks on that batch and writes the results back.  With
-// depth 2 the host plans batch k+1 and its H2D copy runs while the device solves batch k. ----
+// ---- pipelined host-buffer entry points: submit() hands a batch to one of `depth` slots (own device pool, pinned
+// staging, stream and -- with SLSLAM_PIPELINE_ASYNC_HOST -- own host thread, which plans, stages and enqueues it) and
+// returns; wait() blocks on that batch and writes the results back.  The host work and the H2D copy of batch k+1 run
+// while the device solves batch k; with the host threads two batches are planned / staged side by side. ----
 struct slslam_lba_pipeline {
   int device = 0, depth = 2, flags = 0;
   struct Slot {
@@ -710,66 +712,28 @@ struct slslam_lba_pipeline {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     slslam_lba_batch* b = nullptr;
+    std::vector<slslam_lba_desc> descs;
     std::vector<double*> params;
     slslam_summary* summ = nullptr;
     int64_t ticket = -1;
+    // host thread of the slot (SLSLAM_PIPELINE_ASYNC_HOST): state 0 idle, 1 posted, 2 enqueued (rc / err valid)
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    int state = 0, rc = SLSLAM_OK;
+    bool quit = false;
+    std::string err;
   };
-  std::vector<Slot> slots;
+  std::vector<std::unique_ptr<Slot>> slots;
   int64_t next_ticket = 0;
 };
 
-static int pipeline_finish(slslam_lba_pipeline* p, slslam_lba_pipeline::Slot& s) {
-  if (!s.b) return SLSLAM_OK;
-  int rc = SLSLAM_OK;
-  cudaError_t e = cudaEventSynchronize(s.done);
-  if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); cudaGetLastError(); rc = SLSLAM_ERR_CUDA; }
-  slslam_lba_batch* b = s.b;
-  if (rc == SLSLAM_OK) {
-    const slslam_summary* h_summ = (const slslam_summary*)(b->h_params + b->total_params);
-    for (int i = 0; i < b->n; ++i) {
-      memcpy(s.params[i], b->h_params + b->param_off[i], (size_t)b->nparams[i] * 8);
-      if (s.summ) s.summ[i] = h_summ[i];
-    }
-  }
-  slslam_lba_batch_destroy(b);
-  s.b = nullptr; s.ticket = -1;
-  (void)p;
-  return rc;
-}
-
-int slslam_lba_pipeline_create(int32_t device, int32_t depth, int32_t flags, slslam_lba_pipeline** out) {
-  if (!out) return SLSLAM_ERR_INVALID;
-  *out = nullptr;
-  if (depth < 1 || depth > 8) return SLSLAM_ERR_INVALID;
-  int rc = ensure_device(device);
-  if (rc != SLSLAM_OK) return rc;
-  slslam_lba_pipeline* p = new (std::nothrow) slslam_lba_pipeline();
-  if (!p) return SLSLAM_ERR_INVALID;
-  cudaGetDevice(&p->device);
-  p->depth = depth; p->flags = flags;
-  p->slots.resize(depth);
-  for (auto& s : p->slots) {
-    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) {
-      set_last_error(cudaGetErrorString(cudaGetLastError()));
-      slslam_lba_pipeline_destroy(p);
-      return SLSLAM_ERR_CUDA;
-    }
-  }
-  *out = p;
-  return SLSLAM_OK;
-}
-
-int slslam_lba_pipeline_submit(slslam_lba_pipeline* p, int32_t n, const slslam_lba_desc* descs, double* const* params_inout,
-                               slslam_summary* summaries_out, int64_t* ticket_out) {
-  if (!p || n <= 0 || !descs || !params_inout) return SLSLAM_ERR_INVALID;
+// plan + stage + H2D + launch + D2H enqueue of the slot's posted batch, on the slot's stream
+static int pipeline_enqueue(slslam_lba_pipeline* p, slslam_lba_pipeline::Slot& s) {
   cudaSetDevice(p->device);
-  auto& s = p->slots[(size_t)(p->next_ticket % p->depth)];
-  int rc = pipeline_finish(p, s);        // the slot's previous batch (submitted `depth` calls ago) must have drained
-  if (rc != SLSLAM_OK) return rc;
+  const int n = (int)s.descs.size();
   slslam_lba_batch* b = nullptr;
-  rc = batch_create_impl(n, descs, (const double* const*)params_inout, -1, 0, &s.ws, s.stream, &b,
-                         (p->flags & SLSLAM_PIPELINE_PARALLEL_STAGING) != 0);
+  int rc = batch_create_impl(n, s.descs.data(), (const double* const*)s.params.data(), -1, 0, &s.ws, s.stream, &b);
   if (rc != SLSLAM_OK) return rc;
   rc = slslam_lba_batch_solve(b, s.stream);
   if (rc == SLSLAM_OK) {
@@ -785,8 +749,103 @@ int slslam_lba_pipeline_submit(slslam_lba_pipeline* p, int32_t n, const slslam_l
     return rc;
   }
   s.b = b;
+  return SLSLAM_OK;
+}
+
+static void pipeline_worker(slslam_lba_pipeline* p, slslam_lba_pipeline::Slot* s) {
+  for (;;) {
+    {
+      std::unique_lock<std::mutex> lk(s->m);
+      s->cv.wait(lk, [&] { return s->state == 1 || s->quit; });
+      if (s->quit) return;
+    }
+    const int rc = pipeline_enqueue(p, *s);
+    {
+      std::lock_guard<std::mutex> lk(s->m);
+      s->rc = rc;
+      s->err = rc == SLSLAM_OK ? "" : slslam_last_error();
+      s->state = 2;
+    }
+    s->cv.notify_all();
+  }
+}
+
+// Blocks until the slot's batch (if any) has left the device, writes its results to the caller's arrays, frees the slot.
+static int pipeline_finish(slslam_lba_pipeline* p, slslam_lba_pipeline::Slot& s) {
+  if (s.ticket < 0) return SLSLAM_OK;
+  int rc = SLSLAM_OK;
+  if (p->flags & SLSLAM_PIPELINE_ASYNC_HOST) {
+    std::unique_lock<std::mutex> lk(s.m);
+    s.cv.wait(lk, [&] { return s.state == 2; });
+    rc = s.rc;
+    if (rc != SLSLAM_OK) set_last_error(s.err.c_str());
+    s.state = 0;
+  }
+  slslam_lba_batch* b = s.b;
+  if (rc == SLSLAM_OK && b) {
+    cudaError_t e = cudaEventSynchronize(s.done);
+    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); cudaGetLastError(); rc = SLSLAM_ERR_CUDA; }
+  }
+  if (rc == SLSLAM_OK && b) {
+    const slslam_summary* h_summ = (const slslam_summary*)(b->h_params + b->total_params);
+    for (int i = 0; i < b->n; ++i) {
+      memcpy(s.params[i], b->h_params + b->param_off[i], (size_t)b->nparams[i] * 8);
+      if (s.summ) s.summ[i] = h_summ[i];
+    }
+  }
+  if (b) slslam_lba_batch_destroy(b);
+  s.b = nullptr; s.ticket = -1;
+  return rc;
+}
+
+int slslam_lba_pipeline_create(int32_t device, int32_t depth, int32_t flags, slslam_lba_pipeline** out) {
+  if (!out) return SLSLAM_ERR_INVALID;
+  *out = nullptr;
+  if (depth < 1 || depth > 8) return SLSLAM_ERR_INVALID;
+  int rc = ensure_device(device);
+  if (rc != SLSLAM_OK) return rc;
+  slslam_lba_pipeline* p = new (std::nothrow) slslam_lba_pipeline();
+  if (!p) return SLSLAM_ERR_INVALID;
+  cudaGetDevice(&p->device);
+  p->depth = depth; p->flags = flags;
+  for (int k = 0; k < depth; ++k) p->slots.emplace_back(new slslam_lba_pipeline::Slot());
+  for (auto& sp : p->slots) {
+    auto& s = *sp;
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) {
+      set_last_error(cudaGetErrorString(cudaGetLastError()));
+      slslam_lba_pipeline_destroy(p);
+      return SLSLAM_ERR_CUDA;
+    }
+    if (flags & SLSLAM_PIPELINE_ASYNC_HOST) s.th = std::thread(pipeline_worker, p, &s);
+  }
+  *out = p;
+  return SLSLAM_OK;
+}
+
+int slslam_lba_pipeline_submit(slslam_lba_pipeline* p, int32_t n, const slslam_lba_desc* descs, double* const* params_inout,
+                               slslam_summary* summaries_out, int64_t* ticket_out) {
+  if (!p || n <= 0 || !descs || !params_inout) return SLSLAM_ERR_INVALID;
+  // argument errors are reported here, before anything is queued (the same checks run again inside the enqueue)
+  for (int i = 0; i < n; ++i) {
+    const int rc = validate_desc(descs[i]);
+    if (rc != SLSLAM_OK) return rc;
+    if (!params_inout[i]) return SLSLAM_ERR_INVALID;
+  }
+  cudaSetDevice(p->device);
+  auto& s = *p->slots[(size_t)(p->next_ticket % p->depth)];
+  int rc = pipeline_finish(p, s);        // the slot's previous batch (submitted `depth` calls ago) must have drained
+  if (rc != SLSLAM_OK) return rc;
+  s.descs.assign(descs, descs + n);
   s.params.assign(params_inout, params_inout + n);
   s.summ = summaries_out;
+  if (p->flags & SLSLAM_PIPELINE_ASYNC_HOST) {
+    { std::lock_guard<std::mutex> lk(s.m); s.state = 1; }
+    s.cv.notify_all();
+  } else {
+    rc = pipeline_enqueue(p, s);
+    if (rc != SLSLAM_OK) return rc;
+  }
   s.ticket = p->next_ticket++;
   if (ticket_out) *ticket_out = s.ticket;
   return SLSLAM_OK;
@@ -796,10 +855,10 @@ int slslam_lba_pipeline_wait(slslam_lba_pipeline* p, int64_t ticket) {
   if (!p) return SLSLAM_ERR_INVALID;
   cudaSetDevice(p->device);
   int rc = SLSLAM_OK;
-  for (auto& s : p->slots) {
-    if (!s.b) continue;
-    if (ticket < 0 || s.ticket == ticket) {
-      const int r = pipeline_finish(p, s);
+  for (auto& sp : p->slots) {
+    if (sp->ticket < 0) continue;
+    if (ticket < 0 || sp->ticket == ticket) {
+      const int r = pipeline_finish(p, *sp);
       if (r != SLSLAM_OK) rc = r;
     }
   }
@@ -809,7 +868,17 @@ int slslam_lba_pipeline_wait(slslam_lba_pipeline* p, int64_t ticket) {
 void slslam_lba_pipeline_destroy(slslam_lba_pipeline* p) {
   if (!p) return;
   cudaSetDevice(p->device);
-  for (auto& s : p->slots) {
+  for (auto& sp : p->slots) {
+    auto& s = *sp;
+    if (s.th.joinable()) {
+      {
+        std::unique_lock<std::mutex> lk(s.m);
+        s.cv.wait(lk, [&] { return s.state != 1; });    // let a posted batch finish its enqueue
+        s.quit = true;
+      }
+      s.cv.notify_all();
+      s.th.join();
+    }
     if (s.b) { cudaStreamSynchronize(s.stream); slslam_lba_batch_destroy(s.b); s.b = nullptr; }   // abandoned: results dropped
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);

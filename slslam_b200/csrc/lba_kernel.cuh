@@ -66,6 +66,8 @@ struct SmemLayout {
   int camx, camxt, camR, camRt, cscale, linex, linext, lscale, lineLU, ltrig, ltrigt, V, Vred, wacc, yc, misc, tri, pbuf, Z, obs, meta, total;
   int z_in_smem, obs_in_smem;
   int G;   // CTAs per window of this launch
+  int koff;                   // pair-block offsets of the CTA [nkeys + 1] ints (always staged)
+  int items, items_in_smem;   // the CTA's pair list staged in shared memory when it fits (offset in doubles)
 };
 
 __host__ __device__ inline int lba_vlen(int Cf) {
@@ -73,7 +75,8 @@ __host__ __device__ inline int lba_vlen(int Cf) {
   return nkeys * 36 + 3 * n + NSCAL;   // S blocks | g_c | sum Z u | diag H_cc | scalars
 }
 
-__host__ inline SmemLayout lba_layout(int C, int Cf, int max_lines_cta, int max_slots_cta, int CS, size_t smem_limit_bytes) {
+__host__ inline SmemLayout lba_layout(int C, int Cf, int max_lines_cta, int max_slots_cta, int CS, size_t smem_limit_bytes,
+                                      int max_items_cta = 0) {
   SmemLayout l;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
@@ -89,6 +92,7 @@ __host__ inline SmemLayout lba_layout(int C, int Cf, int max_lines_cta, int max_
   l.yc = take(6 * (Cf > 0 ? Cf : 1) + 8);
   l.misc = take(64 + LBA_NW * NSCAL);
   l.tri = take((Cf * (Cf + 1) / 2 + 2) / 2 + 1);   // int table: key -> (I, K)
+  l.koff = take((Cf * (Cf + 1) / 2 + 2) / 2 + 1);  // int table: key -> first item of the CTA's pair block (rebased to 0)
   l.pbuf = l.wacc;   // reduced solve scratch (48 Cf doubles: original panel rows | u | acc) reuses the accumulators, dead by then
   l.Z = o;
   const size_t zbytes = (size_t)ZST * max_slots_cta * 8;
@@ -101,6 +105,12 @@ __host__ inline SmemLayout lba_layout(int C, int Cf, int max_lines_cta, int max_
   // pairs 46 k -> 62 k cycles per iteration).
   l.obs_in_smem = (l.z_in_smem && (size_t)(o + 9 * max_slots_cta) * 8 <= smem_limit_bytes) ? 1 : 0;
   if (l.obs_in_smem) o += 9 * max_slots_cta;
+  // third: the CTA's pair list (4 B per pair): the pair pass chases claim -> offsets -> items -> Z rows; the offsets are
+  // always in shared memory, and with the items there too no L2 round trip is left on that chain
+  const int item_words = max_items_cta + 2;
+  l.items = o;
+  l.items_in_smem = (max_items_cta > 0 && (size_t)(o + (item_words + 1) / 2) * 8 <= smem_limit_bytes) ? 1 : 0;
+  if (l.items_in_smem) o += (item_words + 1) / 2;
   l.total = o;
   return l;
 }
@@ -171,6 +181,8 @@ struct Ctx {
   double* Zbuf;   // this CTA's Z blocks (shared or global)
   const double* obs;   // this CTA's observations [nslots][8] (shared or global)
   const int2* meta;    // this CTA's slot metadata (shared or global)
+  const int* koff;     // this CTA's pair-block offsets [nkeys + 1] (shared, rebased to 0, or global)
+  const uint32_t* items;   // pair list the offsets index (shared or global)
 };
 
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
@@ -381,45 +393,58 @@ __device__ void schur_pairs(const Ctx& c) {
   const WinHdr& h = *c.h;
   double* V = c.sm + c.lay.V;
   int* next_key = reinterpret_cast<int*>(c.sm + c.lay.misc + 7);
-  const int* koff = h.key_off + (size_t)c.rank * (h.nkeys + 1);
+  const int* koff = c.koff;
+  const uint32_t* items = c.items;
+  const int nkeys = h.nkeys;
   int key = c.warp;
   int beg = 0, end = 0;
   uint32_t item = 0;
-  if (key < h.nkeys) {
-    beg = __ldg(koff + key); end = __ldg(koff + key + 1);
-    if (beg + c.lane < end) item = __ldg(h.items + beg + c.lane);
+  if (key < nkeys) {
+    beg = koff[key]; end = koff[key + 1];
+    if (beg + c.lane < end) item = items[beg + c.lane];
   }
-  while (key < h.nkeys) {
+  while (key < nkeys) {
     // claim the next block and prefetch its range and first items while this one is being accumulated
     int nkey = 0;
     if (c.lane == 0) nkey = atomicAdd(next_key, 1);
     nkey = __shfl_sync(0xffffffffu, nkey, 0);
     int nbeg = 0, nend = 0;
-    if (nkey < h.nkeys) { nbeg = __ldg(koff + nkey); nend = __ldg(koff + nkey + 1); }
-    double acc[36];
-#pragma unroll
-    for (int k = 0; k < 36; ++k) acc[k] = 0.0;
-    for (int it = beg + c.lane; it < end; it += 32) {
-      const uint32_t cur = item;
-      if (it + 32 < end) item = __ldg(h.items + it + 32);
-      const double2* zi = reinterpret_cast<const double2*>(c.Zbuf + (size_t)(cur & 0xffffu) * ZST);
-      const double2* zj = reinterpret_cast<const double2*>(c.Zbuf + (size_t)(cur >> 16) * ZST);
-      double Zi[24], Zj[24];
-#pragma unroll
-      for (int k = 0; k < 12; ++k) { const double2 a = zi[k], b = zj[k]; Zi[2 * k] = a.x; Zi[2 * k + 1] = a.y; Zj[2 * k] = b.x; Zj[2 * k + 1] = b.y; }
-#pragma unroll
-      for (int p = 0; p < 6; ++p)
-#pragma unroll
-        for (int q = 0; q < 6; ++q)
-          acc[6 * p + q] += Zi[4 * p] * Zj[4 * q] + Zi[4 * p + 1] * Zj[4 * q + 1] + Zi[4 * p + 2] * Zj[4 * q + 2] + Zi[4 * p + 3] * Zj[4 * q + 3];
+    uint32_t nitem = 0;
+    if (nkey < nkeys) {
+      nbeg = koff[nkey]; nend = koff[nkey + 1];
+      if (nbeg + c.lane < nend) nitem = items[nbeg + c.lane];   // in flight during the whole block below
     }
-    if (nkey < h.nkeys && nbeg + c.lane < nend) item = __ldg(h.items + nbeg + c.lane);
-    double tail[4];
+    if (beg == end) {
+      // no line of this CTA sees both cameras (always so for the diagonal blocks, whose terms the linearisation folds
+      // into the camera accumulators): the block is zero, no reduction needed
+      V[key * 36 + c.lane] = 0.0;
+      if (c.lane < 4) V[key * 36 + 32 + c.lane] = 0.0;
+    } else {
+      double acc[36];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) tail[k] = warp_sum(acc[32 + k]);
-    warp_reduce_scatter32(acc, c.lane);
-    V[key * 36 + c.lane] = -acc[0];
-    if (c.lane < 4) V[key * 36 + 32 + c.lane] = -(c.lane == 0 ? tail[0] : c.lane == 1 ? tail[1] : c.lane == 2 ? tail[2] : tail[3]);
+      for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+      for (int it = beg + c.lane; it < end; it += 32) {
+        const uint32_t cur = item;
+        if (it + 32 < end) item = items[it + 32];
+        const double2* zi = reinterpret_cast<const double2*>(c.Zbuf + (size_t)(cur & 0xffffu) * ZST);
+        const double2* zj = reinterpret_cast<const double2*>(c.Zbuf + (size_t)(cur >> 16) * ZST);
+        double Zi[24], Zj[24];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) { const double2 a = zi[k], b = zj[k]; Zi[2 * k] = a.x; Zi[2 * k + 1] = a.y; Zj[2 * k] = b.x; Zj[2 * k + 1] = b.y; }
+#pragma unroll
+        for (int p = 0; p < 6; ++p)
+#pragma unroll
+          for (int q = 0; q < 6; ++q)
+            acc[6 * p + q] += Zi[4 * p] * Zj[4 * q] + Zi[4 * p + 1] * Zj[4 * q + 1] + Zi[4 * p + 2] * Zj[4 * q + 2] + Zi[4 * p + 3] * Zj[4 * q + 3];
+      }
+      double tail[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tail[k] = warp_sum(acc[32 + k]);
+      warp_reduce_scatter32(acc, c.lane);
+      V[key * 36 + c.lane] = -acc[0];
+      if (c.lane < 4) V[key * 36 + 32 + c.lane] = -(c.lane == 0 ? tail[0] : c.lane == 1 ? tail[1] : c.lane == 2 ? tail[2] : tail[3]);
+    }
+    item = nitem;
     key = nkey; beg = nbeg; end = nend;
   }
 }
@@ -992,6 +1017,20 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
     c.obs = sm + lay.obs; c.meta = smeta;
   } else {
     c.obs = h.obs + (size_t)c.slot0 * 8; c.meta = h.meta + c.slot0;
+  }
+  {
+    const int* gk = h.key_off + (size_t)c.rank * (h.nkeys + 1);
+    int* sk = reinterpret_cast<int*>(sm + lay.koff);
+    const int base = __ldg(gk), cnt = __ldg(gk + h.nkeys) - base;
+    for (int i = c.tid; i <= h.nkeys; i += LBA_NT) sk[i] = __ldg(gk + i) - base;
+    c.koff = sk;
+    if (lay.items_in_smem) {
+      uint32_t* si = reinterpret_cast<uint32_t*>(sm + lay.items);
+      for (int i = c.tid; i < cnt; i += LBA_NT) si[i] = __ldg(h.items + base + i);
+      c.items = si;
+    } else {
+      c.items = h.items + base;
+    }
   }
   const int C = h.C, Cf = h.Cf, n = h.n, vlen = h.vlen;
   const int g_off = h.nkeys * 36, zu_off = g_off + n, hd_off = zu_off + n, sc_off = hd_off + n;

@@ -21,8 +21,10 @@ __device__ __forceinline__ double pivot_rsqrt(double d) {
   return y;
 }
 
-// Per-camera block staged in shared memory: R (9, row-major), dR/dw_k (3 x 9), t (3), pad -> 40 doubles.
-constexpr int CAM_STRIDE = 40;
+// Per-camera block staged in shared memory: R (9, row-major), dR/dw_k (3 x 9), t (3), pad.  The lanes of a tile read
+// the same element of different cameras with 8-byte loads; an odd stride (41 doubles = 82 words, 18 c mod 32 banks)
+// keeps up to 16 cameras on distinct bank pairs, where 40 put every other camera on the same pair.
+constexpr int CAM_STRIDE = 41;
 
 // R = exp([w]x) with the first-order branch R = I + [w]x when |w|^2 == 0, which is what
 // ceres::AngleAxisRotatePoint evaluates (reference src/lba_problem.h:75-76; the newest keyframe is exactly
