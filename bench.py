@@ -315,19 +315,20 @@ def main():
     Kp = max(20, K)
     prepared = capi.PreparedBatch(windows, max_iters=MAX_ITERS)
     pipe_runs = {}
-    for name, flags in (("host_on_caller_thread", 0), ("host_thread_per_slot", capi.LbaPipeline.ASYNC_HOST)):
-        pipe = capi.LbaPipeline(device=local_rank, depth=2, flags=flags)
+    for name, flags, depth in (("host_on_caller_thread_depth2", 0, 2), ("host_thread_per_slot_depth3", capi.LbaPipeline.ASYNC_HOST, 3),
+                               ("host_thread_per_slot_depth4", capi.LbaPipeline.ASYNC_HOST, 4)):
+        pipe = capi.LbaPipeline(device=local_rank, depth=depth, flags=flags)
         for _ in range(3):
             pipe.wait(pipe.submit(prepared))
         barrier()
         t0 = time.perf_counter()
-        prev = None
+        tickets = []
         for _ in range(Kp):
-            t = pipe.submit(prepared)
-            if prev is not None:
-                ps, ss = pipe.wait(prev)
-            prev = t
-        ps, ss = pipe.wait(prev)
+            tickets.append(pipe.submit(prepared))
+            if len(tickets) >= depth:            # depth - 1 batches stay in flight behind the one being read back
+                ps, ss = pipe.wait(tickets.pop(0))
+        while tickets:
+            ps, ss = pipe.wait(tickets.pop(0))
         pipe_s = time.perf_counter() - t0
         assert sum(s_["iterations"] for s_ in ss) == iters_per_step
         tp_ = torch.tensor([pipe_s], dtype=torch.float64, device="cuda")
@@ -395,7 +396,7 @@ def main():
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(windows), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": Kp, "api": f"slslam_lba_pipeline_submit / _wait, depth 2, {e2e_mode} (host buffers; every step is "
+                    "steps": Kp, "api": f"slslam_lba_pipeline_submit / _wait, {e2e_mode} (host buffers; every step is "
                                         "validated, planned, staged to pinned memory, copied H2D, solved and read back D2H; "
                                         "host work and H2D of step k+1 overlap the kernel of step k)",
                     "pipelined": pipe_runs,

@@ -442,7 +442,17 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
       CS = std::min((int)MAX_G, CS * 2);
       continue;
     }
-    CUDA_TRY_OR(cudaFuncSetAttribute(lba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes), { delete b; return SLSLAM_ERR_CUDA; });
+    // the opt-in limit is raised once per device to the maximum and never lowered: batches of different shapes may be
+    // enqueued from several host threads (pipeline slots), and a per-batch value would race with another thread's launch
+    {
+      static std::mutex attr_mutex;
+      static bool attr_set[16] = {false};
+      std::lock_guard<std::mutex> lk(attr_mutex);
+      if (b->device < 0 || b->device >= 16 || !attr_set[b->device]) {
+        CUDA_TRY_OR(cudaFuncSetAttribute(lba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin), { delete b; return SLSLAM_ERR_CUDA; });
+        if (b->device >= 0 && b->device < 16) attr_set[b->device] = true;
+      }
+    }
     if (CS > cap) { set_last_error("more CTAs per window than the device keeps resident"); delete b; return SLSLAM_ERR_CUDA; }
     b->max_active = std::max(1, cap / CS);
     placed = true;

@@ -511,14 +511,14 @@ __device__ void group_allreduce(const Ctx& c, int vlen, int max_idx, unsigned in
   const int per = (vlen + c.G - 1) / c.G;
   const int beg = c.rank * per, end = min(vlen, beg + per);
   for (int i = beg + c.tid; i < end; i += LBA_NT) {
-    // eight peer loads in flight at a time (each is an L2 round trip), combined in rank order
+    // up to 24 peer loads in flight at a time (each is an L2 round trip; one batch for G <= 24), combined in rank order
     double s = 0.0;
-    for (int r0 = 0; r0 < c.G; r0 += 8) {
-      double v[8];
+    for (int r0 = 0; r0 < c.G; r0 += 24) {
+      double v[24];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = (r0 + u < c.G) ? __ldcg(h.Vg + (size_t)(r0 + u) * h.vpad + i) : 0.0;
+      for (int u = 0; u < 24; ++u) v[u] = (r0 + u < c.G) ? __ldcg(h.Vg + (size_t)(r0 + u) * h.vpad + i) : 0.0;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) if (r0 + u < c.G) s = (i == max_idx) ? fmax(s, v[u]) : s + v[u];
+      for (int u = 0; u < 24; ++u) if (r0 + u < c.G) s = (i == max_idx) ? fmax(s, v[u]) : s + v[u];
     }
     h.Vr[i] = s;
   }
@@ -536,8 +536,15 @@ __device__ void group_allreduce(const Ctx& c, int vlen, int max_idx, unsigned in
 // six independent dot products.  On exit yc = (S + D_c)^-1 (g_c - sum Z u).  Returns false (uniformly) if a pivot
 // is not positive.
 __device__ bool reduced_solve(const Ctx& c, double radius, long long* ph) {
-  long long tq = clock64();
-#define RSPHASE(i) { const long long now_ = clock64(); ph[i] += now_ - tq; tq = now_; }
+  // diagnostics (build with -DSLSLAM_RS_PHASES): thread 0 only, counters in shared memory (ph[NPHASE + 1] is this
+  // function's running timestamp).  Off by default: thread 0 is on the critical path of every block column.
+#ifdef SLSLAM_RS_PHASES
+  if (c.tid == 0) ph[NPHASE + 1] = clock64();
+#define RSPHASE(i) { if (c.tid == 0) { const long long now_ = clock64(); ph[i] += now_ - ph[NPHASE + 1]; ph[NPHASE + 1] = now_; } }
+#else
+  (void)ph;
+#define RSPHASE(i)
+#endif
   const WinHdr& h = *c.h;
   double* V = c.sm + c.lay.V;
   double* yc = c.sm + c.lay.yc;
@@ -711,8 +718,15 @@ __device__ bool reduced_solve(const Ctx& c, double radius, long long* ph) {
 // The pivot blocks are LM-damped and Jacobi-scaled, so forming their inverses costs no accuracy that matters here
 // (parity with the oracle's plain Cholesky is unchanged: tests/test_lba_gpu.py).
 __device__ bool reduced_solve_blockinv(const Ctx& c, double radius, long long* ph) {
-  long long tq = clock64();
-#define RSPHASE(i) { const long long now_ = clock64(); ph[i] += now_ - tq; tq = now_; }
+  // diagnostics (build with -DSLSLAM_RS_PHASES): thread 0 only, counters in shared memory (ph[NPHASE + 1] is this
+  // function's running timestamp).  Off by default: thread 0 is on the critical path of every block column.
+#ifdef SLSLAM_RS_PHASES
+  if (c.tid == 0) ph[NPHASE + 1] = clock64();
+#define RSPHASE(i) { if (c.tid == 0) { const long long now_ = clock64(); ph[i] += now_ - ph[NPHASE + 1]; ph[NPHASE + 1] = now_; } }
+#else
+  (void)ph;
+#define RSPHASE(i)
+#endif
   const WinHdr& h = *c.h;
   double* V = c.sm + c.lay.V;
   double* yc = c.sm + c.lay.yc;
@@ -995,7 +1009,7 @@ __device__ void cta_sum(const Ctx& c, const double* vals, double* dst, bool is_m
 
 __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __restrict__ hdrs, SmemLayout lay) {
   extern __shared__ __align__(16) double sm[];
-  const long long t0k = clock64();
+  if (threadIdx.x == 0) reinterpret_cast<long long*>(sm + lay.misc + 24)[NPHASE + 2] = clock64();   // launch timestamp (diagnostics)
   Ctx c;
   c.G = lay.G;
   c.rank = (int)(blockIdx.x % (unsigned)lay.G);
@@ -1088,12 +1102,14 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
   int successful = 0, unsuccessful = 0, invalid = 0, term = SLSLAM_NO_CONVERGENCE, iters = 0;
   bool first_lin = true;
 
-  long long ph[NPHASE];
-#pragma unroll
-  for (int k = 0; k < NPHASE; ++k) ph[k] = 0;
-  long long tk = clock64();
-  const long long t_begin = t0k;
-#define PHASE(i) { const long long now_ = clock64(); ph[i] += now_ - tk; tk = now_; }
+  // per-phase cycle counters (diagnostics): kept in shared memory and touched by thread 0 only, so that they do not
+  // occupy ~30 registers of every thread; ph[NPHASE] is the running timestamp
+  long long* ph = reinterpret_cast<long long*>(sm + lay.misc + 24);
+  if (c.tid == 0) {
+    for (int k = 0; k < NPHASE; ++k) ph[k] = 0;
+    ph[NPHASE] = clock64();
+  }
+#define PHASE(i) { if (c.tid == 0) { const long long now_ = clock64(); ph[i] += now_ - ph[NPHASE]; ph[NPHASE] = now_; } }
   PHASE(0)
   for (int it = 0; it < h.max_iters; ++it) {
     // -- K1/K2: linearise at x with the current radius --
@@ -1168,17 +1184,15 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
       if (c.G > 1) {
         if (c.tid < 4) h.scalg[c.rank * 8 + c.tid] = scal[c.tid];
         group_barrier(c, bar_target);
-        for (int r0 = 0; r0 < c.G; r0 += 4) {
-          double v[4][4];
+        // one L2 round trip: thread r fetches CTA r's four scalars, then every thread sums them in rank order
+        double* gath = sm + lay.wacc;                       // [G][4] (the accumulators are dead during the trial sweep)
+        if (c.tid < 4 * c.G) gath[c.tid] = __ldcg(h.scalg + (c.tid >> 2) * 8 + (c.tid & 3));
+        __syncthreads();
+        for (int r = 0; r < c.G; ++r) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) v[u][k] = (r0 + u < c.G) ? __ldcg(h.scalg + (r0 + u) * 8 + k) : 0.0;
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) trial[k] += v[u][k];
+          for (int k = 0; k < 4; ++k) trial[k] += gath[4 * r + k];
         }
+        __syncthreads();                                    // the next linearisation clears the accumulators
       } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k) trial[k] = scal[k];
@@ -1240,7 +1254,7 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
     s.num_successful_steps = successful; s.num_unsuccessful_steps = unsuccessful; s.termination_type = term; s.iterations = iters;
     *h.summary = s;
     if (h.phase_cycles) {
-      ph[9] = clock64() - t_begin;
+      ph[9] = clock64() - ph[NPHASE + 2];
 #pragma unroll
       for (int k = 0; k < NPHASE; ++k) h.phase_cycles[k] = ph[k];
     }
