@@ -129,6 +129,43 @@ def test_motion_only_ba(gpu):
     assert np.array_equal(pg[6:], w.parameters[6:])
 
 
+def test_motion_only_fast_path(gpu):
+    """The dedicated motion-only kernel (moba_kernel.cuh) behind slslam_lba_solve / _solve_batch: same answer as the
+    oracle and as the general kernel, lines and the constant camera untouched, batches of different sizes."""
+    import os
+    oracle = _oracle()
+    ws = [synth.motion_only_window(30 + i, num_lines=nl, sigma_px=sg) for i, (nl, sg) in
+          enumerate([(60, 0.5), (200, 1.0), (17, 0.2), (400, 0.5)])]
+    ps, ss = gpu.lba_solve_batch(ws, max_iters=10)
+    assert gpu.last_timings()["plan_ms"] == 0.0          # the fast path has no plan stage
+    for w, p, s in zip(ws, ps, ss):
+        po, so = oracle.lba_solve(w, max_iters=10, solver=1)
+        assert _rel(s["initial_cost"], so["initial_cost"]) < 1e-11
+        assert _rel(s["final_cost"], so["final_cost"]) < 1e-6
+        assert _rel(s["fixed_cost"] + 1.0, so["fixed_cost"] + 1.0) < 1e-12 and s["fixed_cost"] > 0
+        assert np.abs(p[:6] - po[:6]).max() < 1e-8
+        assert np.array_equal(p[6:], w.parameters[6:])
+        assert s["iterations"] == so["iterations"] and s["termination"] == so["termination"]
+        p1, s1 = gpu.lba_solve(w, max_iters=10)            # single entry point: same kernel, same bits
+        assert np.array_equal(p1, p) and s1 == s
+    os.environ["SLSLAM_NO_MOBA_FASTPATH"] = "1"            # the general kernel on the same windows
+    try:
+        pg, sg = gpu.lba_solve_batch(ws, max_iters=10)
+        assert gpu.last_timings()["plan_ms"] > 0.0
+    finally:
+        del os.environ["SLSLAM_NO_MOBA_FASTPATH"]
+    for p, s, q, t in zip(ps, ss, pg, sg):
+        assert _rel(s["final_cost"], t["final_cost"]) < 1e-9 and s["iterations"] == t["iterations"]
+        assert np.abs(p - q).max() < 1e-9
+    # not robust, and a window that is NOT motion-only falls through to the general path
+    w = ws[1]
+    p, s = gpu.lba_solve(w, max_iters=10, robust=False)
+    po, so = oracle.lba_solve(w, max_iters=10, robust=False, solver=1)
+    assert _rel(s["final_cost"], so["final_cost"]) < 1e-6 and np.abs(p[:6] - po[:6]).max() < 1e-8
+    gpu.lba_solve(synth.window_S(3), max_iters=3)
+    assert gpu.last_timings()["plan_ms"] > 0.0
+
+
 def test_solve_M_window(gpu):
     """BASELINE.json configs[1]: 10 KF / 2 k lines / 10 k observations."""
     w = synth.window_M(0, sigma_px=0.5)
