@@ -649,7 +649,7 @@ static int moba_solve_batch(int n, const slslam_lba_desc* descs, double* const* 
     memcpy(host + o_p[i], params_inout[i], 8 * np[i]);
   }
   const double t1 = now_ms();
-  const size_t smem = (size_t)(12 + 2 * CAM_STRIDE + 6 + MOBA_NW * 28 + 2 + (size_t)MOBA_OBS_STRIDE * std::max(max_free, 1)) * 8;
+  const size_t smem = ((size_t)MOBA_FIXED_DOUBLES + (size_t)MOBA_OBS_STRIDE * std::max(max_free, 1)) * 8;
   {
     static std::mutex attr_mutex;
     static bool attr_set[16] = {false};

@@ -19,6 +19,7 @@ constexpr int MOBA_NT = 256;
 constexpr int MOBA_NW = MOBA_NT / 32;
 constexpr int MOBA_MAX_FREE_OBS = 1024;   // observations of the free camera staged in shared memory (25 doubles each)
 constexpr int MOBA_OBS_STRIDE = 25;       // ob[8] | xh yh zh xb (12) | d ist2 s1 | pad(2) -> odd stride, conflict-free
+constexpr int MOBA_FIXED_DOUBLES = 12 + 2 * CAM_STRIDE + 6 + (MOBA_NW + 1) * 28 + 2;   // shared memory before the staged observations
 
 struct MobaHdr {
   int C, L, N, free_cam, max_iters, robust;
@@ -39,23 +40,26 @@ __device__ __forceinline__ double moba_warp_sum(double v) {
 }
 
 // CTA sum of NV per-thread values in a fixed order (lanes by butterfly, warps 0..7 in order); every thread gets the sums.
+// wsc: [MOBA_NW][NV] warp partials, then [NV] totals.
 template <int NV>
 __device__ __forceinline__ void moba_cta_sum(double* v, double* wsc, int tid) {
   const int lane = tid & 31, warp = tid >> 5;
+  double* tot = wsc + MOBA_NW * 28;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const double s = moba_warp_sum(v[k]);
     if (lane == 0) wsc[warp * NV + k] = s;
   }
   __syncthreads();
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
+  if (tid < NV) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < MOBA_NW; ++w) s += wsc[w * NV + k];
-    v[k] = s;
+    for (int w = 0; w < MOBA_NW; ++w) s += wsc[w * NV + tid];
+    tot[tid] = s;
   }
   __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = tot[k];
 }
 
 __device__ __forceinline__ void moba_load_trig(const double* __restrict__ so, LineTrig& lt) {
@@ -74,9 +78,9 @@ __global__ void __launch_bounds__(MOBA_NT, 1) lba_motion_only_kernel(const MobaH
   double* camR = sm + 12;                  // [CAM_STRIDE] R, dR/dw, t at x
   double* camRt = camR + CAM_STRIDE;       // [CAM_STRIDE] at the trial point
   double* cscale = camRt + CAM_STRIDE;     // [6] Jacobi scale
-  double* wsc = cscale + 6;                // [MOBA_NW][28] reduction scratch
-  int* nfree_s = reinterpret_cast<int*>(wsc + MOBA_NW * 28);
-  double* fobs = wsc + MOBA_NW * 28 + 2;   // [nfree][MOBA_OBS_STRIDE]
+  double* wsc = cscale + 6;                // [MOBA_NW][28] + [28] reduction scratch
+  int* nfree_s = reinterpret_cast<int*>(wsc + (MOBA_NW + 1) * 28);
+  double* fobs = sm + MOBA_FIXED_DOUBLES;  // [nfree][MOBA_OBS_STRIDE]
   const int C = h.C, N = h.N, fc = h.free_cam;
   const double* lines = h.params_in + 6 * C;
   const bool robust = h.robust != 0;
