@@ -209,6 +209,24 @@ def ncu_dram_traffic():
     return None, None
 
 
+def ncu_fp64_flops():
+    """fp64 flops one lba_solve_kernel launch of this workload executes (2 x DFMA + DMUL + DADD thread instructions, from
+    the committed `ncu --set full` capture: rate per elapsed cycle x elapsed cycles); the work per launch is deterministic."""
+    path = os.path.join(ROOT, "profiles", "r1_lba_solve_kernel_ncu_raw.csv")
+    try:
+        v = {}
+        for ln in open(path):
+            f = ln.rstrip("\n").split(",")
+            if len(f) >= 3:
+                v[f[0]] = f[2]
+        k = "smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed"
+        per_cycle = 2.0 * float(v[k % "dfma"]) + float(v[k % "dmul"]) + float(v[k % "dadd"])
+        cycles = float(v.get("smsp__cycles_elapsed.avg") or v["sm__cycles_elapsed.avg"])
+        return per_cycle * cycles
+    except Exception:
+        return None
+
+
 def workload_config(windows):
     w = windows[0]
     return {"workload": f"{len(windows)} independent M windows per GPU (10 KF / {w.num_lines} lines / {w.num_observations} obs each), "
@@ -391,6 +409,15 @@ def main():
         traffic, traffic_src = ncu_dram_traffic()
         kernel_ms = float(np.mean(ms))
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        # what actually bounds the kernel: the fp64 pipe (64 DFMA / clk / SM).  Not the contract's roofline object, a reading aid.
+        flops = ncu_fp64_flops()
+        sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        fp64_peak = sm_count * 64 * 2 * float(clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+        compute = {"bound": "fp64 pipe", "achieved": (flops / (kernel_ms * 1e-3) / 1e12) if flops else None, "peak": fp64_peak,
+                   "unit": "TFLOP/s", "frac": (flops / (kernel_ms * 1e-3) / 1e12 / fp64_peak) if flops else None,
+                   "fp64_flops_per_launch": flops,
+                   "source": "executed DFMA/DMUL/DADD thread instructions of the committed ncu capture (profiles/) / live kernel time; "
+                             "peak = SMs x 64 DFMA/clk x 2 x max SM clock (nominal, not measured)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -410,6 +437,7 @@ def main():
                          "note": "fp64-issue / latency bound by construction (SURVEY.md §7, DESIGN.md §3.4): the whole LM loop "
                                  "runs out of shared memory and L2, so DRAM traffic is far below the algorithmic bytes and the "
                                  "HBM fraction cannot approach 1; ncu: fp64 pipe ~18 % active, 8 warps/SM"},
+            "compute": compute,
             "lm_iterations_per_step": iters_per_step, "kernel_config": info, "wall_s_timed_region": wall,
             "final_cost_window0": summ[0]["final_cost"],
         }

@@ -26,7 +26,11 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_fp64.sum.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__sass_thread_inst_executed_op_dfma_pred_on.sum", "sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained",
         "sm__sass_thread_inst_executed_op_dadd_pred_on.sum", "sm__sass_thread_inst_executed_op_dmul_pred_on.sum",
-        "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "launch__registers_per_thread", "launch__grid_size",
+        "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed",
+        "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed",
+        "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed", "smsp__cycles_elapsed.avg", "smsp__cycles_elapsed.max",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "memory_l1_wavefronts_shared", "memory_l1_wavefronts_shared_ideal",
+        "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "sm__cycles_elapsed.avg", "launch__registers_per_thread", "launch__grid_size",
         "launch__block_size", "launch__cluster_size", "launch__cluster_max_active", "launch__shared_mem_per_block_dynamic",
         "launch__waves_per_multiprocessor", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
