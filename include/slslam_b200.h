@@ -133,6 +133,11 @@ int slslam_lba_batch_phase_cycles(slslam_lba_batch* b, void* cuda_stream, int32_
 /* Bytes one host-buffer solve of this batch moves: plan + parameters up, parameters + summaries down. */
 int slslam_lba_batch_transfer_bytes(const slslam_lba_batch* b, int64_t* h2d_bytes, int64_t* d2h_bytes);
 void slslam_lba_batch_destroy(slslam_lba_batch* b);
+/* Test hook: builds the plan of every window twice -- on the device (the product path) and with the host planner --
+ * for the same group size and compares every array bit for bit.  0 = identical, 1 = the device planner deferred to the
+ * host planner for this batch, 2 = mismatch (detail[0] window, detail[1] field, detail[2] index), < 0 = error. */
+int slslam_lba_plan_check(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t cluster_size,
+                          int32_t* detail);
 
 /* ---- pipelined host-buffer form (throughput over independent batches, BASELINE.json configs[3]) ----
  * submit() validates the arguments and hands the batch to one of `depth` slots, each with its own device pool, pinned

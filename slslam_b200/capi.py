@@ -22,7 +22,7 @@ EXPORTS = [
     "slslam_version", "slslam_strerror", "slslam_last_error", "slslam_device_count", "slslam_lba_get_limits",
     "slslam_lba_solve", "slslam_lba_solve_batch", "slslam_lba_last_timings", "slslam_lba_batch_create", "slslam_lba_batch_solve",
     "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_max_active_clusters", "slslam_lba_batch_transfer_bytes", "slslam_lba_batch_phase_cycles", "slslam_lba_batch_destroy",
-    "slslam_lba_pipeline_create", "slslam_lba_pipeline_submit", "slslam_lba_pipeline_wait", "slslam_lba_pipeline_destroy",
+    "slslam_lba_plan_check", "slslam_lba_pipeline_create", "slslam_lba_pipeline_submit", "slslam_lba_pipeline_wait", "slslam_lba_pipeline_destroy",
     "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate", "slslam_po_last_solve_ms",
 ]
 
@@ -100,6 +100,7 @@ def lib():
         L.slslam_lba_batch_phase_cycles.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.c_int32]
         L.slslam_lba_batch_destroy.argtypes = [C.c_void_p]
         L.slslam_lba_batch_destroy.restype = None
+        L.slslam_lba_plan_check.argtypes = [C.c_int32, C.POINTER(LbaDesc), C.POINTER(dp), C.c_int32, ip]
         L.slslam_lba_pipeline_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
         L.slslam_lba_pipeline_submit.argtypes = [C.c_void_p, C.c_int32, C.POINTER(LbaDesc), C.POINTER(dp), C.POINTER(Summary),
                                                  C.POINTER(C.c_int64)]
@@ -246,6 +247,17 @@ class LbaBatch:
             self.close()
         except Exception:
             pass
+
+
+def lba_plan_check(windows, cluster_size=0, **kw):
+    """Device planner against host planner (slslam_lba_plan_check): returns (code, [window, field, index])."""
+    pb = PreparedBatch(windows, **kw)
+    pp = (dp * pb.n)(*[_d(p) for p in pb.p0])
+    detail = (C.c_int32 * 3)()
+    rc = lib().slslam_lba_plan_check(pb.n, pb.descs, pp, cluster_size, detail)
+    if rc < 0:
+        _check(rc)
+    return rc, list(detail)
 
 
 class PreparedBatch:

@@ -20,6 +20,7 @@
 #include "common_host.h"
 #include "lba_kernel.cuh"
 #include "moba_kernel.cuh"
+#include "lba_plan_kernel.cuh"
 
 namespace slslam {
 
@@ -242,6 +243,11 @@ struct slslam_lba_batch {
   unsigned int* d_bar = nullptr; size_t bar_bytes = 0;   // group barrier counters, zeroed before every launch
   bool borrowed = false;   // device pool and pinned staging belong to a Workspace (the calling thread's or a pipeline slot's)
   slslam::Workspace* ws = nullptr;
+  // device-side plan (lba_plan_kernel.cuh): where its outputs live in the pool, for the planner parity check
+  bool device_planned = false;
+  struct DevPlanOff { size_t obs, meta, gid, items, koff, hdr; int slot_cap, item_cap; };
+  std::vector<DevPlanOff> dp;
+  std::vector<slslam::PlanInfo> dp_info;
 };
 
 namespace slslam {
@@ -388,6 +394,20 @@ class HostPool {
 template <class F>
 static void parallel_for(int n, F fn) { HostPool::get().run(n, fn); }
 
+// The dynamic shared memory opt-in of the solve kernel is raised once per device to the maximum and never lowered:
+// batches of different shapes may be enqueued from several host threads (pipeline slots), and a per-batch value would
+// race with another thread's launch.
+static int set_solve_kernel_smem_limit(int device, int smem_optin) {
+  static std::mutex attr_mutex;
+  static bool attr_set[16] = {false};
+  std::lock_guard<std::mutex> lk(attr_mutex);
+  if (device < 0 || device >= 16 || !attr_set[device]) {
+    CUDA_TRY(cudaFuncSetAttribute(lba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+    if (device >= 0 && device < 16) attr_set[device] = true;
+  }
+  return SLSLAM_OK;
+}
+
 static int build_plans(int n, const slslam_lba_desc* descs, int CS, std::vector<WindowPlan>& plans) {
   plans.resize(n);   // existing plan objects keep their vector capacity
   std::vector<int> rcs(n, SLSLAM_OK);
@@ -396,8 +416,8 @@ static int build_plans(int n, const slslam_lba_desc* descs, int CS, std::vector<
   return SLSLAM_OK;
 }
 
-static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,
-                             int32_t cluster_size, Workspace* ws, cudaStream_t stream, slslam_lba_batch** out) {
+static int batch_create_host_plan(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,
+                                  int32_t cluster_size, Workspace* ws, cudaStream_t stream, slslam_lba_batch** out) {
   if (!out) return SLSLAM_ERR_INVALID;
   *out = nullptr;
   if (n <= 0 || !descs || !params) return SLSLAM_ERR_INVALID;
@@ -443,17 +463,7 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
       CS = std::min((int)MAX_G, CS * 2);
       continue;
     }
-    // the opt-in limit is raised once per device to the maximum and never lowered: batches of different shapes may be
-    // enqueued from several host threads (pipeline slots), and a per-batch value would race with another thread's launch
-    {
-      static std::mutex attr_mutex;
-      static bool attr_set[16] = {false};
-      std::lock_guard<std::mutex> lk(attr_mutex);
-      if (b->device < 0 || b->device >= 16 || !attr_set[b->device]) {
-        CUDA_TRY_OR(cudaFuncSetAttribute(lba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin), { delete b; return SLSLAM_ERR_CUDA; });
-        if (b->device >= 0 && b->device < 16) attr_set[b->device] = true;
-      }
-    }
+    { const int arc = set_solve_kernel_smem_limit(b->device, smem_optin); if (arc != SLSLAM_OK) { delete b; return arc; } }
     if (CS > cap) { set_last_error("more CTAs per window than the device keeps resident"); delete b; return SLSLAM_ERR_CUDA; }
     b->max_active = std::max(1, cap / CS);
     placed = true;
@@ -566,6 +576,251 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
   if (ws) { g_timing[0] = t_planned - t_begin; g_timing[1] = now_ms() - t_planned; }
   *out = b;
   return SLSLAM_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device-planned batch: the caller's arrays are copied to the device as they are (through pinned staging, or straight
+// from the caller's memory when that is already page-locked) and lba_plan_kernel builds the plan there.  The host does
+// no per-observation work.  Returns SLSLAM_PLAN_FALLBACK when the host planner has to take over (a camera observing a
+// line twice, a batch whose shared-memory shape needs the group-size search).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SLSLAM_PLAN_FALLBACK = -1000;
+
+static int validate_desc_light(const slslam_lba_desc& d) {
+  if (d.num_cameras < 0 || d.num_lines < 0 || d.num_observations < 0 || d.max_iterations < 0) return SLSLAM_ERR_INVALID;
+  if (d.num_observations > 0 && (!d.camera_index || !d.line_index || !d.fixed_index || !d.observations)) return SLSLAM_ERR_INVALID;
+  if (d.num_cameras > MAX_CAMS) return SLSLAM_ERR_UNSUPPORTED;
+  return SLSLAM_OK;
+}
+
+static bool is_page_locked(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,
+                                    int32_t cluster_size, Workspace* ws, cudaStream_t stream, slslam_lba_batch** out) {
+  if (!out) return SLSLAM_ERR_INVALID;
+  *out = nullptr;
+  if (n <= 0 || !descs || !params) return SLSLAM_ERR_INVALID;
+  for (int i = 0; i < n; ++i) {
+    const int rc = validate_desc_light(descs[i]);
+    if (rc != SLSLAM_OK) return rc;
+    if (!params[i]) return SLSLAM_ERR_INVALID;
+    const int np = 6 * descs[i].num_cameras + 4 * descs[i].num_lines;
+    for (int k = 0; k < np; ++k) if (!std::isfinite(params[i][k])) return SLSLAM_ERR_NUMERICAL;
+  }
+  const double t_begin = now_ms();
+  int rc = ensure_device(device);
+  if (rc != SLSLAM_OK) {
+    // no device: argument errors still take precedence over the missing GPU (the index checks otherwise run on the device)
+    for (int i = 0; i < n; ++i) { const int v = validate_desc(descs[i]); if (v != SLSLAM_OK) return v; }
+    return rc;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  long long max_obs = 0;
+  int Lmax = 0, Cmax = 1;
+  for (int i = 0; i < n; ++i) {
+    max_obs = std::max<long long>(max_obs, descs[i].num_observations);
+    Lmax = std::max(Lmax, descs[i].num_lines); Cmax = std::max(Cmax, descs[i].num_cameras);
+  }
+  const int cap = resident_ctas(dev);
+  int smem_optin = 0;
+  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  int CS = pick_group_size(dev, n, max_obs, cluster_size);
+  if (cluster_size <= 0) {
+    // the per-line state of a CTA (50 doubles per line) has to fit beside ~48 KB of fixed state: lower bound on the group size
+    const long long per_line = 50 * 8, room = std::max(16384, smem_optin - 49152);
+    const int cs_min = (int)std::min<long long>(MAX_G, ((long long)Lmax * per_line * 11 / 10 + room - 1) / room);
+    CS = std::max(CS, std::max(1, cs_min));
+  }
+  if (CS > cap) return SLSLAM_PLAN_FALLBACK;
+
+  slslam_lba_batch* b = new (std::nothrow) slslam_lba_batch();
+  if (!b) return SLSLAM_ERR_INVALID;
+  b->device = dev; b->n = n; b->borrowed = ws != nullptr; b->ws = ws; b->device_planned = true; b->CS = CS;
+  if (ws) b->plans.swap(ws->plans);
+  b->plans.resize(n);
+  b->dp.resize(n); b->dp_info.resize(n);
+
+  // ---- pool layout: [uploaded: PlanIn | WinHdr | parameters | raw arrays] [device only: plan outputs, scratch, results, group scratch] ----
+  size_t off = 0;
+  auto reserve = [&](size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; };
+  const size_t o_pin_in = reserve(sizeof(PlanIn) * n), o_hdr = reserve(sizeof(WinHdr) * n);
+  b->param_off.resize(n); b->trace_off.resize(n); b->nparams.resize(n);
+  size_t tp = 0, tt = 0;
+  for (int i = 0; i < n; ++i) {
+    b->nparams[i] = 6 * descs[i].num_cameras + 4 * descs[i].num_lines;
+    b->param_off[i] = tp; tp += (size_t)((b->nparams[i] + 1) & ~1);
+    b->trace_off[i] = tt; tt += (size_t)std::max(1, descs[i].max_iterations) * SLSLAM_TRACE_WIDTH;
+  }
+  b->total_params = tp; b->total_trace = tt;
+  const size_t o_par = reserve(tp * 8);
+  std::vector<size_t> o_ci(n), o_li(n), o_fi(n), o_raw(n);
+  std::vector<char> direct(n, 0);   // observations copied straight from page-locked caller memory
+  for (int i = 0; i < n; ++i) {
+    const size_t N = (size_t)descs[i].num_observations;
+    o_ci[i] = reserve(4 * N); o_li[i] = reserve(4 * N); o_fi[i] = reserve(8 * N);
+  }
+  // observations last, so that the ones that are DMA'd directly leave no hole in the staged prefix
+  for (int i = 0; i < n; ++i) {
+    const size_t N = (size_t)descs[i].num_observations;
+    direct[i] = (N * 64 >= 65536 && is_page_locked(descs[i].observations)) ? 1 : 0;
+  }
+  for (int i = 0; i < n; ++i) if (!direct[i]) o_raw[i] = reserve(64 * (size_t)descs[i].num_observations);
+  const size_t upload = off;
+  for (int i = 0; i < n; ++i) if (direct[i]) o_raw[i] = reserve(64 * (size_t)descs[i].num_observations);
+  struct Scratch { size_t cnt, start, fill, lconst, order, first, seg, cta, slotl, mask, pos; };
+  std::vector<Scratch> sc(n);
+  std::vector<size_t> o_vg(n), o_vr(n), o_sg(n), o_z(n);
+  const int Cf_cap = std::min(Cmax, (int)MAX_FREE_CAMS);
+  const int nkeys_cap = Cf_cap * (Cf_cap + 1) / 2, vpad_cap = (lba_vlen(Cf_cap) + 31) & ~31;
+  // Z staging in global memory only when the Z rows of a CTA may not fit in shared memory
+  bool want_zg = false;
+  for (int i = 0; i < n; ++i) {
+    const size_t N = (size_t)descs[i].num_observations, L = (size_t)descs[i].num_lines;
+    auto& d = b->dp[i];
+    d.slot_cap = (int)(2 * N + 32 * (size_t)MAX_G); d.item_cap = (int)(N * 31 / 2 + 1);
+    d.obs = reserve((size_t)d.slot_cap * 64); d.meta = reserve((size_t)d.slot_cap * 8); d.gid = reserve(4 * L + 4);
+    d.items = reserve((size_t)d.item_cap * 4 + 4); d.koff = reserve((size_t)MAX_G * (nkeys_cap + 1) * 4 + 4);
+    d.hdr = o_hdr + sizeof(WinHdr) * i;
+    Scratch& s = sc[i];
+    s.cnt = reserve(4 * L + 4); s.start = reserve(4 * L + 8); s.fill = reserve(4 * L + 4); s.lconst = reserve(4 * L + 4);
+    s.order = reserve(4 * N + 4); s.first = reserve(4 * L + 4); s.seg = reserve(4 * L + 4); s.cta = reserve(4 * L + 4);
+    s.slotl = reserve((size_t)d.slot_cap * 4); s.mask = reserve(4 * L + 4); s.pos = reserve(32 * L + 4);
+    const size_t slots_est = N / (size_t)CS * 5 / 4 + 96;
+    if (49152 + L / (size_t)CS * 400 + slots_est * ZST * 8 > (size_t)smem_optin) want_zg = true;
+  }
+  const size_t o_info = reserve(sizeof(PlanInfo) * n);
+  const size_t o_pout = reserve(tp * 8), o_summ = reserve(sizeof(slslam_summary) * n), o_trace = reserve(tt * 8),
+               o_phase = reserve(sizeof(long long) * NPHASE * n);
+  for (int i = 0; i < n; ++i) {
+    o_vg[i] = reserve((size_t)CS * vpad_cap * 8); o_vr[i] = reserve((size_t)vpad_cap * 8); o_sg[i] = reserve((size_t)CS * 8 * 8);
+  }
+  const size_t o_bar = reserve((size_t)n * 128);
+  b->bar_bytes = (size_t)n * 128;
+  for (int i = 0; i < n; ++i) o_z[i] = want_zg ? reserve((size_t)b->dp[i].slot_cap * ZST * 8) : 0;
+  const size_t result_bytes = tp * 8 + sizeof(slslam_summary) * n + sizeof(PlanInfo) * n + 512;
+  char* host = nullptr;
+  std::vector<char> host_vec;
+  PlanInfo* h_info = nullptr;
+  if (ws) {
+    rc = ws->ensure(dev, off, upload, result_bytes);
+    if (rc != SLSLAM_OK) { slslam_lba_batch_destroy(b); return rc; }
+    b->d_pool = ws->d_pool; host = ws->h_pin; b->h_params = (double*)ws->h_res;
+    h_info = (PlanInfo*)(ws->h_res + ((tp * 8 + sizeof(slslam_summary) * n + 255) & ~(size_t)255));
+  } else {
+    CUDA_TRY_OR(cudaMalloc((void**)&b->d_pool, off), { delete b; return SLSLAM_ERR_CUDA; });
+    host_vec.resize(upload);
+    host = host_vec.data();
+    CUDA_TRY_OR(cudaMallocHost((void**)&b->h_params, std::max<size_t>(tp, 1) * 8), { slslam_lba_batch_destroy(b); return SLSLAM_ERR_CUDA; });
+    h_info = b->dp_info.data();
+  }
+  char* dp = b->d_pool;
+  b->d_hdrs = (WinHdr*)(dp + o_hdr);
+  b->d_params_in = (double*)(dp + o_par); b->d_params_out = (double*)(dp + o_pout);
+  b->d_trace = (double*)(dp + o_trace); b->d_summ = (slslam_summary*)(dp + o_summ);
+  b->d_phase = (long long*)(dp + o_phase); b->d_bar = (unsigned int*)(dp + o_bar);
+  // ---- staging: headers and the caller's arrays as they are (one thread, one buffer, one copy) ----
+  for (int i = 0; i < n; ++i) {
+    const slslam_lba_desc& d = descs[i];
+    const size_t N = (size_t)d.num_observations;
+    WindowPlan& wp = b->plans[i];
+    wp.C = d.num_cameras; wp.L = d.num_lines; wp.N = d.num_observations; wp.max_iters = d.max_iterations; wp.robust = d.robust ? 1 : 0;
+    wp.huber_a = d.huber_delta > 0 ? d.huber_delta : 1.0 / 406.05;
+    wp.baseline = d.baseline >= 0 ? d.baseline : 0.12;
+    wp.ftol = d.function_tolerance > 0 ? d.function_tolerance : 1e-6;
+    wp.gtol = d.gradient_tolerance > 0 ? d.gradient_tolerance : 1e-10;
+    wp.ptol = d.parameter_tolerance > 0 ? d.parameter_tolerance : 1e-8;
+    wp.radius0 = d.initial_trust_region_radius > 0 ? d.initial_trust_region_radius : 1e4;
+    const auto& q = b->dp[i];
+    WinHdr h; memset(&h, 0, sizeof(h));
+    h.C = wp.C; h.L = wp.L; h.max_iters = wp.max_iters; h.robust = wp.robust;
+    h.huber_a = wp.huber_a; h.baseline = wp.baseline; h.ftol = wp.ftol; h.gtol = wp.gtol; h.ptol = wp.ptol; h.radius0 = wp.radius0;
+    h.obs = (const double*)(dp + q.obs); h.meta = (const int2*)(dp + q.meta); h.line_gid = (const int*)(dp + q.gid);
+    h.items = (const uint32_t*)(dp + q.items); h.key_off = (const int*)(dp + q.koff);
+    h.params_in = b->d_params_in + b->param_off[i]; h.params_out = b->d_params_out + b->param_off[i];
+    h.Zg = want_zg ? (double*)(dp + o_z[i]) : nullptr;
+    h.Vg = (double*)(dp + o_vg[i]); h.Vr = (double*)(dp + o_vr[i]); h.scalg = (double*)(dp + o_sg[i]);
+    h.bar = (unsigned int*)(dp + o_bar + (size_t)i * 128);
+    h.summary = b->d_summ + i;
+    h.trace = ws ? nullptr : b->d_trace + b->trace_off[i];
+    h.phase_cycles = ws ? nullptr : b->d_phase + (size_t)NPHASE * i;
+    memcpy(host + o_hdr + sizeof(WinHdr) * i, &h, sizeof(h));
+    const Scratch& s = sc[i];
+    PlanIn pi; memset(&pi, 0, sizeof(pi));
+    pi.C = wp.C; pi.L = wp.L; pi.N = wp.N; pi.CS = CS; pi.slot_cap = q.slot_cap; pi.item_cap = q.item_cap;
+    pi.cam_idx = (const int*)(dp + o_ci[i]); pi.line_idx = (const int*)(dp + o_li[i]); pi.fixed = (const int*)(dp + o_fi[i]);
+    pi.obs_raw = (const double*)(dp + o_raw[i]);
+    pi.obs = (double*)(dp + q.obs); pi.meta = (int2*)(dp + q.meta); pi.line_gid = (int*)(dp + q.gid);
+    pi.items = (uint32_t*)(dp + q.items); pi.key_off = (int*)(dp + q.koff);
+    pi.hdr = (WinHdr*)(dp + q.hdr); pi.info = (PlanInfo*)(dp + o_info) + i;
+    pi.line_cnt = (int*)(dp + s.cnt); pi.line_start = (int*)(dp + s.start); pi.fill = (int*)(dp + s.fill); pi.lconst = (int*)(dp + s.lconst);
+    pi.order = (int*)(dp + s.order); pi.first_slot = (int*)(dp + s.first); pi.seg_start = (int*)(dp + s.seg); pi.line_cta = (int*)(dp + s.cta);
+    pi.slot_line = (int*)(dp + s.slotl); pi.line_mask = (unsigned*)(dp + s.mask); pi.pos_of_cf = (unsigned char*)(dp + s.pos);
+    memcpy(host + o_pin_in + sizeof(PlanIn) * i, &pi, sizeof(pi));
+    memcpy(host + o_par + b->param_off[i] * 8, params[i], (size_t)b->nparams[i] * 8);
+    memcpy(host + o_ci[i], d.camera_index, 4 * N);
+    memcpy(host + o_li[i], d.line_index, 4 * N);
+    memcpy(host + o_fi[i], d.fixed_index, 8 * N);
+    if (!direct[i]) memcpy(host + o_raw[i], d.observations, 64 * N);
+  }
+  const double t_staged = now_ms();
+  b->upload_bytes = upload;
+  cudaError_t e = cudaSuccess;
+  if (ws) cudaEventRecord(ws->ev[0], stream);
+  e = cudaMemcpyAsync(dp, host, upload, cudaMemcpyHostToDevice, stream);
+  for (int i = 0; i < n && e == cudaSuccess; ++i) {
+    if (!direct[i]) continue;
+    const size_t bytes = 64 * (size_t)descs[i].num_observations;
+    e = cudaMemcpyAsync(dp + o_raw[i], descs[i].observations, bytes, cudaMemcpyHostToDevice, stream);
+    b->upload_bytes += bytes;
+  }
+  if (e == cudaSuccess) {
+    lba_plan_kernel<<<n, PLAN_NT, 0, stream>>>((const PlanIn*)(dp + o_pin_in));
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_info, dp + o_info, sizeof(PlanInfo) * n, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); cudaGetLastError(); slslam_lba_batch_destroy(b); return SLSLAM_ERR_CUDA; }
+  int Cfmax = 0, mlines = 1, mslots = 32, mitems = 0, flags = 0;
+  for (int i = 0; i < n; ++i) {
+    const PlanInfo& pi = h_info[i];
+    b->dp_info[i] = pi;
+    flags |= pi.error;
+    Cfmax = std::max(Cfmax, pi.Cf); mlines = std::max(mlines, pi.max_lines_cta); mslots = std::max(mslots, pi.max_slots_cta);
+    mitems = std::max(mitems, pi.max_items_cta);
+    b->plans[i].Cf = pi.Cf; b->plans[i].nkeys = pi.Cf * (pi.Cf + 1) / 2; b->plans[i].has_unobserved_blocks = pi.has_unobserved != 0;
+    b->plans[i].max_lines_cta = pi.max_lines_cta; b->plans[i].max_slots_cta = pi.max_slots_cta; b->plans[i].max_items_cta = pi.max_items_cta;
+  }
+  if (flags & PLAN_ERR_INDEX) { slslam_lba_batch_destroy(b); return SLSLAM_ERR_INVALID; }
+  if (flags & (PLAN_DUPLICATE_CAMERA | PLAN_ERR_CAPACITY)) { slslam_lba_batch_destroy(b); return SLSLAM_PLAN_FALLBACK; }
+  if (flags & PLAN_ERR_LIMIT) {
+    // too many free cameras / observations per line are final; "too many slots per CTA" may go away with a larger group
+    slslam_lba_batch_destroy(b);
+    return SLSLAM_PLAN_FALLBACK;
+  }
+  b->lay = lba_layout(Cmax, Cfmax, mlines, mslots, CS, (size_t)smem_optin, mitems);
+  b->smem_bytes = (size_t)b->lay.total * 8;
+  if (b->smem_bytes > (size_t)smem_optin || (!b->lay.z_in_smem && !want_zg)) { slslam_lba_batch_destroy(b); return SLSLAM_PLAN_FALLBACK; }
+  rc = set_solve_kernel_smem_limit(dev, smem_optin);
+  if (rc != SLSLAM_OK) { slslam_lba_batch_destroy(b); return rc; }
+  b->max_active = std::max(1, cap / CS);
+  if (ws) { g_timing[0] = 0.0; g_timing[1] = now_ms() - t_begin; (void)t_staged; }
+  *out = b;
+  return SLSLAM_OK;
+}
+
+static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,
+                             int32_t cluster_size, Workspace* ws, cudaStream_t stream, slslam_lba_batch** out) {
+  if (!getenv("SLSLAM_HOST_PLAN")) {
+    const int rc = batch_create_device_plan(n, descs, params, device, cluster_size, ws, stream, out);
+    if (rc != SLSLAM_PLAN_FALLBACK) return rc;
+  }
+  return batch_create_host_plan(n, descs, params, device, cluster_size, ws, stream, out);
 }
 
 }  // namespace slslam
@@ -693,6 +948,69 @@ void slslam_lba_get_limits(slslam_lba_limits* out) {
   if (!out) return;
   out->max_cameras = MAX_CAMS; out->max_free_cameras = MAX_FREE_CAMS; out->max_observations_per_line = 32;
   out->max_cluster_size = MAX_G;
+}
+
+int slslam_lba_plan_check(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t cluster_size,
+                          int32_t* detail) {
+  // Planner parity: the device-built plan (lba_plan_kernel.cuh) against the host planner (build_plan) for the same group
+  // size, array by array, bit for bit.  Returns 0 when identical, 1 when the device planner asked for the host
+  // fallback, 2 on a mismatch (detail[0] = window, detail[1] = field, detail[2] = index), < 0 on errors.
+  if (detail) detail[0] = detail[1] = detail[2] = -1;
+  slslam_lba_batch* b = nullptr;
+  int rc = batch_create_device_plan(n, descs, params, -1, cluster_size, nullptr, nullptr, &b);
+  if (rc == SLSLAM_PLAN_FALLBACK) return 1;
+  if (rc != SLSLAM_OK) return rc;
+  std::vector<WindowPlan> plans;
+  rc = build_plans(n, descs, b->CS, plans);
+  if (rc != SLSLAM_OK) { slslam_lba_batch_destroy(b); return rc; }
+  int result = 0;
+  auto fail = [&](int w, int field, long long idx) { if (result == 0) { result = 2; if (detail) { detail[0] = w; detail[1] = field; detail[2] = (int)idx; } } };
+  for (int i = 0; i < n && result == 0; ++i) {
+    const WindowPlan& hp = plans[i];
+    const PlanInfo& pi = b->dp_info[i];
+    const auto& q = b->dp[i];
+    WinHdr h;
+    cudaMemcpy(&h, b->d_pool + q.hdr, sizeof(h), cudaMemcpyDeviceToHost);
+    if (pi.Cf != hp.Cf || h.Cf != hp.Cf || h.nkeys != hp.nkeys || h.n != 6 * hp.Cf || h.vlen != lba_vlen(hp.Cf)) fail(i, 1, 0);
+    if (pi.max_lines_cta != hp.max_lines_cta) fail(i, 2, 0);
+    if (pi.max_slots_cta != hp.max_slots_cta) fail(i, 3, 0);
+    if (pi.max_items_cta != hp.max_items_cta) fail(i, 4, 0);
+    if ((pi.has_unobserved != 0) != hp.has_unobserved_blocks) fail(i, 5, 0);
+    for (int r = 0; r <= MAX_G; ++r) {
+      if (h.cta_slot_off[r] != hp.cta_slot_off[r]) fail(i, 6, r);
+      if (h.cta_line_off[r] != hp.cta_line_off[r]) fail(i, 7, r);
+    }
+    for (int c = 0; c < MAX_CAMS; ++c) if (h.cam_free[c] != hp.cam_free[c]) fail(i, 8, c);
+    if (result) break;
+    const size_t ns = hp.meta.size();
+    if ((size_t)pi.nslots != ns) { fail(i, 9, 0); break; }
+    std::vector<int2> meta(ns);
+    std::vector<double> obs(ns * 8);
+    cudaMemcpy(meta.data(), b->d_pool + q.meta, ns * sizeof(int2), cudaMemcpyDeviceToHost);
+    cudaMemcpy(obs.data(), b->d_pool + q.obs, ns * 64, cudaMemcpyDeviceToHost);
+    for (size_t k = 0; k < ns; ++k) {
+      if (meta[k].x != hp.meta[k].x || meta[k].y != hp.meta[k].y) { fail(i, 10, (long long)k); break; }
+      const int j = hp.slot_src[k];
+      for (int e = 0; e < 8; ++e) {
+        const double want = j >= 0 ? descs[i].observations[8 * (size_t)j + e] : 0.0;
+        if (memcmp(&want, &obs[8 * k + e], 8) != 0) { fail(i, 11, (long long)k); break; }
+      }
+      if (result) break;
+    }
+    if (result) break;
+    std::vector<int> gid(hp.line_gid.size());
+    cudaMemcpy(gid.data(), b->d_pool + q.gid, gid.size() * 4, cudaMemcpyDeviceToHost);
+    for (size_t k = 0; k < gid.size(); ++k) if (gid[k] != hp.line_gid[k]) { fail(i, 12, (long long)k); break; }
+    if ((size_t)pi.nitems != hp.items.size()) { fail(i, 13, 0); break; }
+    std::vector<uint32_t> items(hp.items.size());
+    cudaMemcpy(items.data(), b->d_pool + q.items, items.size() * 4, cudaMemcpyDeviceToHost);
+    for (size_t k = 0; k < items.size(); ++k) if (items[k] != hp.items[k]) { fail(i, 14, (long long)k); break; }
+    std::vector<int> koff(hp.key_off.size());
+    cudaMemcpy(koff.data(), b->d_pool + q.koff, koff.size() * 4, cudaMemcpyDeviceToHost);
+    for (size_t k = 0; k < koff.size(); ++k) if (koff[k] != hp.key_off[k]) { fail(i, 15, (long long)k); break; }
+  }
+  slslam_lba_batch_destroy(b);
+  return result;
 }
 
 int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,

@@ -197,7 +197,6 @@ __device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, d
   const WinHdr& h = *c.h;
   double* sm = c.sm;
   const double* camR = sm + c.lay.camR;
-  const double* linex = sm + c.lay.linex;
   const double* cscale = sm + c.lay.cscale;
   double* lscale = sm + c.lay.lscale;
   double* lineLU = sm + c.lay.lineLU;

@@ -211,6 +211,50 @@ def test_pipeline_matches_one_shot(gpu, flags):
     pipe.close()
 
 
+def test_device_plan_matches_host_plan(gpu):
+    """The plan built on the device (lba_plan_kernel.cuh, the product path) equals the host planner's bit for bit: slot
+    metadata, gathered observations, line partition, pair lists, offsets -- for every group size and window kind."""
+    cases = [[synth.window_S(0)], [synth.window_S(1, shuffle=True)], [synth.window_M(2, sigma_px=1.0, start="far")],
+             [synth.motion_only_window(3)], [synth.window_S(4, anchored=False)],
+             [synth.window_S(10 + i, sigma_px=0.5) for i in range(5)],
+             [synth.make_window(7, 6, 80, 360), synth.window_M(8), synth.make_window(9, 3, 12, 40)],
+             [synth.make_window(20 + i, 10, 2000, 10000) for i in range(8)]]
+    w = synth.window_S(5)                                    # a steady-state window: the oldest cameras constant
+    fi = w.fixed_index.reshape(-1, 2).copy(); fi[:, 0] = (w.camera_index < 3).astype(np.int32); w.fixed_index = fi.ravel()
+    cases.append([w])
+    w = synth.window_S(6)                                    # some constant lines, some unobserved lines and cameras
+    fi = w.fixed_index.reshape(-1, 2).copy(); fi[:, 1] = (w.line_index % 7 == 0).astype(np.int32); w.fixed_index = fi.ravel()
+    keep = (w.line_index % 11 != 3) & (w.camera_index != 4)
+    w.camera_index, w.line_index = w.camera_index[keep].copy(), w.line_index[keep].copy()
+    w.fixed_index = w.fixed_index.reshape(-1, 2)[keep].ravel().copy()
+    w.observations = w.observations.reshape(-1, 8)[keep].ravel().copy()
+    cases.append([w])
+    for ws in cases:
+        for cs in (0, 1, 2, 4, 8, 16, 18, 48):
+            rc, detail = gpu.lba_plan_check(ws, cluster_size=cs)
+            assert rc in (0, 1), (len(ws), cs, rc, detail)
+            if cs == 0 or cs >= 8:
+                assert rc == 0, ("unexpected host fallback", len(ws), cs)
+    # a camera observing one line twice is left to the host planner (code 1), and the solve still goes through
+    w = synth.window_S(0)
+    w.camera_index = w.camera_index.copy()
+    for l in range(w.num_lines):
+        idx = [i for i in np.flatnonzero(w.line_index == l) if w.camera_index[i] >= 1]    # camera 0 is the constant one
+        if len(idx) >= 2:
+            w.camera_index[idx[1]] = w.camera_index[idx[0]]
+            break
+    rc, _ = gpu.lba_plan_check([w])
+    assert rc == 1
+    p, s = gpu.lba_solve(w, max_iters=3)
+    assert np.isfinite(s["final_cost"])
+    # index errors are found on the device and reported as invalid arguments
+    bad = synth.window_S(1)
+    bad.camera_index = bad.camera_index.copy(); bad.camera_index[5] = 99
+    with pytest.raises(gpu.SlslamError) as e:
+        gpu.lba_solve(bad)
+    assert e.value.code == -1
+
+
 def test_determinism(gpu):
     w = synth.window_S(9, sigma_px=1.0, start="far")
     a, sa = gpu.lba_solve(w, max_iters=10)
