@@ -331,7 +331,7 @@ def main():
     # (b) pipelined (slslam_lba_pipeline_*, depth 2): the same per-step work, but the host plans and stages step k+1, and
     # its H2D copy runs, while the device solves step k; the results of step k are read back before step k+2 is submitted
     Kp = max(20, K)
-    prepared = capi.PreparedBatch(windows, max_iters=MAX_ITERS)
+    prepared = capi.PreparedBatch(windows, pin=True, max_iters=MAX_ITERS)     # observations in page-locked host memory
     pipe_runs = {}
     for name, flags, depth in (("host_on_caller_thread_depth2", 0, 2), ("host_thread_per_slot_depth3", capi.LbaPipeline.ASYNC_HOST, 3),
                                ("host_thread_per_slot_depth4", capi.LbaPipeline.ASYNC_HOST, 4)):
@@ -423,8 +423,8 @@ def main():
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(windows), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": Kp, "api": f"slslam_lba_pipeline_submit / _wait, {e2e_mode} (host buffers; every step is "
-                                        "validated, planned, staged to pinned memory, copied H2D, solved and read back D2H; "
+                    "steps": Kp, "api": f"slslam_lba_pipeline_submit / _wait, {e2e_mode} (host buffers, observations page-locked; "
+                                        "every step is validated, copied H2D, planned on the device, solved and read back D2H; "
                                         "host work and H2D of step k+1 overlap the kernel of step k)",
                     "pipelined": pipe_runs,
                     "synchronous": {"value": sync_value, "unit": UNIT, "steps": Ke,

@@ -263,9 +263,19 @@ def lba_plan_check(windows, cluster_size=0, **kw):
 class PreparedBatch:
     """Descs of a list of windows marshalled once (the numpy arrays stay referenced), for repeated submission."""
 
-    def __init__(self, windows, **kw):
+    def __init__(self, windows, pin=False, **kw):
         self.windows = list(windows)
         self.n = len(self.windows)
+        if pin:
+            # observations in page-locked host memory: the library then DMAs them straight from the caller's array
+            import copy
+            import torch
+            pinned = []
+            for w in self.windows:
+                w = copy.copy(w)
+                w.observations = torch.from_numpy(np.ascontiguousarray(w.observations, np.float64)).pin_memory().numpy()
+                pinned.append(w)
+            self.windows = pinned
         self.keeps = [lba_desc(w, **kw) for w in self.windows]
         self.descs = (LbaDesc * self.n)(*[k.desc for k in self.keeps])
         self.p0 = [np.ascontiguousarray(w.parameters, np.float64) for w in self.windows]

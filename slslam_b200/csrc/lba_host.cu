@@ -317,17 +317,42 @@ static int resident_ctas(int device) {
   return table[device];
 }
 
-// CTAs per window.  One LM iteration of a window on G CTAs costs about fixed + per_obs * N / G (profiles/: ~55 k +
-// 156 N / G cycles on B200), all CTAs of a launch must be co-resident, so: spread the batch over the whole GPU, but keep
-// at least three 32-lane tiles per CTA, and fall back to several launches (waves) of G = 1 when there are more
-// windows than SMs.
-static int pick_group_size(int device, int nwin, long long max_obs, int requested) {
+// CTAs per window.  One LM iteration of a window on G CTAs costs about fixed + per_obs * N / G (profiles/: ~45 k +
+// 156 N / G cycles on B200) and all CTAs of a launch must be co-resident.  A batch that does not fit in one launch runs
+// in waves; the number of waves and the group size are chosen together so that the waves are equally full (29 + 3
+// windows cost two full waves; 16 + 16 with larger groups is faster).  `cs_min`: lower bound from shared memory (the
+// per-line state of a CTA must fit); at least three 32-lane tiles per CTA; beyond ~48 CTAs the exchange grows faster
+// than the sweeps shrink (profiles/r1_cluster_vs_group.txt).
+static int pick_group_size(int device, int nwin, long long max_obs, int requested, int cs_min = 1) {
   if (requested > 0) return std::min(requested, (int)MAX_G);
   const int cap = std::max(1, resident_ctas(device));
-  int g = std::max(1, cap / std::max(1, nwin));
+  cs_min = std::max(1, std::min(cs_min, std::min(cap, (int)MAX_G)));
   const long long tiles = (max_obs + 27) / 28;
-  g = (int)std::min<long long>(g, std::max<long long>(1, tiles / 3));
-  return std::min(g, 48);   // beyond ~48 CTAs the exchange grows faster than the sweeps shrink (profiles/r1_cluster_vs_group.txt)
+  const int cs_max = std::max(cs_min, (int)std::min<long long>(48, std::max<long long>(1, tiles / 3)));
+  const int w0 = (nwin + cap / cs_min - 1) / std::max(1, cap / cs_min);
+  int best = cs_min;
+  double best_t = 1e300;
+  for (int w = std::max(1, w0); w <= w0 + 3; ++w) {
+    const int per = (nwin + w - 1) / w;
+    const int cs = std::max(cs_min, std::min(cs_max, cap / std::max(1, per)));
+    if ((long long)cs * per > cap) continue;
+    const double t = w * (45000.0 + 156.0 * (double)max_obs / cs);
+    if (t < best_t - 1e-9) { best_t = t; best = cs; }
+  }
+  return best;
+}
+
+// Shared-memory lower bound on the group size: 50 doubles of per-line state per line beside ~48 KB of fixed state.
+static int min_group_size_for_lines(int Lmax, int smem_optin) {
+  const long long per_line = 50 * 8, room = std::max(16384, smem_optin - 49152);
+  return (int)std::max<long long>(1, std::min<long long>(MAX_G, ((long long)Lmax * per_line * 11 / 10 + room - 1) / room));
+}
+
+// Windows per wave for `n` windows when `fit` groups are resident at once: equally full waves.
+static int balanced_wave(int n, int fit) {
+  fit = std::max(1, fit);
+  const int waves = (n + fit - 1) / fit;
+  return std::max(1, (n + waves - 1) / waves);
 }
 
 // fn(i) for i in [0, n) on up to 8 host threads (the plans of different windows are independent work).  The workers
@@ -444,7 +469,9 @@ static int batch_create_host_plan(int32_t n, const slslam_lba_desc* descs, const
   int smem_optin = 0;
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device);
   bool placed = false;
-  int CS = pick_group_size(b->device, n, max_obs, cluster_size);
+  int Lmax = 0;
+  for (int i = 0; i < n; ++i) Lmax = std::max(Lmax, descs[i].num_lines);
+  int CS = pick_group_size(b->device, n, max_obs, cluster_size, min_group_size_for_lines(Lmax, smem_optin));
   for (int attempt = 0; attempt < 8 && !placed; ++attempt) {
     rc = build_plans(n, descs, CS, b->plans);
     if (rc != SLSLAM_OK) { delete b; return rc; }
@@ -465,7 +492,7 @@ static int batch_create_host_plan(int32_t n, const slslam_lba_desc* descs, const
     }
     { const int arc = set_solve_kernel_smem_limit(b->device, smem_optin); if (arc != SLSLAM_OK) { delete b; return arc; } }
     if (CS > cap) { set_last_error("more CTAs per window than the device keeps resident"); delete b; return SLSLAM_ERR_CUDA; }
-    b->max_active = std::max(1, cap / CS);
+    b->max_active = balanced_wave(n, cap / CS);
     placed = true;
   }
   if (!placed) {
@@ -630,14 +657,20 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
   const int cap = resident_ctas(dev);
   int smem_optin = 0;
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  int CS = pick_group_size(dev, n, max_obs, cluster_size);
-  if (cluster_size <= 0) {
-    // the per-line state of a CTA (50 doubles per line) has to fit beside ~48 KB of fixed state: lower bound on the group size
-    const long long per_line = 50 * 8, room = std::max(16384, smem_optin - 49152);
-    const int cs_min = (int)std::min<long long>(MAX_G, ((long long)Lmax * per_line * 11 / 10 + room - 1) / room);
-    CS = std::max(CS, std::max(1, cs_min));
-  }
+  const int CS = pick_group_size(dev, n, max_obs, cluster_size, min_group_size_for_lines(Lmax, smem_optin));
   if (CS > cap) return SLSLAM_PLAN_FALLBACK;
+  // the plan kernel keeps 13 bytes per line of a window in shared memory
+  const size_t plan_smem = 13 * (size_t)Lmax + 16;
+  if (plan_smem > (size_t)smem_optin - 4096) return SLSLAM_PLAN_FALLBACK;
+  {
+    static std::mutex attr_mutex;
+    static bool attr_set[16] = {false};
+    std::lock_guard<std::mutex> lk(attr_mutex);
+    if (dev < 0 || dev >= 16 || !attr_set[dev]) {
+      CUDA_TRY(cudaFuncSetAttribute(lba_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 4096));
+      if (dev >= 0 && dev < 16) attr_set[dev] = true;
+    }
+  }
 
   slslam_lba_batch* b = new (std::nothrow) slslam_lba_batch();
   if (!b) return SLSLAM_ERR_INVALID;
@@ -673,7 +706,7 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
   for (int i = 0; i < n; ++i) if (!direct[i]) o_raw[i] = reserve(64 * (size_t)descs[i].num_observations);
   const size_t upload = off;
   for (int i = 0; i < n; ++i) if (direct[i]) o_raw[i] = reserve(64 * (size_t)descs[i].num_observations);
-  struct Scratch { size_t cnt, start, fill, lconst, order, first, seg, cta, slotl, mask, pos; };
+  struct Scratch { size_t cnt, start, fill, lconst, order, slotl, pos; };
   std::vector<Scratch> sc(n);
   std::vector<size_t> o_vg(n), o_vr(n), o_sg(n), o_z(n);
   const int Cf_cap = std::min(Cmax, (int)MAX_FREE_CAMS);
@@ -689,8 +722,8 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
     d.hdr = o_hdr + sizeof(WinHdr) * i;
     Scratch& s = sc[i];
     s.cnt = reserve(4 * L + 4); s.start = reserve(4 * L + 8); s.fill = reserve(4 * L + 4); s.lconst = reserve(4 * L + 4);
-    s.order = reserve(4 * N + 4); s.first = reserve(4 * L + 4); s.seg = reserve(4 * L + 4); s.cta = reserve(4 * L + 4);
-    s.slotl = reserve((size_t)d.slot_cap * 4); s.mask = reserve(4 * L + 4); s.pos = reserve(32 * L + 4);
+    s.order = reserve(4 * N + 4);
+    s.slotl = reserve((size_t)d.slot_cap * 4); s.pos = reserve(32 * L + 4);
     const size_t slots_est = N / (size_t)CS * 5 / 4 + 96;
     if (49152 + L / (size_t)CS * 400 + slots_est * ZST * 8 > (size_t)smem_optin) want_zg = true;
   }
@@ -759,8 +792,8 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
     pi.items = (uint32_t*)(dp + q.items); pi.key_off = (int*)(dp + q.koff);
     pi.hdr = (WinHdr*)(dp + q.hdr); pi.info = (PlanInfo*)(dp + o_info) + i;
     pi.line_cnt = (int*)(dp + s.cnt); pi.line_start = (int*)(dp + s.start); pi.fill = (int*)(dp + s.fill); pi.lconst = (int*)(dp + s.lconst);
-    pi.order = (int*)(dp + s.order); pi.first_slot = (int*)(dp + s.first); pi.seg_start = (int*)(dp + s.seg); pi.line_cta = (int*)(dp + s.cta);
-    pi.slot_line = (int*)(dp + s.slotl); pi.line_mask = (unsigned*)(dp + s.mask); pi.pos_of_cf = (unsigned char*)(dp + s.pos);
+    pi.order = (int*)(dp + s.order);
+    pi.slot_line = (int*)(dp + s.slotl); pi.pos_of_cf = (unsigned char*)(dp + s.pos);
     memcpy(host + o_pin_in + sizeof(PlanIn) * i, &pi, sizeof(pi));
     memcpy(host + o_par + b->param_off[i] * 8, params[i], (size_t)b->nparams[i] * 8);
     memcpy(host + o_ci[i], d.camera_index, 4 * N);
@@ -780,7 +813,7 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
     b->upload_bytes += bytes;
   }
   if (e == cudaSuccess) {
-    lba_plan_kernel<<<n, PLAN_NT, 0, stream>>>((const PlanIn*)(dp + o_pin_in));
+    lba_plan_kernel<<<n, PLAN_NT, plan_smem, stream>>>((const PlanIn*)(dp + o_pin_in));
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(h_info, dp + o_info, sizeof(PlanInfo) * n, cudaMemcpyDeviceToHost, stream);
@@ -808,8 +841,9 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
   if (b->smem_bytes > (size_t)smem_optin || (!b->lay.z_in_smem && !want_zg)) { slslam_lba_batch_destroy(b); return SLSLAM_PLAN_FALLBACK; }
   rc = set_solve_kernel_smem_limit(dev, smem_optin);
   if (rc != SLSLAM_OK) { slslam_lba_batch_destroy(b); return rc; }
-  b->max_active = std::max(1, cap / CS);
-  if (ws) { g_timing[0] = 0.0; g_timing[1] = now_ms() - t_begin; (void)t_staged; }
+  b->max_active = balanced_wave(n, cap / CS);
+  // "plan" here = H2D + device plan kernel + read-back of the sizes (the host waits for it); "stage" = the pinned staging
+  if (ws) { g_timing[0] = now_ms() - t_staged; g_timing[1] = t_staged - t_begin; }
   *out = b;
   return SLSLAM_OK;
 }

@@ -45,11 +45,7 @@ struct PlanIn {
   int* fill;                 // [L]
   int* lconst;               // [L]
   int* order;                // [N] observation indices grouped by line, ascending inside a line
-  int* first_slot;           // [L] per device line: CTA-local slot of its first observation
-  int* seg_start;            // [L] per device line: lane of its first observation
-  int* line_cta;             // [L] per device line: owning CTA
   int* slot_line;            // [slot_cap] device line of the slot or -1
-  unsigned* line_mask;       // [L] per device line: set of reduced camera indices observing it (constant lines: 0)
   unsigned char* pos_of_cf;  // [L][32] per device line: position (0..31) of the observation of reduced camera cf
 };
 
@@ -92,6 +88,13 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
   __shared__ int s_cam_free[MAX_CAMS];
   __shared__ int s_cta_line_off[MAX_G + 1], s_cta_slot_off[MAX_G + 1];
   __shared__ int s_wsum[PLAN_NW + 1];
+  // per device line, in dynamic shared memory (13 bytes per line of the window): the sequential and pointer-chasing
+  // steps below would otherwise pay an L2 round trip per line
+  extern __shared__ __align__(16) unsigned char plan_dyn[];
+  int* s_line = reinterpret_cast<int*>(plan_dyn);                  // first_slot (CTA-local) | seg_start << 16 | cta << 22
+  unsigned* s_mask = reinterpret_cast<unsigned*>(plan_dyn) + L;    // reduced cameras observing the line
+  int* s_dstart = reinterpret_cast<int*>(plan_dyn) + 2 * (size_t)L;   // first entry of the line in `order`
+  unsigned char* s_cnt = plan_dyn + 12 * (size_t)L;                // observations of the line (<= 32)
 
   if (tid == 0) {
     s_cam_used = 0u; s_cam_const = 0u; s_err = PLAN_OK; s_unobs = 0; s_max_lines = 1; s_max_slots = 32; s_max_items = 0;
@@ -140,7 +143,11 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
       if (l < L) {
         p.line_start[l] = carry + ex;
         p.fill[l] = carry + ex;
-        if (k > 0) p.line_gid[dcarry + dex] = l;
+        if (k > 0) {
+          p.line_gid[dcarry + dex] = l;
+          s_cnt[dcarry + dex] = (unsigned char)min(k, 255);
+          s_dstart[dcarry + dex] = carry + ex;
+        }
       }
       carry += tot; dcarry += dtot;
     }
@@ -175,7 +182,7 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
       int lo = 0, hi = nd;    // smallest li in [0, nd] with prefix(li) >= target; prefix(nd) = N >= target
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const long long pre = p.line_start[p.line_gid[mid]];
+        const long long pre = s_dstart[mid];
         if (pre >= target) hi = mid; else lo = mid + 1;
       }
       li = lo;
@@ -190,9 +197,9 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
     const int r = tid, lb = s_cta_line_off[r], le = s_cta_line_off[r + 1];
     int slots = 0, ln = 0;
     for (int li = lb; li < le; ++li) {
-      const int k = p.line_cnt[p.line_gid[li]];
+      const int k = s_cnt[li];
       if (ln + k > 32) { slots += 32 - ln; ln = 0; }
-      p.seg_start[li] = ln; p.first_slot[li] = slots; p.line_cta[li] = r;
+      s_line[li] = (slots & 0xffff) | (ln << 16) | (r << 22);
       slots += k; ln += k;
       if (ln == 32) ln = 0;
     }
@@ -221,8 +228,8 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
   for (int s = tid; s < total_slots; s += PLAN_NT) p.slot_line[s] = -1;
   __syncthreads();
   for (int li = tid; li < nd; li += PLAN_NT) {
-    const int k = p.line_cnt[p.line_gid[li]];
-    const int g0 = s_cta_slot_off[p.line_cta[li]] + p.first_slot[li];
+    const int k = s_cnt[li], pk = s_line[li];
+    const int g0 = s_cta_slot_off[pk >> 22] + (pk & 0xffff);
     for (int a = 0; a < k; ++a) p.slot_line[g0 + a] = li;
   }
   __syncthreads();
@@ -232,12 +239,13 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
     const int li = p.slot_line[s];
     int cam = -1 - lane, src = -1;
     int2 m; m.x = (lane << 8) | (1 << 14); m.y = 0;
-    int l = 0, k = 0, a = 0, r = 0;
+    int l = 0, k = 0, a = 0, r = 0, pk = 0;
     if (li >= 0) {
-      l = p.line_gid[li]; k = p.line_cnt[l]; r = p.line_cta[li];
-      a = s - (s_cta_slot_off[r] + p.first_slot[li]);
-      src = p.order[p.line_start[l] + a];
+      pk = s_line[li]; k = s_cnt[li]; r = pk >> 22;
+      a = s - (s_cta_slot_off[r] + (pk & 0xffff));
+      src = p.order[s_dstart[li] + a];
       cam = p.cam_idx[src];
+      l = p.line_idx[src];
     }
     const unsigned same = __match_any_sync(0xffffffffu, cam);
     if (li >= 0) {
@@ -246,7 +254,7 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
       if (p.lconst[l]) flags |= F_LINE_FIXED;
       if ((s_cam_const >> cam) & 1u) flags |= F_CAM_FIXED;
       if (a == 0) flags |= F_HEAD;
-      m.x = cam | (p.seg_start[li] << 8) | (k << 14) | (flags << 24);
+      m.x = cam | (((pk >> 16) & 0x3f) << 8) | (k << 14) | (flags << 24);
       m.y = (li - s_cta_line_off[r]) | (round << 20);
     }
     p.meta[s] = m;
@@ -262,7 +270,7 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
   }
   // per device line: the set of reduced cameras that see it (none when the line is constant) and where each sits
   for (int li = tid; li < nd; li += PLAN_NT) {
-    const int l = p.line_gid[li], k = p.line_cnt[l], b = p.line_start[l];
+    const int l = p.line_gid[li], k = s_cnt[li], b = s_dstart[li];
     unsigned mask = 0u;
     if (!p.lconst[l]) {
       for (int a = 0; a < k; ++a) {
@@ -273,7 +281,7 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
         p.pos_of_cf[(size_t)li * 32 + cf] = (unsigned char)a;
       }
     }
-    p.line_mask[li] = mask;
+    s_mask[li] = mask;
   }
   __syncthreads();
   if (s_err) {
@@ -292,7 +300,7 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
       const int cb = key - ca * (ca + 1) / 2;
       if (ca != cb) {
         const unsigned need = (1u << ca) | (1u << cb);
-        for (int li = s_cta_line_off[r]; li < s_cta_line_off[r + 1]; ++li) cnt += (p.line_mask[li] & need) == need;
+        for (int li = s_cta_line_off[r]; li < s_cta_line_off[r + 1]; ++li) cnt += (s_mask[li] & need) == need;
       }
     }
     p.key_off[t] = cnt;
@@ -323,8 +331,8 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
       const unsigned need = (1u << ca) | (1u << cb);
       int pos = p.key_off[t];
       for (int li = s_cta_line_off[r]; li < s_cta_line_off[r + 1]; ++li) {
-        if ((p.line_mask[li] & need) != need) continue;
-        const uint32_t fs = (uint32_t)p.first_slot[li];
+        if ((s_mask[li] & need) != need) continue;
+        const uint32_t fs = (uint32_t)(s_line[li] & 0xffff);
         const uint32_t si = fs + p.pos_of_cf[(size_t)li * 32 + ca], sj = fs + p.pos_of_cf[(size_t)li * 32 + cb];
         p.items[pos++] = si | (sj << 16);
       }
