@@ -370,7 +370,8 @@ def main():
             return ps_, ss_
 
         nwin_all = len(windows) * world
-        bufs = shard.pack_for_ranks(allw, world) if rank == 0 else None     # window assembly, not transfer: untimed
+        bufs = shard.pack_for_ranks(allw, world, pin=True) if rank == 0 else None     # window assembly, not transfer: untimed
+        rsizes = shard.result_sizes(allw, world) if rank == 0 else [0] * world
         for rep in range(3):           # the first repetitions warm NCCL's point-to-point channels
             barrier()
             t0 = time.perf_counter()
@@ -381,7 +382,7 @@ def main():
             t1 = time.perf_counter()
             ps_, ss_ = solve_fn(local, MAX_ITERS)
             t2 = time.perf_counter()
-            outp, outs = shard.gather_results(ps_, ss_, idx, nwin_all, device=dev)
+            outp, outs = shard.gather_results(ps_, ss_, idx, nwin_all, device=dev, sizes=rsizes)
             torch.cuda.synchronize()
             barrier()
             t3 = time.perf_counter()

@@ -1,18 +1,25 @@
 #!/bin/bash
-# Run under gpurun: parity tests, bench line, ncu launch list and one full capture of the LBA solve kernel.
+# Run under gpurun (one GPU): parity tests, bench lines (ours + reference arm), ncu launch list and one full capture of
+# the LBA solve kernel, PO launch list and timing, phase cycles, batch-size scaling, e2e split, staging experiment,
+# motion-only latency.  scripts/make_profile_summary.py <tag> <round> then turns gpurun_out/ into profiles/.
 # usage: scripts/gpu_profile.sh <tag>
 tag=${1:-r1}
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python bench.py --steps 50 --warmup 5 > gpurun_out/bench_${tag}.json 2> gpurun_out/bench_${tag}.err; tail -c 3000 gpurun_out/bench_${tag}.json
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_${tag}.json 2>> gpurun_out/bench_${tag}.err; cat gpurun_out/bench_ref_${tag}.json
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_${tag}.csv \
+nproc > gpurun_out/host_${tag}.txt; lscpu | grep -E "Model name|Socket|NUMA node\(s\)" >> gpurun_out/host_${tag}.txt
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+timeout 600 python bench.py > gpurun_out/bench_${tag}.json 2> gpurun_out/bench_${tag}.err; tail -c 3000 gpurun_out/bench_${tag}.json
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_${tag}.json 2>> gpurun_out/bench_${tag}.err; cat gpurun_out/bench_ref_${tag}.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_${tag}.csv \
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_a_${tag}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:lba_solve -s 3 -c 1 -f -o gpurun_out/prof_lba_${tag} \
+cp slslam_b200/libslslam_b200.so gpurun_out/lib_${tag}.so
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:lba_solve -s 3 -c 1 -f -o gpurun_out/prof_lba_${tag} \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_b_${tag}.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_po_${tag}.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_po_${tag}.csv \
     python scripts/po_profile.py 1 > gpurun_out/ncu_po_${tag}.log 2>&1
-python scripts/po_profile.py 3 2>&1 | tee gpurun_out/po_${tag}.txt
-python scripts/phase_profile.py all > gpurun_out/phase_${tag}.txt 2>&1
-python scripts/e2e_profile.py > gpurun_out/e2e_${tag}.txt 2>&1
-python scripts/h2d_test2.py > gpurun_out/h2d_${tag}.txt 2>&1
+timeout 300 python scripts/po_profile.py 3 2>&1 | tee gpurun_out/po_${tag}.txt
+timeout 300 python scripts/phase_profile.py all > gpurun_out/phase_${tag}.txt 2>&1
+timeout 300 python scripts/phase_profile.py scale > gpurun_out/phase_scale_${tag}.txt 2>&1
+timeout 300 python scripts/e2e_profile.py > gpurun_out/e2e_${tag}.txt 2>&1
+timeout 300 python scripts/h2d_test2.py > gpurun_out/h2d_${tag}.txt 2>&1
+timeout 300 python scripts/motion_only_profile.py > gpurun_out/moba_${tag}.txt 2>&1
+ls -la gpurun_out | tail -25

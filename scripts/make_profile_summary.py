@@ -51,14 +51,17 @@ if os.path.exists(rep):
                     or h.startswith("smsp__pcsamp_warps_issue_stalled") and not h.endswith("not_issued"):
                 w.writerow([h, units[i]] + [r[i] for r in rows[2:]])
     by = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_by_line.py"), rep,
-                         os.path.join(ROOT, "slslam_b200", "libslslam_b200.so"), "lba_solve", "40"], capture_output=True, text=True).stdout
+                         os.path.join(G, f"lib_{tag}.so") if os.path.exists(os.path.join(G, f"lib_{tag}.so"))
+                         else os.path.join(ROOT, "slslam_b200", "libslslam_b200.so"), "lba_solve", "60"], capture_output=True, text=True).stdout
     open(os.path.join(P, f"{rnd}_lba_solve_kernel_by_source_line.txt"), "w").write(
         "# ncu --set full --import-source on, samples and instructions aggregated by CUDA source line (scripts/ncu_by_line.py)\n" + by)
 
 for src, dst in ((f"launches_{tag}.csv", f"{rnd}_launches_bench_lba.csv"), (f"launches_po_{tag}.csv", f"{rnd}_launches_po_solve.csv"),
                  (f"bench_{tag}.json", f"{rnd}_bench_ours.json"), (f"bench_ref_{tag}.json", f"{rnd}_bench_reference_arm.json"),
                  (f"po_{tag}.txt", f"{rnd}_po_solve_timing.txt"), (f"phase_{tag}.txt", f"{rnd}_lba_phase_cycles.txt"),
-                 (f"e2e_{tag}.txt", f"{rnd}_lba_e2e_split.txt"), (f"h2d_{tag}.txt", f"{rnd}_h2d_staging.txt")):
+                 (f"e2e_{tag}.txt", f"{rnd}_lba_e2e_split.txt"), (f"h2d_{tag}.txt", f"{rnd}_h2d_staging.txt"),
+                 (f"phase_scale_{tag}.txt", f"{rnd}_lba_batch_size_scaling.txt"), (f"moba_{tag}.txt", f"{rnd}_motion_only_ba.txt"),
+                 (f"host_{tag}.txt", f"{rnd}_host_cpu.txt")):
     if os.path.exists(os.path.join(G, src)):
         shutil.copy(os.path.join(G, src), os.path.join(P, dst))
 

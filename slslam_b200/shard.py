@@ -102,15 +102,35 @@ def _exchange(ops, dist):
             req.wait()
 
 
-def pack_for_ranks(windows, world: int):
+def pack_for_ranks(windows, world: int, pin: bool = False):
     """Rank-0 side assembly: one contiguous byte buffer per destination rank, holding that rank's windows back to back
-    (int64 count, int64 byte sizes, then the packed windows).  Window w goes to rank w mod world."""
+    (int64 count, int64 byte sizes, then the packed windows).  Window w goes to rank w mod world.  With `pin` the buffers
+    live in page-locked memory (numpy views of pinned torch tensors), so the scatter can DMA them without staging."""
     out = []
     for r in range(world):
         mine = [pack_window(windows[w]) for w in local_indices(len(windows), r, world)]
         head = np.array([len(mine)] + [m.size for m in mine], np.int64).view(np.uint8)
-        out.append(np.concatenate([head] + mine) if mine else head.copy())
+        parts = [head] + mine
+        total = sum(p.size for p in parts)
+        if pin:
+            import torch
+            buf = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory().numpy()[:total]
+        else:
+            buf = np.empty(total, np.uint8)
+        o = 0
+        for p in parts:
+            buf[o:o + p.size] = p
+            o += p.size
+        out.append(buf)
     return out
+
+
+def _is_pinned(arr) -> bool:
+    try:
+        import torch
+        return torch.from_numpy(arr).is_pinned()
+    except Exception:
+        return False
 
 
 def unpack_many(buf: np.ndarray):
@@ -140,14 +160,30 @@ def scatter_packed(bufs, device=None, group=None):
     ops, keep, recv = [], [], None
     if rank == 0:
         for r in range(1, world):
-            t = _to_device(bufs[r], dev)
+            if dev.type == "cuda" and _is_pinned(bufs[r]):
+                t = torch.from_numpy(bufs[r]).to(dev, non_blocking=True)     # all copies in flight, stream-ordered before the sends
+            else:
+                t = _to_device(bufs[r], dev)
             keep.append(t)
             ops.append(dist.P2POp(dist.isend, t, r, group=group))
     else:
         recv = torch.empty(int(sizes[rank]), dtype=torch.uint8, device=dev)
         ops.append(dist.P2POp(dist.irecv, recv, 0, group=group))
     _exchange(ops, dist)
-    return bufs[0] if rank == 0 else recv.cpu().numpy()
+    if rank == 0:
+        return bufs[0]
+    if dev.type != "cuda":
+        return recv.numpy()
+    # device -> page-locked host (cached): the solver DMAs the observations straight out of this buffer again
+    key = ("recv", dev.index)
+    stage = _PINNED.get(key)
+    if stage is None or stage.numel() < recv.numel():
+        stage = torch.empty(max(recv.numel(), 1 << 16), dtype=torch.uint8).pin_memory()
+        _PINNED[key] = stage
+    view = stage[:recv.numel()]
+    view.copy_(recv, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return view.numpy()
 
 
 def scatter_windows(windows, device=None, group=None):
@@ -168,7 +204,13 @@ def scatter_windows(windows, device=None, group=None):
     return local, idx
 
 
-def gather_results(params, summaries, indices, num_windows, device=None, group=None):
+def result_sizes(windows, world: int):
+    """Float64 elements of every rank's result buffer, computable on rank 0 from the windows it scattered."""
+    return [sum(SUMMARY_WIDTH + 1 + 6 * windows[w].num_cameras + 4 * windows[w].num_lines
+                for w in local_indices(len(windows), r, world)) for r in range(world)]
+
+
+def gather_results(params, summaries, indices, num_windows, device=None, group=None, sizes=None):
     """Every rank passes the parameters / summaries of its windows (global `indices`); rank 0 returns the full lists in
     window order, other ranks return (None, None).  One float64 buffer per rank: per window the summary row, the
     parameter count and the parameters; one size all-gather, then one grouped send/recv per rank."""
@@ -180,9 +222,12 @@ def gather_results(params, summaries, indices, num_windows, device=None, group=N
     for p, s in zip(params, summaries):
         parts += [summary_to_row(s), np.array([float(len(p))]), np.ascontiguousarray(p, np.float64)]
     mine = np.concatenate(parts) if parts else np.zeros(0)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([mine.size], dtype=torch.int64, device=dev), group=group)
-    sizes = [int(t.item()) for t in sizes]
+    if sizes is None:
+        # rank 0 does not know the other ranks' sizes: one small all-gather (skipped when the caller passes `sizes`,
+        # which every rank can compute when it knows the window shapes; only rank 0 uses them)
+        sz = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(sz, torch.tensor([mine.size], dtype=torch.int64, device=dev), group=group)
+        sizes = [int(t.item()) for t in sz]
     ops, keep, bufs = [], [], {}
     if rank == 0:
         for r in range(1, world):
