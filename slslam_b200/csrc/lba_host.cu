@@ -659,8 +659,8 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const int CS = pick_group_size(dev, n, max_obs, cluster_size, min_group_size_for_lines(Lmax, smem_optin));
   if (CS > cap) return SLSLAM_PLAN_FALLBACK;
-  // the plan kernel keeps 13 bytes per line of a window in shared memory
-  const size_t plan_smem = 13 * (size_t)Lmax + 16;
+  // the plan kernel keeps 13 + min(C, 24) bytes per line of a window in shared memory
+  const size_t plan_smem = (13 + (size_t)std::min(Cmax, (int)MAX_FREE_CAMS)) * (size_t)Lmax + 16;
   if (plan_smem > (size_t)smem_optin - 4096) return SLSLAM_PLAN_FALLBACK;
   {
     static std::mutex attr_mutex;
@@ -706,7 +706,7 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
   for (int i = 0; i < n; ++i) if (!direct[i]) o_raw[i] = reserve(64 * (size_t)descs[i].num_observations);
   const size_t upload = off;
   for (int i = 0; i < n; ++i) if (direct[i]) o_raw[i] = reserve(64 * (size_t)descs[i].num_observations);
-  struct Scratch { size_t cnt, start, fill, lconst, order, slotl, pos; };
+  struct Scratch { size_t cnt, start, fill, lconst, order, slotl; };
   std::vector<Scratch> sc(n);
   std::vector<size_t> o_vg(n), o_vr(n), o_sg(n), o_z(n);
   const int Cf_cap = std::min(Cmax, (int)MAX_FREE_CAMS);
@@ -723,7 +723,7 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
     Scratch& s = sc[i];
     s.cnt = reserve(4 * L + 4); s.start = reserve(4 * L + 8); s.fill = reserve(4 * L + 4); s.lconst = reserve(4 * L + 4);
     s.order = reserve(4 * N + 4);
-    s.slotl = reserve((size_t)d.slot_cap * 4); s.pos = reserve(32 * L + 4);
+    s.slotl = reserve((size_t)d.slot_cap * 4);
     const size_t slots_est = N / (size_t)CS * 5 / 4 + 96;
     if (49152 + L / (size_t)CS * 400 + slots_est * ZST * 8 > (size_t)smem_optin) want_zg = true;
   }
@@ -793,7 +793,7 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
     pi.hdr = (WinHdr*)(dp + q.hdr); pi.info = (PlanInfo*)(dp + o_info) + i;
     pi.line_cnt = (int*)(dp + s.cnt); pi.line_start = (int*)(dp + s.start); pi.fill = (int*)(dp + s.fill); pi.lconst = (int*)(dp + s.lconst);
     pi.order = (int*)(dp + s.order);
-    pi.slot_line = (int*)(dp + s.slotl); pi.pos_of_cf = (unsigned char*)(dp + s.pos);
+    pi.slot_line = (int*)(dp + s.slotl);
     memcpy(host + o_pin_in + sizeof(PlanIn) * i, &pi, sizeof(pi));
     memcpy(host + o_par + b->param_off[i] * 8, params[i], (size_t)b->nparams[i] * 8);
     memcpy(host + o_ci[i], d.camera_index, 4 * N);

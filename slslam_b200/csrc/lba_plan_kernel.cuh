@@ -46,7 +46,6 @@ struct PlanIn {
   int* lconst;               // [L]
   int* order;                // [N] observation indices grouped by line, ascending inside a line
   int* slot_line;            // [slot_cap] device line of the slot or -1
-  unsigned char* pos_of_cf;  // [L][32] per device line: position (0..31) of the observation of reduced camera cf
 };
 
 // Block-wide exclusive scan of v (one value per thread); returns the exclusive prefix, *total gets the block total.
@@ -88,13 +87,15 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
   __shared__ int s_cam_free[MAX_CAMS];
   __shared__ int s_cta_line_off[MAX_G + 1], s_cta_slot_off[MAX_G + 1];
   __shared__ int s_wsum[PLAN_NW + 1];
-  // per device line, in dynamic shared memory (13 bytes per line of the window): the sequential and pointer-chasing
+  // per device line, in dynamic shared memory (13 + min(C, 24) bytes per line of the window): the sequential and pointer-chasing
   // steps below would otherwise pay an L2 round trip per line
   extern __shared__ __align__(16) unsigned char plan_dyn[];
   int* s_line = reinterpret_cast<int*>(plan_dyn);                  // first_slot (CTA-local) | seg_start << 16 | cta << 22
   unsigned* s_mask = reinterpret_cast<unsigned*>(plan_dyn) + L;    // reduced cameras observing the line
   int* s_dstart = reinterpret_cast<int*>(plan_dyn) + 2 * (size_t)L;   // first entry of the line in `order`
   unsigned char* s_cnt = plan_dyn + 12 * (size_t)L;                // observations of the line (<= 32)
+  unsigned char* s_pos = plan_dyn + 13 * (size_t)L;                // [L][pstride] position in the line of reduced camera cf
+  const int pstride = min(C, (int)MAX_FREE_CAMS);
 
   if (tid == 0) {
     s_cam_used = 0u; s_cam_const = 0u; s_err = PLAN_OK; s_unobs = 0; s_max_lines = 1; s_max_slots = 32; s_max_items = 0;
@@ -102,14 +103,29 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
   for (int l = tid; l < L; l += PLAN_NT) { p.line_cnt[l] = 0; p.lconst[l] = 0; }
   __syncthreads();
 
-  // ---- A: counts per line, sticky constants, index validation ----
-  for (int i = tid; i < N; i += PLAN_NT) {
-    const int c = p.cam_idx[i], l = p.line_idx[i];
-    if (c < 0 || c >= C || l < 0 || l >= L) { atomicOr(&s_err, PLAN_ERR_INDEX); continue; }
-    atomicAdd(&p.line_cnt[l], 1);
-    atomicOr(&s_cam_used, 1u << c);
-    if (p.fixed[2 * i]) atomicOr(&s_cam_const, 1u << c);
-    if (p.fixed[2 * i + 1]) p.lconst[l] = 1;
+  // ---- A: counts per line, sticky constants, index validation (camera sets combined per warp before they touch the
+  // two shared words, which every thread of the CTA would otherwise hammer) ----
+  for (int base = 0; base < N; base += PLAN_NT) {
+    const int i = base + tid;
+    unsigned used = 0u, cst = 0u, bad = 0u;
+    if (i < N) {
+      const int c = p.cam_idx[i], l = p.line_idx[i];
+      if (c < 0 || c >= C || l < 0 || l >= L) {
+        bad = 1u;
+      } else {
+        atomicAdd(&p.line_cnt[l], 1);
+        used = 1u << c;
+        const int2 fx = reinterpret_cast<const int2*>(p.fixed)[i];
+        if (fx.x) cst = 1u << c;
+        if (fx.y) p.lconst[l] = 1;
+      }
+    }
+    used = __reduce_or_sync(0xffffffffu, used); cst = __reduce_or_sync(0xffffffffu, cst); bad = __reduce_or_sync(0xffffffffu, bad);
+    if (lane == 0) {
+      if (used) atomicOr(&s_cam_used, used);
+      if (cst) atomicOr(&s_cam_const, cst);
+      if (bad) atomicOr(&s_err, PLAN_ERR_INDEX);
+    }
   }
   __syncthreads();
   if (s_err & PLAN_ERR_INDEX) {
@@ -164,12 +180,16 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
   __syncthreads();
   for (int l = tid; l < L; l += PLAN_NT) {
     const int b = p.line_start[l], k = p.line_cnt[l];
+    if (k < 2) continue;
+    int v[32];                                   // one round trip for the loads, the sort itself in thread-local memory
+    for (int a = 0; a < k; ++a) v[a] = p.order[b + a];
     for (int a = 1; a < k; ++a) {
-      const int v = p.order[b + a];
+      const int x = v[a];
       int q = a;
-      while (q > 0 && p.order[b + q - 1] > v) { p.order[b + q] = p.order[b + q - 1]; --q; }
-      p.order[b + q] = v;
+      while (q > 0 && v[q - 1] > x) { v[q] = v[q - 1]; --q; }
+      v[q] = x;
     }
+    for (int a = 0; a < k; ++a) p.order[b + a] = v[a];
   }
   // ---- E: lines over the CTAs of the group, balancing observation counts ----
   if (tid < CS) {
@@ -278,7 +298,7 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
         if (cf < 0) continue;
         if ((mask >> cf) & 1u) atomicOr(&s_err, PLAN_DUPLICATE_CAMERA);
         mask |= 1u << cf;
-        p.pos_of_cf[(size_t)li * 32 + cf] = (unsigned char)a;
+        s_pos[(size_t)li * pstride + cf] = (unsigned char)a;
       }
     }
     s_mask[li] = mask;
@@ -333,7 +353,7 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
       for (int li = s_cta_line_off[r]; li < s_cta_line_off[r + 1]; ++li) {
         if ((s_mask[li] & need) != need) continue;
         const uint32_t fs = (uint32_t)(s_line[li] & 0xffff);
-        const uint32_t si = fs + p.pos_of_cf[(size_t)li * 32 + ca], sj = fs + p.pos_of_cf[(size_t)li * 32 + cb];
+        const uint32_t si = fs + s_pos[(size_t)li * pstride + ca], sj = fs + s_pos[(size_t)li * pstride + cb];
         p.items[pos++] = si | (sj << 16);
       }
     }

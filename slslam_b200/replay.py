@@ -98,13 +98,32 @@ def observe(poses_cw, P, Q, sigma_px, seed, lines_per_kf, reach=14):
     return obs
 
 
-def run(poses_wc_true, solve, window_size=10, max_iters=10, sigma_px=0.5, seed=0, lines_per_kf=30,
-        odo_noise=(2e-3, 2e-2), anchor_first=True, max_keyframes=None, record=None):
-    """Replays the trajectory.  Returns the estimated camera->world poses [K][6] and per-window statistics."""
+def export_dataset(obs_dir, poses_wc_true, sigma_px=0.5, seed=0, lines_per_kf=30, max_keyframes=None):
+    """Writes the synthetic scene's stereo observations as the reference's per-frame files (`%04d.txt`, pixels;
+    dataset_io.write_frame_observations), one file per keyframe.  Returns the number of files."""
+    from . import dataset_io
     K = len(poses_wc_true) if max_keyframes is None else min(max_keyframes, len(poses_wc_true))
     truth_cw = np.stack([pose_inverse(T) for T in poses_wc_true[:K]])
     P, Q = make_scene(poses_wc_true[:K], seed, lines_per_kf)
-    obs = observe(truth_cw, P, Q, sigma_px, seed, lines_per_kf)
+    for k, cur in enumerate(observe(truth_cw, P, Q, sigma_px, seed, lines_per_kf)):
+        dataset_io.write_frame_observations(obs_dir, k, {lid: dataset_io.to_pixels(ob) for lid, ob in cur.items()})
+    return K
+
+
+def run(poses_wc_true, solve, window_size=10, max_iters=10, sigma_px=0.5, seed=0, lines_per_kf=30,
+        odo_noise=(2e-3, 2e-2), anchor_first=True, max_keyframes=None, record=None, obs_dir=None, motion_only=None):
+    """Replays the trajectory.  Returns the estimated camera->world poses [K][6] and per-window statistics.
+    obs_dir: read the observations from the reference's per-frame files (export_dataset) instead of generating them.
+    motion_only: optional solver for the per-frame motion-only BA (reference src/slam.cpp:578-675): before a keyframe
+    enters the window its pose is refined against the current map with every line held constant."""
+    K = len(poses_wc_true) if max_keyframes is None else min(max_keyframes, len(poses_wc_true))
+    truth_cw = np.stack([pose_inverse(T) for T in poses_wc_true[:K]])
+    if obs_dir is not None:
+        from . import dataset_io
+        obs = [dataset_io.read_frame_observations(obs_dir, k) for k in range(K)]
+    else:
+        P, Q = make_scene(poses_wc_true[:K], seed, lines_per_kf)
+        obs = observe(truth_cw, P, Q, sigma_px, seed, lines_per_kf)
     rng = np.random.default_rng(seed + 2)
     est = np.zeros((K, 6))                  # world->camera estimates
     est[0] = truth_cw[0]
@@ -116,6 +135,24 @@ def run(poses_wc_true, solve, window_size=10, max_iters=10, sigma_px=0.5, seed=0
             rel = pose_compose(truth_cw[k], pose_inverse(truth_cw[k - 1]))
             rel = rel + np.concatenate([rng.normal(0, odo_noise[0], 3), rng.normal(0, odo_noise[1], 3)])
             est[k] = pose_compose(rel, est[k - 1])
+        if k > 0 and motion_only is not None:
+            # motion-only BA as SLAM::motion_only_ba packs it: camera 0 = this keyframe (free), camera 1 = identity
+            # (constant), two observations per common line (this frame, previous keyframe), lines expressed in the
+            # previous keyframe's frame and constant
+            common = [l for l in obs[k] if l in lines and l in obs[k - 1]]
+            if len(common) >= 6:
+                Tp = est[k - 1]
+                ci, li, fi, ob_arr = [], [], [], []
+                for j, l in enumerate(common):
+                    ci += [0, 1]; li += [j, j]; fi += [0, 1, 1, 1]; ob_arr += [obs[k][l], obs[k - 1][l]]
+                params = np.zeros(12 + 4 * len(common))
+                params[:6] = pose_compose(est[k], pose_inverse(Tp))
+                for j, l in enumerate(common):
+                    params[12 + 4 * j:16 + 4 * j] = line_transform(lines[l], Tp)
+                wm = Window(2, len(common), np.asarray(ci, np.int32), np.asarray(li, np.int32), np.asarray(fi, np.int32),
+                            np.asarray(ob_arr, np.float64).ravel(), params, params.copy(), dict(keyframe=k, kind="motion_only"))
+                out, _ = motion_only(wm, max_iters)
+                est[k] = pose_compose(out[:6], Tp)
         for lid, ob in obs[k].items():      # landmark initialisation from the first stereo view
             if lid not in lines:
                 tri = triangulate(ob)

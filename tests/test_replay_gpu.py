@@ -67,3 +67,35 @@ def test_myungdong_pose_graph(gpu):
     assert sg["iterations"] == so["iterations"] and sg["termination"] == so["termination"]
     assert np.abs(pg - po).max() < 1e-5
     assert sg["final_cost"] < 0.5 * sg["initial_cost"]
+
+
+def test_replay_with_motion_only_ba_per_keyframe(gpu):
+    """The reference's per-frame step in front of the window solve (src/slam.cpp:578-675): every incoming keyframe is
+    first refined by motion-only BA against the current map -- through the dedicated kernel -- then enters the LBA
+    window.  Motion-only windows are checked against the oracle one by one; the trajectory must beat dead reckoning."""
+    from oracle import oracle
+    traj = np.load(os.path.join(GOLD, "traj_it3f_wolc.npy"))
+    kw = dict(max_keyframes=16, sigma_px=0.2, seed=5, odo_noise=(5e-3, 5e-2), lines_per_kf=24, max_iters=10)
+    seen = []
+
+    def gpu_solve(w, it):
+        return gpu.lba_solve(w, max_iters=it)
+
+    def gpu_motion_only(w, it):
+        p, s = gpu.lba_solve(w, max_iters=it)
+        assert gpu.last_timings()["plan_ms"] == 0.0            # the motion-only fast path has no plan stage
+        seen.append((w, p, s))
+        return p, s
+
+    def no_solve(w, it):
+        return w.parameters.copy(), dict(initial_cost=0.0, final_cost=0.0, iterations=0)
+
+    est, st = replay.run(traj, gpu_solve, motion_only=gpu_motion_only, **kw)
+    est_0, _ = replay.run(traj, no_solve, **kw)
+    assert len(seen) >= 10
+    for w, p, s in seen:
+        po, so = oracle.lba_solve(w, max_iters=10, solver=1)
+        assert abs(s["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]
+        assert np.abs(p[:6] - po[:6]).max() < 1e-7
+        assert s["final_cost"] <= s["initial_cost"]
+    assert replay.trajectory_rmse(est, traj) < 0.25 * replay.trajectory_rmse(est_0, traj)
