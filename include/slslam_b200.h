@@ -130,6 +130,9 @@ int slslam_lba_batch_max_active_clusters(const slslam_lba_batch* b, int32_t* max
  * (init, linearise, pairs, fold, allreduce, gradient, reduced solve, trial, decide, total, then the reduced solve split:
  * prep, factor + panel, trailing update, back-substitution); n <= 14. */
 int slslam_lba_batch_phase_cycles(slslam_lba_batch* b, void* cuda_stream, int32_t window, int64_t* cycles_out, int32_t n);
+/* Diagnostics of the device planner: SM cycles from kernel start to the end of its phases (counts + constants, scan,
+ * grouping by line, partition + tile packing, slot table, slot metadata + gather, pair lists, total) for `window`. */
+int slslam_lba_batch_plan_cycles(const slslam_lba_batch* b, int32_t window, int32_t* cycles8);
 /* Bytes one host-buffer solve of this batch moves: plan + parameters up, parameters + summaries down. */
 int slslam_lba_batch_transfer_bytes(const slslam_lba_batch* b, int64_t* h2d_bytes, int64_t* d2h_bytes);
 void slslam_lba_batch_destroy(slslam_lba_batch* b);

@@ -21,10 +21,12 @@ def run(windows, cs, reps=10):
     _, ss = b.download(sp)
     it = sum(s["iterations"] for s in ss)
     ph = b.phase_cycles(0, sp)
-    info = b.info(); b.close()
+    info = b.info(); pc = b.plan_cycles(0); b.close()
     n0 = ss[0]["iterations"]
     print(f"nwin={len(windows)} CS={info['cluster_size']} act={info['max_active_clusters']} zsm={info['z_in_smem']} smem={info['smem_bytes_per_cta']} ms={ms:.3f} iters={it} "
           f"-> {it/ms*1e3:.0f} it/s, {ms*1e3/ n0:.1f} us/iter(win0)")
+    if pc:
+        print("   plan kernel, cumulative cycles: " + " ".join(f"{k}={v}" for k, v in pc.items()))
     print("   cycles/iter: " + " ".join(f"{k}={v/(n0 if k not in ('init','total') else 1):.0f}" for k, v in ph.items()), flush=True)
 
 if __name__ == "__main__":

@@ -21,7 +21,7 @@ TERMINATION = {0: "NO_CONVERGENCE", 1: "GRADIENT_TOLERANCE", 2: "FUNCTION_TOLERA
 EXPORTS = [
     "slslam_version", "slslam_strerror", "slslam_last_error", "slslam_device_count", "slslam_lba_get_limits",
     "slslam_lba_solve", "slslam_lba_solve_batch", "slslam_lba_last_timings", "slslam_lba_batch_create", "slslam_lba_batch_solve",
-    "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_max_active_clusters", "slslam_lba_batch_transfer_bytes", "slslam_lba_batch_phase_cycles", "slslam_lba_batch_destroy",
+    "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_max_active_clusters", "slslam_lba_batch_transfer_bytes", "slslam_lba_batch_phase_cycles", "slslam_lba_batch_plan_cycles", "slslam_lba_batch_destroy",
     "slslam_lba_plan_check", "slslam_lba_pipeline_create", "slslam_lba_pipeline_submit", "slslam_lba_pipeline_wait", "slslam_lba_pipeline_destroy",
     "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate", "slslam_po_last_solve_ms",
 ]
@@ -98,6 +98,7 @@ def lib():
         L.slslam_lba_batch_max_active_clusters.argtypes = [C.c_void_p, ip]
         L.slslam_lba_batch_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.slslam_lba_batch_phase_cycles.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.c_int32]
+        L.slslam_lba_batch_plan_cycles.argtypes = [C.c_void_p, C.c_int32, ip]
         L.slslam_lba_batch_destroy.argtypes = [C.c_void_p]
         L.slslam_lba_batch_destroy.restype = None
         L.slslam_lba_plan_check.argtypes = [C.c_int32, C.POINTER(LbaDesc), C.POINTER(dp), C.c_int32, ip]
@@ -219,6 +220,15 @@ class LbaBatch:
         buf = (C.c_int64 * 14)()
         _check(lib().slslam_lba_batch_phase_cycles(self._h, C.c_void_p(stream), window, buf, 14))
         return dict(zip(self.PHASES, list(buf)))
+
+    PLAN_PHASES = ("counts", "scan", "group_by_line", "partition_tiles", "slot_table", "slot_meta_gather", "pair_lists", "total")
+
+    def plan_cycles(self, window=0):
+        """Cumulative SM cycles of the device planner's phases (empty dict when the host planner built this batch)."""
+        buf = (C.c_int32 * 8)()
+        if lib().slslam_lba_batch_plan_cycles(self._h, window, buf) != 0:
+            return {}
+        return dict(zip(self.PLAN_PHASES, list(buf)))
 
     def upload(self, params=None, stream=None):
         ps = self._p0 if params is None else [np.ascontiguousarray(p, np.float64) for p in params]

@@ -815,6 +815,11 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
   if (e == cudaSuccess) {
     lba_plan_kernel<<<n, PLAN_NT, plan_smem, stream>>>((const PlanIn*)(dp + o_pin_in));
     e = cudaGetLastError();
+    if (e == cudaSuccess) {
+      const int gx = (int)std::max<long long>(1, std::min<long long>(32, (max_obs * 4 + 2047) / 2048));
+      lba_gather_obs_kernel<<<dim3((unsigned)gx, (unsigned)n), 256, 0, stream>>>((const PlanIn*)(dp + o_pin_in));
+      e = cudaGetLastError();
+    }
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(h_info, dp + o_info, sizeof(PlanInfo) * n, cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
@@ -1112,6 +1117,12 @@ int slslam_lba_batch_info(const slslam_lba_batch* b, int32_t* cluster_size, int3
   if (threads_per_cta) *threads_per_cta = LBA_NT;
   if (smem_bytes_per_cta) *smem_bytes_per_cta = (int32_t)b->smem_bytes;
   if (z_in_smem) *z_in_smem = b->lay.z_in_smem;
+  return SLSLAM_OK;
+}
+
+int slslam_lba_batch_plan_cycles(const slslam_lba_batch* b, int32_t window, int32_t* cycles8) {
+  if (!b || !cycles8 || window < 0 || window >= b->n || !b->device_planned) return SLSLAM_ERR_INVALID;
+  for (int k = 0; k < 8; ++k) cycles8[k] = b->dp_info[(size_t)window].phase_cycles[k];
   return SLSLAM_OK;
 }
 

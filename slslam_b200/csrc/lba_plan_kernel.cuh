@@ -21,6 +21,7 @@ constexpr int PLAN_OK = 0, PLAN_ERR_INDEX = 1, PLAN_ERR_LIMIT = 2, PLAN_DUPLICAT
 
 struct PlanInfo {
   int error, Cf, max_lines_cta, max_slots_cta, max_items_cta, nslots, nitems, has_unobserved;
+  int phase_cycles[8];   // diagnostics: SM cycles of thread 0 up to the end of phases A, C, D, F, G, H, I, J
 };
 
 struct PlanIn {
@@ -45,7 +46,7 @@ struct PlanIn {
   int* fill;                 // [L]
   int* lconst;               // [L]
   int* order;                // [N] observation indices grouped by line, ascending inside a line
-  int* slot_line;            // [slot_cap] device line of the slot or -1
+  int* slot_line;            // [slot_cap] device line of the slot or -1; on exit the caller's observation index or -1
 };
 
 // Block-wide exclusive scan of v (one value per thread); returns the exclusive prefix, *total gets the block total.
@@ -97,8 +98,12 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
   unsigned char* s_pos = plan_dyn + 13 * (size_t)L;                // [L][pstride] position in the line of reduced camera cf
   const int pstride = min(C, (int)MAX_FREE_CAMS);
 
+  __shared__ int s_ph[8];
+  const long long t_start = clock64();
+#define PLAN_PHASE(i) { if (tid == 0) s_ph[i] = (int)(clock64() - t_start); }
   if (tid == 0) {
     s_cam_used = 0u; s_cam_const = 0u; s_err = PLAN_OK; s_unobs = 0; s_max_lines = 1; s_max_slots = 32; s_max_items = 0;
+    for (int k = 0; k < 8; ++k) s_ph[k] = 0;
   }
   for (int l = tid; l < L; l += PLAN_NT) { p.line_cnt[l] = 0; p.lconst[l] = 0; }
   __syncthreads();
@@ -129,9 +134,10 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
   }
   __syncthreads();
   if (s_err & PLAN_ERR_INDEX) {
-    if (tid == 0) { PlanInfo o; o.error = s_err; o.Cf = 0; o.max_lines_cta = 1; o.max_slots_cta = 32; o.max_items_cta = 0; o.nslots = 0; o.nitems = 0; o.has_unobserved = 0; *p.info = o; }
+    if (tid == 0) { PlanInfo o = {}; o.error = s_err; o.Cf = 0; o.max_lines_cta = 1; o.max_slots_cta = 32; o.max_items_cta = 0; o.nslots = 0; o.nitems = 0; o.has_unobserved = 0; *p.info = o; }
     return;
   }
+  PLAN_PHASE(0)
   // ---- B: reduced camera indices ----
   if (tid == 0) {
     int Cf = 0;
@@ -171,10 +177,11 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
   }
   __syncthreads();
   if (s_err) {
-    if (tid == 0) { PlanInfo o; o.error = s_err; o.Cf = s_Cf; o.max_lines_cta = 1; o.max_slots_cta = 32; o.max_items_cta = 0; o.nslots = 0; o.nitems = 0; o.has_unobserved = s_unobs; *p.info = o; }
+    if (tid == 0) { PlanInfo o = {}; o.error = s_err; o.Cf = s_Cf; o.max_lines_cta = 1; o.max_slots_cta = 32; o.max_items_cta = 0; o.nslots = 0; o.nitems = 0; o.has_unobserved = s_unobs; *p.info = o; }
     return;
   }
   const int nd = s_nd, Cf = s_Cf, nkeys = s_nkeys;
+  PLAN_PHASE(1)
   // ---- D: group by line; inside a line ascending observation index (= the host's stable counting sort) ----
   for (int i = tid; i < N; i += PLAN_NT) p.order[atomicAdd(&p.fill[p.line_idx[i]], 1)] = i;
   __syncthreads();
@@ -191,6 +198,8 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
     }
     for (int a = 0; a < k; ++a) p.order[b + a] = v[a];
   }
+  __syncthreads();
+  PLAN_PHASE(2)
   // ---- E: lines over the CTAs of the group, balancing observation counts ----
   if (tid < CS) {
     const int r = tid;
@@ -240,10 +249,11 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
   }
   __syncthreads();
   if (s_err) {
-    if (tid == 0) { PlanInfo o; o.error = s_err; o.Cf = Cf; o.max_lines_cta = s_max_lines; o.max_slots_cta = s_max_slots; o.max_items_cta = 0; o.nslots = 0; o.nitems = 0; o.has_unobserved = s_unobs; *p.info = o; }
+    if (tid == 0) { PlanInfo o = {}; o.error = s_err; o.Cf = Cf; o.max_lines_cta = s_max_lines; o.max_slots_cta = s_max_slots; o.max_items_cta = 0; o.nslots = 0; o.nitems = 0; o.has_unobserved = s_unobs; *p.info = o; }
     return;
   }
   const int total_slots = s_total_slots;
+  PLAN_PHASE(3)
   // ---- G: slot -> device line ----
   for (int s = tid; s < total_slots; s += PLAN_NT) p.slot_line[s] = -1;
   __syncthreads();
@@ -251,9 +261,13 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
     const int k = s_cnt[li], pk = s_line[li];
     const int g0 = s_cta_slot_off[pk >> 22] + (pk & 0xffff);
     for (int a = 0; a < k; ++a) p.slot_line[g0 + a] = li;
+    s_mask[li] = 0u;
   }
   __syncthreads();
-  // ---- H: slot metadata, observations gathered into slot order, per-line camera sets (warp = tile, lane = slot) ----
+  PLAN_PHASE(4)
+  // ---- H: slot metadata and per-line camera sets (warp = tile, lane = slot).  The observations themselves are
+  // gathered into slot order by lba_gather_obs_kernel afterwards, over many CTAs: doing that copy (1.3 MB in, 1.3 MB out
+  // per 10 k observations, in scattered 64-byte rows) on this one SM made this phase half of the kernel. ----
   for (int tile = warp; tile < total_slots / 32; tile += PLAN_NW) {
     const int s = tile * 32 + lane;
     const int li = p.slot_line[s];
@@ -270,45 +284,31 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
     const unsigned same = __match_any_sync(0xffffffffu, cam);
     if (li >= 0) {
       const int round = __popc(same & ((1u << lane) - 1u));
+      const int lc = p.lconst[l];
       int flags = F_VALID;
-      if (p.lconst[l]) flags |= F_LINE_FIXED;
+      if (lc) flags |= F_LINE_FIXED;
       if ((s_cam_const >> cam) & 1u) flags |= F_CAM_FIXED;
       if (a == 0) flags |= F_HEAD;
       m.x = cam | (((pk >> 16) & 0x3f) << 8) | (k << 14) | (flags << 24);
       m.y = (li - s_cta_line_off[r]) | (round << 20);
-    }
-    p.meta[s] = m;
-    double2* dst = reinterpret_cast<double2*>(p.obs + (size_t)s * 8);
-    if (src >= 0) {
-      const double2* so = reinterpret_cast<const double2*>(p.obs_raw + (size_t)src * 8);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) dst[q] = so[q];
-    } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) dst[q] = make_double2(0.0, 0.0);
-    }
-  }
-  // per device line: the set of reduced cameras that see it (none when the line is constant) and where each sits
-  for (int li = tid; li < nd; li += PLAN_NT) {
-    const int l = p.line_gid[li], k = s_cnt[li], b = s_dstart[li];
-    unsigned mask = 0u;
-    if (!p.lconst[l]) {
-      for (int a = 0; a < k; ++a) {
-        const int cf = s_cam_free[p.cam_idx[p.order[b + a]]];
-        if (cf < 0) continue;
-        if ((mask >> cf) & 1u) atomicOr(&s_err, PLAN_DUPLICATE_CAMERA);
-        mask |= 1u << cf;
+      // the line's set of reduced cameras (constant lines: none) and where each camera's observation sits
+      const int cf = lc ? -1 : s_cam_free[cam];
+      if (cf >= 0) {
+        const unsigned old = atomicOr(&s_mask[li], 1u << cf);
+        if ((old >> cf) & 1u) atomicOr(&s_err, PLAN_DUPLICATE_CAMERA);
         s_pos[(size_t)li * pstride + cf] = (unsigned char)a;
       }
     }
-    s_mask[li] = mask;
+    p.meta[s] = m;
+    p.slot_line[s] = src;                 // from here on: slot -> caller's observation index (or -1), for the gather
   }
   __syncthreads();
   if (s_err) {
     // a camera observing the same line twice: the host planner handles that (rare; never produced by the reference)
-    if (tid == 0) { PlanInfo o; o.error = s_err; o.Cf = Cf; o.max_lines_cta = s_max_lines; o.max_slots_cta = s_max_slots; o.max_items_cta = 0; o.nslots = total_slots; o.nitems = 0; o.has_unobserved = s_unobs; *p.info = o; }
+    if (tid == 0) { PlanInfo o = {}; o.error = s_err; o.Cf = Cf; o.max_lines_cta = s_max_lines; o.max_slots_cta = s_max_slots; o.max_items_cta = 0; o.nslots = total_slots; o.nitems = 0; o.has_unobserved = s_unobs; *p.info = o; }
     return;
   }
+  PLAN_PHASE(5)
   // ---- I: pair blocks.  Task (r, key): the lines of CTA r seen by both cameras of the block, in line order ----
   const int kstride = nkeys + 1, ntask = CS * kstride;
   for (int t = tid; t < ntask; t += PLAN_NT) {
@@ -359,17 +359,34 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
     }
   }
   __syncthreads();
+  PLAN_PHASE(6)
   // ---- J: the header fields the solve kernel needs, and the sizes the host needs for the launch ----
   WinHdr* h = p.hdr;
   if (tid == 0) {
     h->Cf = Cf; h->n = 6 * Cf; h->nkeys = nkeys; h->vlen = lba_vlen(Cf); h->vpad = (lba_vlen(Cf) + 31) & ~31;
-    PlanInfo o;
+    PlanInfo o = {};
     o.error = s_err; o.Cf = Cf; o.max_lines_cta = s_max_lines; o.max_slots_cta = s_max_slots; o.max_items_cta = s_max_items;
     o.nslots = total_slots; o.nitems = s_total_items; o.has_unobserved = s_unobs;
+    s_ph[7] = (int)(clock64() - t_start);
+    for (int k = 0; k < 8; ++k) o.phase_cycles[k] = s_ph[k];
     *p.info = o;
   }
+#undef PLAN_PHASE
   for (int r = tid; r <= MAX_G; r += PLAN_NT) { h->cta_slot_off[r] = s_cta_slot_off[r]; h->cta_line_off[r] = s_cta_line_off[r]; }
   for (int c = tid; c < MAX_CAMS; c += PLAN_NT) h->cam_free[c] = (signed char)s_cam_free[c];
+}
+
+// Observations into slot order: 4 threads per 64-byte row, rows of a window spread over gridDim.x CTAs (blockIdx.y =
+// window).  Reads the slot -> observation table and the slot count the plan kernel left behind (stream-ordered after it).
+__global__ void __launch_bounds__(256) lba_gather_obs_kernel(const PlanIn* __restrict__ ins) {
+  const PlanIn& p = ins[blockIdx.y];
+  const int total = p.info->error ? 0 : p.info->nslots * 4;
+  const double2* raw = reinterpret_cast<const double2*>(p.obs_raw);
+  double2* out = reinterpret_cast<double2*>(p.obs);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int src = p.slot_line[idx >> 2];
+    out[idx] = src >= 0 ? raw[(size_t)src * 4 + (idx & 3)] : make_double2(0.0, 0.0);
+  }
 }
 
 }  // namespace slslam

@@ -128,6 +128,7 @@ def run(poses_wc_true, solve, window_size=10, max_iters=10, sigma_px=0.5, seed=0
     est = np.zeros((K, 6))                  # world->camera estimates
     est[0] = truth_cw[0]
     lines = {}                              # line id -> orth parameters in the world frame
+    refined = set()                         # lines written back by at least one LBA window
     stats = []
     W = window_size
     for k in range(K):
@@ -139,7 +140,9 @@ def run(poses_wc_true, solve, window_size=10, max_iters=10, sigma_px=0.5, seed=0
             # motion-only BA as SLAM::motion_only_ba packs it: camera 0 = this keyframe (free), camera 1 = identity
             # (constant), two observations per common line (this frame, previous keyframe), lines expressed in the
             # previous keyframe's frame and constant
-            common = [l for l in obs[k] if l in lines and l in obs[k - 1]]
+            # (only map lines an LBA window has already refined: a line triangulated from one stereo pair has a depth
+            # error of decimetres and, held constant, would drag the pose with it)
+            common = [l for l in obs[k] if l in refined and l in obs[k - 1]]
             if len(common) >= 6:
                 Tp = est[k - 1]
                 ci, li, fi, ob_arr = [], [], [], []
@@ -200,6 +203,7 @@ def run(poses_wc_true, solve, window_size=10, max_iters=10, sigma_px=0.5, seed=0
                 est[c] = pose_compose(out[6 * slot:6 * slot + 6], Tn)
         for l in lids:
             lines[l] = line_transform(out[6 * len(cams) + 4 * lslot[l]:6 * len(cams) + 4 * lslot[l] + 4], Tn_inv)
+            refined.add(l)
     return np.stack([pose_inverse(T) for T in est]), stats
 
 
