@@ -6,7 +6,9 @@ M windows (10 KF / 2 k lines / 10 k observations, BASELINE.json configs[1]; 8 pe
 of configs[3]).  Weak scaling: every rank owns its own windows, no data-path collective.
 
   value     LM iterations / s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
-  e2e       the same through the host-buffer C-ABI call slslam_lba_solve_batch (plan + H2D + solve + D2H in the timed region)
+  e2e       the same work per step through the host-buffer C ABI (validation, staging, H2D, device plan, solve, D2H in
+            the timed region), submitted through slslam_lba_pipeline_* so that step k+1's host work and copy overlap step
+            k's kernel; the blocking slslam_lba_solve_batch call is timed beside it (e2e.synchronous)
   roofline  algorithmic bytes of the solve kernel / its event-timed duration against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline / --impl reference   the CPU oracle (a restatement of the reference's Ceres path; Ceres itself cannot be
             built here) timed on the host cores
