@@ -177,6 +177,15 @@ float slslam_po_last_solve_ms(void);
 int slslam_po_evaluate(const slslam_po_desc* desc, const double* poses, double* residuals, double* jac_pose1,
                        double* jac_pose2, double* cost_out);
 
+/* ---- RANSAC hypothesis scoring: the inner loops of SLAM::ransac_motion (reference src/slam.cpp:398-412) ----
+ * Every motion hypothesis h (poses[12h..]: R row-major 9, t 3; previous keyframe -> current frame) against every common
+ * line k (lines[6k..]: closest point, direction, in the previous keyframe's frame; obs[8k..]: normalised stereo endpoints
+ * in the current frame) through SLAM::reprojection_error (src/slam.cpp:691-726, its float / double mix kept).
+ * scores[h] = number of lines with error < thr, or -1 when the hypothesis is skipped (|t| > 1, :400-401);
+ * inlier [n_hyp][n_lines] (1/0) and errors [n_hyp][n_lines] may be NULL.  thr is parameter.h:56 error_thr (5 / focal). */
+int slslam_ransac_score(int32_t n_hyp, const double* poses, int32_t n_lines, const double* lines, const double* obs,
+                        double baseline, double thr, int32_t* scores, uint8_t* inlier, float* errors);
+
 #ifdef __cplusplus
 }
 #endif

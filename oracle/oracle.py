@@ -51,6 +51,9 @@ def lib():
         L.oracle_po_cost.restype = C.c_double
         L.oracle_po_solve.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, dp, dp, dp, dp, dp]
         L.oracle_po_solve.restype = C.c_int
+        L.oracle_ransac_score.argtypes = [C.c_int, dp, C.c_int, dp, dp, C.c_double, C.c_double, ip,
+                                          C.POINTER(C.c_ubyte), C.POINTER(C.c_float)]
+        L.oracle_ransac_score.restype = None
     return _LIB
 
 
@@ -128,3 +131,15 @@ def po_solve(g, max_iters=10, lm_opts=None, params=None):
     lib().oracle_po_solve(g.num_poses, g.num_edges, max_iters, _i(a), _i(b), _d(c), None if o is None else _d(o),
                           _d(p), _d(s), _d(trace))
     return p, _summary(s, trace, max_iters)
+
+
+def ransac_score(poses, lines, obs, baseline=0.12, thr=5.0 / 406.05):
+    """poses [H][12] (R row-major, t), lines [K][6] (closest point, direction), obs [K][8] -> (scores [H], inlier [H][K], errors [H][K])."""
+    poses = np.ascontiguousarray(poses, np.float64); lines = np.ascontiguousarray(lines, np.float64)
+    obs = np.ascontiguousarray(obs, np.float64)
+    H, K = poses.shape[0], lines.shape[0]
+    scores = np.zeros(H, np.int32); inl = np.zeros((H, K), np.uint8); err = np.zeros((H, K), np.float32)
+    lib().oracle_ransac_score(H, _d(poses), K, _d(lines), _d(obs), baseline, thr,
+                              scores.ctypes.data_as(C.POINTER(C.c_int)), inl.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                              err.ctypes.data_as(C.POINTER(C.c_float)))
+    return scores, inl, err

@@ -707,6 +707,38 @@ void write_summary(const LMSummary& s, double* out) {
 
 }  // namespace
 
+
+// ---- RANSAC hypothesis scoring ----
+// SLAM::reprojection_error (reference src/slam.cpp:691-726) restated with its mixed precision kept: `error` and `sql`
+// are `float` in the reference, everything else double.  line = (closest point, direction) in the previous keyframe's
+// frame; T maps that frame to the current one; ft = normalised stereo endpoints in the current frame.
+static float ransac_reprojection_error(const double* ft, const double* R, const double* t_in, const double* line, double baseline) {
+  float error = 0;
+  double t[3] = {t_in[0], t_in[1], t_in[2]};
+  const double* cp = line;
+  const double* dv = line + 3;
+  for (int i = 0; i < 2; ++i) {
+    double p1[3], p2[3];
+    if (i == 0) {
+      p1[0] = ft[0]; p1[1] = ft[1]; p1[2] = 1; p2[0] = ft[2]; p2[1] = ft[3]; p2[2] = 1;
+    } else {
+      t[0] -= baseline;
+      p1[0] = ft[4]; p1[1] = ft[5]; p1[2] = 1; p2[0] = ft[6]; p2[1] = ft[7]; p2[2] = 1;
+    }
+    double cpc[3], dvc[3];
+    for (int r = 0; r < 3; ++r) {
+      cpc[r] = (R[3 * r] * cp[0] + R[3 * r + 1] * cp[1] + R[3 * r + 2] * cp[2]) + t[r];     // gc_point_to_pose, src/gc.cpp:55-57
+      dvc[r] = R[3 * r] * dv[0] + R[3 * r + 1] * dv[1] + R[3 * r + 2] * dv[2];
+    }
+    double nc[3] = {cpc[1] * dvc[2] - cpc[2] * dvc[1], cpc[2] * dvc[0] - cpc[0] * dvc[2], cpc[0] * dvc[1] - cpc[1] * dvc[0]};
+    const float sql = (float)std::sqrt(nc[0] * nc[0] + nc[1] * nc[1]);
+    for (int r = 0; r < 3; ++r) nc[r] /= sql;
+    error += std::fabs((nc[0] * p1[0] + nc[1] * p1[1]) + nc[2] * p1[2]);
+    error += std::fabs((nc[0] * p2[0] + nc[1] * p2[1]) + nc[2] * p2[2]);
+  }
+  return error / 4.0;
+}
+
 extern "C" {
 
 int oracle_trace_width() { return TRACE_W; }
@@ -794,6 +826,31 @@ int oracle_po_solve(int K, int E, int max_iters, const int* idx1, const int* idx
   levenberg_marquardt(p, o, &s, trace);
   write_summary(s, summary8);
   return 0;
+}
+
+// Scores n_hyp motion hypotheses (R row-major 9 | t 3 per hypothesis) against n_lines lines: the inner loops of
+// SLAM::ransac_motion (reference src/slam.cpp:398-412).  scores[h] = number of inliers, or -1 when the hypothesis is
+// skipped (|t| > 1, :400-401); inlier[h][k] = 1 when error < thr.  errors (optional) [n_hyp][n_lines] floats.
+void oracle_ransac_score(int n_hyp, const double* poses, int n_lines, const double* lines, const double* obs,
+                         double baseline, double thr, int* scores, unsigned char* inlier, float* errors) {
+  for (int h = 0; h < n_hyp; ++h) {
+    const double* R = poses + 12 * (size_t)h;
+    const double* t = R + 9;
+    if (std::sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]) > 1) {
+      scores[h] = -1;
+      for (int k = 0; k < n_lines; ++k) { inlier[(size_t)h * n_lines + k] = 0; if (errors) errors[(size_t)h * n_lines + k] = 0.f; }
+      continue;
+    }
+    int score = 0;
+    for (int k = 0; k < n_lines; ++k) {
+      const float e = ransac_reprojection_error(obs + 8 * (size_t)k, R, t, lines + 6 * (size_t)k, baseline);
+      if (errors) errors[(size_t)h * n_lines + k] = e;
+      const bool in = e < thr;
+      inlier[(size_t)h * n_lines + k] = in ? 1 : 0;
+      score += in ? 1 : 0;
+    }
+    scores[h] = score;
+  }
 }
 
 }  // extern "C"

@@ -22,4 +22,5 @@ timeout 300 python scripts/phase_profile.py scale > gpurun_out/phase_scale_${tag
 timeout 300 python scripts/e2e_profile.py > gpurun_out/e2e_${tag}.txt 2>&1
 timeout 300 python scripts/h2d_test2.py > gpurun_out/h2d_${tag}.txt 2>&1
 timeout 300 python scripts/motion_only_profile.py > gpurun_out/moba_${tag}.txt 2>&1
+timeout 300 python scripts/ransac_profile.py > gpurun_out/ransac_${tag}.txt 2>&1
 ls -la gpurun_out | tail -25

@@ -23,7 +23,7 @@ EXPORTS = [
     "slslam_lba_solve", "slslam_lba_solve_batch", "slslam_lba_last_timings", "slslam_lba_batch_create", "slslam_lba_batch_solve",
     "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_max_active_clusters", "slslam_lba_batch_transfer_bytes", "slslam_lba_batch_phase_cycles", "slslam_lba_batch_plan_cycles", "slslam_lba_batch_destroy",
     "slslam_lba_plan_check", "slslam_lba_pipeline_create", "slslam_lba_pipeline_submit", "slslam_lba_pipeline_wait", "slslam_lba_pipeline_destroy",
-    "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate", "slslam_po_last_solve_ms",
+    "slslam_ransac_score", "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate", "slslam_po_last_solve_ms",
 ]
 
 dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
@@ -108,6 +108,8 @@ def lib():
         L.slslam_lba_pipeline_wait.argtypes = [C.c_void_p, C.c_int64]
         L.slslam_lba_pipeline_destroy.argtypes = [C.c_void_p]
         L.slslam_lba_pipeline_destroy.restype = None
+        L.slslam_ransac_score.argtypes = [C.c_int32, dp, C.c_int32, dp, dp, C.c_double, C.c_double, ip,
+                                          C.POINTER(C.c_uint8), C.POINTER(C.c_float)]
         L.slslam_lba_evaluate.argtypes = [C.POINTER(LbaDesc), dp, dp, dp, dp, dp]
         L.slslam_po_solve.argtypes = [C.POINTER(PoDesc), dp, C.POINTER(Summary)]
         L.slslam_po_solve_trace.argtypes = [C.POINTER(PoDesc), dp, C.POINTER(Summary), dp]
@@ -364,3 +366,17 @@ def po_evaluate(g, params=None):
     cost = C.c_double()
     _check(lib().slslam_po_evaluate(C.byref(k.desc), _d(p), _d(r), _d(J1), _d(J2), C.cast(C.byref(cost), dp)))
     return r, J1, J2, cost.value
+
+
+def ransac_score(poses, lines, obs, baseline=0.12, thr=5.0 / 406.05, want_inliers=True, want_errors=True):
+    """slslam_ransac_score: poses [H][12] (R row-major, t), lines [K][6], obs [K][8] -> (scores, inlier, errors)."""
+    poses = np.ascontiguousarray(poses, np.float64); lines = np.ascontiguousarray(lines, np.float64)
+    obs = np.ascontiguousarray(obs, np.float64)
+    H, K = poses.shape[0], lines.shape[0]
+    scores = np.zeros(H, np.int32)
+    inl = np.zeros((H, K), np.uint8) if want_inliers else None
+    err = np.zeros((H, K), np.float32) if want_errors else None
+    _check(lib().slslam_ransac_score(H, _d(poses), K, _d(lines), _d(obs), baseline, thr, _i(scores),
+                                     inl.ctypes.data_as(C.POINTER(C.c_uint8)) if want_inliers else None,
+                                     err.ctypes.data_as(C.POINTER(C.c_float)) if want_errors else None))
+    return scores, inl, err

@@ -1,0 +1,89 @@
+"""RANSAC hypothesis scoring (reference src/slam.cpp:398-412, 691-726): oracle known answers on
+CPU, bit-exact GPU parity (scores, inlier masks and the float errors themselves)."""
+import numpy as np
+import pytest
+
+from slslam_b200 import synth
+
+BASELINE, THR = 0.12, 5.0 / 406.05
+
+
+def _oracle():
+    from oracle import oracle
+    oracle.lib()
+    return oracle
+
+
+def make_case(seed, n_lines=120, n_hyp=64, sigma_px=0.3):
+    """Lines in the previous keyframe's frame, a true motion T (previous -> current), stereo observations in the current
+    frame, and hypotheses = T perturbed by growing amounts (a few with |t| > 1, which the reference skips)."""
+    rng = np.random.default_rng(seed)
+    w = rng.normal(0, 0.03, 3); t = np.array([rng.normal(0, 0.05), rng.normal(0, 0.05), -0.75 + rng.normal(0, 0.05)])
+    R = synth.rodrigues(w)
+    lines, obs = np.zeros((n_lines, 6)), np.zeros((n_lines, 8))
+    for k in range(n_lines):
+        z = rng.uniform(3, 12)
+        mid = np.array([rng.uniform(-0.6, 0.6) * z, rng.uniform(-0.4, 0.4) * z, z])
+        v = rng.normal(size=3); v /= np.linalg.norm(v)
+        lines[k, :3], lines[k, 3:] = mid - v * (mid @ v), v
+        P, Q = R @ (mid - 0.6 * v) + t, R @ (mid + 0.6 * v) + t
+        ends = [P, Q, P - [BASELINE, 0, 0], Q - [BASELINE, 0, 0]]
+        obs[k] = np.concatenate([[e[0] / e[2], e[1] / e[2]] for e in ends]) + rng.normal(0, sigma_px / 406.05, 8)
+    poses = np.zeros((n_hyp, 12))
+    for h in range(n_hyp):
+        s = 0.0 if h == 0 else 10.0 ** rng.uniform(-4, -0.5)
+        Rh = synth.rodrigues(w + rng.normal(0, s, 3))
+        th = t + rng.normal(0, 3 * s, 3) + (np.array([0, 0, 2.0]) if h % 17 == 5 else 0)
+        poses[h, :9], poses[h, 9:] = Rh.ravel(), th
+    return poses, lines, obs, (R, t)
+
+
+def test_oracle_known_answers():
+    oracle = _oracle()
+    poses, lines, obs, (R, t) = make_case(0, sigma_px=0.0)
+    scores, inl, err = oracle.ransac_score(poses, lines, obs, BASELINE, THR)
+    assert scores[0] == lines.shape[0] and err[0].max() < 1e-6          # the true motion explains noise-free observations
+    assert (scores[np.linalg.norm(poses[:, 9:], axis=1) > 1] == -1).all() and (scores == -1).sum() >= 3
+    ok = scores >= 0
+    assert (scores[ok] == inl[ok].sum(1)).all() and (scores[ok] <= scores[0]).all()
+    # independent numpy restatement of SLAM::reprojection_error for one pair (double precision; the oracle's float steps
+    # move the result by < 1e-6 relative)
+    h, k = 7, 11
+    Rh, th = poses[h, :9].reshape(3, 3), poses[h, 9:].copy()
+    e = 0.0
+    for i in range(2):
+        if i == 1:
+            th[0] -= BASELINE
+        n = np.cross(Rh @ lines[k, :3] + th, Rh @ lines[k, 3:])
+        n = n / np.hypot(n[0], n[1])
+        e += abs(n @ [obs[k, 4 * i], obs[k, 4 * i + 1], 1]) + abs(n @ [obs[k, 4 * i + 2], obs[k, 4 * i + 3], 1])
+    assert abs(err[h, k] - e / 4) <= 2e-6 * max(e / 4, 1e-3)
+    # the threshold is 5 px: with 0.3 px noise the true motion keeps every line, a 0.1 rad error keeps almost none
+    poses, lines, obs, _ = make_case(1, sigma_px=0.3)
+    scores, _, _ = oracle.ransac_score(poses, lines, obs, BASELINE, THR)
+    assert scores[0] == lines.shape[0]
+    bad = poses[:1].copy(); bad[0, :9] = (synth.rodrigues(np.array([0.0, 0.1, 0.0])) @ bad[0, :9].reshape(3, 3)).ravel()
+    assert oracle.ransac_score(bad, lines, obs, BASELINE, THR)[0][0] < 0.2 * lines.shape[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,n_lines,n_hyp", [(0, 120, 64), (1, 300, 500), (2, 1, 3), (3, 257, 1), (4, 1000, 2000)])
+def test_gpu_scoring_is_bit_exact(gpu, seed, n_lines, n_hyp):
+    oracle = _oracle()
+    poses, lines, obs, _ = make_case(seed, n_lines, n_hyp)
+    so, io, eo = oracle.ransac_score(poses, lines, obs, BASELINE, THR)
+    sg, ig, eg = gpu.ransac_score(poses, lines, obs, BASELINE, THR)
+    assert np.array_equal(sg, so)
+    assert np.array_equal(ig, io)
+    assert np.array_equal(eg.view(np.uint32), eo.view(np.uint32))            # the float errors, bit for bit
+    s2, i2, e2 = gpu.ransac_score(poses, lines, obs, BASELINE, THR, want_inliers=False, want_errors=False)
+    assert np.array_equal(s2, so) and i2 is None and e2 is None
+
+
+@pytest.mark.gpu
+def test_gpu_scoring_edge_cases(gpu):
+    poses, lines, obs, _ = make_case(5, 10, 4)
+    s, i, e = gpu.ransac_score(poses[:0], lines, obs)
+    assert s.shape == (0,)
+    s, i, e = gpu.ransac_score(poses, lines[:0], obs[:0])
+    assert (s[np.linalg.norm(poses[:, 9:], axis=1) <= 1] == 0).all()
