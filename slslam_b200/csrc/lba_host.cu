@@ -606,252 +606,7 @@ static int batch_create_host_plan(int32_t n, const slslam_lba_desc* descs, const
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------
-// Device-planned batch: the caller's arrays are copied to the device as they are (through pinned staging, or straight
-// from the caller's memory when that is already page-locked) and lba_plan_kernel builds the plan there.  The host does
-// no per-observation work.  Returns SLSLAM_PLAN_FALLBACK when the host planner has to take over (a camera observing a
-// line twice, a batch whose shared-memory shape needs the group-size search).
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int SLSLAM_PLAN_FALLBACK = -1000;
-
-static int validate_desc_light(const slslam_lba_desc& d) {
-  if (d.num_cameras < 0 || d.num_lines < 0 || d.num_observations < 0 || d.max_iterations < 0) return SLSLAM_ERR_INVALID;
-  if (d.num_observations > 0 && (!d.camera_index || !d.line_index || !d.fixed_index || !d.observations)) return SLSLAM_ERR_INVALID;
-  if (d.num_cameras > MAX_CAMS) return SLSLAM_ERR_UNSUPPORTED;
-  return SLSLAM_OK;
-}
-
-static bool is_page_locked(const void* p) {
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-  return a.type == cudaMemoryTypeHost;
-}
-
-static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,
-                                    int32_t cluster_size, Workspace* ws, cudaStream_t stream, slslam_lba_batch** out) {
-  if (!out) return SLSLAM_ERR_INVALID;
-  *out = nullptr;
-  if (n <= 0 || !descs || !params) return SLSLAM_ERR_INVALID;
-  for (int i = 0; i < n; ++i) {
-    const int rc = validate_desc_light(descs[i]);
-    if (rc != SLSLAM_OK) return rc;
-    if (!params[i]) return SLSLAM_ERR_INVALID;
-    const int np = 6 * descs[i].num_cameras + 4 * descs[i].num_lines;
-    for (int k = 0; k < np; ++k) if (!std::isfinite(params[i][k])) return SLSLAM_ERR_NUMERICAL;
-  }
-  const double t_begin = now_ms();
-  int rc = ensure_device(device);
-  if (rc != SLSLAM_OK) {
-    // no device: argument errors still take precedence over the missing GPU (the index checks otherwise run on the device)
-    for (int i = 0; i < n; ++i) { const int v = validate_desc(descs[i]); if (v != SLSLAM_OK) return v; }
-    return rc;
-  }
-  int dev = 0;
-  cudaGetDevice(&dev);
-  long long max_obs = 0;
-  int Lmax = 0, Cmax = 1;
-  for (int i = 0; i < n; ++i) {
-    max_obs = std::max<long long>(max_obs, descs[i].num_observations);
-    Lmax = std::max(Lmax, descs[i].num_lines); Cmax = std::max(Cmax, descs[i].num_cameras);
-  }
-  const int cap = resident_ctas(dev);
-  int smem_optin = 0;
-  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  const int CS = pick_group_size(dev, n, max_obs, cluster_size, min_group_size_for_lines(Lmax, smem_optin));
-  if (CS > cap) return SLSLAM_PLAN_FALLBACK;
-  // the plan kernel keeps 13 + min(C, 24) bytes per line of a window in shared memory
-  const size_t plan_smem = (13 + (size_t)std::min(Cmax, (int)MAX_FREE_CAMS)) * (size_t)Lmax + 16;
-  if (plan_smem > (size_t)smem_optin - 4096) return SLSLAM_PLAN_FALLBACK;
-  {
-    static std::mutex attr_mutex;
-    static bool attr_set[16] = {false};
-    std::lock_guard<std::mutex> lk(attr_mutex);
-    if (dev < 0 || dev >= 16 || !attr_set[dev]) {
-      CUDA_TRY(cudaFuncSetAttribute(lba_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 4096));
-      if (dev >= 0 && dev < 16) attr_set[dev] = true;
-    }
-  }
-
-  slslam_lba_batch* b = new (std::nothrow) slslam_lba_batch();
-  if (!b) return SLSLAM_ERR_INVALID;
-  b->device = dev; b->n = n; b->borrowed = ws != nullptr; b->ws = ws; b->device_planned = true; b->CS = CS;
-  if (ws) b->plans.swap(ws->plans);
-  b->plans.resize(n);
-  b->dp.resize(n); b->dp_info.resize(n);
-
-  // ---- pool layout: [uploaded: PlanIn | WinHdr | parameters | raw arrays] [device only: plan outputs, scratch, results, group scratch] ----
-  size_t off = 0;
-  auto reserve = [&](size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; };
-  const size_t o_pin_in = reserve(sizeof(PlanIn) * n), o_hdr = reserve(sizeof(WinHdr) * n);
-  b->param_off.resize(n); b->trace_off.resize(n); b->nparams.resize(n);
-  size_t tp = 0, tt = 0;
-  for (int i = 0; i < n; ++i) {
-    b->nparams[i] = 6 * descs[i].num_cameras + 4 * descs[i].num_lines;
-    b->param_off[i] = tp; tp += (size_t)((b->nparams[i] + 1) & ~1);
-    b->trace_off[i] = tt; tt += (size_t)std::max(1, descs[i].max_iterations) * SLSLAM_TRACE_WIDTH;
-  }
-  b->total_params = tp; b->total_trace = tt;
-  const size_t o_par = reserve(tp * 8);
-  std::vector<size_t> o_ci(n), o_li(n), o_fi(n), o_raw(n);
-  std::vector<char> direct(n, 0);   // observations copied straight from page-locked caller memory
-  for (int i = 0; i < n; ++i) {
-    const size_t N = (size_t)descs[i].num_observations;
-    o_ci[i] = reserve(4 * N); o_li[i] = reserve(4 * N); o_fi[i] = reserve(8 * N);
-  }
-  // observations last, so that the ones that are DMA'd directly leave no hole in the staged prefix
-  for (int i = 0; i < n; ++i) {
-    const size_t N = (size_t)descs[i].num_observations;
-    direct[i] = (N * 64 >= 65536 && is_page_locked(descs[i].observations)) ? 1 : 0;
-  }
-  for (int i = 0; i < n; ++i) if (!direct[i]) o_raw[i] = reserve(64 * (size_t)descs[i].num_observations);
-  const size_t upload = off;
-  for (int i = 0; i < n; ++i) if (direct[i]) o_raw[i] = reserve(64 * (size_t)descs[i].num_observations);
-  struct Scratch { size_t cnt, start, fill, lconst, order, slotl; };
-  std::vector<Scratch> sc(n);
-  std::vector<size_t> o_vg(n), o_vr(n), o_sg(n), o_z(n);
-  const int Cf_cap = std::min(Cmax, (int)MAX_FREE_CAMS);
-  const int nkeys_cap = Cf_cap * (Cf_cap + 1) / 2, vpad_cap = (lba_vlen(Cf_cap) + 31) & ~31;
-  // Z staging in global memory only when the Z rows of a CTA may not fit in shared memory
-  bool want_zg = false;
-  for (int i = 0; i < n; ++i) {
-    const size_t N = (size_t)descs[i].num_observations, L = (size_t)descs[i].num_lines;
-    auto& d = b->dp[i];
-    d.slot_cap = (int)(2 * N + 32 * (size_t)MAX_G); d.item_cap = (int)(N * 31 / 2 + 1);
-    d.obs = reserve((size_t)d.slot_cap * 64); d.meta = reserve((size_t)d.slot_cap * 8); d.gid = reserve(4 * L + 4);
-    d.items = reserve((size_t)d.item_cap * 4 + 4); d.koff = reserve((size_t)MAX_G * (nkeys_cap + 1) * 4 + 4);
-    d.hdr = o_hdr + sizeof(WinHdr) * i;
-    Scratch& s = sc[i];
-    s.cnt = reserve(4 * L + 4); s.start = reserve(4 * L + 8); s.fill = reserve(4 * L + 4); s.lconst = reserve(4 * L + 4);
-    s.order = reserve(4 * N + 4);
-    s.slotl = reserve((size_t)d.slot_cap * 4);
-    const size_t slots_est = N / (size_t)CS * 5 / 4 + 96;
-    if (49152 + L / (size_t)CS * 400 + slots_est * ZST * 8 > (size_t)smem_optin) want_zg = true;
-  }
-  const size_t o_info = reserve(sizeof(PlanInfo) * n);
-  const size_t o_pout = reserve(tp * 8), o_summ = reserve(sizeof(slslam_summary) * n), o_trace = reserve(tt * 8),
-               o_phase = reserve(sizeof(long long) * NPHASE * n);
-  for (int i = 0; i < n; ++i) {
-    o_vg[i] = reserve((size_t)CS * vpad_cap * 8); o_vr[i] = reserve((size_t)vpad_cap * 8); o_sg[i] = reserve((size_t)CS * 8 * 8);
-  }
-  const size_t o_bar = reserve((size_t)n * 128);
-  b->bar_bytes = (size_t)n * 128;
-  for (int i = 0; i < n; ++i) o_z[i] = want_zg ? reserve((size_t)b->dp[i].slot_cap * ZST * 8) : 0;
-  const size_t result_bytes = tp * 8 + sizeof(slslam_summary) * n + sizeof(PlanInfo) * n + 512;
-  char* host = nullptr;
-  std::vector<char> host_vec;
-  PlanInfo* h_info = nullptr;
-  if (ws) {
-    rc = ws->ensure(dev, off, upload, result_bytes);
-    if (rc != SLSLAM_OK) { slslam_lba_batch_destroy(b); return rc; }
-    b->d_pool = ws->d_pool; host = ws->h_pin; b->h_params = (double*)ws->h_res;
-    h_info = (PlanInfo*)(ws->h_res + ((tp * 8 + sizeof(slslam_summary) * n + 255) & ~(size_t)255));
-  } else {
-    CUDA_TRY_OR(cudaMalloc((void**)&b->d_pool, off), { delete b; return SLSLAM_ERR_CUDA; });
-    host_vec.resize(upload);
-    host = host_vec.data();
-    CUDA_TRY_OR(cudaMallocHost((void**)&b->h_params, std::max<size_t>(tp, 1) * 8), { slslam_lba_batch_destroy(b); return SLSLAM_ERR_CUDA; });
-    h_info = b->dp_info.data();
-  }
-  char* dp = b->d_pool;
-  b->d_hdrs = (WinHdr*)(dp + o_hdr);
-  b->d_params_in = (double*)(dp + o_par); b->d_params_out = (double*)(dp + o_pout);
-  b->d_trace = (double*)(dp + o_trace); b->d_summ = (slslam_summary*)(dp + o_summ);
-  b->d_phase = (long long*)(dp + o_phase); b->d_bar = (unsigned int*)(dp + o_bar);
-  // ---- staging: headers and the caller's arrays as they are (one thread, one buffer, one copy) ----
-  for (int i = 0; i < n; ++i) {
-    const slslam_lba_desc& d = descs[i];
-    const size_t N = (size_t)d.num_observations;
-    WindowPlan& wp = b->plans[i];
-    wp.C = d.num_cameras; wp.L = d.num_lines; wp.N = d.num_observations; wp.max_iters = d.max_iterations; wp.robust = d.robust ? 1 : 0;
-    wp.huber_a = d.huber_delta > 0 ? d.huber_delta : 1.0 / 406.05;
-    wp.baseline = d.baseline >= 0 ? d.baseline : 0.12;
-    wp.ftol = d.function_tolerance > 0 ? d.function_tolerance : 1e-6;
-    wp.gtol = d.gradient_tolerance > 0 ? d.gradient_tolerance : 1e-10;
-    wp.ptol = d.parameter_tolerance > 0 ? d.parameter_tolerance : 1e-8;
-    wp.radius0 = d.initial_trust_region_radius > 0 ? d.initial_trust_region_radius : 1e4;
-    const auto& q = b->dp[i];
-    WinHdr h; memset(&h, 0, sizeof(h));
-    h.C = wp.C; h.L = wp.L; h.max_iters = wp.max_iters; h.robust = wp.robust;
-    h.huber_a = wp.huber_a; h.baseline = wp.baseline; h.ftol = wp.ftol; h.gtol = wp.gtol; h.ptol = wp.ptol; h.radius0 = wp.radius0;
-    h.obs = (const double*)(dp + q.obs); h.meta = (const int2*)(dp + q.meta); h.line_gid = (const int*)(dp + q.gid);
-    h.items = (const uint32_t*)(dp + q.items); h.key_off = (const int*)(dp + q.koff);
-    h.params_in = b->d_params_in + b->param_off[i]; h.params_out = b->d_params_out + b->param_off[i];
-    h.Zg = want_zg ? (double*)(dp + o_z[i]) : nullptr;
-    h.Vg = (double*)(dp + o_vg[i]); h.Vr = (double*)(dp + o_vr[i]); h.scalg = (double*)(dp + o_sg[i]);
-    h.bar = (unsigned int*)(dp + o_bar + (size_t)i * 128);
-    h.summary = b->d_summ + i;
-    h.trace = ws ? nullptr : b->d_trace + b->trace_off[i];
-    h.phase_cycles = ws ? nullptr : b->d_phase + (size_t)NPHASE * i;
-    memcpy(host + o_hdr + sizeof(WinHdr) * i, &h, sizeof(h));
-    const Scratch& s = sc[i];
-    PlanIn pi; memset(&pi, 0, sizeof(pi));
-    pi.C = wp.C; pi.L = wp.L; pi.N = wp.N; pi.CS = CS; pi.slot_cap = q.slot_cap; pi.item_cap = q.item_cap;
-    pi.cam_idx = (const int*)(dp + o_ci[i]); pi.line_idx = (const int*)(dp + o_li[i]); pi.fixed = (const int*)(dp + o_fi[i]);
-    pi.obs_raw = (const double*)(dp + o_raw[i]);
-    pi.obs = (double*)(dp + q.obs); pi.meta = (int2*)(dp + q.meta); pi.line_gid = (int*)(dp + q.gid);
-    pi.items = (uint32_t*)(dp + q.items); pi.key_off = (int*)(dp + q.koff);
-    pi.hdr = (WinHdr*)(dp + q.hdr); pi.info = (PlanInfo*)(dp + o_info) + i;
-    pi.line_cnt = (int*)(dp + s.cnt); pi.line_start = (int*)(dp + s.start); pi.fill = (int*)(dp + s.fill); pi.lconst = (int*)(dp + s.lconst);
-    pi.order = (int*)(dp + s.order);
-    pi.slot_line = (int*)(dp + s.slotl);
-    memcpy(host + o_pin_in + sizeof(PlanIn) * i, &pi, sizeof(pi));
-    memcpy(host + o_par + b->param_off[i] * 8, params[i], (size_t)b->nparams[i] * 8);
-    memcpy(host + o_ci[i], d.camera_index, 4 * N);
-    memcpy(host + o_li[i], d.line_index, 4 * N);
-    memcpy(host + o_fi[i], d.fixed_index, 8 * N);
-    if (!direct[i]) memcpy(host + o_raw[i], d.observations, 64 * N);
-  }
-  const double t_staged = now_ms();
-  b->upload_bytes = upload;
-  cudaError_t e = cudaSuccess;
-  if (ws) cudaEventRecord(ws->ev[0], stream);
-  e = cudaMemcpyAsync(dp, host, upload, cudaMemcpyHostToDevice, stream);
-  for (int i = 0; i < n && e == cudaSuccess; ++i) {
-    if (!direct[i]) continue;
-    const size_t bytes = 64 * (size_t)descs[i].num_observations;
-    e = cudaMemcpyAsync(dp + o_raw[i], descs[i].observations, bytes, cudaMemcpyHostToDevice, stream);
-    b->upload_bytes += bytes;
-  }
-  if (e == cudaSuccess) {
-    lba_plan_kernel<<<n, PLAN_NT, plan_smem, stream>>>((const PlanIn*)(dp + o_pin_in));
-    e = cudaGetLastError();
-    if (e == cudaSuccess) {
-      const int gx = (int)std::max<long long>(1, std::min<long long>(32, (max_obs * 4 + 2047) / 2048));
-      lba_gather_obs_kernel<<<dim3((unsigned)gx, (unsigned)n), 256, 0, stream>>>((const PlanIn*)(dp + o_pin_in));
-      e = cudaGetLastError();
-    }
-  }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(h_info, dp + o_info, sizeof(PlanInfo) * n, cudaMemcpyDeviceToHost, stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-  if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); cudaGetLastError(); slslam_lba_batch_destroy(b); return SLSLAM_ERR_CUDA; }
-  int Cfmax = 0, mlines = 1, mslots = 32, mitems = 0, flags = 0;
-  for (int i = 0; i < n; ++i) {
-    const PlanInfo& pi = h_info[i];
-    b->dp_info[i] = pi;
-    flags |= pi.error;
-    Cfmax = std::max(Cfmax, pi.Cf); mlines = std::max(mlines, pi.max_lines_cta); mslots = std::max(mslots, pi.max_slots_cta);
-    mitems = std::max(mitems, pi.max_items_cta);
-    b->plans[i].Cf = pi.Cf; b->plans[i].nkeys = pi.Cf * (pi.Cf + 1) / 2; b->plans[i].has_unobserved_blocks = pi.has_unobserved != 0;
-    b->plans[i].max_lines_cta = pi.max_lines_cta; b->plans[i].max_slots_cta = pi.max_slots_cta; b->plans[i].max_items_cta = pi.max_items_cta;
-  }
-  if (flags & PLAN_ERR_INDEX) { slslam_lba_batch_destroy(b); return SLSLAM_ERR_INVALID; }
-  if (flags & (PLAN_DUPLICATE_CAMERA | PLAN_ERR_CAPACITY)) { slslam_lba_batch_destroy(b); return SLSLAM_PLAN_FALLBACK; }
-  if (flags & PLAN_ERR_LIMIT) {
-    // too many free cameras / observations per line are final; "too many slots per CTA" may go away with a larger group
-    slslam_lba_batch_destroy(b);
-    return SLSLAM_PLAN_FALLBACK;
-  }
-  b->lay = lba_layout(Cmax, Cfmax, mlines, mslots, CS, (size_t)smem_optin, mitems);
-  b->smem_bytes = (size_t)b->lay.total * 8;
-  if (b->smem_bytes > (size_t)smem_optin || (!b->lay.z_in_smem && !want_zg)) { slslam_lba_batch_destroy(b); return SLSLAM_PLAN_FALLBACK; }
-  rc = set_solve_kernel_smem_limit(dev, smem_optin);
-  if (rc != SLSLAM_OK) { slslam_lba_batch_destroy(b); return rc; }
-  b->max_active = balanced_wave(n, cap / CS);
-  // "plan" here = H2D + device plan kernel + read-back of the sizes (the host waits for it); "stage" = the pinned staging
-  if (ws) { g_timing[0] = now_ms() - t_staged; g_timing[1] = t_staged - t_begin; }
-  *out = b;
-  return SLSLAM_OK;
-}
+#include "lba_device_plan.inl"
 
 static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,
                              int32_t cluster_size, Workspace* ws, cudaStream_t stream, slslam_lba_batch** out) {
@@ -864,122 +619,7 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
 
 }  // namespace slslam
 
-namespace slslam {
-
-// Motion-only BA (reference src/slam.cpp:578-675): exactly one used, non-constant camera and every observed line
-// constant (constants are sticky per block, reference src/lba_problem.cpp:88-91).  Such a window needs no plan at all:
-// the caller's arrays go to the device as they are and lba_motion_only_kernel (moba_kernel.cuh) does the rest.
-static bool moba_candidate(const slslam_lba_desc& d, int* free_cam, int* nfree) {
-  const int C = d.num_cameras, L = d.num_lines, N = d.num_observations;
-  if (N <= 0 || C <= 0 || L <= 0 || C > MAX_CAMS) return false;
-  char cam_used[MAX_CAMS] = {0}, cam_const[MAX_CAMS] = {0};
-  int cnt[MAX_CAMS] = {0};
-  std::vector<char> line_const((size_t)L, 0);
-  for (int i = 0; i < N; ++i) {
-    const int c = d.camera_index[i];
-    cam_used[c] = 1; ++cnt[c];
-    if (d.fixed_index[2 * i]) cam_const[c] = 1;
-    if (d.fixed_index[2 * i + 1]) line_const[d.line_index[i]] = 1;
-  }
-  for (int i = 0; i < N; ++i) if (!line_const[d.line_index[i]]) return false;
-  int fc = -1;
-  for (int c = 0; c < C; ++c) {
-    if (cam_used[c] && !cam_const[c]) { if (fc >= 0) return false; fc = c; }
-  }
-  if (fc < 0 || cnt[fc] > MOBA_MAX_FREE_OBS) return false;
-  *free_cam = fc; *nfree = cnt[fc];
-  return true;
-}
-
-// n motion-only problems: one staging buffer, one H2D copy, one launch (a CTA per problem), one D2H copy.
-static int moba_solve_batch(int n, const slslam_lba_desc* descs, double* const* params_inout, slslam_summary* summaries_out,
-                            const int* free_cam, const int* nfree) {
-  const double t0 = now_ms();
-  int rc = ensure_device(-1);
-  if (rc != SLSLAM_OK) return rc;
-  int device = 0;
-  cudaGetDevice(&device);
-  size_t off = 0;
-  auto reserve = [&](size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; };
-  const size_t o_hdr = reserve(sizeof(MobaHdr) * n);
-  std::vector<size_t> o_ci(n), o_li(n), o_ob(n), o_p(n), o_po(n), np(n);
-  int max_free = 0;
-  for (int i = 0; i < n; ++i) {
-    const size_t N = (size_t)descs[i].num_observations;
-    np[i] = (size_t)6 * descs[i].num_cameras + (size_t)4 * descs[i].num_lines;
-    o_ci[i] = reserve(4 * N); o_li[i] = reserve(4 * N); o_ob[i] = reserve(64 * N); o_p[i] = reserve(8 * np[i]);
-    max_free = std::max(max_free, nfree[i]);
-  }
-  const size_t upload = off;
-  size_t res = 0;
-  for (int i = 0; i < n; ++i) { o_po[i] = res; res += (np[i] + 1) & ~(size_t)1; }
-  const size_t o_pout = reserve(res * 8), o_summ = reserve(sizeof(slslam_summary) * n);
-  const size_t result_bytes = res * 8 + sizeof(slslam_summary) * n + 256;
-  rc = g_ws.ensure(device, off, upload, result_bytes);
-  if (rc != SLSLAM_OK) return rc;
-  char* host = g_ws.h_pin;
-  char* dev = g_ws.d_pool;
-  for (int i = 0; i < n; ++i) {
-    const slslam_lba_desc& d = descs[i];
-    const size_t N = (size_t)d.num_observations;
-    MobaHdr h; memset(&h, 0, sizeof(h));
-    h.C = d.num_cameras; h.L = d.num_lines; h.N = d.num_observations; h.free_cam = free_cam[i];
-    h.max_iters = d.max_iterations; h.robust = d.robust ? 1 : 0;
-    h.huber_a = d.huber_delta > 0 ? d.huber_delta : 1.0 / 406.05;
-    h.baseline = d.baseline >= 0 ? d.baseline : 0.12;
-    h.ftol = d.function_tolerance > 0 ? d.function_tolerance : 1e-6;
-    h.gtol = d.gradient_tolerance > 0 ? d.gradient_tolerance : 1e-10;
-    h.ptol = d.parameter_tolerance > 0 ? d.parameter_tolerance : 1e-8;
-    h.radius0 = d.initial_trust_region_radius > 0 ? d.initial_trust_region_radius : 1e4;
-    h.cam_idx = (const int*)(dev + o_ci[i]); h.line_idx = (const int*)(dev + o_li[i]);
-    h.obs = (const double*)(dev + o_ob[i]); h.params_in = (const double*)(dev + o_p[i]);
-    h.params_out = (double*)(dev + o_pout) + o_po[i];
-    h.summary = (slslam_summary*)(dev + o_summ) + i;
-    h.trace = nullptr;
-    memcpy(host + o_hdr + sizeof(MobaHdr) * i, &h, sizeof(h));
-    memcpy(host + o_ci[i], d.camera_index, 4 * N);
-    memcpy(host + o_li[i], d.line_index, 4 * N);
-    memcpy(host + o_ob[i], d.observations, 64 * N);
-    memcpy(host + o_p[i], params_inout[i], 8 * np[i]);
-  }
-  const double t1 = now_ms();
-  const size_t smem = ((size_t)MOBA_FIXED_DOUBLES + (size_t)MOBA_OBS_STRIDE * std::max(max_free, 1)) * 8;
-  {
-    static std::mutex attr_mutex;
-    static bool attr_set[16] = {false};
-    std::lock_guard<std::mutex> lk(attr_mutex);
-    if (device < 0 || device >= 16 || !attr_set[device]) {
-      int smem_optin = 0;
-      cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-      CUDA_TRY(cudaFuncSetAttribute(lba_motion_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-      if (device >= 0 && device < 16) attr_set[device] = true;
-    }
-  }
-  CUDA_TRY(cudaEventRecord(g_ws.ev[0], nullptr));
-  CUDA_TRY(cudaMemcpyAsync(dev, host, upload, cudaMemcpyHostToDevice, nullptr));
-  CUDA_TRY(cudaEventRecord(g_ws.ev[1], nullptr));
-  lba_motion_only_kernel<<<n, MOBA_NT, smem>>>((const MobaHdr*)(dev + o_hdr));
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaEventRecord(g_ws.ev[2], nullptr));
-  double* h_par = (double*)g_ws.h_res;
-  slslam_summary* h_summ = (slslam_summary*)(h_par + res);
-  CUDA_TRY(cudaMemcpyAsync(h_par, dev + o_pout, res * 8, cudaMemcpyDeviceToHost, nullptr));
-  CUDA_TRY(cudaMemcpyAsync(h_summ, dev + o_summ, sizeof(slslam_summary) * n, cudaMemcpyDeviceToHost, nullptr));
-  CUDA_TRY(cudaEventRecord(g_ws.ev[3], nullptr));
-  CUDA_TRY(cudaStreamSynchronize(nullptr));
-  const double t2 = now_ms();
-  for (int i = 0; i < n; ++i) {
-    memcpy(params_inout[i], h_par + o_po[i], np[i] * 8);
-    if (summaries_out) summaries_out[i] = h_summ[i];
-  }
-  const double t3 = now_ms();
-  float ms = 0.f;
-  for (int k = 0; k < 3; ++k) { cudaEventElapsedTime(&ms, g_ws.ev[k], g_ws.ev[k + 1]); g_timing[5 + k] = ms; }
-  g_timing[0] = 0.0; g_timing[1] = t1 - t0; g_timing[2] = t2 - t1; g_timing[3] = t3 - t2; g_timing[4] = t3 - t0;
-  return SLSLAM_OK;
-}
-
-}  // namespace slslam
+#include "moba_host.inl"
 
 extern "C" {
 
@@ -1204,191 +844,7 @@ int slslam_lba_solve_batch(int32_t n, const slslam_lba_desc* descs, double* cons
   return rc;
 }
 
-// ---- pipelined host-buffer entry points: submit() hands a batch to one of `depth` slots (own device pool, pinned
-// staging, stream and -- with SLSLAM_PIPELINE_ASYNC_HOST -- own host thread, which plans, stages and enqueues it) and
-// returns; wait() blocks on that batch and writes the results back.  The host work and the H2D copy of batch k+1 run
-// while the device solves batch k; with the host threads two batches are planned / staged side by side. ----
-struct slslam_lba_pipeline {
-  int device = 0, depth = 2, flags = 0;
-  struct Slot {
-    slslam::Workspace ws;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t done = nullptr;
-    slslam_lba_batch* b = nullptr;
-    std::vector<slslam_lba_desc> descs;
-    std::vector<double*> params;
-    slslam_summary* summ = nullptr;
-    int64_t ticket = -1;
-    // host thread of the slot (SLSLAM_PIPELINE_ASYNC_HOST): state 0 idle, 1 posted, 2 enqueued (rc / err valid)
-    std::thread th;
-    std::mutex m;
-    std::condition_variable cv;
-    int state = 0, rc = SLSLAM_OK;
-    bool quit = false;
-    std::string err;
-  };
-  std::vector<std::unique_ptr<Slot>> slots;
-  int64_t next_ticket = 0;
-};
-
-// plan + stage + H2D + launch + D2H enqueue of the slot's posted batch, on the slot's stream
-static int pipeline_enqueue(slslam_lba_pipeline* p, slslam_lba_pipeline::Slot& s) {
-  cudaSetDevice(p->device);
-  const int n = (int)s.descs.size();
-  slslam_lba_batch* b = nullptr;
-  int rc = batch_create_impl(n, s.descs.data(), (const double* const*)s.params.data(), -1, 0, &s.ws, s.stream, &b);
-  if (rc != SLSLAM_OK) return rc;
-  rc = slslam_lba_batch_solve(b, s.stream);
-  if (rc == SLSLAM_OK) {
-    slslam_summary* h_summ = (slslam_summary*)(b->h_params + b->total_params);
-    cudaError_t e = cudaMemcpyAsync(b->h_params, b->d_params_out, b->total_params * 8, cudaMemcpyDeviceToHost, s.stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_summ, b->d_summ, sizeof(slslam_summary) * n, cudaMemcpyDeviceToHost, s.stream);
-    if (e == cudaSuccess) e = cudaEventRecord(s.done, s.stream);
-    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); cudaGetLastError(); rc = SLSLAM_ERR_CUDA; }
-  }
-  if (rc != SLSLAM_OK) {
-    cudaStreamSynchronize(s.stream);
-    slslam_lba_batch_destroy(b);
-    return rc;
-  }
-  s.b = b;
-  return SLSLAM_OK;
-}
-
-static void pipeline_worker(slslam_lba_pipeline* p, slslam_lba_pipeline::Slot* s) {
-  for (;;) {
-    {
-      std::unique_lock<std::mutex> lk(s->m);
-      s->cv.wait(lk, [&] { return s->state == 1 || s->quit; });
-      if (s->quit) return;
-    }
-    const int rc = pipeline_enqueue(p, *s);
-    {
-      std::lock_guard<std::mutex> lk(s->m);
-      s->rc = rc;
-      s->err = rc == SLSLAM_OK ? "" : slslam_last_error();
-      s->state = 2;
-    }
-    s->cv.notify_all();
-  }
-}
-
-// Blocks until the slot's batch (if any) has left the device, writes its results to the caller's arrays, frees the slot.
-static int pipeline_finish(slslam_lba_pipeline* p, slslam_lba_pipeline::Slot& s) {
-  if (s.ticket < 0) return SLSLAM_OK;
-  int rc = SLSLAM_OK;
-  if (p->flags & SLSLAM_PIPELINE_ASYNC_HOST) {
-    std::unique_lock<std::mutex> lk(s.m);
-    s.cv.wait(lk, [&] { return s.state == 2; });
-    rc = s.rc;
-    if (rc != SLSLAM_OK) set_last_error(s.err.c_str());
-    s.state = 0;
-  }
-  slslam_lba_batch* b = s.b;
-  if (rc == SLSLAM_OK && b) {
-    cudaError_t e = cudaEventSynchronize(s.done);
-    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); cudaGetLastError(); rc = SLSLAM_ERR_CUDA; }
-  }
-  if (rc == SLSLAM_OK && b) {
-    const slslam_summary* h_summ = (const slslam_summary*)(b->h_params + b->total_params);
-    for (int i = 0; i < b->n; ++i) {
-      memcpy(s.params[i], b->h_params + b->param_off[i], (size_t)b->nparams[i] * 8);
-      if (s.summ) s.summ[i] = h_summ[i];
-    }
-  }
-  if (b) slslam_lba_batch_destroy(b);
-  s.b = nullptr; s.ticket = -1;
-  return rc;
-}
-
-int slslam_lba_pipeline_create(int32_t device, int32_t depth, int32_t flags, slslam_lba_pipeline** out) {
-  if (!out) return SLSLAM_ERR_INVALID;
-  *out = nullptr;
-  if (depth < 1 || depth > 8) return SLSLAM_ERR_INVALID;
-  int rc = ensure_device(device);
-  if (rc != SLSLAM_OK) return rc;
-  slslam_lba_pipeline* p = new (std::nothrow) slslam_lba_pipeline();
-  if (!p) return SLSLAM_ERR_INVALID;
-  cudaGetDevice(&p->device);
-  p->depth = depth; p->flags = flags;
-  for (int k = 0; k < depth; ++k) p->slots.emplace_back(new slslam_lba_pipeline::Slot());
-  for (auto& sp : p->slots) {
-    auto& s = *sp;
-    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) {
-      set_last_error(cudaGetErrorString(cudaGetLastError()));
-      slslam_lba_pipeline_destroy(p);
-      return SLSLAM_ERR_CUDA;
-    }
-    if (flags & SLSLAM_PIPELINE_ASYNC_HOST) s.th = std::thread(pipeline_worker, p, &s);
-  }
-  *out = p;
-  return SLSLAM_OK;
-}
-
-int slslam_lba_pipeline_submit(slslam_lba_pipeline* p, int32_t n, const slslam_lba_desc* descs, double* const* params_inout,
-                               slslam_summary* summaries_out, int64_t* ticket_out) {
-  if (!p || n <= 0 || !descs || !params_inout) return SLSLAM_ERR_INVALID;
-  // argument errors are reported here, before anything is queued (the same checks run again inside the enqueue)
-  for (int i = 0; i < n; ++i) {
-    const int rc = validate_desc(descs[i]);
-    if (rc != SLSLAM_OK) return rc;
-    if (!params_inout[i]) return SLSLAM_ERR_INVALID;
-  }
-  cudaSetDevice(p->device);
-  auto& s = *p->slots[(size_t)(p->next_ticket % p->depth)];
-  int rc = pipeline_finish(p, s);        // the slot's previous batch (submitted `depth` calls ago) must have drained
-  if (rc != SLSLAM_OK) return rc;
-  s.descs.assign(descs, descs + n);
-  s.params.assign(params_inout, params_inout + n);
-  s.summ = summaries_out;
-  if (p->flags & SLSLAM_PIPELINE_ASYNC_HOST) {
-    { std::lock_guard<std::mutex> lk(s.m); s.state = 1; }
-    s.cv.notify_all();
-  } else {
-    rc = pipeline_enqueue(p, s);
-    if (rc != SLSLAM_OK) return rc;
-  }
-  s.ticket = p->next_ticket++;
-  if (ticket_out) *ticket_out = s.ticket;
-  return SLSLAM_OK;
-}
-
-int slslam_lba_pipeline_wait(slslam_lba_pipeline* p, int64_t ticket) {
-  if (!p) return SLSLAM_ERR_INVALID;
-  cudaSetDevice(p->device);
-  int rc = SLSLAM_OK;
-  for (auto& sp : p->slots) {
-    if (sp->ticket < 0) continue;
-    if (ticket < 0 || sp->ticket == ticket) {
-      const int r = pipeline_finish(p, *sp);
-      if (r != SLSLAM_OK) rc = r;
-    }
-  }
-  return rc;
-}
-
-void slslam_lba_pipeline_destroy(slslam_lba_pipeline* p) {
-  if (!p) return;
-  cudaSetDevice(p->device);
-  for (auto& sp : p->slots) {
-    auto& s = *sp;
-    if (s.th.joinable()) {
-      {
-        std::unique_lock<std::mutex> lk(s.m);
-        s.cv.wait(lk, [&] { return s.state != 1; });    // let a posted batch finish its enqueue
-        s.quit = true;
-      }
-      s.cv.notify_all();
-      s.th.join();
-    }
-    if (s.b) { cudaStreamSynchronize(s.stream); slslam_lba_batch_destroy(s.b); s.b = nullptr; }   // abandoned: results dropped
-    if (s.stream) cudaStreamDestroy(s.stream);
-    if (s.done) cudaEventDestroy(s.done);
-    s.ws.release();
-  }
-  delete p;
-}
+#include "lba_pipeline.inl"
 
 void slslam_lba_last_timings(double* ms5) {   // 8 values, see the header
   if (ms5) for (int k = 0; k < 8; ++k) ms5[k] = g_timing[k];

@@ -66,3 +66,24 @@ def test_validation_precedes_device(lib):
         capi.lba_solve(w)
     assert e.value.code == -1
     assert lib.slslam_strerror(-2).decode().startswith("problem exceeds")
+
+
+def test_new_entry_points_fail_loudly_without_gpu(lib):
+    """Pipeline, planner check and RANSAC scoring: argument errors first, then SLSLAM_ERR_CUDA -- never a CPU result."""
+    import ctypes as C
+    if lib.slslam_device_count() > 0:
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    assert lib.slslam_lba_pipeline_create(-1, 0, 0, C.byref(h)) == -1            # depth out of range
+    assert lib.slslam_lba_pipeline_create(-1, 2, 0, C.byref(h)) == -3 and not h.value
+    poses, lines, obs = np.zeros((2, 12)), np.zeros((3, 6)), np.zeros((3, 8))
+    scores = np.full(2, 7, np.int32)
+    with pytest.raises(capi.SlslamError) as e:
+        capi.ransac_score(poses, lines, obs)
+    assert e.value.code == -3
+    assert lib.slslam_ransac_score(2, None, 3, capi._d(lines), capi._d(obs), 0.12, 0.01, capi._i(scores), None, None) == -1
+    assert (scores == 7).all()
+    w = synth.make_window(0, 3, 12, 40)
+    with pytest.raises(capi.SlslamError) as e:
+        capi.lba_plan_check([w])
+    assert e.value.code == -3
