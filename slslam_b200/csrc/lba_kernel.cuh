@@ -1175,7 +1175,9 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
         camxt[i] = camx[i] - (cf >= 0 ? yc[6 * cf + i % 6] * cscale[6 * cf + i % 6] : 0.0);
       }
       __syncthreads();
-      if (c.tid < C) cam_precompute(camxt + 6 * c.tid, camRt + CAM_STRIDE * c.tid, false);
+      // with the rotation derivatives already: an accepted step (the usual case) then adopts this block by a copy
+      // instead of evaluating the same sincos again while every other thread waits
+      if (c.tid < C) cam_precompute(camxt + 6 * c.tid, camRt + CAM_STRIDE * c.tid, true);
       __syncthreads();
       double part[4];
       trial_sweep(c, part);
@@ -1227,8 +1229,7 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
       for (int i = c.tid; i < 6 * C; i += LBA_NT) camx[i] = camxt[i];
       for (int i = c.tid; i < 4 * c.nlines; i += LBA_NT) linex[i] = linext[i];
       for (int i = c.tid; i < 8 * c.nlines; i += LBA_NT) sm[lay.ltrig + i] = sm[lay.ltrigt + i];
-      __syncthreads();
-      if (c.tid < C) cam_precompute(camx + 6 * c.tid, camR + CAM_STRIDE * c.tid, true);
+      for (int i = c.tid; i < CAM_STRIDE * C; i += LBA_NT) camR[i] = camRt[i];
       __syncthreads();
       cost = new_cost;
       const double t = 2.0 * rel - 1.0;

@@ -62,6 +62,37 @@ __device__ __forceinline__ void moba_cta_sum(double* v, double* wsc, int tid) {
   for (int k = 0; k < NV; ++k) v[k] = tot[k];
 }
 
+// The 28-value sum of the linearisation: a transposing warp reduction (31 shuffle-adds for 32 values, lane l ends up
+// with the warp total of value l) instead of 28 butterflies of 5, then the same fixed-order combine over the warps.
+__device__ __forceinline__ void moba_cta_sum28(double* a, double* wsc, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  double* tot = wsc + MOBA_NW * 28;
+  double v[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = k < 28 ? a[k] : 0.0;
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int k = 0; k < half; ++k) {
+      const double send = upper ? v[k] : v[k + half];
+      const double keep = upper ? v[k + half] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  if (lane < 28) wsc[warp * 28 + lane] = v[0];
+  __syncthreads();
+  if (tid < 28) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < MOBA_NW; ++w) s += wsc[w * 28 + tid];
+    tot[tid] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 28; ++k) a[k] = tot[k];
+}
+
 __device__ __forceinline__ void moba_load_trig(const double* __restrict__ so, LineTrig& lt) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) { lt.xh[k] = so[8 + k]; lt.yh[k] = so[11 + k]; lt.zh[k] = so[14 + k]; lt.xb[k] = so[17 + k]; }
@@ -183,7 +214,7 @@ __global__ void __launch_bounds__(MOBA_NT, 1) lba_motion_only_kernel(const MobaH
         a[21 + p] += Jc[p] * r[0] + Jc[6 + p] * r[1] + Jc[12 + p] * r[2] + Jc[18 + p] * r[3];
       }
     }
-    moba_cta_sum<28>(a, wsc, tid);
+    moba_cta_sum28(a, wsc, tid);
     cost = a[27];
     // gradient max norm with the unscaled Jacobian; |x|^2 of the free camera
     double x_norm2 = 0.0;
@@ -244,7 +275,7 @@ __global__ void __launch_bounds__(MOBA_NT, 1) lba_motion_only_kernel(const MobaH
       __syncthreads();
       if (tid < 6) camxt[tid] = camx[tid] - (tid == 0 ? y[0] : tid == 1 ? y[1] : tid == 2 ? y[2] : tid == 3 ? y[3] : tid == 4 ? y[4] : y[5]) * cscale[tid];
       __syncthreads();
-      if (tid == 0) cam_precompute(camxt, camRt, false);
+      if (tid == 0) cam_precompute(camxt, camRt, true);     // derivatives too: an accepted step adopts the block by a copy
       __syncthreads();
       double v[1] = {0.0};
       for (int i = tid; i < nfree; i += MOBA_NT) {
@@ -278,8 +309,7 @@ __global__ void __launch_bounds__(MOBA_NT, 1) lba_motion_only_kernel(const MobaH
       if (tr) tr[5] = 1.0;
       __syncthreads();
       if (tid < 6) camx[tid] = camxt[tid];
-      __syncthreads();
-      if (tid == 0) cam_precompute(camx, camR, true);
+      if (tid < CAM_STRIDE) camR[tid] = camRt[tid];
       __syncthreads();
       cost = new_cost;
       const double t = 2.0 * rel - 1.0;
