@@ -208,6 +208,7 @@ __device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, d
   __syncwarp();
   double cost = 0.0, fixed_cost = 0.0, gmax = 0.0, fail = 0.0;
   const bool robust = h.robust != 0;
+  const double inv_radius = 1.0 / radius;            // one division per sweep; the per-line LM diagonals multiply
   for (int tile = c.warp; tile < c.ntiles; tile += LBA_NW) {
     const int ls = tile * 32 + c.lane;               // CTA-local slot
     const int2 mt = c.meta[ls];
@@ -284,7 +285,7 @@ __device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, d
       // LM diagonal of the line block and its Cholesky factor (every lane of the segment computes the same values)
       double D[4], Lm[10], u[4], inv[4];
 #pragma unroll
-      for (int p = 0; p < 4; ++p) D[p] = clampd(hg[L4(p, p)], 1e-6, 1e32) / radius;
+      for (int p = 0; p < 4; ++p) D[p] = clampd(hg[L4(p, p)], 1e-6, 1e32) * inv_radius;
       bool ok = true;
       {
         double a00 = hg[0] + D[0];
@@ -313,7 +314,7 @@ __device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, d
         if (line_free) {
           const double* lsc = lscale + 4 * ll;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) gmax = fmax(gmax, fabs(hg[10 + k] / lsc[k]));
+          for (int k = 0; k < 4; ++k) gmax = fmax(gmax, fabs(hg[10 + k] * pivot_rcp(lsc[k])));
         }
       }
       // Z = (Jc^T Jl) L^-T, row p of Z solves z L^T = W_p

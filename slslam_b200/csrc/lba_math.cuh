@@ -21,6 +21,17 @@ __device__ __forceinline__ double pivot_rsqrt(double d) {
   return y;
 }
 
+// 1 / d from the hardware approximation (MUFU.RCP64H) and two Newton steps; same remarks as pivot_rsqrt.
+__device__ __forceinline__ double pivot_rcp(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
 // Per-camera block staged in shared memory: R (9, row-major), dR/dw_k (3 x 9), t (3), pad.  The lanes of a tile read
 // the same element of different cameras with 8-byte loads; an odd stride (41 doubles = 82 words, 18 c mod 32 banks)
 // keeps up to 16 cameras on distinct bank pairs, where 40 put every other camera on the same pair.
@@ -111,7 +122,7 @@ __device__ __forceinline__ void line_trig_sc(const double* sc, LineTrig& lt) {
   lt.yh[0] = s1 * s2 * c3 - c1 * s3; lt.yh[1] = s1 * s2 * s3 + c1 * c3; lt.yh[2] = s1 * c2;
   lt.zh[0] = c1 * s2 * c3 + s1 * s3; lt.zh[1] = c1 * s2 * s3 - s1 * c3; lt.zh[2] = c1 * c2;
   lt.xb[0] = -s2 * c3; lt.xb[1] = -s2 * s3; lt.xb[2] = -c2;
-  const double ist = 1.0 / st;
+  const double ist = pivot_rcp(st);
   lt.d = ct * ist;
   lt.ist2 = ist * ist;
   lt.s1 = s1;
@@ -147,8 +158,9 @@ __device__ __forceinline__ void obs_eval(const double* __restrict__ cpre, const 
   const double nA1 = lt.d * m[1] + (t2 * q[0] - t0 * q[2]);
   const double nA2 = lt.d * m[2] + (t0 * q[1] - t1 * q[0]);
   const double nB0 = nA0, nB1 = nA1 + bl * q[2], nB2 = nA2 - bl * q[1];
-  const double isA = 1.0 / sqrt(nA0 * nA0 + nA1 * nA1);
-  const double isB = 1.0 / sqrt(nB0 * nB0 + nB1 * nB1);
+  // 1 / sqrt by the hardware seed + two Newton steps (a few ulp; ~8 instructions instead of the ~50 of sqrt + divide)
+  const double isA = pivot_rsqrt(nA0 * nA0 + nA1 * nA1);
+  const double isB = pivot_rsqrt(nB0 * nB0 + nB1 * nB1);
   const double hA0 = nA0 * isA, hA1 = nA1 * isA, hA2 = nA2 * isA;
   const double hB0 = nB0 * isB, hB1 = nB1 * isB, hB2 = nB2 * isB;
   r[0] = -(ob[0] * hA0 + ob[1] * hA1 + hA2);
@@ -216,17 +228,6 @@ __device__ __forceinline__ void obs_eval(const double* __restrict__ cpre, const 
 #undef SLSLAM_COL
 }
 
-// 1 / d from the hardware approximation (MUFU.RCP64H) and two Newton steps; same remarks as pivot_rsqrt.
-__device__ __forceinline__ double pivot_rcp(double d) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-  double e = fma(-d, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-d, y, 1.0);
-  y = fma(y, e, y);
-  return y;
-}
-
 // Inverse of a symmetric positive definite 3x3 [a b c; b d e; c e f] by cofactors: one reciprocal instead of three
 // dependent square roots.  o = {i00, i01, i02, i11, i12, i22}.  Returns false if a leading minor is not positive.
 __device__ __forceinline__ bool spd3_inverse(double a, double b, double c, double d, double e, double f, double* o) {
@@ -241,8 +242,9 @@ __device__ __forceinline__ bool spd3_inverse(double a, double b, double c, doubl
 // HuberLoss(a) on s = |r|^2 with the rho'' <= 0 corrector: returns rho, sets sqrt(rho').
 __device__ __forceinline__ double huber_rho(double s, double a, bool robust, double& sqrt_rho1) {
   if (!robust || s <= a * a) { sqrt_rho1 = 1.0; return s; }
-  const double rs = sqrt(s);
-  sqrt_rho1 = sqrt(a / rs);
+  const double ri = pivot_rsqrt(s), rs = s * ri;        // sqrt(s) = s / sqrt(s)
+  const double q = a * ri;                              // rho' = a / sqrt(s)
+  sqrt_rho1 = q * pivot_rsqrt(q);
   return 2.0 * a * rs - a * a;
 }
 
