@@ -435,7 +435,7 @@ __device__ void schur_pairs(const Ctx& c) {
         for (int p = 0; p < 6; ++p)
 #pragma unroll
           for (int q = 0; q < 6; ++q)
-            acc[6 * p + q] += Zi[4 * p] * Zj[4 * q] + Zi[4 * p + 1] * Zj[4 * q + 1] + Zi[4 * p + 2] * Zj[4 * q + 2] + Zi[4 * p + 3] * Zj[4 * q + 3];
+            acc[6 * p + q] = fma(Zi[4 * p + 3], Zj[4 * q + 3], fma(Zi[4 * p + 2], Zj[4 * q + 2], fma(Zi[4 * p + 1], Zj[4 * q + 1], fma(Zi[4 * p], Zj[4 * q], acc[6 * p + q]))));   // 4 chained FMAs (36 independent chains) instead of mul + 3 fma + add
       }
       double tail[4];
 #pragma unroll
