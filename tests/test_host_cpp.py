@@ -117,6 +117,22 @@ def test_lba_through_cpp_boundary(demo, gpu, tmp_path):
 
 
 @pytest.mark.gpu
+def test_motion_only_ba_through_cpp_boundary(demo, gpu, tmp_path):
+    """SLAM::motion_only_ba's problem (reference src/slam.cpp:578-675) through the same LBAProblem call sequence: the
+    library routes it to the motion-only kernel; only camera 0 may change."""
+    from oracle import oracle
+    w = synth.motion_only_window(21, num_lines=80)
+    inp, out = str(tmp_path / "m.bin"), str(tmp_path / "o.bin")
+    _write_lba(inp, w, 10)
+    head, params, _ = _run(demo, "lba", inp, out)
+    po, so = oracle.lba_solve(w, max_iters=10, solver=1)
+    assert head["error_code"] == 0
+    assert abs(head["final_cost"] - so["final_cost"]) < 1e-6 * so["final_cost"]
+    assert np.abs(params[:6] - po[:6]).max() < 1e-8
+    assert np.array_equal(params[6:], w.parameters[6:])
+
+
+@pytest.mark.gpu
 def test_po_through_cpp_boundary(demo, gpu, tmp_path):
     from oracle import oracle
     g = synth.make_pose_graph(1, num_poses=40, neighbours=2, num_loops=3)
