@@ -58,3 +58,31 @@ def test_replay_from_exported_dataset_matches_in_memory(tmp_path):
         assert np.array_equal(a.camera_index, b.camera_index) and np.array_equal(a.line_index, b.line_index)
         assert np.abs(a.observations - b.observations).max() < 1e-14
         assert np.abs(a.parameters - b.parameters).max() < 1e-9
+
+
+def test_replay_motion_only_windows_have_the_reference_shape():
+    """The per-keyframe motion-only step builds what SLAM::motion_only_ba packs (reference src/slam.cpp:578-640): two
+    cameras (camera 1 = identity, constant), every line constant, two observations per line.  CPU oracle as the solver."""
+    from oracle import oracle
+    traj = np.load(os.path.join(GOLD, "traj_it3f_wolc.npy"))
+    seen = []
+
+    def cpu(w, it):
+        return oracle.lba_solve(w, max_iters=it, solver=1)
+
+    def cpu_motion_only(w, it):
+        seen.append(w)
+        return oracle.lba_solve(w, max_iters=it, solver=1)
+
+    est, stats = replay.run(traj, cpu, motion_only=cpu_motion_only, max_keyframes=6, sigma_px=0.2, seed=5,
+                            odo_noise=(5e-3, 5e-2), lines_per_kf=16, max_iters=6)
+    assert len(seen) >= 3 and len(stats) == 5
+    for w in seen:
+        assert w.num_cameras == 2 and w.num_observations == 2 * w.num_lines >= 12
+        assert np.array_equal(w.parameters[6:12], np.zeros(6))                     # camera 1: identity
+        fx = w.fixed_index.reshape(-1, 2)
+        assert (fx[:, 1] == 1).all()                                               # every line constant
+        assert (fx[w.camera_index == 1, 0] == 1).all() and (fx[w.camera_index == 0, 0] == 0).all()
+        p, s = oracle.lba_solve(w, max_iters=6, solver=1)
+        assert s["final_cost"] < s["initial_cost"] and s["fixed_cost"] > 0
+        assert np.array_equal(p[6:], w.parameters[6:])                             # only camera 0 moves
