@@ -1,6 +1,8 @@
-// Host side of the LBA path behind the C ABI (include/slslam_b200.h): validation, the per-solve "symbolic" plan
-// (observations grouped by line and packed into 32-lane tiles, lines partitioned over the CTAs of a cluster,
-// camera-pair list for the Schur blocks), upload, cluster launch, download.
+// Host side of the LBA path behind the C ABI (include/slslam_b200.h): argument checks, staging of the caller's arrays,
+// launches (device planner -> solve kernel, or the motion-only kernel), download; plus the HOST planner, which builds the
+// same per-solve "symbolic" plan as lba_plan_kernel.cuh (observations grouped by line and packed into 32-lane tiles,
+// lines partitioned over the CTAs of a window's group, camera-pair list for the Schur blocks) and serves as fallback
+// and as parity reference of the device planner.  Parts: lba_device_plan.inl, moba_host.inl, lba_pipeline.inl.
 // Replaces what LBAProblem::build + ceres::Solve do on the host (reference src/lba_problem.cpp:54-93).
 #include <algorithm>
 #include <chrono>

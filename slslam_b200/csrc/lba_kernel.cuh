@@ -8,7 +8,7 @@
 //       Huber corrector, Jacobi scaling; per-line H_ll / g_l by segmented warp shuffles.
 //   K2  Schur assembly: per-line 4x4 Cholesky in registers, Z_i = (Jc_i^T Jl_i) L^-T staged in shared memory
 //       (or L2 when it does not fit), per-camera H_cc / g_c in warp-private accumulators, camera-pair blocks
-//       S_(ci,cj) -= sum_l Z_i Z_j^T from a host-built pair list (warp per block, lanes over lines, shuffle
+//       S_(ci,cj) -= sum_l Z_i Z_j^T from the planner's pair list (warp per block, lanes over lines, shuffle
 //       reduce: deterministic, no atomics), group reduce-scatter + all-gather through L2 scratch.
 //   K3  blocked Cholesky + substitution of the reduced camera system (<= 6*MAX_FREE_CAMS), line back-substitution.
 //   K4  trial-cost sweep, step acceptance, trust-region radius, termination tests: identical on every CTA.
