@@ -1021,14 +1021,27 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
   c.slot0 = h.cta_slot_off[c.rank]; c.nslots = h.cta_slot_off[c.rank + 1] - c.slot0; c.ntiles = c.nslots / 32;
   c.line0 = h.cta_line_off[c.rank]; c.nlines = h.cta_line_off[c.rank + 1] - c.line0;
   c.Zbuf = lay.z_in_smem ? (sm + lay.Z) : (h.Zg + (size_t)c.slot0 * ZST);
+  // Staging of the CTA's observations (64 B per slot) and slot metadata (8 B per slot), once per solve: two 1-D TMA bulk
+  // copies (cp.async.bulk global -> shared) issued by one thread and tracked by an mbarrier; they run while the CTA loads
+  // and preprocesses its parameters below, and everybody waits on the mbarrier just before the first sweep.
+  const uint32_t stage_bar = (uint32_t)__cvta_generic_to_shared(sm + lay.misc + 42);
+  const bool staged = lay.obs_in_smem && c.nslots > 0;
   if (lay.obs_in_smem) {
-    // stage the CTA's observations and slot metadata once per solve (coalesced 16-byte loads)
-    double2* so = reinterpret_cast<double2*>(sm + lay.obs);
-    const double2* go = reinterpret_cast<const double2*>(h.obs + (size_t)c.slot0 * 8);
-    for (int i = c.tid; i < 4 * c.nslots; i += LBA_NT) so[i] = __ldg(go + i);
-    int2* smeta = reinterpret_cast<int2*>(sm + lay.meta);
-    for (int i = c.tid; i < c.nslots; i += LBA_NT) smeta[i] = __ldg(h.meta + c.slot0 + i);
-    c.obs = sm + lay.obs; c.meta = smeta;
+    if (staged) {
+      if (c.tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(stage_bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t nb_obs = (uint32_t)c.nslots * 64u, nb_meta = (uint32_t)c.nslots * 8u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(stage_bar), "r"(nb_obs + nb_meta) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(sm + lay.obs)), "l"(h.obs + (size_t)c.slot0 * 8), "r"(nb_obs), "r"(stage_bar)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(sm + lay.meta)), "l"(h.meta + c.slot0), "r"(nb_meta), "r"(stage_bar)
+                     : "memory");
+      }
+    }
+    c.obs = sm + lay.obs; c.meta = reinterpret_cast<const int2*>(sm + lay.meta);
   } else {
     c.obs = h.obs + (size_t)c.slot0 * 8; c.meta = h.meta + c.slot0;
   }
@@ -1077,6 +1090,15 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
     sm[lay.ltrig + 2 * i] = sv; sm[lay.ltrig + 2 * i + 1] = cv;
   }
   __syncthreads();
+  if (staged) {
+    // wait for the bulk copies (phase 0 of the mbarrier; thread 0 initialised it before the first __syncthreads above)
+    uint32_t done = 0;
+    for (int spin = 0; !done; ++spin) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(stage_bar), "r"(0) : "memory");
+      if (spin > (1 << 24)) __trap();     // a lost copy must not hang the GPU
+    }
+  }
 
   // ---- Jacobi scaling from the column norms at x0; initial and fixed cost ----
   double p_cost, p_fixed, p_gmax, p_fail;
