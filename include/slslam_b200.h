@@ -136,6 +136,12 @@ int slslam_lba_batch_plan_cycles(const slslam_lba_batch* b, int32_t window, int3
 /* Bytes one host-buffer solve of this batch moves: plan + parameters up, parameters + summaries down. */
 int slslam_lba_batch_transfer_bytes(const slslam_lba_batch* b, int64_t* h2d_bytes, int64_t* d2h_bytes);
 void slslam_lba_batch_destroy(slslam_lba_batch* b);
+/* The launch shape batch creation chooses for `num_windows` windows of at most `max_observations` observations and
+ * `max_lines` lines on a device that keeps `resident_ctas` CTAs of the solve kernel resident (148 on a B200) with
+ * `smem_bytes_per_cta` of shared memory: CTAs per window and windows per launch (larger batches run in equally full
+ * waves).  Pure host arithmetic, usable without a device. */
+int slslam_lba_launch_shape(int32_t num_windows, int32_t max_observations, int32_t max_lines, int32_t resident_ctas,
+                            int32_t smem_bytes_per_cta, int32_t* ctas_per_window, int32_t* windows_per_wave);
 /* Test hook: builds the plan of every window twice -- on the device (the product path) and with the host planner --
  * for the same group size and compares every array bit for bit.  0 = identical, 1 = the device planner deferred to the
  * host planner for this batch, 2 = mismatch (detail[0] window, detail[1] field, detail[2] index), < 0 = error. */

@@ -22,7 +22,7 @@ EXPORTS = [
     "slslam_version", "slslam_strerror", "slslam_last_error", "slslam_device_count", "slslam_lba_get_limits",
     "slslam_lba_solve", "slslam_lba_solve_batch", "slslam_lba_last_timings", "slslam_lba_batch_create", "slslam_lba_batch_solve",
     "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_max_active_clusters", "slslam_lba_batch_transfer_bytes", "slslam_lba_batch_phase_cycles", "slslam_lba_batch_plan_cycles", "slslam_lba_batch_destroy",
-    "slslam_lba_plan_check", "slslam_lba_pipeline_create", "slslam_lba_pipeline_submit", "slslam_lba_pipeline_wait", "slslam_lba_pipeline_destroy",
+    "slslam_lba_plan_check", "slslam_lba_launch_shape", "slslam_lba_pipeline_create", "slslam_lba_pipeline_submit", "slslam_lba_pipeline_wait", "slslam_lba_pipeline_destroy",
     "slslam_ransac_score", "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate", "slslam_po_last_solve_ms",
 ]
 
@@ -101,6 +101,7 @@ def lib():
         L.slslam_lba_batch_plan_cycles.argtypes = [C.c_void_p, C.c_int32, ip]
         L.slslam_lba_batch_destroy.argtypes = [C.c_void_p]
         L.slslam_lba_batch_destroy.restype = None
+        L.slslam_lba_launch_shape.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, ip, ip]
         L.slslam_lba_plan_check.argtypes = [C.c_int32, C.POINTER(LbaDesc), C.POINTER(dp), C.c_int32, ip]
         L.slslam_lba_pipeline_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
         L.slslam_lba_pipeline_submit.argtypes = [C.c_void_p, C.c_int32, C.POINTER(LbaDesc), C.POINTER(dp), C.POINTER(Summary),
@@ -259,6 +260,14 @@ class LbaBatch:
             self.close()
         except Exception:
             pass
+
+
+def lba_launch_shape(num_windows, max_observations, max_lines, resident_ctas=148, smem_bytes_per_cta=232448):
+    """(CTAs per window, windows per wave) the planner chooses; pure host arithmetic (slslam_lba_launch_shape)."""
+    a, b = C.c_int32(), C.c_int32()
+    _check(lib().slslam_lba_launch_shape(num_windows, max_observations, max_lines, resident_ctas, smem_bytes_per_cta,
+                                         C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def lba_plan_check(windows, cluster_size=0, **kw):

@@ -325,9 +325,9 @@ static int resident_ctas(int device) {
 // windows cost two full waves; 16 + 16 with larger groups is faster).  `cs_min`: lower bound from shared memory (the
 // per-line state of a CTA must fit); at least three 32-lane tiles per CTA; beyond ~48 CTAs the exchange grows faster
 // than the sweeps shrink (profiles/r1_cluster_vs_group.txt).
-static int pick_group_size(int device, int nwin, long long max_obs, int requested, int cs_min = 1) {
+static int pick_group_size_for(int cap, int nwin, long long max_obs, int requested, int cs_min) {
   if (requested > 0) return std::min(requested, (int)MAX_G);
-  const int cap = std::max(1, resident_ctas(device));
+  cap = std::max(1, cap);
   cs_min = std::max(1, std::min(cs_min, std::min(cap, (int)MAX_G)));
   const long long tiles = (max_obs + 27) / 28;
   const int cs_max = std::max(cs_min, (int)std::min<long long>(48, std::max<long long>(1, tiles / 3)));
@@ -342,6 +342,10 @@ static int pick_group_size(int device, int nwin, long long max_obs, int requeste
     if (t < best_t - 1e-9) { best_t = t; best = cs; }
   }
   return best;
+}
+
+static int pick_group_size(int device, int nwin, long long max_obs, int requested, int cs_min = 1) {
+  return pick_group_size_for(resident_ctas(device), nwin, max_obs, requested, cs_min);
 }
 
 // Shared-memory lower bound on the group size: 50 doubles of per-line state per line beside ~48 KB of fixed state.
@@ -692,6 +696,18 @@ int slslam_lba_plan_check(int32_t n, const slslam_lba_desc* descs, const double*
   }
   slslam_lba_batch_destroy(b);
   return result;
+}
+
+int slslam_lba_launch_shape(int32_t num_windows, int32_t max_observations, int32_t max_lines, int32_t resident_ctas,
+                            int32_t smem_bytes_per_cta, int32_t* ctas_per_window, int32_t* windows_per_wave) {
+  // The planner's choice of group size and wave size as a pure function (no device): what batch creation uses with
+  // resident_ctas = SMs x resident CTAs per SM and smem_bytes_per_cta = the opt-in maximum.
+  if (num_windows <= 0 || max_observations < 0 || max_lines < 0 || resident_ctas <= 0 || smem_bytes_per_cta <= 0) return SLSLAM_ERR_INVALID;
+  const int cs = pick_group_size_for(resident_ctas, num_windows, max_observations, 0, min_group_size_for_lines(max_lines, smem_bytes_per_cta));
+  if (cs > resident_ctas) return SLSLAM_ERR_UNSUPPORTED;
+  if (ctas_per_window) *ctas_per_window = cs;
+  if (windows_per_wave) *windows_per_wave = balanced_wave(num_windows, resident_ctas / cs);
+  return SLSLAM_OK;
 }
 
 int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,

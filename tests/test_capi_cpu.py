@@ -87,3 +87,20 @@ def test_new_entry_points_fail_loudly_without_gpu(lib):
     with pytest.raises(capi.SlslamError) as e:
         capi.lba_plan_check([w])
     assert e.value.code == -3
+
+
+def test_launch_shape_policy(lib):
+    """Group size and waves are chosen together (no GPU needed): one launch when the batch fits, equally full waves when
+    it does not, never fewer than three tiles per CTA, never more CTAs than the per-line state needs shared memory for."""
+    assert capi.lba_launch_shape(8, 10000, 2000) == (18, 8)          # the bench shape: 8 x 18 = 144 of 148 SMs
+    assert capi.lba_launch_shape(1, 10000, 2000) == (48, 1)          # a single window: capped at 48 CTAs
+    assert capi.lba_launch_shape(16, 10000, 2000) == (9, 16)
+    assert capi.lba_launch_shape(64, 10000, 2000) == (9, 16)         # 4 x 16, not 18 + 18 + 18 + 10
+    assert capi.lba_launch_shape(32, 10000, 2000) == (9, 16)
+    cs, per = capi.lba_launch_shape(1, 1000, 200)                    # a small window keeps >= 3 tiles per CTA
+    assert 1 <= cs <= 12 and per == 1
+    cs, per = capi.lba_launch_shape(300, 1000, 200)                  # more windows than SMs: one CTA each, in waves
+    assert cs == 1 and per * ((300 + per - 1) // per) >= 300 and per <= 148
+    cs, per = capi.lba_launch_shape(148, 10000, 2000)                # 2 k lines do not fit one CTA's shared memory
+    assert cs >= 4 and cs * per <= 148
+    assert lib.slslam_lba_launch_shape(0, 1, 1, 148, 232448, None, None) == -1
