@@ -49,6 +49,16 @@ def _worker(rank, world, port, out_dir):
     local, idx = sh.scatter_windows(windows)
     np.save(os.path.join(out_dir, f"idx{rank}.npy"), np.array(idx))
     ps, ss = sh.solve_sharded(windows, solve, max_iters=6)
+    # the packed form the bench uses: per-rank buffers, known result sizes (no size all-gather)
+    bufs = sh.pack_for_ranks(windows, world) if rank == 0 else None
+    mine = sh.scatter_packed(bufs)
+    mine_w = [windows[w] for w in sh.local_indices(5, 0, world)] if rank == 0 else sh.unpack_many(mine)
+    p2, s2 = solve(mine_w, 6)
+    sizes = sh.result_sizes(windows, world) if rank == 0 else [0] * world
+    gp, gs = sh.gather_results(p2, s2, sh.local_indices(5, rank, world), 5, sizes=sizes)
+    if rank == 0:
+        assert all(np.array_equal(a, b) for a, b in zip(gp, ps)) and [x["final_cost"] for x in gs] == [x["final_cost"] for x in ss]
+        assert sizes == [sum(8 + 1 + 6 * windows[w].num_cameras + 4 * windows[w].num_lines for w in sh.local_indices(5, r, world)) for r in range(world)]
     if rank == 0:
         np.save(os.path.join(out_dir, "cost.npy"), np.array([s["final_cost"] for s in ss]))
         np.save(os.path.join(out_dir, "iters.npy"), np.array([s["iterations"] for s in ss]))
