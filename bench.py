@@ -286,7 +286,7 @@ def main():
         flush.zero_()
         batch.solve(sptr)
     torch.cuda.synchronize()
-    _, summ = batch.download(sptr)
+    params_gpu, summ = batch.download(sptr)
     iters_per_step = sum(s["iterations"] for s in summ)
 
     sampler = ClockSampler(physical_gpu_index(local_rank))
@@ -442,7 +442,7 @@ def main():
                                  "HBM fraction cannot approach 1; ncu: fp64 pipe ~18 % active, 8 warps/SM"},
             "compute": compute,
             "lm_iterations_per_step": iters_per_step, "kernel_config": info, "wall_s_timed_region": wall,
-            "final_cost_window0": summ[0]["final_cost"],
+            "final_cost_window0": summ[0]["final_cost"], "parity_checked": None,
         }
         if sg is not None:
             line["scatter_gather"] = sg
@@ -465,8 +465,41 @@ def main():
             reps = 2
             iters_c, secs_c = 0, 0.0
             for _ in range(reps):
-                a, b_, _ = oracle_solve_windows(windows, 1)
+                a, b_, res_c = oracle_solve_windows(windows, 1)
                 iters_c += a; secs_c += b_
+            # Parity of the timed configuration itself: every window of the step, GPU against the oracle.  From this start
+            # ('far', Huber, sigma 1 px, stopped at 10 iterations) the 10-iteration LM map is ill-conditioned on some
+            # windows: the oracle against ITSELF with its input moved by one ulp changes its final cost by up to 1e-3
+            # (the radius update amplifies rounding noise; tests/test_lba_gpu.py::test_bench_config_batch checks every
+            # single iteration from identical state to 1e-9).  The check is therefore: final cost within 1e-6, or within
+            # 10x the measured one-ulp width of the oracle's own answer for that window; same iteration / step counts and
+            # termination.  The widths are printed.
+            from oracle import oracle as _orc
+            rng = np.random.default_rng(0)
+            per_window = []
+            for w_, pg_, sg_, (po_, so_) in zip(windows, params_gpu, summ, res_c):
+                C_ = w_.num_cameras
+                width, pwidth = 0.0, 0.0
+                for _ in range(2):
+                    pert = w_.parameters * (1.0 + rng.choice([-1.0, 1.0], size=w_.parameters.shape) * 2.220446049250313e-16)
+                    p1_, s1_ = _orc.lba_solve(w_, max_iters=MAX_ITERS, solver=1, params=pert)
+                    width = max(width, abs(s1_["final_cost"] - so_["final_cost"]) / so_["final_cost"])
+                    pwidth = max(pwidth, float(np.abs(p1_[:6 * C_] - po_[:6 * C_]).max()))
+                d_cost = abs(sg_["final_cost"] - so_["final_cost"]) / so_["final_cost"]
+                d_pose = float(np.abs(pg_[:6 * C_] - po_[:6 * C_]).max())
+                same = (sg_["iterations"] == so_["iterations"] and sg_["num_successful_steps"] == so_["num_successful_steps"]
+                        and sg_["termination"] == so_["termination"])
+                ok_ = same and d_cost <= max(1e-6, 10.0 * width) and d_pose <= max(1e-6, 10.0 * pwidth)
+                per_window.append({"rel_final_cost": d_cost, "oracle_one_ulp_width": width, "abs_pose": d_pose,
+                                   "oracle_one_ulp_pose_width": pwidth, "same_steps_and_termination": same, "ok": ok_})
+                if not ok_:
+                    raise SystemExit(f"bench.py: GPU result differs from the oracle on the timed workload: {per_window[-1]}; {sg_}")
+            line["parity_checked"] = True
+            line["parity"] = {"windows": len(windows), "max_rel_final_cost": max(x["rel_final_cost"] for x in per_window),
+                              "windows_within_1e-6": sum(1 for x in per_window if x["rel_final_cost"] <= 1e-6),
+                              "criterion": "final cost rel <= max(1e-6, 10 x the oracle's own change under a one-ulp input "
+                                           "perturbation), poses likewise, same iterations / steps / termination",
+                              "per_window": per_window, "against": "oracle (CPU restatement, same inputs)"}
             line["cpu_baseline"] = {"value": iters_c / secs_c, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"{reps} x ({len(windows)} M windows x <= {MAX_ITERS} LM iterations), 1 thread "
                                               "(the reference runs Ceres with num_threads = 1, lba_problem.cpp:103,127)",

@@ -125,7 +125,13 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
   if (rc != SLSLAM_OK) {
     out->error = std::string(slslam_strerror(rc)) + " [" + slslam_last_error() + "]";
     out->termination_type = NUMERICAL_FAILURE;
-    if (options.logging_type != SILENT) fprintf(stderr, "%s\n", out->BriefReport().c_str());
+    // The reference adds these fields into its running statistics without looking at the outcome
+    // (src/slam.cpp:949-952), so a failed solve contributes zeros, never the -1 "did not run" markers; and because
+    // LBAProblem::set_options forces SILENT (lba_problem.cpp:130-131) a failure is reported on stderr regardless of it:
+    // a BA that silently became a no-op (e.g. --ba_window_size beyond slslam_lba_get_limits) must be visible.
+    out->initial_cost = out->final_cost = out->fixed_cost = 0.0;
+    out->num_successful_steps = out->num_unsuccessful_steps = 0;
+    fprintf(stderr, "%s\n", out->BriefReport().c_str());
     return;
   }
   out->termination_type = (SolverTerminationType)s.termination_type;

@@ -15,8 +15,9 @@
 
 #include "ceres/ceres.h"
 
-#define MODE_SPARSE_SCHUR 0
-#define MODE_SPARSE_NORMAL_CHOLESKY 1
+// same values as the reference (src/lba_problem.h:32-33)
+#define MODE_SPARSE_SCHUR 1
+#define MODE_SPARSE_NORMAL_CHOLESKY 2
 
 // The reference declares the flag with gflags (DECLARE_bool(robust), defined in src/main.cpp:27).  With gflags on the
 // include path that declaration is used as is; without it a plain global with the same name and default stands in.

@@ -262,7 +262,7 @@ void levenberg_marquardt(P& prob, const LMOptions& opt, LMSummary* sum, double* 
       if (ok) model = prob.model_change(scale.data(), step.data());
     }
     if (tr) tr[2] = model;
-    if (!ok || !(model > 0.0)) {
+    if (!ok || model < 0.0) {
       // invalid step: LevenbergMarquardtStrategy::StepIsInvalid
       ++sum->unsuccessful;
       if (tr) tr[5] = -1.0;

@@ -185,7 +185,13 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
         sorted_cnt[li] = (unsigned char)m; sorted_off[li] = pos_off;
         for (int i = 0; i < m; ++i) {
           const int ca = ocf[ls0 + sorted_pos[pos_off + i]], base = ca * (ca + 1) / 2;
-          for (int j = 0; j < i; ++j) ++kcount[base + ocf[ls0 + sorted_pos[pos_off + j]]];
+          for (int j = 0; j < i; ++j) {
+            const int cb = ocf[ls0 + sorted_pos[pos_off + j]];
+            // A camera observing the line twice (never produced by the reference; the device planner hands such windows
+            // to this one): the two observations' cross term lands on the DIAGONAL block, which must stay symmetric,
+            // -(Z_i Z_j^T + Z_j Z_i^T) -- both orderings are emitted (the reduced solve reads the lower triangle).
+            kcount[base + cb] += (cb == ca) ? 2 : 1;
+          }
         }
         pos_off += m;
       }
@@ -211,7 +217,12 @@ static int build_plan(const slslam_lba_desc& d, int CS, WindowPlan& p) {
       for (int i = 0; i < m; ++i) {
         const int ca = ocf[ls0 + sp[i]], base = ca * (ca + 1) / 2;
         const uint32_t si = fs + sp[i];
-        for (int j = 0; j < i; ++j) p.items[(size_t)kcount[base + ocf[ls0 + sp[j]]]++] = si | ((fs + sp[j]) << 16);
+        for (int j = 0; j < i; ++j) {
+          const int cb = ocf[ls0 + sp[j]];
+          const uint32_t sj = fs + sp[j];
+          p.items[(size_t)kcount[base + cb]++] = si | (sj << 16);
+          if (cb == ca) p.items[(size_t)kcount[base + cb]++] = sj | (si << 16);
+        }
       }
     }
   }
@@ -560,7 +571,7 @@ static int batch_create_host_plan(int32_t n, const slslam_lba_desc* descs, const
   b->d_phase = (long long*)(b->d_pool + o_phase);
   b->d_bar = (unsigned int*)(b->d_pool + o_bar);
   // Staging is done by ONE thread and sent as ONE copy: a pinned buffer written by several cores is read by the DMA
-  // engine at 8.5 GB/s instead of 48 GB/s (measured on the B200 host, scripts/h2d_test.py), and interleaving
+  // engine at 8.5 GB/s instead of 48 GB/s (measured on the B200 host, scripts/h2d_staging_probe.py), and interleaving
   // per-window copies with the staging of the next window slowed the staging more than the overlap saved.
   // (Measured again inside the pipeline, where the copy hides behind the previous kernel: parallel staging still lost,
   // 48.7 k vs 65.7 k LM iterations/s.  Each pipeline slot therefore stages with one thread -- its own.)
@@ -637,6 +648,7 @@ void slslam_lba_get_limits(slslam_lba_limits* out) {
 
 int slslam_lba_plan_check(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t cluster_size,
                           int32_t* detail) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   // Planner parity: the device-built plan (lba_plan_kernel.cuh) against the host planner (build_plan) for the same group
   // size, array by array, bit for bit.  Returns 0 when identical, 1 when the device planner asked for the host
   // fallback, 2 on a mismatch (detail[0] = window, detail[1] = field, detail[2] = index), < 0 on errors.
@@ -700,6 +712,7 @@ int slslam_lba_plan_check(int32_t n, const slslam_lba_desc* descs, const double*
 
 int slslam_lba_launch_shape(int32_t num_windows, int32_t max_observations, int32_t max_lines, int32_t resident_ctas,
                             int32_t smem_bytes_per_cta, int32_t* ctas_per_window, int32_t* windows_per_wave) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   // The planner's choice of group size and wave size as a pure function (no device): what batch creation uses with
   // resident_ctas = SMs x resident CTAs per SM and smem_bytes_per_cta = the opt-in maximum.
   if (num_windows <= 0 || max_observations < 0 || max_lines < 0 || resident_ctas <= 0 || smem_bytes_per_cta <= 0) return SLSLAM_ERR_INVALID;
@@ -712,10 +725,12 @@ int slslam_lba_launch_shape(int32_t num_windows, int32_t max_observations, int32
 
 int slslam_lba_batch_create(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,
                             int32_t cluster_size, slslam_lba_batch** out) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   return batch_create_impl(n, descs, params, device, cluster_size, nullptr, nullptr, out);
 }
 
 int slslam_lba_batch_upload_params(slslam_lba_batch* b, const double* const* params, void* cuda_stream) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   if (!b || !params) return SLSLAM_ERR_INVALID;
   cudaSetDevice(b->device);
   for (int i = 0; i < b->n; ++i) {
@@ -727,6 +742,7 @@ int slslam_lba_batch_upload_params(slslam_lba_batch* b, const double* const* par
 }
 
 int slslam_lba_batch_solve(slslam_lba_batch* b, void* cuda_stream) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   if (!b) return SLSLAM_ERR_INVALID;
   cudaSetDevice(b->device);
   cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -747,6 +763,7 @@ int slslam_lba_batch_solve(slslam_lba_batch* b, void* cuda_stream) {
 
 int slslam_lba_batch_download(slslam_lba_batch* b, void* cuda_stream, double* const* params_out,
                               slslam_summary* summaries_out, double* const* trace_out) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   if (!b) return SLSLAM_ERR_INVALID;
   cudaSetDevice(b->device);
   cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -763,6 +780,7 @@ int slslam_lba_batch_download(slslam_lba_batch* b, void* cuda_stream, double* co
 }
 
 int slslam_lba_batch_max_active_clusters(const slslam_lba_batch* b, int32_t* max_active) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   if (!b || !max_active) return SLSLAM_ERR_INVALID;
   *max_active = b->max_active;
   return SLSLAM_OK;
@@ -770,6 +788,7 @@ int slslam_lba_batch_max_active_clusters(const slslam_lba_batch* b, int32_t* max
 
 int slslam_lba_batch_info(const slslam_lba_batch* b, int32_t* cluster_size, int32_t* threads_per_cta,
                           int32_t* smem_bytes_per_cta, int32_t* z_in_smem) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   if (!b) return SLSLAM_ERR_INVALID;
   if (cluster_size) *cluster_size = b->CS;
   if (threads_per_cta) *threads_per_cta = LBA_NT;
@@ -779,12 +798,14 @@ int slslam_lba_batch_info(const slslam_lba_batch* b, int32_t* cluster_size, int3
 }
 
 int slslam_lba_batch_plan_cycles(const slslam_lba_batch* b, int32_t window, int32_t* cycles8) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   if (!b || !cycles8 || window < 0 || window >= b->n || !b->device_planned) return SLSLAM_ERR_INVALID;
   for (int k = 0; k < 8; ++k) cycles8[k] = b->dp_info[(size_t)window].phase_cycles[k];
   return SLSLAM_OK;
 }
 
 int slslam_lba_batch_phase_cycles(slslam_lba_batch* b, void* cuda_stream, int32_t window, int64_t* cycles_out, int32_t n) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   if (!b || !cycles_out || window < 0 || window >= b->n) return SLSLAM_ERR_INVALID;
   cudaSetDevice(b->device);
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));
@@ -795,6 +816,7 @@ int slslam_lba_batch_phase_cycles(slslam_lba_batch* b, void* cuda_stream, int32_
 }
 
 int slslam_lba_batch_transfer_bytes(const slslam_lba_batch* b, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   if (!b) return SLSLAM_ERR_INVALID;
   if (h2d_bytes) *h2d_bytes = (int64_t)b->upload_bytes;
   if (d2h_bytes) *d2h_bytes = (int64_t)(b->total_params * 8 + sizeof(slslam_summary) * (size_t)b->n);
@@ -813,6 +835,7 @@ void slslam_lba_batch_destroy(slslam_lba_batch* b) {
 }
 
 int slslam_lba_solve_batch(int32_t n, const slslam_lba_desc* descs, double* const* params_inout, slslam_summary* summaries_out) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   if (n <= 0 || !descs || !params_inout) return SLSLAM_ERR_INVALID;
   // motion-only BA (one free camera, constant lines) in every window: the dedicated kernel, no plan
   if (!getenv("SLSLAM_NO_MOBA_FASTPATH")) {
@@ -876,6 +899,7 @@ int slslam_lba_solve(const slslam_lba_desc* desc, double* params_inout, slslam_s
 
 int slslam_lba_evaluate(const slslam_lba_desc* desc, const double* params, double* residuals, double* jac_camera,
                         double* jac_line, double* cost_out) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   if (!desc || !params || !residuals) return SLSLAM_ERR_INVALID;
   int rc = validate_desc(*desc);
   if (rc != SLSLAM_OK) return rc;

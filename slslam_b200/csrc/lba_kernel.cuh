@@ -31,7 +31,6 @@ constexpr int ZST = 26;              // row stride of the Z staging: 13 x 16 B, 
 constexpr int ACC = 39;              // per-camera accumulators: H_cc - sum Z Z^T (21, lower) | g_c (6) | sum Z u (6) | diag H_cc (6)
 constexpr int LLU = 22;              // per-line: L (10, lower) | u = L^-1 g_l (4) | D_l (4) | 1 / l_kk (4)
 constexpr int NSCAL = 8;
-constexpr bool LBA_BLOCKINV_SOLVE = true;   // reduced camera system: explicit 6x6 pivot inverses (true) or block Cholesky (false)
 constexpr int NPHASE = 14;         // init | linearise | pairs | fold | allreduce | gradient | reduced solve | trial | decide | total | solve: prep, factor+panel, trailing, back-substitution
 
 // slot flags (meta.x bits 24..)
@@ -191,9 +190,11 @@ __device__ __forceinline__ double clampd(double v, double lo, double hi) { retur
 // K1 + first half of K2.  MODE 0: column norms only (Jacobi scale at x0).  MODE 1: full.
 // Outputs (MODE 1): Z blocks, lineLU, wacc (warp-private H_cc | g_c | sum Z u), partial scalars in misc.
 // ---------------------------------------------------------------------------------------------------------------
+// `grad_only` (MODE 1): gradient and cost at x only (J^T r per block, no Schur assembly): what Ceres evaluates after the
+// last accepted step of a solve that stops at max_num_iterations, to fill gradient_max_norm and run the gradient test.
 template <int MODE>
 __device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, double* out_fixed_cost, double* out_gmax,
-                                double* out_fail) {
+                                double* out_fail, bool grad_only = false) {
   const WinHdr& h = *c.h;
   double* sm = c.sm;
   const double* camR = sm + c.lay.camR;
@@ -282,6 +283,17 @@ __device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, d
 #pragma unroll
       for (int p = 0; p < 4; ++p) hg[10 + p] = Jl[p] * r[0] + Jl[4 + p] * r[1] + Jl[8 + p] * r[2] + Jl[12 + p] * r[3];
       seg_allsum<14>(hg, c.lane, seg_start, seg_len);
+      if (grad_only) {
+        if (valid && (flags & F_HEAD) && line_free) {
+          const double* lsc = lscale + 4 * ll;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) gmax = fmax(gmax, fabs(hg[10 + k] * pivot_rcp(lsc[k])));
+        }
+#pragma unroll
+        for (int k = 0; k < ACC; ++k) acc[k] = 0.0;
+#pragma unroll
+        for (int p = 0; p < 6; ++p) acc[21 + p] = Jc[p] * r[0] + Jc[6 + p] * r[1] + Jc[12 + p] * r[2] + Jc[18 + p] * r[3];
+      } else {
       // LM diagonal of the line block and its Cholesky factor (every lane of the segment computes the same values)
       double D[4], Lm[10], u[4], inv[4];
 #pragma unroll
@@ -351,6 +363,7 @@ __device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, d
         acc[21 + p] = Jc[p] * r[0] + Jc[6 + p] * r[1] + Jc[12 + p] * r[2] + Jc[18 + p] * r[3];
         acc[27 + p] = Z[4 * p] * u[0] + Z[4 * p + 1] * u[1] + Z[4 * p + 2] * u[2] + Z[4 * p + 3] * u[3];
       }
+      }   // !grad_only
     }
     // rounds: lanes of one line have distinct cameras, so within a round no two lanes touch the same accumulator
     const int nrounds = __reduce_max_sync(0xffffffffu, valid ? round + 1 : 0);
@@ -527,189 +540,9 @@ __device__ void group_allreduce(const Ctx& c, int vlen, int max_idx, unsigned in
   __syncthreads();
 }
 
-// K3: blocked (6x6) right-looking Cholesky of the reduced camera system held block-packed in V, with the right-hand
-// side carried along (forward substitution folded in), then block back-substitution.  Every CTA of the group
-// solves the same system redundantly (same data, same order => same bits), which saves a broadcast.
-// Two barriers per block column: [diagonal factor in registers by every participating thread + panel rows + rhs] |
-// [trailing update + write-back of the factored diagonal block].  A factored diagonal block stores L strictly below
-// the diagonal, 1/l_kk on it and the strict part of L^-1 transposed above it, so the back-substitution of a block is
-// six independent dot products.  On exit yc = (S + D_c)^-1 (g_c - sum Z u).  Returns false (uniformly) if a pivot
-// is not positive.
-__device__ bool reduced_solve(const Ctx& c, double radius, long long* ph) {
-  // diagnostics (build with -DSLSLAM_RS_PHASES): thread 0 only, counters in shared memory (ph[NPHASE + 1] is this
-  // function's running timestamp).  Off by default: thread 0 is on the critical path of every block column.
-#ifdef SLSLAM_RS_PHASES
-  if (c.tid == 0) ph[NPHASE + 1] = clock64();
-#define RSPHASE(i) { if (c.tid == 0) { const long long now_ = clock64(); ph[i] += now_ - ph[NPHASE + 1]; ph[NPHASE + 1] = now_; } }
-#else
-  (void)ph;
-#define RSPHASE(i)
-#endif
-  const WinHdr& h = *c.h;
-  double* V = c.sm + c.lay.V;
-  double* yc = c.sm + c.lay.yc;
-  double* misc = c.sm + c.lay.misc;    // misc[6] failure flag
-  const int* tri = reinterpret_cast<const int*>(c.sm + c.lay.tri);   // key -> I << 8 | K
-  const int Cf = h.Cf, n = h.n;
-  const int g_off = h.nkeys * 36, zu_off = g_off + n, hd_off = zu_off + n;
-  // right-hand side and LM diagonal of the camera blocks
-  for (int i = c.tid; i < n; i += LBA_NT) {
-    yc[i] = V[g_off + i] - V[zu_off + i];
-    const int f = i / 6, p = i - 6 * f;
-    V[(f * (f + 1) / 2 + f) * 36 + 7 * p] += clampd(V[hd_off + i], 1e-6, 1e32) / radius;
-  }
-  if (c.tid == 0) misc[6] = 0.0;
-  __syncthreads();
-  RSPHASE(10)
-  for (int J = 0; J < Cf; ++J) {
-    double* AJJ = V + (J * (J + 1) / 2 + J) * 36;
-    const int nb = Cf - J - 1;
-    const int npanel = 6 * nb;            // threads [0, npanel): panel rows; npanel: rhs; npanel + 1: block write-back
-    double Lr[21], inv[6];
-    bool ok = true;
-    const bool part = c.tid < npanel + 2;
-    if (part) {
-#pragma unroll
-      for (int p = 0; p < 6; ++p)
-#pragma unroll
-        for (int q = 0; q <= p; ++q) Lr[L6(p, q)] = AJJ[6 * p + q];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        double d = Lr[L6(k, k)];
-#pragma unroll
-        for (int m = 0; m < k; ++m) d -= Lr[L6(k, m)] * Lr[L6(k, m)];
-        ok = ok && (d > 0.0);
-        inv[k] = pivot_rsqrt(d);
-        Lr[L6(k, k)] = d * inv[k];
-#pragma unroll
-        for (int p = k + 1; p < 6; ++p) {
-          double s = Lr[L6(p, k)];
-#pragma unroll
-          for (int m = 0; m < k; ++m) s -= Lr[L6(p, m)] * Lr[L6(k, m)];
-          Lr[L6(p, k)] = s * inv[k];
-        }
-      }
-      if (c.tid < npanel) {
-        // panel: row p of block (I,J):  x L_JJ^T = a
-        const int bI = c.tid / 6, p = c.tid - 6 * bI, I = J + 1 + bI;
-        double* a = V + (I * (I + 1) / 2 + J) * 36 + 6 * p;
-        double x[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) x[q] = a[q];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          x[q] *= inv[q];
-#pragma unroll
-          for (int m = q + 1; m < 6; ++m) x[m] -= x[q] * Lr[L6(m, q)];
-        }
-#pragma unroll
-        for (int q = 0; q < 6; ++q) a[q] = x[q];
-      } else if (c.tid == npanel) {
-        // forward-substitute the rhs block: z_J = L_JJ^-1 b_J
-        if (!ok) misc[6] = 1.0;
-        double z[6];
-#pragma unroll
-        for (int p = 0; p < 6; ++p) z[p] = yc[6 * J + p];
-#pragma unroll
-        for (int p = 0; p < 6; ++p) {
-          z[p] *= inv[p];
-#pragma unroll
-          for (int m = p + 1; m < 6; ++m) z[m] -= z[p] * Lr[L6(m, p)];
-        }
-#pragma unroll
-        for (int p = 0; p < 6; ++p) yc[6 * J + p] = z[p];
-      }
-    }
-    __syncthreads();
-    RSPHASE(11)
-    if (c.tid == npanel + 1) {
-      // M = L_JJ^-1 (lower): m_pp = 1/l_pp, m_pq = -m_pp sum_{k=q}^{p-1} l_pk m_kq
-      double Mi[21];
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        Mi[L6(q, q)] = inv[q];
-#pragma unroll
-        for (int p = q + 1; p < 6; ++p) {
-          double s = 0.0;
-#pragma unroll
-          for (int k = q; k < p; ++k) s += Lr[L6(p, k)] * Mi[L6(k, q)];
-          Mi[L6(p, q)] = -s * inv[p];
-        }
-      }
-#pragma unroll
-      for (int p = 0; p < 6; ++p)
-#pragma unroll
-        for (int q = 0; q < 6; ++q) AJJ[6 * p + q] = (q < p) ? Lr[L6(p, q)] : (q == p ? inv[p] : Mi[L6(q, p)]);
-    }
-    // trailing update: A_IK -= L_IJ L_KJ^T for I >= K > J, one ROW of a 6x6 block per thread (six independent
-    // 6-term dot products, so a block column is usually a single pass of the CTA), and b_I -= L_IJ z_J
-    const int nitem = nb * (nb + 1) / 2 * 6;
-    for (int e = c.tid; e < nitem + npanel; e += LBA_NT) {
-      if (e < nitem) {
-        const int blk = e / 6, p = e - 6 * blk;
-        const int t = tri[blk];
-        const int I = J + 1 + (t >> 8), K = J + 1 + (t & 0xff);
-        const double* li = V + (I * (I + 1) / 2 + J) * 36 + 6 * p;
-        const double* lk = V + (K * (K + 1) / 2 + J) * 36;
-        double* dst = V + (I * (I + 1) / 2 + K) * 36 + 6 * p;
-        double a[6], o[6];
-#pragma unroll
-        for (int m = 0; m < 6; ++m) { a[m] = li[m]; o[m] = dst[m]; }
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          double s0 = a[0] * lk[6 * q] + a[1] * lk[6 * q + 1] + a[2] * lk[6 * q + 2];
-          double s1 = a[3] * lk[6 * q + 3] + a[4] * lk[6 * q + 4] + a[5] * lk[6 * q + 5];
-          o[q] -= s0 + s1;
-        }
-#pragma unroll
-        for (int q = 0; q < 6; ++q) dst[q] = o[q];
-      } else {
-        const int rI = e - nitem, bI = rI / 6, I = J + 1 + bI, p = rI - 6 * bI;
-        const double* li = V + (I * (I + 1) / 2 + J) * 36 + 6 * p;
-        double s = 0.0;
-#pragma unroll
-        for (int m = 0; m < 6; ++m) s += li[m] * yc[6 * J + m];
-        yc[6 * I + p] -= s;
-      }
-    }
-    __syncthreads();
-    RSPHASE(12)
-  }
-  const bool failed = misc[6] != 0.0;
-  // back substitution L^T y = z by warp 0: y_J = L_JJ^-T w_J as six dot products with the stored inverse, then every
-  // lane removes the block's contribution from the rows above
-  if (c.warp == 0 && !failed) {
-    for (int J = Cf - 1; J >= 0; --J) {
-      const double* DJ = V + (J * (J + 1) / 2 + J) * 36;
-      double yp = 0.0;
-      if (c.lane < 6) {
-        // (L^-T)[p][m] = M[m][p], m >= p: diagonal holds 1/l_pp, strict part of M sits transposed above the diagonal
-#pragma unroll
-        for (int m = 0; m < 6; ++m) if (m >= c.lane) yp += DJ[6 * c.lane + m] * yc[6 * J + m];
-      }
-      __syncwarp();
-      if (c.lane < 6) yc[6 * J + c.lane] = yp;
-      __syncwarp();
-      for (int e = c.lane; e < 6 * J; e += 32) {
-        const int K = e / 6, q = e - 6 * K;
-        const double* ljk = V + (J * (J + 1) / 2 + K) * 36;    // block (J,K): rows of J, columns of K
-        double s = 0.0;
-#pragma unroll
-        for (int m = 0; m < 6; ++m) s += ljk[6 * m + q] * yc[6 * J + m];
-        yc[6 * K + q] -= s;
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  RSPHASE(13)
-#undef RSPHASE
-  return !failed;
-}
-
-// K3, second form (the one in use): block elimination of the reduced camera system with EXPLICIT inverses of the 6x6
-// pivot blocks.  The Cholesky form above spends its time on a chain of 6 dependent reciprocal square roots per block
-// column (~215 cycles each); here a pivot block is inverted through two closed-form 3x3 cofactor inverses (one
+// K3: block elimination of the reduced camera system held block-packed in V, with EXPLICIT inverses of the 6x6
+// pivot blocks.  A blocked Cholesky spends its time on a chain of 6 dependent reciprocal square roots per block
+// column (~215 cycles each, measured in round 1); here a pivot block is inverted through two closed-form 3x3 cofactor inverses (one
 // reciprocal each) and a 3x3 Schur complement, W = A_JJ^-1.  Per block column J:
 //   phase 1  threads [0, 6 nb]: W in registers (all redundantly); panel rows P_I = A_IJ W (independent dot products,
 //            no substitution chain), the original rows saved to `pbuf`; one thread: u_J = W b_J
@@ -1123,6 +956,7 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
   double gmax = 0.0, gtol_abs = 0.0, x_norm2_cams = 0.0;
   int successful = 0, unsuccessful = 0, invalid = 0, term = SLSLAM_NO_CONVERGENCE, iters = 0;
   bool first_lin = true;
+  bool grad_pending = false;   // a step was accepted and the gradient at the new point has not been evaluated yet
 
   // per-phase cycle counters (diagnostics): kept in shared memory and touched by thread 0 only, so that they do not
   // occupy ~30 registers of every thread; ph[NPHASE] is the running timestamp
@@ -1133,13 +967,19 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
   }
 #define PHASE(i) { if (c.tid == 0) { const long long now_ = clock64(); ph[i] += now_ - ph[NPHASE]; ph[NPHASE] = now_; } }
   PHASE(0)
-  for (int it = 0; it < h.max_iters; ++it) {
+  // Ceres evaluates the Jacobian and runs the gradient test right after every accepted step, also after the one that
+  // uses up max_num_iterations.  Here that evaluation is the next iteration's linearisation; when the last allowed
+  // iteration accepted its step, one more pass (`last`: gradient-only sweep, no Schur assembly) fills cost,
+  // gradient_max_norm and termination_type of the summary the way Ceres does at the iteration cap.
+  for (int it = 0; it <= h.max_iters; ++it) {
+    const bool last = it == h.max_iters;
+    if (last && !grad_pending) break;
     // -- K1/K2: linearise at x with the current radius --
     if (c.tid == 0) *reinterpret_cast<int*>(sm + lay.misc + 7) = LBA_NW;   // pair blocks beyond the first LBA_NW are claimed dynamically
-    linearize_sweep<1>(c, radius, &p_cost, &p_fixed, &p_gmax, &p_fail);
+    linearize_sweep<1>(c, radius, &p_cost, &p_fixed, &p_gmax, &p_fail, last);
     __syncthreads();
     PHASE(1)
-    schur_pairs(c);
+    if (!last) schur_pairs(c);
     for (int i = g_off + c.tid; i < vlen; i += LBA_NT) V[i] = 0.0;
     __syncthreads();
     PHASE(2)
@@ -1167,14 +1007,16 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
       first_lin = false;
     }
     PHASE(5)
+    grad_pending = false;
     if (gmax <= gtol_abs) { term = SLSLAM_GRADIENT_TOLERANCE; break; }
+    if (last) break;
     iters = it + 1;
     double* tr = (h.trace && c.rank == 0 && c.tid == 0) ? h.trace + (size_t)it * SLSLAM_TRACE_WIDTH : nullptr;
     if (tr) { tr[0] = cost; tr[1] = 0; tr[2] = 0; tr[3] = radius; tr[4] = 0; tr[5] = 0; tr[6] = gmax; tr[7] = 0; }
     // camera part of the model decrease needs g_c and D_c before the solve overwrites V
     bool ok = !line_fail;
     double model_c = 0.0;
-    if (Cf > 0) ok = (LBA_BLOCKINV_SOLVE ? reduced_solve_blockinv(c, radius, ph) : reduced_solve(c, radius, ph)) && ok;
+    if (Cf > 0) ok = reduced_solve_blockinv(c, radius, ph) && ok;
     PHASE(6)
     double dn2c = 0.0;
     if (ok && Cf > 0) {
@@ -1225,8 +1067,8 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
     PHASE(7)
     const double model = trial[1] + model_c;
     if (tr) tr[2] = model;
-    if (!ok || !(model > 0.0)) {
-      // LevenbergMarquardtStrategy::StepIsInvalid
+    if (!ok || model < 0.0) {
+      // invalid step: the linear solver failed, or model_cost_change < 0 (Ceres 1.7.0 TrustRegionMinimizer)
       ++unsuccessful;
       if (tr) tr[5] = -1.0;
       if (++invalid >= 5) { term = SLSLAM_NUMERICAL_FAILURE; break; }
@@ -1255,6 +1097,7 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
       for (int i = c.tid; i < CAM_STRIDE * C; i += LBA_NT) camR[i] = camRt[i];
       __syncthreads();
       cost = new_cost;
+      grad_pending = true;
       const double t = 2.0 * rel - 1.0;
       radius = fmin(1e16, radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
       decrease_factor = 2.0;

@@ -98,6 +98,7 @@ static int pipeline_finish(slslam_lba_pipeline* p, slslam_lba_pipeline::Slot& s)
 }
 
 int slslam_lba_pipeline_create(int32_t device, int32_t depth, int32_t flags, slslam_lba_pipeline** out) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   if (!out) return SLSLAM_ERR_INVALID;
   *out = nullptr;
   if (depth < 1 || depth > 8) return SLSLAM_ERR_INVALID;
@@ -124,6 +125,7 @@ int slslam_lba_pipeline_create(int32_t device, int32_t depth, int32_t flags, sls
 
 int slslam_lba_pipeline_submit(slslam_lba_pipeline* p, int32_t n, const slslam_lba_desc* descs, double* const* params_inout,
                                slslam_summary* summaries_out, int64_t* ticket_out) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   if (!p || n <= 0 || !descs || !params_inout) return SLSLAM_ERR_INVALID;
   // argument errors are reported here, before anything is queued (the same checks run again inside the enqueue)
   for (int i = 0; i < n; ++i) {
@@ -151,6 +153,7 @@ int slslam_lba_pipeline_submit(slslam_lba_pipeline* p, int32_t n, const slslam_l
 }
 
 int slslam_lba_pipeline_wait(slslam_lba_pipeline* p, int64_t ticket) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   if (!p) return SLSLAM_ERR_INVALID;
   cudaSetDevice(p->device);
   int rc = SLSLAM_OK;

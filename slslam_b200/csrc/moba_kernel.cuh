@@ -190,7 +190,13 @@ __global__ void __launch_bounds__(MOBA_NT, 1) lba_motion_only_kernel(const MobaH
   double radius = h.radius0, decrease_factor = 2.0, gmax = 0.0, gtol_abs = 0.0;
   int successful = 0, unsuccessful = 0, invalid = 0, term = SLSLAM_NO_CONVERGENCE, iters = 0;
   bool first_lin = true;
-  for (int it = 0; it < h.max_iters; ++it) {
+  // one pass more than max_iters when the last allowed iteration accepted its step: Ceres evaluates the gradient (and runs
+  // the gradient test) right after every accepted step, so cost / gradient_max_norm / termination_type at the iteration
+  // cap come from the final point
+  bool grad_pending = false;
+  for (int it = 0; it <= h.max_iters; ++it) {
+    const bool last = it == h.max_iters;
+    if (last && !grad_pending) break;
     // -- linearise at x: H (21, lower) | g (6) | cost --
     double a[28];
 #pragma unroll
@@ -222,7 +228,9 @@ __global__ void __launch_bounds__(MOBA_NT, 1) lba_motion_only_kernel(const MobaH
 #pragma unroll
     for (int p = 0; p < 6; ++p) { gmax = fmax(gmax, fabs(a[21 + p] / cscale[p])); x_norm2 += camx[p] * camx[p]; }
     if (first_lin) { gtol_abs = h.gtol * fmax(gmax, 2.220446049250313e-16); first_lin = false; }
+    grad_pending = false;
     if (gmax <= gtol_abs) { term = SLSLAM_GRADIENT_TOLERANCE; break; }
+    if (last) break;
     iters = it + 1;
     double* tr = (h.trace && tid == 0) ? h.trace + (size_t)it * SLSLAM_TRACE_WIDTH : nullptr;
     if (tr) { tr[0] = cost; tr[1] = 0; tr[2] = 0; tr[3] = radius; tr[4] = 0; tr[5] = 0; tr[6] = gmax; tr[7] = 0; }
@@ -271,7 +279,7 @@ __global__ void __launch_bounds__(MOBA_NT, 1) lba_motion_only_kernel(const MobaH
     }
     if (tr) tr[2] = model;
     double new_cost = 0.0;
-    if (ok && model > 0.0) {
+    if (ok && !(model < 0.0)) {
       __syncthreads();
       if (tid < 6) camxt[tid] = camx[tid] - (tid == 0 ? y[0] : tid == 1 ? y[1] : tid == 2 ? y[2] : tid == 3 ? y[3] : tid == 4 ? y[4] : y[5]) * cscale[tid];
       __syncthreads();
@@ -288,7 +296,7 @@ __global__ void __launch_bounds__(MOBA_NT, 1) lba_motion_only_kernel(const MobaH
       moba_cta_sum<1>(v, wsc, tid);
       new_cost = v[0];
     }
-    if (!ok || !(model > 0.0)) {
+    if (!ok || model < 0.0) {
       ++unsuccessful;
       if (tr) tr[5] = -1.0;
       if (++invalid >= 5) { term = SLSLAM_NUMERICAL_FAILURE; break; }
@@ -312,6 +320,7 @@ __global__ void __launch_bounds__(MOBA_NT, 1) lba_motion_only_kernel(const MobaH
       if (tid < CAM_STRIDE) camR[tid] = camRt[tid];
       __syncthreads();
       cost = new_cost;
+      grad_pending = true;
       const double t = 2.0 * rel - 1.0;
       radius = fmin(1e16, radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
       decrease_factor = 2.0;

@@ -251,6 +251,7 @@ using namespace slslam;
 extern "C" {
 
 int slslam_po_solve_trace(const slslam_po_desc* desc, double* poses_inout, slslam_summary* summary_out, double* trace_out) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   if (!desc || (!poses_inout && desc->num_poses > 0)) return SLSLAM_ERR_INVALID;
   return po_run(desc, poses_inout, poses_inout, summary_out, trace_out, false, nullptr, nullptr, nullptr, nullptr);
 }
@@ -261,6 +262,7 @@ int slslam_po_solve(const slslam_po_desc* desc, double* poses_inout, slslam_summ
 
 int slslam_po_evaluate(const slslam_po_desc* desc, const double* poses, double* residuals, double* jac_pose1,
                        double* jac_pose2, double* cost_out) {
+  slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   if (!desc || !poses || !residuals) return SLSLAM_ERR_INVALID;
   return po_run(desc, poses, nullptr, nullptr, nullptr, true, residuals, jac_pose1, jac_pose2, cost_out);
 }

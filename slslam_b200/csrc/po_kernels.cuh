@@ -446,7 +446,7 @@ __global__ void po_decide(PoDev d) {
   st->accepted = 0;
   const double model = ok ? -mv : 0.0;
   if (tr) tr[2] = model;
-  if (!ok || !(model > 0.0)) {
+  if (!ok || model < 0.0) {
     ++st->unsuccessful;
     if (tr) tr[5] = -1.0;
     if (++st->invalid >= 5) { st->term = SLSLAM_NUMERICAL_FAILURE; st->done = 1; return; }

@@ -99,7 +99,7 @@ def lm_numpy(w, max_iters, robust=True):
             ok = False
         model = 0.5 * float(y @ (g + diag * y)) if ok else 0.0   # = -(m.(r + m/2)), m = J step, for an exact solve
         rec[2] = model
-        if not ok or not model > 0.0:
+        if not ok or model < 0.0:
             unsucc += 1; rec[5] = -1.0; trace.append(rec); invalid += 1
             if invalid >= 5:
                 term = "NUMERICAL_FAILURE"; break

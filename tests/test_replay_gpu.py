@@ -34,16 +34,25 @@ def test_it3f_sliding_window_replay_matches_oracle(gpu):
     # LBA must beat dead reckoning clearly
     assert rmse_g < 0.25 * rmse_0, (rmse_g, rmse_0)
     # (1) parity on IDENTICAL inputs: every window the GPU replay assembled, solved again by the oracle.  With the
-    # reference's max_num_iterations = 10 nearly every window stops mid-descent (most need > 40 iterations to reach the
-    # function tolerance), so a rounding-level difference can be amplified along the LM path of an ill-conditioned
-    # early window (2-3 cameras); the bulk agrees to 1e-9.
-    rel = []
-    for w, sg in zip(windows, st_g):
+    # reference's max_num_iterations = 10 nearly every window stops mid-descent, and for some windows (the first, 2-camera
+    # one above all) the 10-iteration LM map amplifies rounding noise: no accept / reject decision differs, the gain
+    # ratio's effect on the radius compounds a 1e-12 difference by a decade or two per iteration
+    # (scripts/replay_parity_debug.py prints the traces).  So: 1e-6 wherever the window's result is defined that well,
+    # and otherwise within 10x the width the ORACLE ITSELF shows under a one-ulp perturbation of its input.
+    from test_lba_gpu import _path_sensitivity
+    rel, loose = [], []
+    for i, (w, sg) in enumerate(zip(windows, st_g)):
         _, so = oracle.lba_solve(w, max_iters=10, solver=1)
         assert abs(sg["initial_cost"] - so["initial_cost"]) <= 1e-11 * so["initial_cost"]
         assert sg["iterations"] == so["iterations"]
-        rel.append(abs(sg["final_cost"] - so["final_cost"]) / so["final_cost"])
-    assert np.median(rel) < 1e-9 and max(rel) < 5e-4, (np.median(rel), max(rel))
+        d = abs(sg["final_cost"] - so["final_cost"]) / so["final_cost"]
+        rel.append(d)
+        if d > 1e-6:
+            sens = _path_sensitivity(w, 10, reps=4)
+            loose.append((i, w.num_cameras, d, sens["final"]))
+            assert d <= 10.0 * sens["final"], loose[-1]
+    print("windows above 1e-6 (index, cameras, |gpu - oracle| / cost, oracle one-ulp width):", loose)
+    assert np.median(rel) < 1e-9 and len(loose) <= 2, (np.median(rel), loose)
     # (2) the two replays, each feeding its own write-back into the next window.  Because the windows stop unconverged,
     # the outcome of a window depends on its last accept / reject decisions and a 1e-8 difference is carried and
     # amplified through 35 dependent windows: these are two equally valid LBA runs, compared as such (both cut the
