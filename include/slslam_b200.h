@@ -179,6 +179,24 @@ int slslam_po_solve_trace(const slslam_po_desc* desc, double* poses_inout, slsla
                           double* trace_out);
 /* Device time (CUDA events, ms) of the LM loop of this thread's last slslam_po_solve*, transfers excluded. */
 float slslam_po_last_solve_ms(void);
+/* How this thread's last slslam_po_solve* factored the normal equations.  The reference selects SPARSE_NORMAL_CHOLESKY
+ * (src/po_problem.cpp:68); here the free poses are ordered by minimum degree and the 6x6 blocks of the factor (fill
+ * included) are eliminated by one CTA in one launch per LM iteration.  A graph whose factor is more than a third full,
+ * or with more than max_column_blocks_sparse blocks in one column, goes to the dense blocked factorisation instead. */
+typedef struct slslam_po_stats {
+  int32_t sparse;                 /* 1 = block-sparse path, 0 = dense path */
+  int32_t free_poses;
+  int64_t factor_blocks;          /* 6x6 blocks of L (dense path: Kf (Kf + 1) / 2) */
+  int64_t block_updates;          /* 6x6x6 block products of one numeric factorisation (sparse path) */
+  int32_t max_column_rows;
+  int32_t iterations_enqueued;    /* LM iterations whose kernels were launched (<= max_iterations: early stop) */
+} slslam_po_stats;
+void slslam_po_last_stats(slslam_po_stats* out);
+typedef struct slslam_po_limits {
+  int32_t max_column_blocks_sparse;   /* off-diagonal blocks in one column of L on the sparse path */
+  int32_t max_free_poses_dense;       /* dense fallback: 6 * free poses <= 32 * 8 * 64 */
+} slslam_po_limits;
+void slslam_po_get_limits(slslam_po_limits* out);
 /* residuals [6E], jac_pose1 / jac_pose2 [36E] row-major 6x6 */
 int slslam_po_evaluate(const slslam_po_desc* desc, const double* poses, double* residuals, double* jac_pose1,
                        double* jac_pose2, double* cost_out);

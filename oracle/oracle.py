@@ -51,6 +51,8 @@ def lib():
         L.oracle_po_cost.restype = C.c_double
         L.oracle_po_solve.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, dp, dp, dp, dp, dp]
         L.oracle_po_solve.restype = C.c_int
+        L.oracle_po_solve2.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, dp, dp, C.c_int, dp, dp, dp, dp]
+        L.oracle_po_solve2.restype = C.c_int
         L.oracle_ransac_score.argtypes = [C.c_int, dp, C.c_int, dp, dp, C.c_double, C.c_double, ip,
                                           C.POINTER(C.c_ubyte), C.POINTER(C.c_float)]
         L.oracle_ransac_score.restype = None
@@ -121,16 +123,22 @@ def po_cost(g, params=None):
     return lib().oracle_po_cost(g.num_poses, g.num_edges, _i(a), _i(b), _d(c), _d(p))
 
 
-def po_solve(g, max_iters=10, lm_opts=None, params=None):
+def po_solve(g, max_iters=10, lm_opts=None, params=None, solver=1, want_stats=False):
+    """solver 1 = sparse Cholesky of the normal equations (the reference's SPARSE_NORMAL_CHOLESKY, po_problem.cpp:68),
+    0 = dense Cholesky (cross-check; same step)."""
     p = _f64(g.parameters if params is None else params).copy()
     a, b, c = _i32(g.pose_index_1), _i32(g.pose_index_2), _f64(g.constraints)
     tw = lib().oracle_trace_width()
     trace = np.zeros((max(max_iters, 1), tw))
     s = np.zeros(8)
     o = None if lm_opts is None else _f64(lm_opts)
-    lib().oracle_po_solve(g.num_poses, g.num_edges, max_iters, _i(a), _i(b), _d(c), None if o is None else _d(o),
-                          _d(p), _d(s), _d(trace))
-    return p, _summary(s, trace, max_iters)
+    stats = np.zeros(2)
+    lib().oracle_po_solve2(g.num_poses, g.num_edges, max_iters, _i(a), _i(b), _d(c), None if o is None else _d(o),
+                           int(solver), _d(p), _d(s), _d(trace), _d(stats))
+    out = _summary(s, trace, max_iters)
+    if want_stats:
+        out["factor_flops"], out["factor_nnz"] = float(stats[0]), float(stats[1])
+    return p, out
 
 
 def ransac_score(poses, lines, obs, baseline=0.12, thr=5.0 / 406.05):

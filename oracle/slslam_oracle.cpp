@@ -562,6 +562,126 @@ struct LBAProgram {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Sparse Cholesky: what SPARSE_NORMAL_CHOLESKY (reference src/po_problem.cpp:68) ends in.  Ceres 1.7.0 hands the
+// normal equations to CHOLMOD or CXSparse -- neither is in /root/reference nor installed --: a fill-reducing ordering,
+// a symbolic analysis through the elimination tree, an up-looking numeric factorisation and two triangular solves.
+// Restated here from the published algorithm (T. Davis, "Direct Methods for Sparse Linear Systems", ch. 4: etree,
+// ereach, up-looking cs_chol); the ordering is an exact greedy minimum-degree on the 6x6-block graph instead of AMD
+// (an ordering changes fill and rounding, not the solution).
+// ---------------------------------------------------------------------------------------------
+struct SparseSym {                 // upper triangle of the permuted matrix C = P A P^T, compressed columns
+  int n = 0;
+  std::vector<int> Ap, Ai;
+  std::vector<double> Ax;
+};
+struct SparseChol {
+  int n = 0;
+  std::vector<int> parent, Lp, Li;
+  std::vector<double> Lx;
+  long long flops = 0;
+  // elimination tree of C (upper part given): parent[i] = min { j > i : L(j,i) != 0 }
+  void analyze(const SparseSym& C) {
+    n = C.n;
+    parent.assign(n, -1);
+    std::vector<int> ancestor(n, -1);
+    for (int k = 0; k < n; ++k) {
+      for (int p = C.Ap[k]; p < C.Ap[k + 1]; ++p) {
+        int i = C.Ai[p];
+        while (i != -1 && i < k) {
+          const int inext = ancestor[i];
+          ancestor[i] = k;
+          if (inext == -1) parent[i] = k;
+          i = inext;
+        }
+      }
+    }
+    // column counts by walking every row's reach once (row subtree of the elimination tree)
+    std::vector<int> cnt(n, 1), mark(n, -1);
+    for (int k = 0; k < n; ++k) {
+      mark[k] = k;
+      for (int p = C.Ap[k]; p < C.Ap[k + 1]; ++p) {
+        int i = C.Ai[p];
+        while (i < k && mark[i] != k) { ++cnt[i]; mark[i] = k; i = parent[i]; }
+      }
+    }
+    Lp.assign(n + 1, 0);
+    for (int j = 0; j < n; ++j) Lp[j + 1] = Lp[j] + cnt[j];
+    Li.assign(Lp[n], 0); Lx.assign(Lp[n], 0.0);
+  }
+  // up-looking numeric factorisation: row k of L from a sparse triangular solve with the rows above
+  bool factor(const SparseSym& C) {
+    std::vector<int> c(Lp.begin(), Lp.end() - 1), stack(n), w(n, -1), pattern(n);
+    std::vector<double> x(n, 0.0);
+    flops = 0;
+    for (int k = 0; k < n; ++k) {
+      // ereach: nonzero pattern of row k of L, in topological order on top of `pattern`
+      int top = n;
+      w[k] = k;
+      for (int p = C.Ap[k]; p < C.Ap[k + 1]; ++p) {
+        int i = C.Ai[p];
+        if (i > k) continue;
+        x[i] = C.Ax[p];
+        int len = 0;
+        for (; w[i] != k; i = parent[i]) { stack[len++] = i; w[i] = k; }
+        while (len > 0) pattern[--top] = stack[--len];
+      }
+      double d = x[k];
+      x[k] = 0.0;
+      for (; top < n; ++top) {
+        const int i = pattern[top];
+        const double lki = x[i] / Lx[Lp[i]];
+        x[i] = 0.0;
+        for (int p = Lp[i] + 1; p < c[i]; ++p) x[Li[p]] -= Lx[p] * lki;
+        flops += 2 * (long long)(c[i] - Lp[i]);
+        d -= lki * lki;
+        const int q = c[i]++;
+        Li[q] = k; Lx[q] = lki;
+      }
+      if (!(d > 0.0) || !std::isfinite(d)) return false;
+      const int q = c[k]++;
+      Li[q] = k; Lx[q] = std::sqrt(d);
+    }
+    return true;
+  }
+  void solve(double* b) const {          // L L^T x = b in place
+    for (int j = 0; j < n; ++j) {
+      b[j] /= Lx[Lp[j]];
+      for (int p = Lp[j] + 1; p < Lp[j + 1]; ++p) b[Li[p]] -= Lx[p] * b[j];
+    }
+    for (int j = n - 1; j >= 0; --j) {
+      for (int p = Lp[j] + 1; p < Lp[j + 1]; ++p) b[j] -= Lx[p] * b[Li[p]];
+      b[j] /= Lx[Lp[j]];
+    }
+  }
+};
+
+// Exact greedy minimum-degree elimination order of an undirected graph (adjacency without self loops); ties by index.
+std::vector<int> minimum_degree_order(int nv, std::vector<std::vector<int> > adj) {
+  std::vector<std::vector<char> > has(nv, std::vector<char>(nv, 0));
+  for (int v = 0; v < nv; ++v) for (int u : adj[v]) has[v][u] = 1;
+  std::vector<char> gone(nv, 0);
+  std::vector<int> order;
+  order.reserve(nv);
+  for (int step = 0; step < nv; ++step) {
+    int best = -1, bestdeg = 1 << 30;
+    for (int v = 0; v < nv; ++v) {
+      if (gone[v]) continue;
+      int deg = 0;
+      for (int u : adj[v]) if (!gone[u]) ++deg;
+      if (deg < bestdeg) { bestdeg = deg; best = v; }
+    }
+    gone[best] = 1;
+    order.push_back(best);
+    std::vector<int> nb;
+    for (int u : adj[best]) if (!gone[u]) nb.push_back(u);
+    for (size_t a = 0; a < nb.size(); ++a)
+      for (size_t b = a + 1; b < nb.size(); ++b)
+        if (!has[nb[a]][nb[b]]) { has[nb[a]][nb[b]] = has[nb[b]][nb[a]] = 1; adj[nb[a]].push_back(nb[b]); adj[nb[b]].push_back(nb[a]); }
+  }
+  return order;
+}
+
+// ---------------------------------------------------------------------------------------------
 // PO program: what POProblem::build hands to Ceres (reference src/po_problem.cpp:40-65)
 // ---------------------------------------------------------------------------------------------
 struct POProgram {
@@ -574,6 +694,70 @@ struct POProgram {
   double fixed_cost_ = 0.0;
   std::vector<char> active;
   std::vector<double> r, J1, J2;  // [6E], [36E], [36E]
+  int solver = 1;                 // 1: sparse Cholesky (what the reference selects, po_problem.cpp:68); 0: dense (cross-check)
+  std::vector<int> pos;           // [Kf] position of every reduced block in the elimination order
+  SparseSym C;                    // pattern of the upper triangle of P H P^T (values refilled by every solve)
+  mutable SparseChol chol;
+  std::vector<int> blk_col_start; // scratch of the assembly: first entry of every scalar column
+  long long last_factor_flops() const { return chol.flops; }
+
+  void setup_sparse() {
+    // block graph of the free poses, minimum-degree order, scalar pattern (6x6 blocks, upper triangle, sorted rows)
+    std::vector<std::vector<int> > adj(Kf);
+    for (int e = 0; e < E; ++e) {
+      const int a = slot[idx1[e]], b = slot[idx2[e]];
+      if (a >= 0 && b >= 0 && a != b) { adj[a].push_back(b); adj[b].push_back(a); }
+    }
+    for (int v = 0; v < Kf; ++v) { std::sort(adj[v].begin(), adj[v].end()); adj[v].erase(std::unique(adj[v].begin(), adj[v].end()), adj[v].end()); }
+    const std::vector<int> order = minimum_degree_order(Kf, adj);
+    pos.assign(Kf, 0);
+    for (int k = 0; k < Kf; ++k) pos[order[k]] = k;
+    const int nn = 6 * Kf;
+    C.n = nn; C.Ap.assign(nn + 1, 0); C.Ai.clear();
+    for (int cb = 0; cb < Kf; ++cb) {
+      const int v = order[cb];
+      std::vector<int> rows;                       // block rows above the diagonal in column cb
+      for (int u : adj[v]) if (pos[u] < cb) rows.push_back(pos[u]);
+      std::sort(rows.begin(), rows.end());
+      for (int q = 0; q < 6; ++q) {
+        for (int rb : rows) for (int p = 0; p < 6; ++p) C.Ai.push_back(6 * rb + p);
+        for (int p = 0; p <= q; ++p) C.Ai.push_back(6 * cb + p);
+        C.Ap[6 * cb + q + 1] = (int)C.Ai.size();
+      }
+    }
+    C.Ax.assign(C.Ai.size(), 0.0);
+    chol.analyze(C);
+  }
+  double* entry(int row, int col) {              // row <= col, permuted scalar indices; the pattern holds every block fully
+    const int* b = &C.Ai[C.Ap[col]];
+    const int* e = &C.Ai[C.Ap[col + 1]];
+    const int* it = std::lower_bound(b, e, row);
+    return &C.Ax[it - &C.Ai[0]];
+  }
+  bool solve_sparse(const double* scale, const double* D2, double* y) {
+    const int nn = n();
+    std::fill(C.Ax.begin(), C.Ax.end(), 0.0);
+    std::vector<double> b(nn, 0.0);
+    for (int e = 0; e < E; ++e) {
+      if (!active[e]) continue;
+      const int s1 = slot[idx1[e]], s2 = slot[idx2[e]];
+      for (int k = 0; k < 6; ++k) {
+        int idx[12]; double row[12]; int m = 0;
+        if (s1 >= 0) for (int j = 0; j < 6; ++j) { idx[m] = 6 * pos[s1] + j; row[m++] = J1[36 * (size_t)e + 6 * k + j] * scale[6 * s1 + j]; }
+        if (s2 >= 0 && idx1[e] != idx2[e]) for (int j = 0; j < 6; ++j) { idx[m] = 6 * pos[s2] + j; row[m++] = J2[36 * (size_t)e + 6 * k + j] * scale[6 * s2 + j]; }
+        const double rk = r[6 * (size_t)e + k];
+        for (int p = 0; p < m; ++p) {
+          b[idx[p]] += row[p] * rk;
+          for (int q = 0; q <= p; ++q) *entry(std::min(idx[p], idx[q]), std::max(idx[p], idx[q])) += row[p] * row[q];
+        }
+      }
+    }
+    for (int s0 = 0; s0 < Kf; ++s0) for (int j = 0; j < 6; ++j) *entry(6 * pos[s0] + j, 6 * pos[s0] + j) += D2[6 * s0 + j];
+    if (!chol.factor(C)) return false;
+    chol.solve(b.data());
+    for (int s0 = 0; s0 < Kf; ++s0) for (int j = 0; j < 6; ++j) y[6 * s0 + j] = b[6 * pos[s0] + j];
+    return true;
+  }
 
   void setup() {
     std::vector<char> used(K, 0);
@@ -592,6 +776,7 @@ struct POProgram {
       }
     }
     r.resize(6 * (size_t)E); J1.resize(36 * (size_t)E); J2.resize(36 * (size_t)E);
+    if (solver == 1 && Kf > 0) setup_sparse();
   }
   int n() const { return 6 * Kf; }
   double fixed_cost() const { return fixed_cost_; }
@@ -672,7 +857,8 @@ struct POProgram {
     }
     return -acc;
   }
-  bool solve(const double* scale, const double* D2, double* y) const {
+  bool solve(const double* scale, const double* D2, double* y) {
+    if (solver == 1) return solve_sparse(scale, D2, y);
     const int nn = n();
     std::vector<double> H((size_t)nn * nn, 0.0);
     std::fill(y, y + nn, 0.0);
@@ -682,7 +868,7 @@ struct POProgram {
       for (int k = 0; k < 6; ++k) {
         int idx[12]; double row[12]; int m = 0;
         if (s1 >= 0) for (int j = 0; j < 6; ++j) { idx[m] = 6 * s1 + j; row[m++] = J1[36 * (size_t)e + 6 * k + j] * scale[6 * s1 + j]; }
-        if (s2 >= 0) for (int j = 0; j < 6; ++j) { idx[m] = 6 * s2 + j; row[m++] = J2[36 * (size_t)e + 6 * k + j] * scale[6 * s2 + j]; }
+        if (s2 >= 0 && idx1[e] != idx2[e]) for (int j = 0; j < 6; ++j) { idx[m] = 6 * s2 + j; row[m++] = J2[36 * (size_t)e + 6 * k + j] * scale[6 * s2 + j]; }
         const double rk = r[6 * (size_t)e + k];
         for (int p = 0; p < m; ++p) {
           y[idx[p]] += row[p] * rk;
@@ -814,11 +1000,27 @@ double oracle_po_cost(int K, int E, const int* idx1, const int* idx2, const doub
   return total;
 }
 
-// What ceres::Solve does for a POProblem (reference slam.cpp:1283-1293).
+// What ceres::Solve does for a POProblem (reference slam.cpp:1283-1293).  solver 1: sparse Cholesky of the normal equations
+// (the reference's SPARSE_NORMAL_CHOLESKY); 0: dense Cholesky (cross-check of the sparse code, same step).
+// stats (optional, 2 doubles): flops of the last numeric factorisation, non-zeros of L.
+int oracle_po_solve2(int K, int E, int max_iters, const int* idx1, const int* idx2, const double* cons,
+                     const double* lm_opts, int solver, double* params, double* summary8, double* trace, double* stats) {
+  POProgram p;
+  p.K = K; p.E = E; p.idx1 = idx1; p.idx2 = idx2; p.cons = cons; p.params = params; p.solver = solver;
+  p.setup();
+  LMOptions o; o.max_iterations = max_iters;
+  if (lm_opts) { o.function_tolerance = lm_opts[0]; o.gradient_tolerance = lm_opts[1]; o.parameter_tolerance = lm_opts[2]; o.initial_radius = lm_opts[3]; }
+  LMSummary s;
+  levenberg_marquardt(p, o, &s, trace);
+  write_summary(s, summary8);
+  if (stats) { stats[0] = (double)p.last_factor_flops(); stats[1] = (double)p.chol.Lx.size(); }
+  return 0;
+}
+
 int oracle_po_solve(int K, int E, int max_iters, const int* idx1, const int* idx2, const double* cons,
                     const double* lm_opts, double* params, double* summary8, double* trace) {
   POProgram p;
-  p.K = K; p.E = E; p.idx1 = idx1; p.idx2 = idx2; p.cons = cons; p.params = params;
+  p.K = K; p.E = E; p.idx1 = idx1; p.idx2 = idx2; p.cons = cons; p.params = params; p.solver = 0;
   p.setup();
   LMOptions o; o.max_iterations = max_iters;
   if (lm_opts) { o.function_tolerance = lm_opts[0]; o.gradient_tolerance = lm_opts[1]; o.parameter_tolerance = lm_opts[2]; o.initial_radius = lm_opts[3]; }

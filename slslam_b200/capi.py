@@ -23,7 +23,7 @@ EXPORTS = [
     "slslam_lba_solve", "slslam_lba_solve_batch", "slslam_lba_last_timings", "slslam_lba_batch_create", "slslam_lba_batch_solve",
     "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_max_active_clusters", "slslam_lba_batch_transfer_bytes", "slslam_lba_batch_phase_cycles", "slslam_lba_batch_plan_cycles", "slslam_lba_batch_destroy",
     "slslam_lba_plan_check", "slslam_lba_launch_shape", "slslam_lba_pipeline_create", "slslam_lba_pipeline_submit", "slslam_lba_pipeline_wait", "slslam_lba_pipeline_destroy",
-    "slslam_ransac_score", "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate", "slslam_po_last_solve_ms",
+    "slslam_ransac_score", "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate", "slslam_po_last_solve_ms", "slslam_po_last_stats", "slslam_po_get_limits",
 ]
 
 dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
@@ -48,6 +48,15 @@ class Summary(C.Structure):
     _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double), ("fixed_cost", C.c_double),
                 ("gradient_max_norm", C.c_double), ("num_successful_steps", C.c_int32),
                 ("num_unsuccessful_steps", C.c_int32), ("termination_type", C.c_int32), ("iterations", C.c_int32)]
+
+
+class PoStats(C.Structure):
+    _fields_ = [("sparse", C.c_int32), ("free_poses", C.c_int32), ("factor_blocks", C.c_int64),
+                ("block_updates", C.c_int64), ("max_column_rows", C.c_int32), ("iterations_enqueued", C.c_int32)]
+
+
+class PoLimits(C.Structure):
+    _fields_ = [("max_column_blocks_sparse", C.c_int32), ("max_free_poses_dense", C.c_int32)]
 
 
 class Limits(C.Structure):
@@ -116,6 +125,10 @@ def lib():
         L.slslam_po_solve_trace.argtypes = [C.POINTER(PoDesc), dp, C.POINTER(Summary), dp]
         L.slslam_po_evaluate.argtypes = [C.POINTER(PoDesc), dp, dp, dp, dp, dp]
         L.slslam_po_last_solve_ms.restype = C.c_float
+        L.slslam_po_last_stats.argtypes = [C.POINTER(PoStats)]
+        L.slslam_po_last_stats.restype = None
+        L.slslam_po_get_limits.argtypes = [C.POINTER(PoLimits)]
+        L.slslam_po_get_limits.restype = None
         _LIB = L
     return _LIB
 
@@ -365,6 +378,19 @@ def po_solve(g, params=None, max_iters=10, lm_opts=None):
     tr = np.zeros((max(1, max_iters), TRACE_WIDTH))
     _check(lib().slslam_po_solve_trace(C.byref(k.desc), _d(p), C.byref(s), _d(tr)))
     return p, summary_dict(s, tr)
+
+
+def po_last_stats():
+    """How the last po_solve of this thread factored the normal equations (slslam_po_last_stats)."""
+    st = PoStats()
+    lib().slslam_po_last_stats(C.byref(st))
+    return {k: getattr(st, k) for k, _ in PoStats._fields_}
+
+
+def po_limits():
+    lim = PoLimits()
+    lib().slslam_po_get_limits(C.byref(lim))
+    return {k: getattr(lim, k) for k, _ in PoLimits._fields_}
 
 
 def po_evaluate(g, params=None):

@@ -4,8 +4,10 @@
 // Replaces what POProblem::build + ceres::Solve do (reference src/po_problem.cpp:40-77, src/slam.cpp:1283-1293).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
+#include <set>
 #include <vector>
 
 #include "common_host.h"
@@ -19,7 +21,97 @@ struct PoPlan {
   int K = 0, E = 0, Kf = 0, n = 0;
   std::vector<int> slot, slot_pose, inc_off, inc, blk_i, blk_j, blk_off, contrib;
   std::vector<unsigned char> active;
+  // block-sparse factorisation (symbolic part): elimination order, the blocks of L, the update list of every column
+  bool sparse = false;
+  int nsb = 0, max_rows = 0;
+  long long dense_blocks = 0;
+  std::vector<int> slot_pos, col_off, row_pos, tri_off, blk_dst;
+  std::vector<int2> tri;
 };
+
+// Symbolic analysis of the block graph of the free poses: exact greedy minimum-degree order (ties by index), the
+// structure of every column of L (the eliminated node's remaining neighbours, which become a clique), block numbering
+// and, per column, the (destination, source a, source b) list of its updates.  Returns false when the factor is too
+// full for the sparse kernel to pay (or a column exceeds its shared-memory panel): the dense path takes over.
+static bool build_po_sparse(const slslam_po_desc& d, PoPlan& p) {
+  const int Kf = p.Kf;
+  p.dense_blocks = (long long)Kf * (Kf + 1) / 2;
+  if (Kf == 0) return false;
+  std::vector<std::set<int> > adj(Kf);
+  for (int e = 0; e < d.num_edges; ++e) {
+    const int a = p.slot[d.pose_index_1[e]], b = p.slot[d.pose_index_2[e]];
+    if (a >= 0 && b >= 0 && a != b) { adj[a].insert(b); adj[b].insert(a); }
+  }
+  std::set<std::pair<int, int> > queue;                 // (degree, node)
+  for (int v = 0; v < Kf; ++v) queue.insert(std::make_pair((int)adj[v].size(), v));
+  std::vector<int> order; order.reserve(Kf);
+  std::vector<std::vector<int> > col_nodes(Kf);         // by elimination step: the remaining neighbours
+  long long nblocks = Kf, ntri = 0;
+  for (int step = 0; step < Kf; ++step) {
+    const int v = queue.begin()->second;
+    queue.erase(queue.begin());
+    order.push_back(v);
+    std::vector<int> nb(adj[v].begin(), adj[v].end());
+    for (int u : nb) { queue.erase(std::make_pair((int)adj[u].size(), u)); adj[u].erase(v); }
+    for (size_t a = 0; a < nb.size(); ++a)
+      for (size_t b = a + 1; b < nb.size(); ++b) { adj[nb[a]].insert(nb[b]); adj[nb[b]].insert(nb[a]); }
+    for (int u : nb) queue.insert(std::make_pair((int)adj[u].size(), u));
+    adj[v].clear();
+    nblocks += (long long)nb.size();
+    ntri += (long long)nb.size() * ((long long)nb.size() + 1) / 2;
+    p.max_rows = std::max(p.max_rows, (int)nb.size());
+    col_nodes[step].swap(nb);
+    if (nblocks * 3 > p.dense_blocks && Kf > 64) return false;      // more than a third of the dense factor: not sparse
+    if (ntri > (1LL << 24)) return false;
+  }
+  if (p.max_rows > PO_SP_MAXROWS) return false;
+  p.slot_pos.assign(Kf, 0);
+  for (int k = 0; k < Kf; ++k) p.slot_pos[order[k]] = k;
+  p.col_off.assign(Kf + 1, 0);
+  p.row_pos.clear(); p.row_pos.reserve((size_t)(nblocks - Kf));
+  for (int c = 0; c < Kf; ++c) {
+    std::vector<int> rows;
+    for (int u : col_nodes[c]) rows.push_back(p.slot_pos[u]);
+    std::sort(rows.begin(), rows.end());
+    p.row_pos.insert(p.row_pos.end(), rows.begin(), rows.end());
+    p.col_off[c + 1] = (int)p.row_pos.size();
+  }
+  p.nsb = (int)nblocks;
+  // block id of (row position, column position), row > column: binary search in the column's ascending row list
+  auto block_id = [&](int r, int c) {
+    const int* b = &p.row_pos[p.col_off[c]];
+    const int* e = &p.row_pos[p.col_off[c + 1]];
+    const int* it = std::lower_bound(b, e, r);
+    return Kf + (int)(it - &p.row_pos[0]);
+  };
+  p.tri_off.assign(Kf + 1, 0);
+  p.tri.clear(); p.tri.reserve((size_t)ntri);
+  for (int c = 0; c < Kf; ++c) {
+    const int o0 = p.col_off[c], m = p.col_off[c + 1] - o0;
+    for (int a = 0; a < m; ++a)
+      for (int b = 0; b <= a; ++b) {
+        int2 t;
+        t.x = (a == b) ? p.row_pos[o0 + a] : block_id(p.row_pos[o0 + a], p.row_pos[o0 + b]);
+        t.y = a | (b << 16);
+        p.tri.push_back(t);
+      }
+    p.tri_off[c + 1] = (int)p.tri.size();
+  }
+  // where the structurally non-zero blocks of J^T J go, and which of their two poses is the row block
+  p.blk_dst.resize(p.blk_i.size());
+  for (size_t b = 0; b < p.blk_i.size(); ++b) {
+    const int si = p.blk_i[b], sj = p.blk_j[b];
+    if (si == sj) { p.blk_dst[b] = p.slot_pos[si]; continue; }
+    if (p.slot_pos[si] < p.slot_pos[sj]) {
+      // the row block is the one eliminated later: swap the roles (and the pose1 / pose2 bit of every contribution)
+      std::swap(p.blk_i[b], p.blk_j[b]);
+      for (int u = p.blk_off[b]; u < p.blk_off[b + 1]; ++u) p.contrib[u] ^= 1;
+    }
+    p.blk_dst[b] = block_id(p.slot_pos[p.blk_i[b]], p.slot_pos[p.blk_j[b]]);
+  }
+  p.sparse = true;
+  return true;
+}
 
 static int validate_po(const slslam_po_desc& d) {
   if (d.num_poses < 0 || d.num_edges < 0 || d.max_iterations < 0) return SLSLAM_ERR_INVALID;
@@ -70,12 +162,60 @@ static void build_po_plan(const slslam_po_desc& d, bool all_free, PoPlan& p) {
   }
 }
 
-// One pooled device allocation; `take` hands out 256-byte aligned slices.
+// One pooled device allocation; `reserve` hands out 256-byte aligned slices.
 struct Pool {
   char* base = nullptr;
   size_t off = 0;
   size_t reserve(size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; }
 };
+
+// Grow-only device pool, pinned upload / result staging and events cached per host thread: a solve does no cudaMalloc,
+// cudaMallocHost or cudaFree once the thread has seen a graph of that size (round 1 paid them on every call).
+struct PoWorkspace {
+  int device = -1;
+  char* d_pool = nullptr; size_t d_cap = 0;
+  char* h_up = nullptr; size_t up_cap = 0;
+  char* h_res = nullptr; size_t res_cap = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> it_ev;
+  int ensure(int dev, size_t d_bytes, size_t up_bytes, size_t res_bytes, int iters) {
+    if (device != dev) { release(); device = dev; }
+    if (!ev0) CUDA_TRY(cudaEventCreate(&ev0));
+    if (!ev1) CUDA_TRY(cudaEventCreate(&ev1));
+    while ((int)it_ev.size() < iters) { cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); it_ev.push_back(e); }
+    if (d_bytes > d_cap) {
+      if (d_pool) cudaFree(d_pool);
+      d_pool = nullptr; d_cap = 0;
+      CUDA_TRY(cudaMalloc((void**)&d_pool, d_bytes + d_bytes / 4));
+      d_cap = d_bytes + d_bytes / 4;
+    }
+    if (up_bytes > up_cap) {
+      if (h_up) cudaFreeHost(h_up);
+      h_up = nullptr; up_cap = 0;
+      CUDA_TRY(cudaMallocHost((void**)&h_up, up_bytes + up_bytes / 4));
+      up_cap = up_bytes + up_bytes / 4;
+    }
+    if (res_bytes > res_cap) {
+      if (h_res) cudaFreeHost(h_res);
+      h_res = nullptr; res_cap = 0;
+      CUDA_TRY(cudaMallocHost((void**)&h_res, res_bytes + res_bytes / 4));
+      res_cap = res_bytes + res_bytes / 4;
+    }
+    return SLSLAM_OK;
+  }
+  void release() {
+    if (d_pool) cudaFree(d_pool);
+    if (h_up) cudaFreeHost(h_up);
+    if (h_res) cudaFreeHost(h_res);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    for (cudaEvent_t e : it_ev) cudaEventDestroy(e);
+    it_ev.clear();
+    d_pool = h_up = h_res = nullptr; d_cap = up_cap = res_cap = 0; ev0 = ev1 = nullptr;
+  }
+};
+static thread_local PoWorkspace g_po_ws;
+static thread_local slslam_po_stats g_po_stats;
 
 static int po_run(const slslam_po_desc* desc, const double* poses_in, double* poses_out, slslam_summary* summary_out,
                   double* trace_out, bool evaluate_only, double* res_out, double* j1_out, double* j2_out, double* cost_out) {
@@ -85,19 +225,29 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   for (size_t i = 0; i < 6 * (size_t)K; ++i) if (!std::isfinite(poses_in[i])) return SLSLAM_ERR_NUMERICAL;
   rc = ensure_device(-1);
   if (rc != SLSLAM_OK) return rc;
+  int dev = 0;
+  cudaGetDevice(&dev);
   PoPlan p;
   build_po_plan(*desc, evaluate_only, p);
+  const bool sparse = !evaluate_only && !getenv("SLSLAM_PO_DENSE") && build_po_sparse(*desc, p);
   const int n = p.n, M = n + 1, ld = (M + 7) & ~7, nblk = (int)p.blk_i.size();
   const int max_iters = desc->max_iterations;
   const int nb32 = (n + PO_NB - 1) / PO_NB;
+  memset(&g_po_stats, 0, sizeof(g_po_stats));
+  g_po_stats.free_poses = p.Kf; g_po_stats.sparse = sparse ? 1 : 0;
+  g_po_stats.factor_blocks = sparse ? p.nsb : (int64_t)p.Kf * (p.Kf + 1) / 2;
+  g_po_stats.block_updates = sparse ? (int64_t)p.tri.size() : 0;
+  g_po_stats.max_column_rows = sparse ? p.max_rows : p.Kf;
 
   Pool pool;
-  const size_t Ez = std::max(E, 1), Kz = std::max(K, 1), nz = std::max(n, 1);
+  const size_t Ez = std::max(E, 1), Kz = std::max(K, 1), nz = std::max(n, 1), Kfz = std::max(p.Kf, 1);
   const size_t o_idx1 = pool.reserve(4 * Ez), o_idx2 = pool.reserve(4 * Ez), o_cons = pool.reserve(48 * Ez);
   const size_t o_slot = pool.reserve(4 * Kz), o_spose = pool.reserve(4 * nz), o_act = pool.reserve(Ez);
   const size_t o_incoff = pool.reserve(4 * (p.inc_off.size() + 1)), o_inc = pool.reserve(4 * (p.inc.size() + 1));
   const size_t o_bi = pool.reserve(4 * (size_t)(nblk + 1)), o_bj = pool.reserve(4 * (size_t)(nblk + 1));
   const size_t o_boff = pool.reserve(4 * (size_t)(nblk + 2)), o_contrib = pool.reserve(4 * (p.contrib.size() + 1));
+  const size_t o_spos = pool.reserve(4 * Kfz), o_coff = pool.reserve(4 * (Kfz + 1)), o_rpos = pool.reserve(4 * (p.row_pos.size() + 1));
+  const size_t o_toff = pool.reserve(4 * (Kfz + 1)), o_tri = pool.reserve(8 * (p.tri.size() + 1)), o_bdst = pool.reserve(4 * (size_t)(nblk + 1));
   const size_t o_x = pool.reserve(48 * Kz);
   const size_t o_state = pool.reserve(sizeof(PoState));
   const size_t upload_end = pool.off;
@@ -105,30 +255,46 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   const size_t o_r = pool.reserve(2 * 48 * Ez), o_J1 = pool.reserve(2 * 288 * Ez), o_J2 = pool.reserve(2 * 288 * Ez);
   const size_t o_ce = pool.reserve(2 * 8 * Ez), o_mval = pool.reserve(8 * Ez);
   const size_t o_scale = pool.reserve(8 * nz), o_cn = pool.reserve(8 * nz), o_g = pool.reserve(8 * nz), o_y = pool.reserve(8 * nz);
+  const size_t o_bz = pool.reserve(8 * nz), o_us = pool.reserve(8 * nz), o_yp = pool.reserve(8 * nz);
   const size_t o_summ = pool.reserve(sizeof(slslam_summary));
   const size_t o_trace = pool.reserve(8 * (size_t)SLSLAM_TRACE_WIDTH * std::max(max_iters, 1));
   const size_t o_Ld = pool.reserve(8 * (size_t)PO_NB * PO_NB * std::max(nb32, 1));
   const size_t o_flags = pool.reserve(4 * (size_t)std::max(nb32, 1));
-  const size_t o_H = evaluate_only ? pool.off : pool.reserve(8 * (size_t)M * ld);
-  CUDA_TRY(cudaMalloc((void**)&pool.base, pool.off));
+  const size_t hb_bytes = sparse ? 288 * (size_t)std::max(p.nsb, 1) : 0;
+  const size_t o_Hb = pool.reserve(hb_bytes);
+  const size_t o_H = (evaluate_only || sparse) ? pool.off : pool.reserve(8 * (size_t)M * ld);
+  const size_t res_bytes = 48 * Kz + sizeof(slslam_summary) + 8 * (size_t)SLSLAM_TRACE_WIDTH * std::max(max_iters, 1) + 4 * (size_t)std::max(max_iters, 1) + 1024;
+  PoWorkspace& ws = g_po_ws;
+  rc = ws.ensure(dev, pool.off, upload_end, res_bytes, std::max(max_iters, 1));
+  if (rc != SLSLAM_OK) return rc;
+  pool.base = ws.d_pool;
 
-  std::vector<char> host(upload_end, 0);
+  char* host = ws.h_up;
+  memset(host, 0, upload_end);
   if (E > 0) {
-    memcpy(host.data() + o_idx1, desc->pose_index_1, 4 * (size_t)E);
-    memcpy(host.data() + o_idx2, desc->pose_index_2, 4 * (size_t)E);
-    memcpy(host.data() + o_cons, desc->constraints, 48 * (size_t)E);
-    memcpy(host.data() + o_act, p.active.data(), (size_t)E);
+    memcpy(host + o_idx1, desc->pose_index_1, 4 * (size_t)E);
+    memcpy(host + o_idx2, desc->pose_index_2, 4 * (size_t)E);
+    memcpy(host + o_cons, desc->constraints, 48 * (size_t)E);
+    memcpy(host + o_act, p.active.data(), (size_t)E);
   }
-  if (K > 0) { memcpy(host.data() + o_slot, p.slot.data(), 4 * (size_t)K); memcpy(host.data() + o_x, poses_in, 48 * (size_t)K); }
-  if (p.Kf > 0) memcpy(host.data() + o_spose, p.slot_pose.data(), 4 * (size_t)p.Kf);
-  memcpy(host.data() + o_incoff, p.inc_off.data(), 4 * p.inc_off.size());
-  if (!p.inc.empty()) memcpy(host.data() + o_inc, p.inc.data(), 4 * p.inc.size());
+  if (K > 0) { memcpy(host + o_slot, p.slot.data(), 4 * (size_t)K); memcpy(host + o_x, poses_in, 48 * (size_t)K); }
+  if (p.Kf > 0) memcpy(host + o_spose, p.slot_pose.data(), 4 * (size_t)p.Kf);
+  memcpy(host + o_incoff, p.inc_off.data(), 4 * p.inc_off.size());
+  if (!p.inc.empty()) memcpy(host + o_inc, p.inc.data(), 4 * p.inc.size());
   if (nblk > 0) {
-    memcpy(host.data() + o_bi, p.blk_i.data(), 4 * (size_t)nblk);
-    memcpy(host.data() + o_bj, p.blk_j.data(), 4 * (size_t)nblk);
-    memcpy(host.data() + o_contrib, p.contrib.data(), 4 * p.contrib.size());
+    memcpy(host + o_bi, p.blk_i.data(), 4 * (size_t)nblk);
+    memcpy(host + o_bj, p.blk_j.data(), 4 * (size_t)nblk);
+    memcpy(host + o_contrib, p.contrib.data(), 4 * p.contrib.size());
   }
-  memcpy(host.data() + o_boff, p.blk_off.data(), 4 * p.blk_off.size());
+  memcpy(host + o_boff, p.blk_off.data(), 4 * p.blk_off.size());
+  if (sparse) {
+    memcpy(host + o_spos, p.slot_pos.data(), 4 * (size_t)p.Kf);
+    memcpy(host + o_coff, p.col_off.data(), 4 * p.col_off.size());
+    if (!p.row_pos.empty()) memcpy(host + o_rpos, p.row_pos.data(), 4 * p.row_pos.size());
+    memcpy(host + o_toff, p.tri_off.data(), 4 * p.tri_off.size());
+    if (!p.tri.empty()) memcpy(host + o_tri, p.tri.data(), 8 * p.tri.size());
+    if (nblk > 0) memcpy(host + o_bdst, p.blk_dst.data(), 4 * (size_t)nblk);
+  }
   PoState st; memset(&st, 0, sizeof(st));
   st.radius = desc->initial_trust_region_radius > 0 ? desc->initial_trust_region_radius : 1e4;   // Ceres 1.7.0 defaults
   st.decrease_factor = 2.0;
@@ -136,7 +302,7 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   st.gtol = desc->gradient_tolerance > 0 ? desc->gradient_tolerance : 1e-10;
   st.ptol = desc->parameter_tolerance > 0 ? desc->parameter_tolerance : 1e-8;
   st.max_iters = max_iters; st.term = SLSLAM_NO_CONVERGENCE;
-  memcpy(host.data() + o_state, &st, sizeof(st));
+  memcpy(host + o_state, &st, sizeof(st));
 
   PoDev d; memset(&d, 0, sizeof(d));
   char* B = pool.base;
@@ -154,17 +320,33 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   d.st = (PoState*)(B + o_state);
   d.trace = trace_out ? (double*)(B + o_trace) : nullptr;
   d.summary = (slslam_summary*)(B + o_summ);
+  d.sparse = sparse ? 1 : 0; d.Kf = p.Kf; d.nsb = p.nsb;
+  d.Hb = (double*)(B + o_Hb); d.bz = (double*)(B + o_bz); d.us = (double*)(B + o_us); d.yp = (double*)(B + o_yp);
+  d.slot_pos = (const int*)(B + o_spos); d.col_off = (const int*)(B + o_coff); d.row_pos = (const int*)(B + o_rpos);
+  d.tri_off = (const int*)(B + o_toff); d.tri = (const int2*)(B + o_tri); d.blk_dst = (const int*)(B + o_bdst);
 
   cudaStream_t s = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   unsigned int* d_flags = (unsigned int*)(B + o_flags);
   int bs_ctas = 1;
+  // results land in pinned memory: x | summary | trace | per-iteration copies of PoState::done
+  double* h_x = (double*)ws.h_res;
+  slslam_summary* h_summ = (slslam_summary*)(ws.h_res + 48 * Kz);
+  double* h_trace = (double*)(ws.h_res + 48 * Kz + ((sizeof(slslam_summary) + 255) & ~(size_t)255));
+  volatile int* h_done = (volatile int*)((char*)h_trace + 8 * (size_t)SLSLAM_TRACE_WIDTH * std::max(max_iters, 1));
+  const size_t sp_smem = (size_t)(2 * PO_SP_MAXROWS * 36 + 8) * 8;
+  int enqueued = 0;
   rc = SLSLAM_OK;
 #define PO_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_last_error(cudaGetErrorString(e_)); cudaGetLastError(); rc = SLSLAM_ERR_CUDA; goto done; } } while (0)
-  PO_TRY(cudaMemcpyAsync(B, host.data(), upload_end, cudaMemcpyHostToDevice, s));
+  if (sparse) {
+    static bool attr_set[16] = {false};
+    if (dev < 0 || dev >= 16 || !attr_set[dev]) {
+      PO_TRY(cudaFuncSetAttribute(po_sp_factor_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
+      if (dev >= 0 && dev < 16) attr_set[dev] = true;
+    }
+  }
+  PO_TRY(cudaMemcpyAsync(B, host, upload_end, cudaMemcpyHostToDevice, s));
   if (trace_out) PO_TRY(cudaMemsetAsync(B + o_trace, 0, 8 * (size_t)SLSLAM_TRACE_WIDTH * std::max(max_iters, 1), s));
-  PO_TRY(cudaEventCreate(&ev0)); PO_TRY(cudaEventCreate(&ev1));
-  PO_TRY(cudaEventRecord(ev0, s));
+  PO_TRY(cudaEventRecord(ws.ev0, s));
   if (E > 0) po_linearize<<<(E + 127) / 128, 128, 0, s>>>(d, 0, 1, evaluate_only ? 1 : 0);
   if (evaluate_only) {
     PO_TRY(cudaGetLastError());
@@ -183,32 +365,42 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
     }
     goto done;
   }
-  if (!evaluate_only && n > 0) {
-    // back-substitution spreads its 32-column blocks over co-resident CTAs (cooperative launch)
-    int dev = 0, sms = 1, per_sm = 1;
-    cudaGetDevice(&dev);
+  if (!sparse && n > 0) {
+    // dense path: back-substitution spreads its 32-column blocks over co-resident CTAs (cooperative launch)
+    int sms = 1, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, po_backsolve, 256, 0) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
     bs_ctas = std::max(1, std::min(nb32, sms * std::max(per_sm, 1)));
     bs_ctas = std::min(bs_ctas, 64);
-    if ((nb32 + bs_ctas - 1) / bs_ctas > PO_BS_MAXOWN) { set_last_error("pose graph too large for the back-substitution kernel"); rc = SLSLAM_ERR_UNSUPPORTED; goto done; }
+    if ((nb32 + bs_ctas - 1) / bs_ctas > PO_BS_MAXOWN) {
+      set_last_error("pose graph with a nearly full factor and more than 2730 free poses: beyond the dense fallback (slslam_po_get_limits)");
+      rc = SLSLAM_ERR_UNSUPPORTED; goto done;
+    }
     PO_TRY(cudaMemsetAsync(d_flags, 0, 4 * (size_t)std::max(nb32, 1), s));
   }
   if (n > 0) po_colnorm_grad<<<(n + 127) / 128, 128, 0, s>>>(d, 0);
   po_refresh<<<1, 256, 0, s>>>(d, 1);
   if (n > 0) {
     for (int it = 0; it < max_iters; ++it) {
-      PO_TRY(cudaMemsetAsync(d.H, 0, 8 * (size_t)M * ld, s));
-      po_assemble<<<(nblk * 36 + n + 255) / 256, 256, 0, s>>>(d);
-      for (int k0 = 0; k0 < n; k0 += PO_NB) {
-        const int nb = std::min(PO_NB, n - k0), t0 = k0 + nb;
-        po_chol_panel<<<1 + (M - t0 + PO_TR - 1) / PO_TR, PO_TR, 0, s>>>(d, k0);
-        if (t0 < n) {
-          const int T = (M - t0 + PO_TS - 1) / PO_TS;
-          po_chol_syrk<<<T * (T + 1) / 2, 256, 0, s>>>(d, k0, nb, t0, T);
+      // The loop is enqueued without waiting for the device.  PoState::done of iteration it - 2 (copied to pinned
+      // memory behind that iteration) is looked at only if its event has already completed: after termination at most
+      // a couple of iterations of early-out launches are enqueued instead of all the remaining ones.
+      if (it >= 2 && cudaEventQuery(ws.it_ev[it - 2]) == cudaSuccess && h_done[it - 2]) break;
+      if (sparse) {
+        PO_TRY(cudaMemsetAsync(d.Hb, 0, hb_bytes, s));
+        po_sp_assemble<<<(nblk * 36 + n + 255) / 256, 256, 0, s>>>(d);
+        po_sp_factor_solve<<<1, PO_SP_NT, sp_smem, s>>>(d);
+      } else {
+        PO_TRY(cudaMemsetAsync(d.H, 0, 8 * (size_t)M * ld, s));
+        po_assemble<<<(nblk * 36 + n + 255) / 256, 256, 0, s>>>(d);
+        for (int k0 = 0; k0 < n; k0 += PO_NB) {
+          const int nb = std::min(PO_NB, n - k0), t0 = k0 + nb;
+          po_chol_panel<<<1 + (M - t0 + PO_TR - 1) / PO_TR, PO_TR, 0, s>>>(d, k0);
+          if (t0 < n) {
+            const int T = (M - t0 + PO_TS - 1) / PO_TS;
+            po_chol_syrk<<<T * (T + 1) / 2, 256, 0, s>>>(d, k0, nb, t0, T);
+          }
         }
-      }
-      {
         unsigned int gen = (unsigned int)(it + 1);
         void* args[3] = {(void*)&d, (void*)&d_flags, (void*)&gen};
         PO_TRY(cudaLaunchCooperativeKernel((const void*)po_backsolve, dim3((unsigned)bs_ctas), dim3(256), args, 0, s));
@@ -219,28 +411,29 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
       po_accept<<<(6 * K + 255) / 256, 256, 0, s>>>(d);
       po_colnorm_grad<<<(n + 127) / 128, 128, 0, s>>>(d, 1);
       po_refresh<<<1, 256, 0, s>>>(d, 0);
+      PO_TRY(cudaMemcpyAsync((void*)(h_done + it), &d.st->done, 4, cudaMemcpyDeviceToHost, s));
+      PO_TRY(cudaEventRecord(ws.it_ev[it], s));
+      ++enqueued;
     }
   }
+  g_po_stats.iterations_enqueued = enqueued;
   po_finish<<<1, 1, 0, s>>>(d);
   PO_TRY(cudaGetLastError());
-  PO_TRY(cudaEventRecord(ev1, s));
+  PO_TRY(cudaEventRecord(ws.ev1, s));
   {
-    std::vector<double> xo((size_t)6 * Kz);
     slslam_summary summ;
-    PO_TRY(cudaMemcpyAsync(xo.data(), d.x, 48 * (size_t)Kz, cudaMemcpyDeviceToHost, s));
-    PO_TRY(cudaMemcpyAsync(&summ, d.summary, sizeof(summ), cudaMemcpyDeviceToHost, s));
-    if (trace_out) PO_TRY(cudaMemcpyAsync(trace_out, d.trace, 8 * (size_t)SLSLAM_TRACE_WIDTH * std::max(max_iters, 0), cudaMemcpyDeviceToHost, s));
+    PO_TRY(cudaMemcpyAsync(h_x, d.x, 48 * (size_t)Kz, cudaMemcpyDeviceToHost, s));
+    PO_TRY(cudaMemcpyAsync(h_summ, d.summary, sizeof(summ), cudaMemcpyDeviceToHost, s));
+    if (trace_out) PO_TRY(cudaMemcpyAsync(h_trace, d.trace, 8 * (size_t)SLSLAM_TRACE_WIDTH * std::max(max_iters, 0), cudaMemcpyDeviceToHost, s));
     PO_TRY(cudaStreamSynchronize(s));
-    PO_TRY(cudaEventElapsedTime(&g_po_last_ms, ev0, ev1));
+    PO_TRY(cudaEventElapsedTime(&g_po_last_ms, ws.ev0, ws.ev1));
     // parameters are only overwritten once everything has succeeded
-    if (K > 0) memcpy(poses_out, xo.data(), 48 * (size_t)K);
-    if (summary_out) *summary_out = summ;
+    if (K > 0) memcpy(poses_out, h_x, 48 * (size_t)K);
+    if (trace_out) memcpy(trace_out, h_trace, 8 * (size_t)SLSLAM_TRACE_WIDTH * std::max(max_iters, 0));
+    if (summary_out) *summary_out = *h_summ;
   }
 done:
 #undef PO_TRY
-  if (ev0) cudaEventDestroy(ev0);
-  if (ev1) cudaEventDestroy(ev1);
-  cudaFree(pool.base);
   return rc;
 }
 
@@ -268,5 +461,13 @@ int slslam_po_evaluate(const slslam_po_desc* desc, const double* poses, double* 
 }
 
 float slslam_po_last_solve_ms(void) { return g_po_last_ms; }
+
+void slslam_po_last_stats(slslam_po_stats* out) { if (out) *out = g_po_stats; }
+
+void slslam_po_get_limits(slslam_po_limits* out) {
+  if (!out) return;
+  out->max_column_blocks_sparse = PO_SP_MAXROWS;
+  out->max_free_poses_dense = PO_NB * PO_BS_MAXOWN * 64 / 6;
+}
 
 }  // extern "C"

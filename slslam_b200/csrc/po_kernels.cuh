@@ -12,6 +12,12 @@
 //       po_chol_syrk      trailing update, 64x64 register-tiled
 //       po_backsolve      L^T y = z, right-looking, one CTA
 //       po_step / po_decide / po_accept / po_refresh   trial point, model decrease, step acceptance, termination
+//   K6' block-sparse path (the default): the pose graph's J^T J is block sparse (odometry band + loop edges) and the
+//       reference factors it sparsely (SPARSE_NORMAL_CHOLESKY, po_problem.cpp:68).  The host orders the free poses by
+//       minimum degree and lays out the 6x6 blocks of L (fill included) with, per column, the list of (source, source,
+//       destination) block updates; po_sp_assemble fills the blocks and po_sp_factor_solve -- ONE CTA, one launch --
+//       runs the whole right-looking block factorisation, carries the right-hand side along and back-substitutes.
+//       The dense kernels above remain as the path for graphs whose factor is nearly full.
 // Every reduction has a fixed order (no atomics): results are bit-reproducible.
 #pragma once
 #include <cuda_runtime.h>
@@ -19,6 +25,7 @@
 
 #include "../../include/slslam_b200.h"
 #include "po_math.cuh"
+#include "lba_math.cuh"
 
 namespace slslam {
 
@@ -51,6 +58,16 @@ struct PoDev {
   PoState* st;
   double* trace;                  // [max_iters][SLSLAM_TRACE_WIDTH]
   slslam_summary* summary;
+  // ---- block-sparse factorisation (sparse != 0); `pos` = position of a reduced block in the elimination order ----
+  int sparse, Kf, nsb;            // nsb = blocks of L: Kf diagonal blocks (block id = position) then the off-diagonal ones
+  double* Hb;                     // [nsb][36] row-major 6x6; off-diagonal block (row pos > col pos): rows of the row block
+  double *bz, *us, *yp;           // [n] in position order: right-hand side, u = W b (see the kernel), solution
+  const int* slot_pos;            // [Kf] position of reduced block (slot) s
+  const int* col_off;             // [Kf + 1] first off-diagonal block of column c (block id = Kf + col_off[c] + a)
+  const int* row_pos;             // [nsb - Kf] row position of every off-diagonal block, ascending inside a column
+  const int* tri_off;             // [Kf + 1] updates of column c
+  const int2* tri;                // x: destination block id, y: a | b << 16 (sources: off-diagonal blocks a >= b of the column)
+  const int* blk_dst;             // [nblk] where po_sp_assemble writes the structurally non-zero blocks of J^T J
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -379,6 +396,188 @@ __global__ void __launch_bounds__(256) po_backsolve(PoDev d, unsigned int* flags
     }
     __syncthreads();
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K6' block-sparse: assembly.  One thread per entry of every structurally non-zero block of J^T J (blk_i = row
+// block, the later one in the elimination order; contribution lists as in po_assemble); Hb must have been zeroed (fill).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void po_sp_assemble(PoDev d) {
+  const PoState* st = d.st;
+  if (st->done) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int set = st->cur;
+  if (t < d.nblk * 36) {
+    const int b = t / 36, p = (t % 36) / 6, q = t % 6;
+    const int bi = d.blk_i[b], bj = d.blk_j[b];
+    double s = 0.0;
+    for (int u = d.blk_off[b]; u < d.blk_off[b + 1]; ++u) {
+      const int code = d.contrib[u], e = code >> 1;
+      const double* Ja = ((code & 1) ? d.J2 : d.J1) + ((size_t)set * d.E + e) * 36;
+      const double* Jb = (bi == bj) ? Ja : (((code & 1) ? d.J1 : d.J2) + ((size_t)set * d.E + e) * 36);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s += Ja[6 * k + p] * Jb[6 * k + q];
+    }
+    const int row = 6 * bi + p, col = 6 * bj + q;
+    s *= d.scale[row] * d.scale[col];
+    if (row == col) {
+      const double sc = d.scale[row];
+      s += fmin(fmax(d.cn[row] * sc * sc, 1e-6), 1e32) / st->radius;
+    }
+    d.Hb[(size_t)d.blk_dst[b] * 36 + 6 * p + q] = s;
+  } else {
+    const int i = t - d.nblk * 36;
+    if (i < d.n) d.bz[6 * d.slot_pos[i / 6] + i % 6] = d.g[i] * d.scale[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K6' block-sparse: factorisation + both substitutions in ONE launch of ONE CTA (the elimination order is a chain of
+// dependent block columns; what parallelism a column has -- its panel rows and its block updates -- fits one CTA, and
+// a single CTA keeps the blocks it touches in its L1 between consecutive columns).  Block elimination with explicit
+// inverses of the 6x6 pivot blocks, as in the LBA reduced solve (lba_kernel.cuh): per column c
+//   phase 1  every panel thread forms W = A_cc^-1 in registers (two closed-form 3x3 cofactor inverses + a 3x3 Schur
+//            complement); thread (a, p): row p of P_a = A_ac W, original row kept in shared memory, P written over A_ac;
+//            six threads: u_c = W b_c
+//   phase 2  the planned updates  A_dst -= P_a A_bc^T  (thread per entry, 36 per update) and  b_row(a) -= P_a b_c
+// then, descending, y_c = u_c - sum_a P_ac^T y_row(a) by warp 0.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PO_SP_NT = 1024;
+constexpr int PO_SP_MAXROWS = 160;   // off-diagonal blocks per column the shared-memory panel holds (2 x 288 B each)
+
+__global__ void __launch_bounds__(PO_SP_NT, 1) po_sp_factor_solve(PoDev d) {
+  if (d.st->done) return;
+  extern __shared__ __align__(16) double spsm[];
+  double* orig = spsm;                                  // [MAXROWS][36] original panel rows of the current column
+  double* Pm = spsm + PO_SP_MAXROWS * 36;               // [MAXROWS][36] P = A W
+  double* bc = Pm + PO_SP_MAXROWS * 36;                 // [8] b_c
+  __shared__ int bad;
+  const int tid = threadIdx.x, Kf = d.Kf;
+  if (tid == 0) bad = 0;
+  __syncthreads();
+  for (int c = 0; c < Kf; ++c) {
+    const int o0 = d.col_off[c], m = d.col_off[c + 1] - o0;
+    if (tid < 6 * m + 6) {
+      const double* AJJ = d.Hb + (size_t)c * 36;
+      double A[21], W[21];
+#pragma unroll
+      for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = 0; q <= p; ++q) A[p * (p + 1) / 2 + q] = AJJ[6 * p + q];
+#define L6I(p, q) ((p) * ((p) + 1) / 2 + (q))
+#define SY3(mm, r, cc) mm[(r) <= (cc) ? ((r) == 0 ? (cc) : (r) == 1 ? 2 + (cc) : 5) : ((cc) == 0 ? (r) : (cc) == 1 ? 2 + (r) : 5)]
+      double Ai[6], Si[6], M[9], S[6];
+      bool ok = spd3_inverse(A[L6I(0, 0)], A[L6I(1, 0)], A[L6I(2, 0)], A[L6I(1, 1)], A[L6I(2, 1)], A[L6I(2, 2)], Ai);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+          M[3 * r + cc] = A[L6I(3 + r, 0)] * SY3(Ai, 0, cc) + A[L6I(3 + r, 1)] * SY3(Ai, 1, cc) + A[L6I(3 + r, 2)] * SY3(Ai, 2, cc);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = r; cc < 3; ++cc)
+          SY3(S, r, cc) = A[L6I(3 + cc, 3 + r)] - (M[3 * r] * A[L6I(3 + cc, 0)] + M[3 * r + 1] * A[L6I(3 + cc, 1)] + M[3 * r + 2] * A[L6I(3 + cc, 2)]);
+      ok = spd3_inverse(S[0], S[1], S[2], S[3], S[4], S[5], Si) && ok;
+      double W21[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+          W21[3 * r + cc] = -(SY3(Si, r, 0) * M[cc] + SY3(Si, r, 1) * M[3 + cc] + SY3(Si, r, 2) * M[6 + cc]);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc <= r; ++cc) {
+          W[L6I(r, cc)] = SY3(Ai, r, cc) - (M[r] * W21[cc] + M[3 + r] * W21[3 + cc] + M[6 + r] * W21[6 + cc]);
+          W[L6I(3 + r, 3 + cc)] = SY3(Si, r, cc);
+        }
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) W[L6I(3 + r, cc)] = W21[3 * r + cc];
+#undef SY3
+      if (tid < 6 * m) {
+        const int a = tid / 6, p = tid - 6 * a;
+        double* arow = d.Hb + (size_t)(Kf + o0 + a) * 36 + 6 * p;
+        double av[6], pv[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) av[k] = arow[k];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) s0 += av[k] * W[k >= q ? L6I(k, q) : L6I(q, k)];
+#pragma unroll
+          for (int k = 3; k < 6; ++k) s1 += av[k] * W[k >= q ? L6I(k, q) : L6I(q, k)];
+          pv[q] = s0 + s1;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { orig[36 * a + 6 * p + k] = av[k]; Pm[36 * a + 6 * p + k] = pv[k]; arow[k] = pv[k]; }
+      } else {
+        const int q = tid - 6 * m;
+        if (q == 0 && !ok) bad = 1;
+        double bk[6], uq[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { bk[k] = d.bz[6 * c + k]; if (q == 0) bc[k] = bk[k]; }
+#pragma unroll
+        for (int qq = 0; qq < 6; ++qq) {            // all six (static register indexing), this thread keeps its own
+          double sum = 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) sum += bk[k] * W[k >= qq ? L6I(k, qq) : L6I(qq, k)];
+          uq[qq] = sum;
+        }
+        d.us[6 * c + q] = q == 0 ? uq[0] : q == 1 ? uq[1] : q == 2 ? uq[2] : q == 3 ? uq[3] : q == 4 ? uq[4] : uq[5];
+      }
+#undef L6I
+    }
+    __syncthreads();
+    const int t0 = d.tri_off[c], nt = d.tri_off[c + 1] - t0;
+    for (int e = tid; e < 36 * nt + 6 * m; e += PO_SP_NT) {
+      if (e < 36 * nt) {
+        const int t = e / 36, pq = e - 36 * t, p = pq / 6, q = pq - 6 * p;
+        const int2 tr = d.tri[t0 + t];
+        const double* pa = Pm + 36 * (tr.y & 0xffff) + 6 * p;
+        const double* ob = orig + 36 * (tr.y >> 16) + 6 * q;
+        const double s0 = pa[0] * ob[0] + pa[1] * ob[1] + pa[2] * ob[2];
+        const double s1 = pa[3] * ob[3] + pa[4] * ob[4] + pa[5] * ob[5];
+        d.Hb[(size_t)tr.x * 36 + pq] -= s0 + s1;
+      } else {
+        const int r = e - 36 * nt, a = r / 6, p = r - 6 * a;
+        const double* pa = Pm + 36 * a + 6 * p;
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sum += pa[k] * bc[k];
+        d.bz[6 * d.row_pos[o0 + a] + p] -= sum;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && bad) d.st->chol_fail = 1;
+  // back-substitution by warp 0: y_c = u_c - sum_a P_ac^T y_row(a); lanes over the (a, row) pairs of the column
+  if (tid < 32) {
+    for (int c = Kf - 1; c >= 0; --c) {
+      const int o0 = d.col_off[c], m = d.col_off[c + 1] - o0;
+      double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      for (int r = tid; r < 6 * m; r += 32) {
+        const int a = r / 6, p = r - 6 * a;
+        const double yv = d.yp[6 * d.row_pos[o0 + a] + p];
+        const double* prow = d.Hb + (size_t)(Kf + o0 + a) * 36 + 6 * p;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) acc[q] += prow[q] * yv;
+      }
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+      }
+      if (tid < 6) d.yp[6 * c + tid] = d.us[6 * c + tid] - (tid == 0 ? acc[0] : tid == 1 ? acc[1] : tid == 2 ? acc[2] : tid == 3 ? acc[3] : tid == 4 ? acc[4] : acc[5]);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // solution back in slot order
+  for (int i = tid; i < d.n; i += PO_SP_NT) d.y[i] = d.yp[6 * d.slot_pos[i / 6] + i % 6];
 }
 
 // trial point x' = x - scale*y on the free poses, and the per-edge part of the model decrease -(m.(r + m/2)), m = J delta

