@@ -104,6 +104,17 @@ int slslam_lba_solve(const slslam_lba_desc* desc, double* params_inout, slslam_s
 int slslam_lba_solve_batch(int32_t n, const slslam_lba_desc* descs, double* const* params_inout,
                            slslam_summary* summaries_out);
 
+/* The same with DEVICE-resident inputs: every array the descs point to, and params_dev_inout[i], are device pointers on
+ * the current device (typically slices of a buffer NCCL just received: SURVEY.md 8e, window w -> rank w mod G).  Nothing
+ * is staged or copied: the plan kernel reads the arrays where they are, the parameters are updated IN PLACE, and the
+ * summaries go to summaries_dev_out (device, may be NULL) and / or summaries_host_out (host, may be NULL).  With
+ * summaries_host_out == NULL the call returns once the solve is enqueued on `cuda_stream`; otherwise it waits for it.
+ * Index errors are found on the device (SLSLAM_ERR_INVALID); non-finite parameters are not screened; windows that need
+ * the host planner (a camera observing one line twice) return SLSLAM_ERR_UNSUPPORTED; on a failure detected after the
+ * launch the parameters may have been modified.  16-byte alignment of `observations` is required. */
+int slslam_lba_solve_batch_device(int32_t n, const slslam_lba_desc* descs, double* const* params_dev_inout,
+                                  slslam_summary* summaries_dev_out, slslam_summary* summaries_host_out, void* cuda_stream);
+
 /* Host wall-clock split (ms) of this thread's last slslam_lba_solve / slslam_lba_solve_batch:
  * plan | staging + H2D enqueue | launch + device solve + D2H | copy-out | total, then device time by CUDA events:
  * H2D | kernel | D2H.  ms8 receives 8 doubles. */

@@ -20,7 +20,7 @@ TERMINATION = {0: "NO_CONVERGENCE", 1: "GRADIENT_TOLERANCE", 2: "FUNCTION_TOLERA
 
 EXPORTS = [
     "slslam_version", "slslam_strerror", "slslam_last_error", "slslam_device_count", "slslam_lba_get_limits",
-    "slslam_lba_solve", "slslam_lba_solve_batch", "slslam_lba_last_timings", "slslam_lba_batch_create", "slslam_lba_batch_solve",
+    "slslam_lba_solve", "slslam_lba_solve_batch", "slslam_lba_solve_batch_device", "slslam_lba_last_timings", "slslam_lba_batch_create", "slslam_lba_batch_solve",
     "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_max_active_clusters", "slslam_lba_batch_transfer_bytes", "slslam_lba_batch_phase_cycles", "slslam_lba_batch_plan_cycles", "slslam_lba_batch_destroy",
     "slslam_lba_plan_check", "slslam_lba_launch_shape", "slslam_lba_pipeline_create", "slslam_lba_pipeline_submit", "slslam_lba_pipeline_wait", "slslam_lba_pipeline_destroy",
     "slslam_ransac_score", "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate", "slslam_po_last_solve_ms", "slslam_po_last_stats", "slslam_po_get_limits",
@@ -96,6 +96,8 @@ def lib():
         L.slslam_lba_get_limits.argtypes = [C.POINTER(Limits)]
         L.slslam_lba_solve.argtypes = [C.POINTER(LbaDesc), dp, C.POINTER(Summary)]
         L.slslam_lba_solve_batch.argtypes = [C.c_int32, C.POINTER(LbaDesc), C.POINTER(dp), C.POINTER(Summary)]
+        L.slslam_lba_solve_batch_device.argtypes = [C.c_int32, C.POINTER(LbaDesc), C.POINTER(dp), C.c_void_p, C.POINTER(Summary),
+                                                    C.c_void_p]
         L.slslam_lba_batch_create.argtypes = [C.c_int32, C.POINTER(LbaDesc), C.POINTER(dp), C.c_int32, C.c_int32,
                                               C.POINTER(C.c_void_p)]
         L.slslam_lba_batch_solve.argtypes = [C.c_void_p, C.c_void_p]
@@ -200,6 +202,26 @@ def lba_solve_batch(windows, **kw):
     ss = (Summary * len(windows))()
     _check(lib().slslam_lba_solve_batch(len(windows), descs, pp, ss))
     return ps, [summary_dict(s) for s in ss]
+
+
+def lba_solve_batch_device(shapes, base_ptr, offsets, max_iters=10, robust=True, summaries_dev_ptr=None,
+                           want_host_summaries=True, stream=None, lm_opts=None):
+    """slslam_lba_solve_batch_device: windows whose arrays already live in DEVICE memory (for instance in a buffer NCCL
+    received).  shapes[i] = (C, L, N); offsets[i] = dict(camera_index=, line_index=, fixed_index=, observations=,
+    parameters=) byte offsets from `base_ptr` (a device address).  Parameters are updated in place on the device;
+    returns the summaries (host copies) when asked, else None (the call then only enqueues)."""
+    n = len(shapes)
+    o = [0.0, 0.0, 0.0, 0.0] if lm_opts is None else list(lm_opts)
+    descs = (LbaDesc * n)()
+    pp = (dp * n)()
+    for i, ((Cc, Ll, Nn), off) in enumerate(zip(shapes, offsets)):
+        descs[i] = LbaDesc(Cc, Ll, Nn, max_iters, C.cast(base_ptr + off["camera_index"], ip), C.cast(base_ptr + off["line_index"], ip),
+                           C.cast(base_ptr + off["fixed_index"], ip), C.cast(base_ptr + off["observations"], dp), int(robust),
+                           0.0, -1.0, o[0], o[1], o[2], o[3])
+        pp[i] = C.cast(base_ptr + off["parameters"], dp)
+    ss = (Summary * n)() if want_host_summaries else None
+    _check(lib().slslam_lba_solve_batch_device(n, descs, pp, C.c_void_p(summaries_dev_ptr), ss, C.c_void_p(stream)))
+    return [summary_dict(x) for x in ss] if want_host_summaries else None
 
 
 class LbaBatch:

@@ -21,8 +21,12 @@ static bool is_page_locked(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
+// `device_inputs`: the arrays the descs point to, and `params`, are DEVICE memory (e.g. a buffer NCCL just received):
+// nothing is staged or copied, the plan kernel reads the caller's arrays where they are, the solve kernel updates the
+// parameters in place and writes the summaries to `summ_dev` when given.  Only the headers (< 1 KB per window) go up.
 static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,
-                                    int32_t cluster_size, Workspace* ws, cudaStream_t stream, slslam_lba_batch** out) {
+                                    int32_t cluster_size, Workspace* ws, cudaStream_t stream, slslam_lba_batch** out,
+                                    bool device_inputs = false, slslam_summary* summ_dev = nullptr) {
   if (!out) return SLSLAM_ERR_INVALID;
   *out = nullptr;
   if (n <= 0 || !descs || !params) return SLSLAM_ERR_INVALID;
@@ -30,6 +34,7 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
     const int rc = validate_desc_light(descs[i]);
     if (rc != SLSLAM_OK) return rc;
     if (!params[i]) return SLSLAM_ERR_INVALID;
+    if (device_inputs) continue;
     const int np = 6 * descs[i].num_cameras + 4 * descs[i].num_lines;
     for (int k = 0; k < np; ++k) if (!std::isfinite(params[i][k])) return SLSLAM_ERR_NUMERICAL;
   }
@@ -37,7 +42,7 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
   int rc = ensure_device(device);
   if (rc != SLSLAM_OK) {
     // no device: argument errors still take precedence over the missing GPU (the index checks otherwise run on the device)
-    for (int i = 0; i < n; ++i) { const int v = validate_desc(descs[i]); if (v != SLSLAM_OK) return v; }
+    if (!device_inputs) for (int i = 0; i < n; ++i) { const int v = validate_desc(descs[i]); if (v != SLSLAM_OK) return v; }
     return rc;
   }
   int dev = 0;
@@ -85,21 +90,23 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
     b->trace_off[i] = tt; tt += (size_t)std::max(1, descs[i].max_iterations) * SLSLAM_TRACE_WIDTH;
   }
   b->total_params = tp; b->total_trace = tt;
-  const size_t o_par = reserve(tp * 8);
+  const size_t o_par = device_inputs ? off : reserve(tp * 8);
   std::vector<size_t> o_ci(n), o_li(n), o_fi(n), o_raw(n);
   std::vector<char> direct(n, 0);   // observations copied straight from page-locked caller memory
-  for (int i = 0; i < n; ++i) {
-    const size_t N = (size_t)descs[i].num_observations;
-    o_ci[i] = reserve(4 * N); o_li[i] = reserve(4 * N); o_fi[i] = reserve(8 * N);
+  if (!device_inputs) {
+    for (int i = 0; i < n; ++i) {
+      const size_t N = (size_t)descs[i].num_observations;
+      o_ci[i] = reserve(4 * N); o_li[i] = reserve(4 * N); o_fi[i] = reserve(8 * N);
+    }
+    // observations last, so that the ones that are DMA'd directly leave no hole in the staged prefix
+    for (int i = 0; i < n; ++i) {
+      const size_t N = (size_t)descs[i].num_observations;
+      direct[i] = (N * 64 >= 65536 && is_page_locked(descs[i].observations)) ? 1 : 0;
+    }
+    for (int i = 0; i < n; ++i) if (!direct[i]) o_raw[i] = reserve(64 * (size_t)descs[i].num_observations);
   }
-  // observations last, so that the ones that are DMA'd directly leave no hole in the staged prefix
-  for (int i = 0; i < n; ++i) {
-    const size_t N = (size_t)descs[i].num_observations;
-    direct[i] = (N * 64 >= 65536 && is_page_locked(descs[i].observations)) ? 1 : 0;
-  }
-  for (int i = 0; i < n; ++i) if (!direct[i]) o_raw[i] = reserve(64 * (size_t)descs[i].num_observations);
   const size_t upload = off;
-  for (int i = 0; i < n; ++i) if (direct[i]) o_raw[i] = reserve(64 * (size_t)descs[i].num_observations);
+  if (!device_inputs) for (int i = 0; i < n; ++i) if (direct[i]) o_raw[i] = reserve(64 * (size_t)descs[i].num_observations);
   struct Scratch { size_t cnt, start, fill, lconst, order, slotl; };
   std::vector<Scratch> sc(n);
   std::vector<size_t> o_vg(n), o_vr(n), o_sg(n), o_z(n);
@@ -122,7 +129,8 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
     if (49152 + L / (size_t)CS * 400 + slots_est * ZST * 8 > (size_t)smem_optin) want_zg = true;
   }
   const size_t o_info = reserve(sizeof(PlanInfo) * n);
-  const size_t o_pout = reserve(tp * 8), o_summ = reserve(sizeof(slslam_summary) * n), o_trace = reserve(tt * 8),
+  const size_t o_pout = device_inputs ? off : reserve(tp * 8);
+  const size_t o_summ = reserve(sizeof(slslam_summary) * n), o_trace = reserve(tt * 8),
                o_phase = reserve(sizeof(long long) * NPHASE * n);
   for (int i = 0; i < n; ++i) {
     o_vg[i] = reserve((size_t)CS * vpad_cap * 8); o_vr[i] = reserve((size_t)vpad_cap * 8); o_sg[i] = reserve((size_t)CS * 8 * 8);
@@ -170,10 +178,11 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
     h.obs = (const double*)(dp + q.obs); h.meta = (const int2*)(dp + q.meta); h.line_gid = (const int*)(dp + q.gid);
     h.items = (const uint32_t*)(dp + q.items); h.key_off = (const int*)(dp + q.koff);
     h.params_in = b->d_params_in + b->param_off[i]; h.params_out = b->d_params_out + b->param_off[i];
+    if (device_inputs) { h.params_in = params[i]; h.params_out = const_cast<double*>(params[i]); }   // in place: every read of a block precedes the first group barrier, every write follows the last
     h.Zg = want_zg ? (double*)(dp + o_z[i]) : nullptr;
     h.Vg = (double*)(dp + o_vg[i]); h.Vr = (double*)(dp + o_vr[i]); h.scalg = (double*)(dp + o_sg[i]);
     h.bar = (unsigned int*)(dp + o_bar + (size_t)i * 128);
-    h.summary = b->d_summ + i;
+    h.summary = summ_dev ? summ_dev + i : b->d_summ + i;
     h.trace = ws ? nullptr : b->d_trace + b->trace_off[i];
     h.phase_cycles = ws ? nullptr : b->d_phase + (size_t)NPHASE * i;
     memcpy(host + o_hdr + sizeof(WinHdr) * i, &h, sizeof(h));
@@ -182,6 +191,7 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
     pi.C = wp.C; pi.L = wp.L; pi.N = wp.N; pi.CS = CS; pi.slot_cap = q.slot_cap; pi.item_cap = q.item_cap;
     pi.cam_idx = (const int*)(dp + o_ci[i]); pi.line_idx = (const int*)(dp + o_li[i]); pi.fixed = (const int*)(dp + o_fi[i]);
     pi.obs_raw = (const double*)(dp + o_raw[i]);
+    if (device_inputs) { pi.cam_idx = d.camera_index; pi.line_idx = d.line_index; pi.fixed = d.fixed_index; pi.obs_raw = d.observations; }
     pi.obs = (double*)(dp + q.obs); pi.meta = (int2*)(dp + q.meta); pi.line_gid = (int*)(dp + q.gid);
     pi.items = (uint32_t*)(dp + q.items); pi.key_off = (int*)(dp + q.koff);
     pi.hdr = (WinHdr*)(dp + q.hdr); pi.info = (PlanInfo*)(dp + o_info) + i;
@@ -189,12 +199,14 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
     pi.order = (int*)(dp + s.order);
     pi.slot_line = (int*)(dp + s.slotl);
     memcpy(host + o_pin_in + sizeof(PlanIn) * i, &pi, sizeof(pi));
+    if (device_inputs) continue;
     memcpy(host + o_par + b->param_off[i] * 8, params[i], (size_t)b->nparams[i] * 8);
     memcpy(host + o_ci[i], d.camera_index, 4 * N);
     memcpy(host + o_li[i], d.line_index, 4 * N);
     memcpy(host + o_fi[i], d.fixed_index, 8 * N);
     if (!direct[i]) memcpy(host + o_raw[i], d.observations, 64 * N);
   }
+  b->inplace = device_inputs;
   const double t_staged = now_ms();
   b->upload_bytes = upload;
   cudaError_t e = cudaSuccess;

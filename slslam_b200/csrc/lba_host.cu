@@ -254,6 +254,7 @@ struct slslam_lba_batch {
   size_t upload_bytes = 0;
   int max_active = 0;   // windows of this shape the device keeps resident at once (a larger batch runs in waves)
   unsigned int* d_bar = nullptr; size_t bar_bytes = 0;   // group barrier counters, zeroed before every launch
+  bool inplace = false;    // device-resident inputs: parameters are read and written where the caller keeps them
   bool borrowed = false;   // device pool and pinned staging belong to a Workspace (the calling thread's or a pipeline slot's)
   slslam::Workspace* ws = nullptr;
   // device-side plan (lba_plan_kernel.cuh): where its outputs live in the pool, for the planner parity check
@@ -748,7 +749,7 @@ int slslam_lba_batch_solve(slslam_lba_batch* b, void* cuda_stream) {
   cudaStream_t st = (cudaStream_t)cuda_stream;
   bool need_copy = false;
   for (const auto& p : b->plans) need_copy = need_copy || p.has_unobserved_blocks;
-  if (need_copy) CUDA_TRY(cudaMemcpyAsync(b->d_params_out, b->d_params_in, b->total_params * 8, cudaMemcpyDeviceToDevice, st));
+  if (need_copy && !b->inplace) CUDA_TRY(cudaMemcpyAsync(b->d_params_out, b->d_params_in, b->total_params * 8, cudaMemcpyDeviceToDevice, st));
   CUDA_TRY(cudaMemsetAsync(b->d_bar, 0, b->bar_bytes, st));
   // cooperative launches (every CTA of a group must be resident: the group barrier spins), `max_active` windows per wave
   SmemLayout lay = b->lay;
@@ -882,6 +883,34 @@ int slslam_lba_solve_batch(int32_t n, const slslam_lba_desc* descs, double* cons
   slslam_lba_batch_destroy(b);
   const double t3 = now_ms();
   g_timing[2] = t2 - t1; g_timing[3] = t3 - t2; g_timing[4] = t3 - t0;
+  return rc;
+}
+
+int slslam_lba_solve_batch_device(int32_t n, const slslam_lba_desc* descs, double* const* params_dev_inout,
+                                  slslam_summary* summaries_dev_out, slslam_summary* summaries_host_out, void* cuda_stream) {
+  slslam::set_last_error("");
+  if (n <= 0 || !descs || !params_dev_inout) return SLSLAM_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  slslam_lba_batch* b = nullptr;
+  const double t0 = now_ms();
+  int rc = batch_create_device_plan(n, descs, (const double* const*)params_dev_inout, -1, 0, &g_ws, st, &b, true, summaries_dev_out);
+  if (rc == SLSLAM_PLAN_FALLBACK) {
+    set_last_error("window shape needs the host planner (a camera observing a line twice, or a group-size search), which cannot read device-resident inputs");
+    return SLSLAM_ERR_UNSUPPORTED;
+  }
+  if (rc != SLSLAM_OK) return rc;
+  const double t1 = now_ms();
+  rc = slslam_lba_batch_solve(b, st);
+  if (rc == SLSLAM_OK && summaries_host_out) {
+    // the summaries are the only thing read back; without this the call returns as soon as the solve is enqueued
+    slslam_summary* h_summ = (slslam_summary*)(b->h_params);
+    cudaError_t e = cudaMemcpyAsync(h_summ, summaries_dev_out ? summaries_dev_out : b->d_summ, sizeof(slslam_summary) * n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); cudaGetLastError(); rc = SLSLAM_ERR_CUDA; }
+    else memcpy(summaries_host_out, h_summ, sizeof(slslam_summary) * n);
+  }
+  slslam_lba_batch_destroy(b);
+  g_timing[2] = now_ms() - t1; g_timing[3] = 0; g_timing[4] = now_ms() - t0;
   return rc;
 }
 

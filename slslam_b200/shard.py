@@ -269,3 +269,215 @@ def solve_sharded(windows, solve_fn, max_iters=10, device=None, group=None):
     else:
         ps, ss = [], []
     return gather_results(ps, ss, idx, int(cnt.item()), device=device, group=group)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Device path (round 2): the scattered buffer is solved WHERE NCCL PUT IT.  One buffer per rank, 256-byte aligned
+# sections:  header | result region (parameters of every window back to back, then one 48-byte summary per window) |
+# per window: camera_index, line_index, fixed_index, observations.  The solver (slslam_lba_solve_batch_device) reads the
+# arrays in place, updates the parameters in place and writes the summaries into the result region, so the gather is
+# ONE send of one contiguous slice per rank, rank 0 receives all slices into one device buffer and reads it back with
+# ONE copy into page-locked memory.  No device -> host -> device round trip, no per-window copies.
+# ---------------------------------------------------------------------------------------------------------------------
+_ALIGN = 256
+SUMMARY_BYTES = 48       # sizeof(slslam_summary): 4 doubles + 4 int32
+
+
+def _up(x, a=_ALIGN):
+    return (x + a - 1) // a * a
+
+
+class RankLayout:
+    """Byte offsets inside one rank's buffer, a pure function of the window shapes [(C, L, N), ...]."""
+
+    def __init__(self, shapes):
+        self.shapes = [tuple(int(v) for v in s) for s in shapes]
+        n = len(self.shapes)
+        self.header = 0
+        o = _up(16 + 24 * n)
+        self.result_begin = o
+        self.param_off = []
+        for (Cc, Ll, Nn) in self.shapes:
+            self.param_off.append(o)
+            o += 8 * ((6 * Cc + 4 * Ll + 1) // 2 * 2)
+        self.summary_off = o
+        o += SUMMARY_BYTES * n
+        self.result_end = o
+        o = _up(o)
+        self.arrays = []
+        for (Cc, Ll, Nn) in self.shapes:
+            ci = o; li = ci + 4 * Nn; fi = li + 4 * Nn; ob = _up(fi + 8 * Nn, 16)
+            self.arrays.append(dict(camera_index=ci, line_index=li, fixed_index=fi, observations=ob))
+            o = _up(ob + 64 * Nn)
+        self.total = max(o, _ALIGN)
+
+    @property
+    def result_bytes(self):
+        return self.result_end - self.result_begin
+
+    def offsets(self):
+        return [dict(a, parameters=p) for a, p in zip(self.arrays, self.param_off)]
+
+
+def pack_rank_buffer(windows, pin=False):
+    """The windows of one rank in the RankLayout format (numpy uint8; page-locked when `pin`)."""
+    lay = RankLayout([(w.num_cameras, w.num_lines, w.num_observations) for w in windows])
+    if pin:
+        import torch
+        buf = torch.zeros(lay.total, dtype=torch.uint8).pin_memory().numpy()
+    else:
+        buf = np.zeros(lay.total, np.uint8)
+    head = np.array([_MAGIC, len(windows)] + [v for s in lay.shapes for v in s], np.int64)
+    buf[:head.nbytes] = head.view(np.uint8)
+    for w, a, po in zip(windows, lay.arrays, lay.param_off):
+        N = w.num_observations
+        buf[a["camera_index"]:a["camera_index"] + 4 * N] = np.ascontiguousarray(w.camera_index, np.int32).view(np.uint8)
+        buf[a["line_index"]:a["line_index"] + 4 * N] = np.ascontiguousarray(w.line_index, np.int32).view(np.uint8)
+        buf[a["fixed_index"]:a["fixed_index"] + 8 * N] = np.ascontiguousarray(w.fixed_index, np.int32).view(np.uint8)
+        buf[a["observations"]:a["observations"] + 64 * N] = np.ascontiguousarray(w.observations, np.float64).view(np.uint8)
+        p = np.ascontiguousarray(w.parameters, np.float64)
+        buf[po:po + p.nbytes] = p.view(np.uint8)
+    return buf, lay
+
+
+def unpack_results(region: np.ndarray, lay: RankLayout):
+    """Result region (host bytes) of one rank -> (parameter arrays, summary dicts)."""
+    ps, ss = [], []
+    base = lay.result_begin
+    for i, (Cc, Ll, Nn) in enumerate(lay.shapes):
+        o = lay.param_off[i] - base
+        ps.append(region[o:o + 8 * (6 * Cc + 4 * Ll)].view(np.float64).copy())
+        so = lay.summary_off - base + SUMMARY_BYTES * i
+        d = region[so:so + 32].view(np.float64)
+        k = region[so + 32:so + 48].view(np.int32)
+        ss.append(dict(initial_cost=float(d[0]), final_cost=float(d[1]), fixed_cost=float(d[2]), gradient_max_norm=float(d[3]),
+                       num_successful_steps=int(k[0]), num_unsuccessful_steps=int(k[1]),
+                       termination=_TERM[int(k[2])] if 0 <= int(k[2]) < len(_TERM) else "?", iterations=int(k[3])))
+    return ps, ss
+
+
+class DeviceSharder:
+    """Scatter -> solve in place -> gather for a fixed set of window shapes, every buffer allocated once.
+
+    rank 0 constructs it with the full window list, the other ranks with None; the shapes travel in one broadcast at
+    construction.  `origin`: "host" = rank 0's buffers start in page-locked host memory and are copied to its GPU
+    destination by destination, each NCCL send starting as soon as its chunk has landed (rank r solves while later
+    chunks are still on their way); "device" = they start in rank 0's HBM (what `value` assumes for its inputs) and the
+    scatter is NVLink only.  `solve(recv)` is injected by the caller (the product passes capi.lba_solve_batch_device).
+    """
+
+    def __init__(self, windows, device, group=None, pin=True):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.dev = torch.device(device)
+        cuda = self.dev.type == "cuda"
+        nwin = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        if self.rank == 0:
+            nwin[0] = len(windows)
+        dist.broadcast(nwin, 0, group=group)
+        self.num_windows = int(nwin.item())
+        shapes = torch.zeros(max(1, self.num_windows), 3, dtype=torch.int64, device=self.dev)
+        if self.rank == 0:
+            shapes[:self.num_windows] = torch.tensor([[w.num_cameras, w.num_lines, w.num_observations] for w in windows], dtype=torch.int64)
+        dist.broadcast(shapes, 0, group=group)
+        shapes = shapes.cpu().numpy()[:self.num_windows]
+        self.layouts = [RankLayout([shapes[w] for w in local_indices(self.num_windows, r, self.world)]) for r in range(self.world)]
+        self.lay = self.layouts[self.rank]
+        self.recv = torch.zeros(self.lay.total, dtype=torch.uint8, device=self.dev)        # this rank's windows, solved in place
+        if self.rank == 0:
+            self.host_bufs = [pack_rank_buffer([windows[w] for w in local_indices(self.num_windows, r, self.world)], pin=pin and cuda)[0]
+                              for r in range(self.world)]
+            self.stage = [torch.zeros(self.layouts[r].total, dtype=torch.uint8, device=self.dev) for r in range(self.world)]
+            self.res_off = np.concatenate([[0], np.cumsum([_up(self.layouts[r].result_bytes) for r in range(self.world)])]).astype(np.int64)
+            self.res_dev = torch.zeros(int(self.res_off[-1]), dtype=torch.uint8, device=self.dev)
+            self.res_host = torch.zeros(int(self.res_off[-1]), dtype=torch.uint8)
+            if cuda:
+                self.res_host = self.res_host.pin_memory()
+        self._pending = []
+
+    def preload_device(self):
+        """origin = "device": put rank 0's packed buffers into its HBM (untimed; the windows then start on the device)."""
+        if self.rank == 0:
+            for r in range(self.world):
+                self.stage[r].copy_(self.torch.from_numpy(self.host_bufs[r]))
+            if self.dev.type == "cuda":
+                self.torch.cuda.synchronize(self.dev)
+
+    def scatter(self, origin="host"):
+        """After this call self.recv holds this rank's buffer (device).  Asynchronous on CUDA: the recv is enqueued."""
+        torch, dist = self.torch, self.dist
+        if self.rank == 0:
+            order = list(range(1, self.world)) + [0]                      # the other ranks first: they wait for us
+            for r in order:
+                if origin == "host":
+                    src = torch.from_numpy(self.host_bufs[r])
+                    (self.recv if r == 0 else self.stage[r]).copy_(src, non_blocking=True)
+                elif r == 0:
+                    self.recv.copy_(self.stage[0], non_blocking=True)
+                if r != 0:
+                    # an individual send per destination: it is ordered behind the copy just enqueued on the current
+                    # stream, and the next destination's copy overlaps it
+                    if self.dev.type == "cuda":
+                        self._pending.append(dist.isend(self.stage[r], r, group=self.group))
+                    else:
+                        dist.send(self.stage[r], r, group=self.group)
+        else:
+            if self.dev.type == "cuda":
+                self._pending.append(dist.irecv(self.recv, 0, group=self.group))
+            else:
+                dist.recv(self.recv, 0, group=self.group)
+
+    def wait_scatter(self):
+        """Orders the current stream behind the receive (no host wait on CUDA): call before the solve is enqueued."""
+        for req in self._pending:
+            req.wait()
+        self._pending = []
+
+    def views(self):
+        """Host-side helper for CPU tests: numpy views of this rank's windows inside self.recv (CPU tensors only)."""
+        buf = self.recv.numpy()
+        out = []
+        for (Cc, Ll, Nn), off in zip(self.lay.shapes, self.lay.offsets()):
+            out.append(Window(Cc, Ll, buf[off["camera_index"]:off["camera_index"] + 4 * Nn].view(np.int32),
+                              buf[off["line_index"]:off["line_index"] + 4 * Nn].view(np.int32),
+                              buf[off["fixed_index"]:off["fixed_index"] + 8 * Nn].view(np.int32),
+                              buf[off["observations"]:off["observations"] + 64 * Nn].view(np.float64),
+                              buf[off["parameters"]:off["parameters"] + 8 * (6 * Cc + 4 * Ll)].view(np.float64), None, {}))
+        return out
+
+    def store_summary(self, i, s):
+        """CPU tests: write window i's summary into the result region the way the device kernel does."""
+        buf = self.recv.numpy()
+        o = self.lay.summary_off + SUMMARY_BYTES * i
+        buf[o:o + 32].view(np.float64)[:] = [s["initial_cost"], s["final_cost"], s.get("fixed_cost", 0.0), s.get("gradient_max_norm", 0.0)]
+        buf[o + 32:o + 48].view(np.int32)[:] = [s["num_successful_steps"], s["num_unsuccessful_steps"],
+                                                _TERM.index(s["termination"]) if s["termination"] in _TERM else -1, s["iterations"]]
+
+    def gather(self):
+        """Rank 0 returns (params, summaries) of all windows in window order; the others (None, None)."""
+        torch, dist = self.torch, self.dist
+        lay = self.lay
+        mine = self.recv[lay.result_begin:lay.result_end]
+        if self.rank != 0:
+            dist.send(mine, 0, group=self.group)
+            return None, None
+        ops = []
+        for r in range(1, self.world):
+            n = self.layouts[r].result_bytes
+            if n:
+                ops.append(dist.P2POp(dist.irecv, self.res_dev[int(self.res_off[r]):int(self.res_off[r]) + n], r, group=self.group))
+        self.res_dev[:lay.result_bytes].copy_(mine, non_blocking=True)
+        _exchange(ops, dist)
+        self.res_host.copy_(self.res_dev, non_blocking=True)               # ONE device -> host copy for all ranks
+        if self.dev.type == "cuda":
+            torch.cuda.current_stream(self.dev).synchronize()
+        host = self.res_host.numpy()
+        out_p, out_s = [None] * self.num_windows, [None] * self.num_windows
+        for r in range(self.world):
+            n = self.layouts[r].result_bytes
+            ps, ss = unpack_results(host[int(self.res_off[r]):int(self.res_off[r]) + n], self.layouts[r])
+            for w, p, s_ in zip(local_indices(self.num_windows, r, self.world), ps, ss):
+                out_p[w], out_s[w] = p, s_
+        return out_p, out_s

@@ -23,6 +23,17 @@ def test_partition_and_pack_round_trip():
         assert np.array_equal(getattr(u, k), getattr(w, k))
     with pytest.raises(ValueError):
         shard.unpack_window(b[:-8])
+    # device-path layout: aligned sections, result region contiguous, round trip through the packed buffer
+    ws = [synth.make_window(3 + i, 4, 30 + i, 100 + 3 * i) for i in range(3)]
+    buf, lay = shard.pack_rank_buffer(ws)
+    assert buf.size == lay.total and lay.total % 256 == 0 and lay.result_begin % 256 == 0
+    assert all(o["observations"] % 16 == 0 and o["parameters"] % 16 == 0 for o in lay.offsets())
+    assert lay.param_off[0] == lay.result_begin and lay.summary_off + 48 * 3 == lay.result_end
+    ps, ss = shard.unpack_results(buf[lay.result_begin:lay.result_end], lay)
+    assert all(np.array_equal(p, w_.parameters) for p, w_ in zip(ps, ws)) and len(ss) == 3
+    lay2 = shard.RankLayout([(w_.num_cameras, w_.num_lines, w_.num_observations) for w_ in ws])
+    assert lay2.offsets() == lay.offsets() and lay2.total == lay.total
+    assert shard.RankLayout([]).total == 256 and shard.RankLayout([]).result_bytes == 0
     m = synth.window_M(0)
     # ~0.87 MB per M window
     assert abs(shard.pack_window(m).size - 864_560) < 4000
@@ -59,6 +70,25 @@ def _worker(rank, world, port, out_dir):
     if rank == 0:
         assert all(np.array_equal(a, b) for a, b in zip(gp, ps)) and [x["final_cost"] for x in gs] == [x["final_cost"] for x in ss]
         assert sizes == [sum(8 + 1 + 6 * windows[w].num_cameras + 4 * windows[w].num_lines for w in sh.local_indices(5, r, world)) for r in range(world)]
+    # the device path's host logic (layout, in-place solve, one result slice per rank) on CPU tensors over gloo
+    ds = sh.DeviceSharder(windows, "cpu")
+    assert ds.num_windows == 5 and [len(l.shapes) for l in ds.layouts] == [3, 2]
+    for origin in ("host", "device"):
+        if origin == "device":
+            ds.preload_device()
+        ds.scatter(origin=origin)
+        ds.wait_scatter()
+        for i, w in enumerate(ds.views()):
+            p_, s_ = oracle.lba_solve(w, max_iters=6, solver=1)
+            w.parameters[:] = p_                       # in place, as slslam_lba_solve_batch_device does
+            ds.store_summary(i, s_)
+        dp_, dss_ = ds.gather()
+        if rank == 0:
+            assert all(np.array_equal(a, b) for a, b in zip(dp_, ps))
+            for a, b in zip(dss_, ss):
+                assert all(a[k] == b[k] for k in ("initial_cost", "final_cost", "iterations", "termination", "num_successful_steps"))
+        else:
+            assert dp_ is None and dss_ is None
     if rank == 0:
         np.save(os.path.join(out_dir, "cost.npy"), np.array([s["final_cost"] for s in ss]))
         np.save(os.path.join(out_dir, "iters.npy"), np.array([s["iterations"] for s in ss]))
