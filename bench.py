@@ -359,46 +359,78 @@ def main():
     e2e_mode = max(pipe_runs, key=pipe_runs.get)
     e2e_value = pipe_runs[e2e_mode]
 
-    # ---- N > 1: what the NCCL scatter / gather of whole windows around the batch costs ----
+    # ---- N > 1: the sharded solve of SURVEY.md §8e with the NCCL scatter / gather INSIDE the timed region ----
+    # Rank 0 holds all windows_per_gpu x N windows (window w -> rank w mod N); timed per repetition, on the device (CUDA
+    # events on every rank's stream, max over ranks): scatter -> plan + solve where NCCL put the buffer
+    # (slslam_lba_solve_batch_device) -> gather of parameters + summaries into rank 0's page-locked memory.
+    #   origin "host":   rank 0's packed buffers start in page-locked HOST memory; its H2D copies are chunked by destination
+    #                    and every NCCL send starts when its chunk has landed (48 MB over one PCIe link is the floor)
+    #   origin "device": they start in rank 0's HBM, as `value` assumes for its inputs; the scatter is NVLink only
     sg = None
     if world > 1:
         from slslam_b200 import shard
         dev = torch.device("cuda", local_rank)
-        allw = [windows[j % len(windows)] for j in range(len(windows) * world)] if rank == 0 else None
-        results = {}
-
-        def solve_fn(ws, max_iters):
-            ps_, ss_ = capi.lba_solve_batch(ws, max_iters=max_iters)
-            return ps_, ss_
-
         nwin_all = len(windows) * world
-        bufs = shard.pack_for_ranks(allw, world, pin=True) if rank == 0 else None     # window assembly, not transfer: untimed
-        rsizes = shard.result_sizes(allw, world) if rank == 0 else [0] * world
-        for rep in range(3):           # the first repetitions warm NCCL's point-to-point channels
+        # every rank generated its own windows above; rank 0 collects their packed form once (set-up, untimed) and from
+        # then on holds all of them, as §8e describes
+        ds = shard.DeviceSharder(None, dev, local_windows=windows)
+        lay = ds.lay
+
+        def solve_in_place():
+            capi.lba_solve_batch_device(lay.shapes, ds.recv.data_ptr(), lay.offsets(), max_iters=MAX_ITERS,
+                                        summaries_dev_ptr=ds.recv.data_ptr() + lay.summary_off, want_host_summaries=False,
+                                        stream=torch.cuda.current_stream().cuda_stream)
+
+        sg = {}
+        for origin in ("device", "host"):
+            if origin == "device":
+                ds.preload_device()
+            reps, tms, outs = 6, [], None
+            for rep in range(reps):                     # the first repetitions warm NCCL's point-to-point channels
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ds.scatter(origin=origin)
+                ds.wait_scatter()
+                if lay.shapes:
+                    solve_in_place()
+                have = ds.gather_raw()                  # rank 0 returns once every result sits in its page-locked memory
+                e1.record()
+                torch.cuda.synchronize()
+                outp, outs_ = ds.unpack_gathered() if have else (None, None)
+                tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                tms.append(float(tt.item()))
+                if rank == 0:
+                    outs = outs_
+            # stage split of one more repetition, with synchronisation points between the stages (diagnostic only)
             barrier()
             t0 = time.perf_counter()
-            mine = shard.scatter_packed(bufs, device=dev)
-            local = [allw[w] for w in shard.local_indices(nwin_all, 0, world)] if rank == 0 else shard.unpack_many(mine)
-            idx = shard.local_indices(nwin_all, rank, world)
-            torch.cuda.synchronize()
+            ds.scatter(origin=origin); ds.wait_scatter(); torch.cuda.synchronize(); barrier()
             t1 = time.perf_counter()
-            ps_, ss_ = solve_fn(local, MAX_ITERS)
+            if lay.shapes:
+                solve_in_place()
+            torch.cuda.synchronize(); barrier()
             t2 = time.perf_counter()
-            outp, outs = shard.gather_results(ps_, ss_, idx, nwin_all, device=dev, sizes=rsizes)
-            torch.cuda.synchronize()
-            barrier()
+            ds.gather_raw(); torch.cuda.synchronize(); barrier()
             t3 = time.perf_counter()
-            results = {"scatter_ms": 1e3 * (t1 - t0), "solve_ms": 1e3 * (t2 - t1), "gather_ms": 1e3 * (t3 - t2)}
-        tt = torch.tensor([results["scatter_ms"], results["solve_ms"], results["gather_ms"]], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                it_all = sum(s_["iterations"] for s_ in outs)
+                best = min(tms[2:])
+                sg[origin] = {"ms_per_step": best, "ms_all_repetitions": tms, "lm_iterations": it_all,
+                              "lm_iterations_per_s_including_transfer": it_all / (best * 1e-3),
+                              "stages_ms_synchronised": {"scatter": 1e3 * (t1 - t0), "plan_and_solve": 1e3 * (t2 - t1), "gather": 1e3 * (t3 - t2)}}
         if rank == 0:
-            nbytes = sum(shard.packed_size(w.num_cameras, w.num_lines, w.num_observations) for w in allw)
-            it_all = sum(s_["iterations"] for s_ in outs)
-            sg = {"windows": len(allw), "scatter_bytes": int(nbytes * (world - 1) / world), "scatter_ms": float(tt[0]),
-                  "solve_ms": float(tt[1]), "gather_ms": float(tt[2]),
-                  "lm_iterations_per_s_including_transfer": it_all / (1e-3 * float(tt.sum())),
-                  "note": "windows packed per destination rank beforehand; timed: pinned H2D + one grouped NCCL send/recv per rank + D2H, "
-                          "host-buffer solve per rank, gather of parameters + summaries (one buffer per rank)"}
+            sg["windows"] = nwin_all
+            sg["scatter_bytes"] = int(sum(ds.layouts[r].total for r in range(1, world)))
+            sg["gather_bytes"] = int(sum(ds.layouts[r].result_bytes for r in range(1, world)))
+            sg["lm_iterations_per_s_including_transfer"] = sg["host"]["lm_iterations_per_s_including_transfer"]
+            sg["note"] = ("window w -> rank w mod N, all windows distinct; timed with CUDA events on every rank, max over ranks, best of the "
+                          "repetitions after two warm-ups; every rank plans and solves in the buffer NCCL delivered (no device->host->device "
+                          "round trip), one result slice per rank, one D2H on rank 0")
+            # the sharded path against the resident batch of this rank (same windows, same kernel): bit-identical costs
+            own = [outs[w_]["final_cost"] for w_ in shard.local_indices(nwin_all, 0, world)]
+            sg["rank0_costs_equal_resident_batch"] = own == [s_["final_cost"] for s_ in summ]
 
     if rank == 0:
         peaks = {}
@@ -425,7 +457,14 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(windows), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": e2e_value if sg is None else sg["lm_iterations_per_s_including_transfer"], "unit": UNIT,
+                    "h2d_bytes_per_step": int(h2d) if sg is None else sg["scatter_bytes"] + int(ds.layouts[0].total),
+                    "d2h_bytes_per_step": int(d2h) if sg is None else sg["gather_bytes"] + int(ds.layouts[0].result_bytes),
+                    "definition": ("N = 1: pipelined host-buffer calls (below)" if sg is None else
+                                   "N > 1: all windows start in rank 0's page-locked host memory; NCCL scatter, solve on every rank, NCCL "
+                                   "gather and the D2H of every result on rank 0 are inside the timed region (scatter_gather.host); the "
+                                   "per-rank host-buffer pipelines, which need no communication, are listed as independent_pipelines"),
+                    "independent_pipelines": e2e_value,
                     "steps": Kp, "api": f"slslam_lba_pipeline_submit / _wait, {e2e_mode} (host buffers, observations page-locked; "
                                         "every step is validated, copied H2D, planned on the device, solved and read back D2H; "
                                         "host work and H2D of step k+1 overlap the kernel of step k)",

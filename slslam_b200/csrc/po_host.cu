@@ -25,7 +25,7 @@ struct PoPlan {
   bool sparse = false;
   int nsb = 0, max_rows = 0;
   long long dense_blocks = 0;
-  std::vector<int> slot_pos, col_off, row_pos, tri_off, blk_dst;
+  std::vector<int> slot_pos, col_off, row_pos, tri_off, blk_dst, bs_chunk;
   std::vector<int2> tri;
 };
 
@@ -108,6 +108,15 @@ static bool build_po_sparse(const slslam_po_desc& d, PoPlan& p) {
       for (int u = p.blk_off[b]; u < p.blk_off[b + 1]; ++u) p.contrib[u] ^= 1;
     }
     p.blk_dst[b] = block_id(p.slot_pos[p.blk_i[b]], p.slot_pos[p.blk_j[b]]);
+  }
+  // chunks of consecutive columns (descending) whose panels fit one shared-memory stage of the back-substitution
+  p.bs_chunk.clear();
+  p.bs_chunk.push_back(Kf);
+  for (int c = Kf; c > 0;) {
+    int lo = c, blocks = 0;
+    while (lo > 0 && blocks + (p.col_off[lo] - p.col_off[lo - 1]) <= PO_SP_MAXROWS + 1) { blocks += p.col_off[lo] - p.col_off[lo - 1]; --lo; }
+    p.bs_chunk.push_back(lo);
+    c = lo;
   }
   p.sparse = true;
   return true;
@@ -248,6 +257,7 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   const size_t o_boff = pool.reserve(4 * (size_t)(nblk + 2)), o_contrib = pool.reserve(4 * (p.contrib.size() + 1));
   const size_t o_spos = pool.reserve(4 * Kfz), o_coff = pool.reserve(4 * (Kfz + 1)), o_rpos = pool.reserve(4 * (p.row_pos.size() + 1));
   const size_t o_toff = pool.reserve(4 * (Kfz + 1)), o_tri = pool.reserve(8 * (p.tri.size() + 1)), o_bdst = pool.reserve(4 * (size_t)(nblk + 1));
+  const size_t o_bsc = pool.reserve(4 * (p.bs_chunk.size() + 1));
   const size_t o_x = pool.reserve(48 * Kz);
   const size_t o_state = pool.reserve(sizeof(PoState));
   const size_t upload_end = pool.off;
@@ -294,6 +304,7 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
     memcpy(host + o_toff, p.tri_off.data(), 4 * p.tri_off.size());
     if (!p.tri.empty()) memcpy(host + o_tri, p.tri.data(), 8 * p.tri.size());
     if (nblk > 0) memcpy(host + o_bdst, p.blk_dst.data(), 4 * (size_t)nblk);
+    memcpy(host + o_bsc, p.bs_chunk.data(), 4 * p.bs_chunk.size());
   }
   PoState st; memset(&st, 0, sizeof(st));
   st.radius = desc->initial_trust_region_radius > 0 ? desc->initial_trust_region_radius : 1e4;   // Ceres 1.7.0 defaults
@@ -324,6 +335,7 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   d.Hb = (double*)(B + o_Hb); d.bz = (double*)(B + o_bz); d.us = (double*)(B + o_us); d.yp = (double*)(B + o_yp);
   d.slot_pos = (const int*)(B + o_spos); d.col_off = (const int*)(B + o_coff); d.row_pos = (const int*)(B + o_rpos);
   d.tri_off = (const int*)(B + o_toff); d.tri = (const int2*)(B + o_tri); d.blk_dst = (const int*)(B + o_bdst);
+  d.bs_chunk = (const int*)(B + o_bsc); d.bs_nchunk = sparse ? (int)p.bs_chunk.size() - 1 : 0;
 
   cudaStream_t s = nullptr;
   unsigned int* d_flags = (unsigned int*)(B + o_flags);
@@ -333,7 +345,7 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   slslam_summary* h_summ = (slslam_summary*)(ws.h_res + 48 * Kz);
   double* h_trace = (double*)(ws.h_res + 48 * Kz + ((sizeof(slslam_summary) + 255) & ~(size_t)255));
   volatile int* h_done = (volatile int*)((char*)h_trace + 8 * (size_t)SLSLAM_TRACE_WIDTH * std::max(max_iters, 1));
-  const size_t sp_smem = (size_t)(2 * PO_SP_MAXROWS * 36 + 8) * 8;
+  const size_t sp_smem = PO_SP_SMEM;
   int enqueued = 0;
   rc = SLSLAM_OK;
 #define PO_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_last_error(cudaGetErrorString(e_)); cudaGetLastError(); rc = SLSLAM_ERR_CUDA; goto done; } } while (0)

@@ -68,6 +68,8 @@ struct PoDev {
   const int* tri_off;             // [Kf + 1] updates of column c
   const int2* tri;                // x: destination block id, y: a | b << 16 (sources: off-diagonal blocks a >= b of the column)
   const int* blk_dst;             // [nblk] where po_sp_assemble writes the structurally non-zero blocks of J^T J
+  const int* bs_chunk;            // [bs_nchunk + 1] descending column boundaries of the back-substitution's staging chunks
+  int bs_nchunk;
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -443,27 +445,59 @@ __global__ void po_sp_assemble(PoDev d) {
 // then, descending, y_c = u_c - sum_a P_ac^T y_row(a) by warp 0.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int PO_SP_NT = 1024;
-constexpr int PO_SP_MAXROWS = 160;   // off-diagonal blocks per column the shared-memory panel holds (2 x 288 B each)
+constexpr int PO_SP_MAXROWS = 160;   // off-diagonal blocks per column (the shared-memory column cache holds 1 + MAXROWS blocks)
+constexpr int PO_SP_YMAX = 6144;     // unknowns whose solution vector is kept in shared memory during the back-substitution
+constexpr int PO_SP_CACHE = (1 + PO_SP_MAXROWS) * 36;                       // doubles per column cache
+constexpr size_t PO_SP_SMEM = (size_t)(2 * PO_SP_CACHE + PO_SP_MAXROWS * 36 + PO_SP_YMAX + 32) * 8;
+
+// Everything on the dependent chain of block columns comes from shared memory: while column c is being eliminated the
+// idle threads fetch column c + 1 (diagonal block, panel, right-hand side) into the second column cache; updates of
+// column c that target column c + 1 are applied to that cache, all other updates are fire-and-forget reductions
+// (red.global.add.f64: no thread waits for L2), ordered per address by the barriers between columns.  Round 2, first
+// version read and wrote global memory in every phase: 3 dependent L2 round trips per column, 752 us per launch for
+// 260 poses (profiles/r2_po_*.txt).
+__device__ __forceinline__ double po_ld_strong(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
 
 __global__ void __launch_bounds__(PO_SP_NT, 1) po_sp_factor_solve(PoDev d) {
   if (d.st->done) return;
   extern __shared__ __align__(16) double spsm[];
-  double* orig = spsm;                                  // [MAXROWS][36] original panel rows of the current column
-  double* Pm = spsm + PO_SP_MAXROWS * 36;               // [MAXROWS][36] P = A W
-  double* bc = Pm + PO_SP_MAXROWS * 36;                 // [8] b_c
+  double* cache0 = spsm;                                // column caches: [0..36) diagonal block, then the panel blocks
+  double* cache1 = spsm + PO_SP_CACHE;
+  double* Pm = spsm + 2 * PO_SP_CACHE;                  // [MAXROWS][36] P = A W of the current column
+  double* ysm = Pm + PO_SP_MAXROWS * 36;                // [YMAX] solution in position order (back-substitution)
+  double* bzc = ysm + PO_SP_YMAX;                       // [2][8] cached right-hand-side block of the current / next column
+  double* bc = bzc + 16;                                // [8] b_c
   __shared__ int bad;
   const int tid = threadIdx.x, Kf = d.Kf;
   if (tid == 0) bad = 0;
+  // column 0 into cache 0
+  {
+    const int m0 = d.col_off[1] - d.col_off[0];
+    for (int i = tid; i < 36 * (1 + m0) + 6; i += PO_SP_NT) {
+      if (i < 36) cache0[i] = d.Hb[i];
+      else if (i < 36 * (1 + m0)) cache0[i] = d.Hb[(size_t)Kf * 36 + (i - 36)];
+      else bzc[i - 36 * (1 + m0)] = d.bz[i - 36 * (1 + m0)];
+    }
+  }
   __syncthreads();
   for (int c = 0; c < Kf; ++c) {
-    const int o0 = d.col_off[c], m = d.col_off[c + 1] - o0;
-    if (tid < 6 * m + 6) {
-      const double* AJJ = d.Hb + (size_t)c * 36;
+    double* cur = (c & 1) ? cache1 : cache0;
+    double* nxt = (c & 1) ? cache0 : cache1;
+    double* bcur = bzc + 8 * (c & 1);
+    double* bnxt = bzc + 8 * ((c + 1) & 1);
+    const int o0 = d.col_off[c], o1 = d.col_off[c + 1], m = o1 - o0;
+    const int o2 = (c + 1 < Kf) ? d.col_off[c + 2] : o1, m1 = o2 - o1;
+    const int nwork = 6 * m + 6, work_end = (nwork + 31) & ~31;
+    if (tid < nwork) {
       double A[21], W[21];
 #pragma unroll
       for (int p = 0; p < 6; ++p)
 #pragma unroll
-        for (int q = 0; q <= p; ++q) A[p * (p + 1) / 2 + q] = AJJ[6 * p + q];
+        for (int q = 0; q <= p; ++q) A[p * (p + 1) / 2 + q] = cur[6 * p + q];
 #define L6I(p, q) ((p) * ((p) + 1) / 2 + (q))
 #define SY3(mm, r, cc) mm[(r) <= (cc) ? ((r) == 0 ? (cc) : (r) == 1 ? 2 + (cc) : 5) : ((cc) == 0 ? (r) : (cc) == 1 ? 2 + (r) : 5)]
       double Ai[6], Si[6], M[9], S[6];
@@ -499,7 +533,8 @@ __global__ void __launch_bounds__(PO_SP_NT, 1) po_sp_factor_solve(PoDev d) {
 #undef SY3
       if (tid < 6 * m) {
         const int a = tid / 6, p = tid - 6 * a;
-        double* arow = d.Hb + (size_t)(Kf + o0 + a) * 36 + 6 * p;
+        const double* arow = cur + 36 * (1 + a) + 6 * p;            // the original row stays in the cache for phase 2
+        double* grow = d.Hb + (size_t)(Kf + o0 + a) * 36 + 6 * p;   // P is kept in global memory for the back-substitution
         double av[6], pv[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) av[k] = arow[k];
@@ -513,13 +548,13 @@ __global__ void __launch_bounds__(PO_SP_NT, 1) po_sp_factor_solve(PoDev d) {
           pv[q] = s0 + s1;
         }
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { orig[36 * a + 6 * p + k] = av[k]; Pm[36 * a + 6 * p + k] = pv[k]; arow[k] = pv[k]; }
+        for (int k = 0; k < 6; ++k) { Pm[36 * a + 6 * p + k] = pv[k]; grow[k] = pv[k]; }
       } else {
         const int q = tid - 6 * m;
         if (q == 0 && !ok) bad = 1;
         double bk[6], uq[6];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { bk[k] = d.bz[6 * c + k]; if (q == 0) bc[k] = bk[k]; }
+        for (int k = 0; k < 6; ++k) { bk[k] = bcur[k]; if (q == 0) bc[k] = bk[k]; }
 #pragma unroll
         for (int qq = 0; qq < 6; ++qq) {            // all six (static register indexing), this thread keeps its own
           double sum = 0.0;
@@ -530,54 +565,99 @@ __global__ void __launch_bounds__(PO_SP_NT, 1) po_sp_factor_solve(PoDev d) {
         d.us[6 * c + q] = q == 0 ? uq[0] : q == 1 ? uq[1] : q == 2 ? uq[2] : q == 3 ? uq[3] : q == 4 ? uq[4] : uq[5];
       }
 #undef L6I
+    } else if (tid >= work_end && c + 1 < Kf) {
+      // the other warps fetch column c + 1: every earlier column's update of it has been issued (as a reduction, or a
+      // store) before the barrier that ended the previous column, so a strong load observes it
+      const int nfetch = 36 * (1 + m1) + 6, nth = PO_SP_NT - work_end;
+      for (int i = tid - work_end; i < nfetch; i += nth) {
+        if (i < 36) nxt[i] = po_ld_strong(d.Hb + (size_t)(c + 1) * 36 + i);
+        else if (i < 36 * (1 + m1)) nxt[i] = po_ld_strong(d.Hb + (size_t)(Kf + o1) * 36 + (i - 36));
+        else bnxt[i - 36 * (1 + m1)] = po_ld_strong(d.bz + 6 * (c + 1) + (i - 36 * (1 + m1)));
+      }
     }
     __syncthreads();
+    if (work_end >= PO_SP_NT && c + 1 < Kf) {
+      // a column so full that no warp was idle: fetch the next one now (rare: the last, dense columns of the factor)
+      const int nfetch = 36 * (1 + m1) + 6;
+      for (int i = tid; i < nfetch; i += PO_SP_NT) {
+        if (i < 36) nxt[i] = po_ld_strong(d.Hb + (size_t)(c + 1) * 36 + i);
+        else if (i < 36 * (1 + m1)) nxt[i] = po_ld_strong(d.Hb + (size_t)(Kf + o1) * 36 + (i - 36));
+        else bnxt[i - 36 * (1 + m1)] = po_ld_strong(d.bz + 6 * (c + 1) + (i - 36 * (1 + m1)));
+      }
+      __syncthreads();
+    }
     const int t0 = d.tri_off[c], nt = d.tri_off[c + 1] - t0;
+    const int pan_lo = Kf + o1, pan_hi = Kf + o2;       // block ids of column c + 1's panel
     for (int e = tid; e < 36 * nt + 6 * m; e += PO_SP_NT) {
       if (e < 36 * nt) {
         const int t = e / 36, pq = e - 36 * t, p = pq / 6, q = pq - 6 * p;
         const int2 tr = d.tri[t0 + t];
         const double* pa = Pm + 36 * (tr.y & 0xffff) + 6 * p;
-        const double* ob = orig + 36 * (tr.y >> 16) + 6 * q;
+        const double* ob = cur + 36 * (1 + (tr.y >> 16)) + 6 * q;
         const double s0 = pa[0] * ob[0] + pa[1] * ob[1] + pa[2] * ob[2];
         const double s1 = pa[3] * ob[3] + pa[4] * ob[4] + pa[5] * ob[5];
-        d.Hb[(size_t)tr.x * 36 + pq] -= s0 + s1;
+        const double sv = s0 + s1;
+        if (tr.x == c + 1) nxt[pq] -= sv;
+        else if (tr.x >= pan_lo && tr.x < pan_hi) nxt[36 * (1 + tr.x - pan_lo) + pq] -= sv;
+        else atomicAdd(d.Hb + (size_t)tr.x * 36 + pq, -sv);          // result unused: a reduction, nobody waits for it
       } else {
         const int r = e - 36 * nt, a = r / 6, p = r - 6 * a;
         const double* pa = Pm + 36 * a + 6 * p;
         double sum = 0.0;
 #pragma unroll
         for (int k = 0; k < 6; ++k) sum += pa[k] * bc[k];
-        d.bz[6 * d.row_pos[o0 + a] + p] -= sum;
+        const int rp = d.row_pos[o0 + a];
+        if (rp == c + 1) bnxt[p] -= sum; else atomicAdd(d.bz + 6 * rp + p, -sum);
       }
     }
     __syncthreads();
   }
   if (tid == 0 && bad) d.st->chol_fail = 1;
-  // back-substitution by warp 0: y_c = u_c - sum_a P_ac^T y_row(a); lanes over the (a, row) pairs of the column
-  if (tid < 32) {
-    for (int c = Kf - 1; c >= 0; --c) {
-      const int o0 = d.col_off[c], m = d.col_off[c + 1] - o0;
-      double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      for (int r = tid; r < 6 * m; r += 32) {
-        const int a = r / 6, p = r - 6 * a;
-        const double yv = d.yp[6 * d.row_pos[o0 + a] + p];
-        const double* prow = d.Hb + (size_t)(Kf + o0 + a) * 36 + 6 * p;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) acc[q] += prow[q] * yv;
-      }
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-      }
-      if (tid < 6) d.yp[6 * c + tid] = d.us[6 * c + tid] - (tid == 0 ? acc[0] : tid == 1 ? acc[1] : tid == 2 ? acc[2] : tid == 3 ? acc[3] : tid == 4 ? acc[4] : acc[5]);
-      __syncwarp();
-    }
-  }
+  // ---- back-substitution, descending: y_c = u_c - sum_a P_ac^T y_row(a).  The P blocks of a chunk of columns (a
+  // contiguous range of Hb) are staged in shared memory by all threads, then warp 0 walks the chunk's columns while the
+  // other warps stage the next chunk.
+  double* yv = (d.n <= PO_SP_YMAX) ? ysm : d.yp;
+  double* stage[2] = {cache0, cache1};
+  const int nchunk = d.bs_nchunk;
+  auto stage_chunk = [&](int k, int first_thread, int nthreads) {
+    if (k >= nchunk) return;
+    const int c_hi = d.bs_chunk[k], c_lo = d.bs_chunk[k + 1];           // columns [c_lo, c_hi)
+    const int b0 = d.col_off[c_lo], nb = d.col_off[c_hi] - b0;
+    double* dst = stage[k & 1];
+    for (int i = tid - first_thread; i < 36 * nb; i += nthreads) dst[i] = __ldcg(d.Hb + (size_t)(Kf + b0) * 36 + i);
+  };
+  stage_chunk(0, 0, PO_SP_NT);
   __syncthreads();
+  for (int k = 0; k < nchunk; ++k) {
+    if (tid >= 32) {
+      stage_chunk(k + 1, 32, PO_SP_NT - 32);
+    } else {
+      const int c_hi = d.bs_chunk[k], c_lo = d.bs_chunk[k + 1];
+      const int b0 = d.col_off[c_lo];
+      const double* Ps = stage[k & 1];
+      for (int c = c_hi - 1; c >= c_lo; --c) {
+        const int o0 = d.col_off[c], m = d.col_off[c + 1] - o0;
+        double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int r = tid; r < 6 * m; r += 32) {
+          const int a = r / 6, p = r - 6 * a;
+          const double yr = yv[6 * d.row_pos[o0 + a] + p];
+          const double* prow = Ps + 36 * (o0 - b0 + a) + 6 * p;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) acc[q] += prow[q] * yr;
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        }
+        if (tid < 6) yv[6 * c + tid] = d.us[6 * c + tid] - (tid == 0 ? acc[0] : tid == 1 ? acc[1] : tid == 2 ? acc[2] : tid == 3 ? acc[3] : tid == 4 ? acc[4] : acc[5]);
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
   // solution back in slot order
-  for (int i = tid; i < d.n; i += PO_SP_NT) d.y[i] = d.yp[6 * d.slot_pos[i / 6] + i % 6];
+  for (int i = tid; i < d.n; i += PO_SP_NT) d.y[i] = yv[6 * d.slot_pos[i / 6] + i % 6];
 }
 
 // trial point x' = x - scale*y on the free poses, and the per-edge part of the model decrease -(m.(r + m/2)), m = J delta

@@ -89,6 +89,22 @@ def _worker(rank, world, port, out_dir):
                 assert all(a[k] == b[k] for k in ("initial_cost", "final_cost", "iterations", "termination", "num_successful_steps"))
         else:
             assert dp_ is None and dss_ is None
+    # every rank contributes its own windows (global index i * world + rank); rank 0 ends up holding all of them
+    mine_l = [sy.make_window(70 + 2 * i + rank, 3, 20 + i, 60 + 5 * i, sigma_px=0.5) for i in range(2)]
+    ds2 = sh.DeviceSharder(None, "cpu", local_windows=mine_l)
+    assert ds2.num_windows == 4
+    ds2.scatter(origin="host"); ds2.wait_scatter()
+    for w_, m_ in zip(ds2.views(), mine_l):
+        assert np.array_equal(w_.observations, m_.observations) and np.array_equal(w_.parameters, m_.parameters)
+        assert np.array_equal(w_.camera_index, m_.camera_index) and np.array_equal(w_.fixed_index, m_.fixed_index)
+        w_.parameters[:] = w_.parameters + 1.0
+    for i in range(2):
+        ds2.store_summary(i, dict(initial_cost=1.0, final_cost=0.5 + rank, num_successful_steps=1, num_unsuccessful_steps=0,
+                                  termination="NO_CONVERGENCE", iterations=1))
+    gp2, gs2 = ds2.gather()
+    if rank == 0:
+        assert [s_["final_cost"] for s_ in gs2] == [0.5, 1.5, 0.5, 1.5]
+        assert np.array_equal(gp2[0], mine_l[0].parameters + 1.0) and np.array_equal(gp2[2], mine_l[1].parameters + 1.0)
     if rank == 0:
         np.save(os.path.join(out_dir, "cost.npy"), np.array([s["final_cost"] for s in ss]))
         np.save(os.path.join(out_dir, "iters.npy"), np.array([s["iterations"] for s in ss]))
