@@ -96,6 +96,10 @@ const char* slslam_strerror(int code);
 const char* slslam_last_error(void);          /* thread-local detail for the last SLSLAM_ERR_CUDA */
 int slslam_device_count(void);                /* usable sm_100 devices; 0 means every solve call fails */
 void slslam_lba_get_limits(slslam_lba_limits* out);
+/* Diagnostic: measured fp64 FMA throughput (TFLOP/s, 2 flops per DFMA) of `device` (< 0: current) from a register-only
+ * kernel of independent DFMA chains, best of a few repetitions (~10 ms).  Both solvers are fp64-issue / latency bound
+ * (the whole LM loop runs out of shared memory), so this -- not HBM bandwidth -- is the ceiling their arithmetic sees. */
+int slslam_measure_fp64_peak(int32_t device, double* tflops_out, double* sm_clock_mhz_out);
 
 /* ---- what replaces ceres::Solve for one LBAProblem: H2D, device LM loop, D2H; parameters updated in place ---- */
 int slslam_lba_solve(const slslam_lba_desc* desc, double* params_inout, slslam_summary* summary_out);
@@ -201,6 +205,7 @@ typedef struct slslam_po_stats {
   int64_t block_updates;          /* 6x6x6 block products of one numeric factorisation (sparse path) */
   int32_t max_column_rows;
   int32_t iterations_enqueued;    /* LM iterations whose kernels were launched (<= max_iterations: early stop) */
+  int64_t factor_cycles[4];       /* last factorisation (sparse path), SM cycles: panel phase, update phase, back-substitution, total */
 } slslam_po_stats;
 void slslam_po_last_stats(slslam_po_stats* out);
 typedef struct slslam_po_limits {

@@ -13,3 +13,4 @@ for _ in range(reps):
     ms = capi.lib().slslam_po_last_solve_ms()
     print(f"PO K={g.num_poses} E={g.num_edges}: iterations {s['iterations']} final {s['final_cost']:.9e} term {s['termination']} "
           f"device {ms:.3f} ms ({ms / max(1, s['iterations']):.3f} ms/iter) wall {wall * 1e3:.1f} ms", flush=True)
+    print("   ", capi.po_last_stats(), flush=True)

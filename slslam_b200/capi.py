@@ -19,7 +19,7 @@ TERMINATION = {0: "NO_CONVERGENCE", 1: "GRADIENT_TOLERANCE", 2: "FUNCTION_TOLERA
                4: "NUMERICAL_FAILURE"}
 
 EXPORTS = [
-    "slslam_version", "slslam_strerror", "slslam_last_error", "slslam_device_count", "slslam_lba_get_limits",
+    "slslam_version", "slslam_strerror", "slslam_last_error", "slslam_device_count", "slslam_lba_get_limits", "slslam_measure_fp64_peak",
     "slslam_lba_solve", "slslam_lba_solve_batch", "slslam_lba_solve_batch_device", "slslam_lba_last_timings", "slslam_lba_batch_create", "slslam_lba_batch_solve",
     "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_max_active_clusters", "slslam_lba_batch_transfer_bytes", "slslam_lba_batch_phase_cycles", "slslam_lba_batch_plan_cycles", "slslam_lba_batch_destroy",
     "slslam_lba_plan_check", "slslam_lba_launch_shape", "slslam_lba_pipeline_create", "slslam_lba_pipeline_submit", "slslam_lba_pipeline_wait", "slslam_lba_pipeline_destroy",
@@ -52,7 +52,8 @@ class Summary(C.Structure):
 
 class PoStats(C.Structure):
     _fields_ = [("sparse", C.c_int32), ("free_poses", C.c_int32), ("factor_blocks", C.c_int64),
-                ("block_updates", C.c_int64), ("max_column_rows", C.c_int32), ("iterations_enqueued", C.c_int32)]
+                ("block_updates", C.c_int64), ("max_column_rows", C.c_int32), ("iterations_enqueued", C.c_int32),
+                ("factor_cycles", C.c_int64 * 4)]
 
 
 class PoLimits(C.Structure):
@@ -184,6 +185,15 @@ def lba_solve(w, params=None, **kw):
     s = Summary()
     _check(lib().slslam_lba_solve(C.byref(k.desc), _d(p), C.byref(s)))
     return p, summary_dict(s)
+
+
+def measure_fp64_peak(device=-1):
+    """(TFLOP/s, SM clock MHz) of a register-only DFMA kernel on `device` (slslam_measure_fp64_peak)."""
+    L = lib()
+    L.slslam_measure_fp64_peak.argtypes = [C.c_int32, dp, dp]
+    t, c = C.c_double(), C.c_double()
+    _check(L.slslam_measure_fp64_peak(device, C.cast(C.byref(t), dp), C.cast(C.byref(c), dp)))
+    return t.value, c.value
 
 
 def last_timings():
@@ -406,7 +416,7 @@ def po_last_stats():
     """How the last po_solve of this thread factored the normal equations (slslam_po_last_stats)."""
     st = PoStats()
     lib().slslam_po_last_stats(C.byref(st))
-    return {k: getattr(st, k) for k, _ in PoStats._fields_}
+    return {k: (list(getattr(st, k)) if k == "factor_cycles" else getattr(st, k)) for k, _ in PoStats._fields_}
 
 
 def po_limits():

@@ -114,7 +114,7 @@ static bool build_po_sparse(const slslam_po_desc& d, PoPlan& p) {
   p.bs_chunk.push_back(Kf);
   for (int c = Kf; c > 0;) {
     int lo = c, blocks = 0;
-    while (lo > 0 && blocks + (p.col_off[lo] - p.col_off[lo - 1]) <= PO_SP_MAXROWS + 1) { blocks += p.col_off[lo] - p.col_off[lo - 1]; --lo; }
+    while (lo > 0 && c - lo < PO_SP_MAXROWS && blocks + (p.col_off[lo] - p.col_off[lo - 1]) <= PO_SP_MAXROWS) { blocks += p.col_off[lo] - p.col_off[lo - 1]; --lo; }
     p.bs_chunk.push_back(lo);
     c = lo;
   }
@@ -267,6 +267,7 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   const size_t o_scale = pool.reserve(8 * nz), o_cn = pool.reserve(8 * nz), o_g = pool.reserve(8 * nz), o_y = pool.reserve(8 * nz);
   const size_t o_bz = pool.reserve(8 * nz), o_us = pool.reserve(8 * nz), o_yp = pool.reserve(8 * nz);
   const size_t o_summ = pool.reserve(sizeof(slslam_summary));
+  const size_t o_spc = pool.reserve(64);
   const size_t o_trace = pool.reserve(8 * (size_t)SLSLAM_TRACE_WIDTH * std::max(max_iters, 1));
   const size_t o_Ld = pool.reserve(8 * (size_t)PO_NB * PO_NB * std::max(nb32, 1));
   const size_t o_flags = pool.reserve(4 * (size_t)std::max(nb32, 1));
@@ -335,6 +336,7 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   d.Hb = (double*)(B + o_Hb); d.bz = (double*)(B + o_bz); d.us = (double*)(B + o_us); d.yp = (double*)(B + o_yp);
   d.slot_pos = (const int*)(B + o_spos); d.col_off = (const int*)(B + o_coff); d.row_pos = (const int*)(B + o_rpos);
   d.tri_off = (const int*)(B + o_toff); d.tri = (const int2*)(B + o_tri); d.blk_dst = (const int*)(B + o_bdst);
+  d.sp_cycles = (long long*)(B + o_spc);
   d.bs_chunk = (const int*)(B + o_bsc); d.bs_nchunk = sparse ? (int)p.bs_chunk.size() - 1 : 0;
 
   cudaStream_t s = nullptr;
@@ -394,10 +396,13 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   po_refresh<<<1, 256, 0, s>>>(d, 1);
   if (n > 0) {
     for (int it = 0; it < max_iters; ++it) {
-      // The loop is enqueued without waiting for the device.  PoState::done of iteration it - 2 (copied to pinned
-      // memory behind that iteration) is looked at only if its event has already completed: after termination at most
-      // a couple of iterations of early-out launches are enqueued instead of all the remaining ones.
-      if (it >= 2 && cudaEventQuery(ws.it_ev[it - 2]) == cudaSuccess && h_done[it - 2]) break;
+      // PoState::done of every iteration is copied to pinned memory behind it.
+      if (it >= 3) {
+        // the host stays at most three iterations ahead of the device (their launches are already queued, so the device
+        // never waits for the host) and stops enqueueing once an iteration it has seen complete reports termination
+        PO_TRY(cudaEventSynchronize(ws.it_ev[it - 3]));
+        if (h_done[it - 3]) break;
+      }
       if (sparse) {
         PO_TRY(cudaMemsetAsync(d.Hb, 0, hb_bytes, s));
         po_sp_assemble<<<(nblk * 36 + n + 255) / 256, 256, 0, s>>>(d);
@@ -440,6 +445,7 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
     PO_TRY(cudaStreamSynchronize(s));
     PO_TRY(cudaEventElapsedTime(&g_po_last_ms, ws.ev0, ws.ev1));
     // parameters are only overwritten once everything has succeeded
+    if (sparse) { long long cyc[4] = {0, 0, 0, 0}; if (cudaMemcpy(cyc, d.sp_cycles, 32, cudaMemcpyDeviceToHost) == cudaSuccess) for (int k = 0; k < 4; ++k) g_po_stats.factor_cycles[k] = cyc[k]; }
     if (K > 0) memcpy(poses_out, h_x, 48 * (size_t)K);
     if (trace_out) memcpy(trace_out, h_trace, 8 * (size_t)SLSLAM_TRACE_WIDTH * std::max(max_iters, 0));
     if (summary_out) *summary_out = *h_summ;

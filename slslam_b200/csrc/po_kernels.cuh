@@ -70,6 +70,7 @@ struct PoDev {
   const int* blk_dst;             // [nblk] where po_sp_assemble writes the structurally non-zero blocks of J^T J
   const int* bs_chunk;            // [bs_nchunk + 1] descending column boundaries of the back-substitution's staging chunks
   int bs_nchunk;
+  long long* sp_cycles;           // [4] diagnostics of po_sp_factor_solve: phase 1, phase 2, back-substitution, total (SM cycles)
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -444,187 +445,246 @@ __global__ void po_sp_assemble(PoDev d) {
 //   phase 2  the planned updates  A_dst -= P_a A_bc^T  (thread per entry, 36 per update) and  b_row(a) -= P_a b_c
 // then, descending, y_c = u_c - sum_a P_ac^T y_row(a) by warp 0.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int PO_SP_NT = 1024;
+constexpr int PO_SP_NT = 512;
 constexpr int PO_SP_MAXROWS = 160;   // off-diagonal blocks per column (the shared-memory column cache holds 1 + MAXROWS blocks)
 constexpr int PO_SP_YMAX = 6144;     // unknowns whose solution vector is kept in shared memory during the back-substitution
+constexpr int PO_SP_TRICAP = 1024;   // updates of one column staged in shared memory (longer lists are read from global memory)
 constexpr int PO_SP_CACHE = (1 + PO_SP_MAXROWS) * 36;                       // doubles per column cache
-constexpr size_t PO_SP_SMEM = (size_t)(2 * PO_SP_CACHE + PO_SP_MAXROWS * 36 + PO_SP_YMAX + 32) * 8;
+constexpr int PO_SP_SMEM_DOUBLES = 2 * PO_SP_CACHE + PO_SP_MAXROWS * 36 + PO_SP_YMAX + 72 + 24 + 2 * PO_SP_TRICAP + PO_SP_MAXROWS + 400;
+constexpr size_t PO_SP_SMEM = (size_t)PO_SP_SMEM_DOUBLES * 8;
 
-// Everything on the dependent chain of block columns comes from shared memory: while column c is being eliminated the
-// idle threads fetch column c + 1 (diagonal block, panel, right-hand side) into the second column cache; updates of
-// column c that target column c + 1 are applied to that cache, all other updates are fire-and-forget reductions
-// (red.global.add.f64: no thread waits for L2), ordered per address by the barriers between columns.  Round 2, first
-// version read and wrote global memory in every phase: 3 dependent L2 round trips per column, 752 us per launch for
-// 260 poses (profiles/r2_po_*.txt).
 __device__ __forceinline__ double po_ld_strong(const double* p) {
   double v;
   asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
 
+// W = A^-1 of a symmetric positive definite 6x6 block given by its lower triangle (row-major 6x6 source): two closed-form
+// 3x3 cofactor inverses and a 3x3 Schur complement (one reciprocal each), as in the LBA reduced solve.
+__device__ __forceinline__ bool po_spd6_inverse(const double* A36, double* W /* [21], lower, L6(p,q) */) {
+#define L6I(p, q) ((p) * ((p) + 1) / 2 + (q))
+#define SY3(mm, r, cc) mm[(r) <= (cc) ? ((r) == 0 ? (cc) : (r) == 1 ? 2 + (cc) : 5) : ((cc) == 0 ? (r) : (cc) == 1 ? 2 + (r) : 5)]
+  double A[21];
+#pragma unroll
+  for (int p = 0; p < 6; ++p)
+#pragma unroll
+    for (int q = 0; q <= p; ++q) A[L6I(p, q)] = A36[6 * p + q];
+  double Ai[6], Si[6], M[9], S[6];
+  bool ok = spd3_inverse(A[L6I(0, 0)], A[L6I(1, 0)], A[L6I(2, 0)], A[L6I(1, 1)], A[L6I(2, 1)], A[L6I(2, 2)], Ai);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+      M[3 * r + cc] = A[L6I(3 + r, 0)] * SY3(Ai, 0, cc) + A[L6I(3 + r, 1)] * SY3(Ai, 1, cc) + A[L6I(3 + r, 2)] * SY3(Ai, 2, cc);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = r; cc < 3; ++cc)
+      SY3(S, r, cc) = A[L6I(3 + cc, 3 + r)] - (M[3 * r] * A[L6I(3 + cc, 0)] + M[3 * r + 1] * A[L6I(3 + cc, 1)] + M[3 * r + 2] * A[L6I(3 + cc, 2)]);
+  ok = spd3_inverse(S[0], S[1], S[2], S[3], S[4], S[5], Si) && ok;
+  double W21[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+      W21[3 * r + cc] = -(SY3(Si, r, 0) * M[cc] + SY3(Si, r, 1) * M[3 + cc] + SY3(Si, r, 2) * M[6 + cc]);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc <= r; ++cc) {
+      W[L6I(r, cc)] = SY3(Ai, r, cc) - (M[r] * W21[cc] + M[3 + r] * W21[3 + cc] + M[6 + r] * W21[6 + cc]);
+      W[L6I(3 + r, 3 + cc)] = SY3(Si, r, cc);
+    }
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) W[L6I(3 + r, cc)] = W21[3 * r + cc];
+#undef SY3
+#undef L6I
+  return ok;
+}
+
+// The dependent chain of the factorisation is, per block column c: P_c = A_c W_c (panel) -> the update of the NEXT
+// pivot block -> its inverse W_{c+1}.  Everything on that chain lives in shared memory:
+//   panel phase   threads (a, p): row p of P_a = A_ac W_c (W_c from shared memory), P written to the panel buffer and to
+//                 global memory (the back-substitution needs it); six threads u_c = W_c b_c.  Meanwhile the idle warps
+//                 fetch column c + 1 (pivot block, panel, right-hand side, its update list and row positions) into the
+//                 second column cache -- every earlier update of it has been issued before the previous barrier.
+//   update phase  warp 0 applies column c's update of the pivot block c + 1 first (the first entry of the list when it
+//                 exists) and inverts it into W_{c+1} while warps 1..31 apply the other updates: into the cache when
+//                 they target column c + 1, otherwise as fire-and-forget reductions (red.global.add.f64; nobody waits
+//                 for L2, and the barriers between columns order the reductions of one address).
+// Round 2, first version: every phase read and wrote global memory and every panel thread inverted the pivot itself,
+// 752 us per launch for 260 poses; the phase counters (slslam_po_stats::factor_cycles) guided this form.
 __global__ void __launch_bounds__(PO_SP_NT, 1) po_sp_factor_solve(PoDev d) {
   if (d.st->done) return;
   extern __shared__ __align__(16) double spsm[];
-  double* cache0 = spsm;                                // column caches: [0..36) diagonal block, then the panel blocks
-  double* cache1 = spsm + PO_SP_CACHE;
-  double* Pm = spsm + 2 * PO_SP_CACHE;                  // [MAXROWS][36] P = A W of the current column
+  double* cache0 = spsm;                                // column caches: [0..36) pivot block, then the panel blocks
+  double* cache1 = cache0 + PO_SP_CACHE;
+  double* Pm = cache1 + PO_SP_CACHE;                    // [MAXROWS][36] P = A W of the current column
   double* ysm = Pm + PO_SP_MAXROWS * 36;                // [YMAX] solution in position order (back-substitution)
-  double* bzc = ysm + PO_SP_YMAX;                       // [2][8] cached right-hand-side block of the current / next column
+  double* Wsm = ysm + PO_SP_YMAX;                       // [2][36] pivot inverse of the current / next column
+  double* bzc = Wsm + 72;                               // [2][8] right-hand-side block of the current / next column
   double* bc = bzc + 16;                                // [8] b_c
+  int2* tri_s = reinterpret_cast<int2*>(bc + 8);        // [2][TRICAP] staged update lists
+  int* rp_s = reinterpret_cast<int*>(tri_s + 2 * PO_SP_TRICAP);   // [2][MAXROWS] staged row positions
+  int* bs_i = rp_s + 2 * PO_SP_MAXROWS;                 // back-substitution: [2][400] ints (column offsets, row positions)
   __shared__ int bad;
-  const int tid = threadIdx.x, Kf = d.Kf;
+  const int tid = threadIdx.x, lane = tid & 31, Kf = d.Kf;
   if (tid == 0) bad = 0;
-  // column 0 into cache 0
-  {
-    const int m0 = d.col_off[1] - d.col_off[0];
-    for (int i = tid; i < 36 * (1 + m0) + 6; i += PO_SP_NT) {
-      if (i < 36) cache0[i] = d.Hb[i];
-      else if (i < 36 * (1 + m0)) cache0[i] = d.Hb[(size_t)Kf * 36 + (i - 36)];
-      else bzc[i - 36 * (1 + m0)] = d.bz[i - 36 * (1 + m0)];
+  long long t_p1 = 0, t_p2 = 0, t_mark = 0, t_start = 0;
+  if (tid == 0) { t_start = clock64(); t_mark = t_start; }
+  // what the idle warps (or, for column 0, everybody) fetch for column cn into cache `dst`
+  auto fetch_column = [&](int cn, double* dst, double* bdst, int first_thread, int nthreads) {
+    const int oa = d.col_off[cn], mm = d.col_off[cn + 1] - oa;
+    const int ta = d.tri_off[cn], ntr = d.tri_off[cn + 1] - ta;
+    const int nblk = 36 * (1 + mm);
+    for (int i = tid - first_thread; i < nblk + 6; i += nthreads) {
+      if (i < 36) dst[i] = po_ld_strong(d.Hb + (size_t)cn * 36 + i);
+      else if (i < nblk) dst[i] = po_ld_strong(d.Hb + (size_t)(Kf + oa) * 36 + (i - 36));
+      else bdst[i - nblk] = po_ld_strong(d.bz + 6 * cn + (i - nblk));
+    }
+    int2* ts = tri_s + (cn & 1) * PO_SP_TRICAP;
+    if (ntr <= PO_SP_TRICAP) for (int i = tid - first_thread; i < ntr; i += nthreads) ts[i] = d.tri[ta + i];
+    int* rs = rp_s + (cn & 1) * PO_SP_MAXROWS;
+    for (int i = tid - first_thread; i < mm; i += nthreads) rs[i] = d.row_pos[oa + i];
+  };
+  fetch_column(0, cache0, bzc, 0, PO_SP_NT);
+  __syncthreads();
+  if (tid < 32) {
+    double W[21];
+    const bool ok = po_spd6_inverse(cache0, W);
+    if (lane == 0) {
+      if (!ok) bad = 1;
+#pragma unroll
+      for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) Wsm[6 * p + q] = W[p >= q ? p * (p + 1) / 2 + q : q * (q + 1) / 2 + p];
     }
   }
   __syncthreads();
   for (int c = 0; c < Kf; ++c) {
     double* cur = (c & 1) ? cache1 : cache0;
     double* nxt = (c & 1) ? cache0 : cache1;
+    const double* Wc = Wsm + 36 * (c & 1);
+    double* Wn = Wsm + 36 * ((c + 1) & 1);
     double* bcur = bzc + 8 * (c & 1);
     double* bnxt = bzc + 8 * ((c + 1) & 1);
     const int o0 = d.col_off[c], o1 = d.col_off[c + 1], m = o1 - o0;
-    const int o2 = (c + 1 < Kf) ? d.col_off[c + 2] : o1, m1 = o2 - o1;
+    const int o2 = (c + 1 < Kf) ? d.col_off[c + 2] : o1;
     const int nwork = 6 * m + 6, work_end = (nwork + 31) & ~31;
+    // ---- panel phase ----
     if (tid < nwork) {
-      double A[21], W[21];
-#pragma unroll
-      for (int p = 0; p < 6; ++p)
-#pragma unroll
-        for (int q = 0; q <= p; ++q) A[p * (p + 1) / 2 + q] = cur[6 * p + q];
-#define L6I(p, q) ((p) * ((p) + 1) / 2 + (q))
-#define SY3(mm, r, cc) mm[(r) <= (cc) ? ((r) == 0 ? (cc) : (r) == 1 ? 2 + (cc) : 5) : ((cc) == 0 ? (r) : (cc) == 1 ? 2 + (r) : 5)]
-      double Ai[6], Si[6], M[9], S[6];
-      bool ok = spd3_inverse(A[L6I(0, 0)], A[L6I(1, 0)], A[L6I(2, 0)], A[L6I(1, 1)], A[L6I(2, 1)], A[L6I(2, 2)], Ai);
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc)
-          M[3 * r + cc] = A[L6I(3 + r, 0)] * SY3(Ai, 0, cc) + A[L6I(3 + r, 1)] * SY3(Ai, 1, cc) + A[L6I(3 + r, 2)] * SY3(Ai, 2, cc);
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cc = r; cc < 3; ++cc)
-          SY3(S, r, cc) = A[L6I(3 + cc, 3 + r)] - (M[3 * r] * A[L6I(3 + cc, 0)] + M[3 * r + 1] * A[L6I(3 + cc, 1)] + M[3 * r + 2] * A[L6I(3 + cc, 2)]);
-      ok = spd3_inverse(S[0], S[1], S[2], S[3], S[4], S[5], Si) && ok;
-      double W21[9];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc)
-          W21[3 * r + cc] = -(SY3(Si, r, 0) * M[cc] + SY3(Si, r, 1) * M[3 + cc] + SY3(Si, r, 2) * M[6 + cc]);
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cc = 0; cc <= r; ++cc) {
-          W[L6I(r, cc)] = SY3(Ai, r, cc) - (M[r] * W21[cc] + M[3 + r] * W21[3 + cc] + M[6 + r] * W21[6 + cc]);
-          W[L6I(3 + r, 3 + cc)] = SY3(Si, r, cc);
-        }
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc) W[L6I(3 + r, cc)] = W21[3 * r + cc];
-#undef SY3
       if (tid < 6 * m) {
         const int a = tid / 6, p = tid - 6 * a;
-        const double* arow = cur + 36 * (1 + a) + 6 * p;            // the original row stays in the cache for phase 2
+        const double* arow = cur + 36 * (1 + a) + 6 * p;            // the original row stays in the cache for the updates
         double* grow = d.Hb + (size_t)(Kf + o0 + a) * 36 + 6 * p;   // P is kept in global memory for the back-substitution
         double av[6], pv[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) av[k] = arow[k];
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
-          double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-          for (int k = 0; k < 3; ++k) s0 += av[k] * W[k >= q ? L6I(k, q) : L6I(q, k)];
-#pragma unroll
-          for (int k = 3; k < 6; ++k) s1 += av[k] * W[k >= q ? L6I(k, q) : L6I(q, k)];
+          const double s0 = av[0] * Wc[q] + av[1] * Wc[6 + q] + av[2] * Wc[12 + q];
+          const double s1 = av[3] * Wc[18 + q] + av[4] * Wc[24 + q] + av[5] * Wc[30 + q];
           pv[q] = s0 + s1;
         }
 #pragma unroll
         for (int k = 0; k < 6; ++k) { Pm[36 * a + 6 * p + k] = pv[k]; grow[k] = pv[k]; }
       } else {
         const int q = tid - 6 * m;
-        if (q == 0 && !ok) bad = 1;
-        double bk[6], uq[6];
+        double sum = 0.0;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { bk[k] = bcur[k]; if (q == 0) bc[k] = bk[k]; }
-#pragma unroll
-        for (int qq = 0; qq < 6; ++qq) {            // all six (static register indexing), this thread keeps its own
-          double sum = 0.0;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) sum += bk[k] * W[k >= qq ? L6I(k, qq) : L6I(qq, k)];
-          uq[qq] = sum;
-        }
-        d.us[6 * c + q] = q == 0 ? uq[0] : q == 1 ? uq[1] : q == 2 ? uq[2] : q == 3 ? uq[3] : q == 4 ? uq[4] : uq[5];
+        for (int k = 0; k < 6; ++k) { const double bk = bcur[k]; sum += bk * Wc[6 * k + q]; if (q == 0) bc[k] = bk; }
+        d.us[6 * c + q] = sum;
       }
-#undef L6I
     } else if (tid >= work_end && c + 1 < Kf) {
-      // the other warps fetch column c + 1: every earlier column's update of it has been issued (as a reduction, or a
-      // store) before the barrier that ended the previous column, so a strong load observes it
-      const int nfetch = 36 * (1 + m1) + 6, nth = PO_SP_NT - work_end;
-      for (int i = tid - work_end; i < nfetch; i += nth) {
-        if (i < 36) nxt[i] = po_ld_strong(d.Hb + (size_t)(c + 1) * 36 + i);
-        else if (i < 36 * (1 + m1)) nxt[i] = po_ld_strong(d.Hb + (size_t)(Kf + o1) * 36 + (i - 36));
-        else bnxt[i - 36 * (1 + m1)] = po_ld_strong(d.bz + 6 * (c + 1) + (i - 36 * (1 + m1)));
-      }
+      fetch_column(c + 1, nxt, bnxt, work_end, PO_SP_NT - work_end);
     }
     __syncthreads();
     if (work_end >= PO_SP_NT && c + 1 < Kf) {
-      // a column so full that no warp was idle: fetch the next one now (rare: the last, dense columns of the factor)
-      const int nfetch = 36 * (1 + m1) + 6;
-      for (int i = tid; i < nfetch; i += PO_SP_NT) {
-        if (i < 36) nxt[i] = po_ld_strong(d.Hb + (size_t)(c + 1) * 36 + i);
-        else if (i < 36 * (1 + m1)) nxt[i] = po_ld_strong(d.Hb + (size_t)(Kf + o1) * 36 + (i - 36));
-        else bnxt[i - 36 * (1 + m1)] = po_ld_strong(d.bz + 6 * (c + 1) + (i - 36 * (1 + m1)));
-      }
+      // a column so full that no warp was idle: fetch the next one now (rare: the last, dense columns of a full factor)
+      fetch_column(c + 1, nxt, bnxt, 0, PO_SP_NT);
       __syncthreads();
     }
+    if (tid == 0) { const long long now = clock64(); t_p1 += now - t_mark; t_mark = now; }
+    // ---- update phase ----
     const int t0 = d.tri_off[c], nt = d.tri_off[c + 1] - t0;
-    const int pan_lo = Kf + o1, pan_hi = Kf + o2;       // block ids of column c + 1's panel
-    for (int e = tid; e < 36 * nt + 6 * m; e += PO_SP_NT) {
-      if (e < 36 * nt) {
-        const int t = e / 36, pq = e - 36 * t, p = pq / 6, q = pq - 6 * p;
-        const int2 tr = d.tri[t0 + t];
-        const double* pa = Pm + 36 * (tr.y & 0xffff) + 6 * p;
-        const double* ob = cur + 36 * (1 + (tr.y >> 16)) + 6 * q;
-        const double s0 = pa[0] * ob[0] + pa[1] * ob[1] + pa[2] * ob[2];
-        const double s1 = pa[3] * ob[3] + pa[4] * ob[4] + pa[5] * ob[5];
-        const double sv = s0 + s1;
-        if (tr.x == c + 1) nxt[pq] -= sv;
-        else if (tr.x >= pan_lo && tr.x < pan_hi) nxt[36 * (1 + tr.x - pan_lo) + pq] -= sv;
-        else atomicAdd(d.Hb + (size_t)tr.x * 36 + pq, -sv);          // result unused: a reduction, nobody waits for it
-      } else {
-        const int r = e - 36 * nt, a = r / 6, p = r - 6 * a;
-        const double* pa = Pm + 36 * a + 6 * p;
-        double sum = 0.0;
+    const int2* tl = (nt <= PO_SP_TRICAP) ? (tri_s + (c & 1) * PO_SP_TRICAP) : (d.tri + t0);
+    const int* rps = rp_s + (c & 1) * PO_SP_MAXROWS;
+    // the update of the next pivot block, when there is one, is the first entry (row c + 1 sorts first in the column)
+    const bool pivot_first = nt > 0 && tl[0].x == c + 1;
+    if (tid < 32) {
+      if (c + 1 < Kf) {
+        if (pivot_first) {
+          const int2 tr = tl[0];
+          for (int pq = lane; pq < 36; pq += 32) {
+            const int p = pq / 6, q = pq - 6 * p;
+            const double* pa = Pm + 36 * (tr.y & 0xffff) + 6 * p;
+            const double* ob = cur + 36 * (1 + (tr.y >> 16)) + 6 * q;
+            const double s0 = pa[0] * ob[0] + pa[1] * ob[1] + pa[2] * ob[2];
+            const double s1 = pa[3] * ob[3] + pa[4] * ob[4] + pa[5] * ob[5];
+            nxt[pq] -= s0 + s1;
+          }
+          __syncwarp();
+        }
+        double W[21];
+        const bool ok = po_spd6_inverse(nxt, W);
+        if (lane == 0) {
+          if (!ok) bad = 1;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) sum += pa[k] * bc[k];
-        const int rp = d.row_pos[o0 + a];
-        if (rp == c + 1) bnxt[p] -= sum; else atomicAdd(d.bz + 6 * rp + p, -sum);
+          for (int p = 0; p < 6; ++p)
+#pragma unroll
+            for (int q = 0; q < 6; ++q) Wn[6 * p + q] = W[p >= q ? p * (p + 1) / 2 + q : q * (q + 1) / 2 + p];
+        }
+      }
+    } else {
+      const int first = pivot_first ? 36 : 0;
+      const int pan_lo = Kf + o1, pan_hi = Kf + o2;     // block ids of column c + 1's panel
+      for (int e = first + tid - 32; e < 36 * nt + 6 * m; e += PO_SP_NT - 32) {
+        if (e < 36 * nt) {
+          const int t = e / 36, pq = e - 36 * t, p = pq / 6, q = pq - 6 * p;
+          const int2 tr = tl[t];
+          const double* pa = Pm + 36 * (tr.y & 0xffff) + 6 * p;
+          const double* ob = cur + 36 * (1 + (tr.y >> 16)) + 6 * q;
+          const double s0 = pa[0] * ob[0] + pa[1] * ob[1] + pa[2] * ob[2];
+          const double s1 = pa[3] * ob[3] + pa[4] * ob[4] + pa[5] * ob[5];
+          const double sv = s0 + s1;
+          if (tr.x >= pan_lo && tr.x < pan_hi) nxt[36 * (1 + tr.x - pan_lo) + pq] -= sv;
+          else if (tr.x == c + 1) nxt[pq] -= sv;                       // (only when the list was not sorted as expected)
+          else atomicAdd(d.Hb + (size_t)tr.x * 36 + pq, -sv);          // result unused: a reduction, nobody waits for it
+        } else {
+          const int r = e - 36 * nt, a = r / 6, p = r - 6 * a;
+          const double* pa = Pm + 36 * a + 6 * p;
+          double sum = 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) sum += pa[k] * bc[k];
+          const int rp = rps[a];
+          if (rp == c + 1) bnxt[p] -= sum; else atomicAdd(d.bz + 6 * rp + p, -sum);
+        }
       }
     }
     __syncthreads();
+    if (tid == 0) { const long long now = clock64(); t_p2 += now - t_mark; t_mark = now; }
   }
   if (tid == 0 && bad) d.st->chol_fail = 1;
   // ---- back-substitution, descending: y_c = u_c - sum_a P_ac^T y_row(a).  The P blocks of a chunk of columns (a
-  // contiguous range of Hb) are staged in shared memory by all threads, then warp 0 walks the chunk's columns while the
-  // other warps stage the next chunk.
+  // contiguous range of Hb), their u, row positions and offsets are staged in shared memory by all threads, then warp 0
+  // walks the chunk's columns while the other warps stage the next chunk.
   double* yv = (d.n <= PO_SP_YMAX) ? ysm : d.yp;
-  double* stage[2] = {cache0, cache1};
+  double* stageP[2] = {cache0, cache1};
+  double* us_s = reinterpret_cast<double*>(tri_s);                // [2][6 * MAXROWS] (the update lists are dead by now)
   const int nchunk = d.bs_nchunk;
   auto stage_chunk = [&](int k, int first_thread, int nthreads) {
     if (k >= nchunk) return;
     const int c_hi = d.bs_chunk[k], c_lo = d.bs_chunk[k + 1];           // columns [c_lo, c_hi)
-    const int b0 = d.col_off[c_lo], nb = d.col_off[c_hi] - b0;
-    double* dst = stage[k & 1];
+    const int b0 = d.col_off[c_lo], nb = d.col_off[c_hi] - b0, ncol = c_hi - c_lo;
+    double* dst = stageP[k & 1];
     for (int i = tid - first_thread; i < 36 * nb; i += nthreads) dst[i] = __ldcg(d.Hb + (size_t)(Kf + b0) * 36 + i);
+    double* ud = us_s + (k & 1) * 6 * PO_SP_MAXROWS;
+    for (int i = tid - first_thread; i < 6 * ncol; i += nthreads) ud[i] = __ldcg(d.us + 6 * c_lo + i);
+    int* id = bs_i + (k & 1) * 400;                                     // [0, ncol]: column offsets, [200, 200 + nb): row positions
+    for (int i = tid - first_thread; i <= ncol; i += nthreads) id[i] = d.col_off[c_lo + i] - b0;
+    for (int i = tid - first_thread; i < nb; i += nthreads) id[200 + i] = d.row_pos[b0 + i];
   };
   stage_chunk(0, 0, PO_SP_NT);
   __syncthreads();
@@ -633,15 +693,16 @@ __global__ void __launch_bounds__(PO_SP_NT, 1) po_sp_factor_solve(PoDev d) {
       stage_chunk(k + 1, 32, PO_SP_NT - 32);
     } else {
       const int c_hi = d.bs_chunk[k], c_lo = d.bs_chunk[k + 1];
-      const int b0 = d.col_off[c_lo];
-      const double* Ps = stage[k & 1];
+      const double* Ps = stageP[k & 1];
+      const double* ud = us_s + (k & 1) * 6 * PO_SP_MAXROWS;
+      const int* id = bs_i + (k & 1) * 400;
       for (int c = c_hi - 1; c >= c_lo; --c) {
-        const int o0 = d.col_off[c], m = d.col_off[c + 1] - o0;
+        const int o0 = id[c - c_lo], m = id[c - c_lo + 1] - o0;
         double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        for (int r = tid; r < 6 * m; r += 32) {
+        for (int r = lane; r < 6 * m; r += 32) {
           const int a = r / 6, p = r - 6 * a;
-          const double yr = yv[6 * d.row_pos[o0 + a] + p];
-          const double* prow = Ps + 36 * (o0 - b0 + a) + 6 * p;
+          const double yr = yv[6 * id[200 + o0 + a] + p];
+          const double* prow = Ps + 36 * (o0 + a) + 6 * p;
 #pragma unroll
           for (int q = 0; q < 6; ++q) acc[q] += prow[q] * yr;
         }
@@ -650,11 +711,15 @@ __global__ void __launch_bounds__(PO_SP_NT, 1) po_sp_factor_solve(PoDev d) {
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
         }
-        if (tid < 6) yv[6 * c + tid] = d.us[6 * c + tid] - (tid == 0 ? acc[0] : tid == 1 ? acc[1] : tid == 2 ? acc[2] : tid == 3 ? acc[3] : tid == 4 ? acc[4] : acc[5]);
+        if (lane < 6) yv[6 * c + lane] = ud[6 * (c - c_lo) + lane] - (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : lane == 3 ? acc[3] : lane == 4 ? acc[4] : acc[5]);
         __syncwarp();
       }
     }
     __syncthreads();
+  }
+  if (tid == 0 && d.sp_cycles) {
+    const long long now = clock64();
+    d.sp_cycles[0] = t_p1; d.sp_cycles[1] = t_p2; d.sp_cycles[2] = now - t_mark; d.sp_cycles[3] = now - t_start;
   }
   // solution back in slot order
   for (int i = tid; i < d.n; i += PO_SP_NT) d.y[i] = yv[6 * d.slot_pos[i / 6] + i % 6];
