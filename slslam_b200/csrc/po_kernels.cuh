@@ -534,20 +534,33 @@ __global__ void __launch_bounds__(PO_SP_NT, 1) po_sp_factor_solve(PoDev d) {
   if (tid == 0) bad = 0;
   long long t_p1 = 0, t_p2 = 0, t_mark = 0, t_start = 0;
   if (tid == 0) { t_start = clock64(); t_mark = t_start; }
-  // what the idle warps (or, for column 0, everybody) fetch for column cn into cache `dst`
+  // What the idle warps (or, for column 0, everybody) fetch for column cn into cache `dst`.  ONE concatenated index space
+  // (blocks | right-hand side | update list | row positions): a thread issues its load(s) before it stores anything, so
+  // the whole fetch is one L2 round trip instead of one per array (it sits on the barrier of the panel phase).
   auto fetch_column = [&](int cn, double* dst, double* bdst, int first_thread, int nthreads) {
     const int oa = d.col_off[cn], mm = d.col_off[cn + 1] - oa;
     const int ta = d.tri_off[cn], ntr = d.tri_off[cn + 1] - ta;
-    const int nblk = 36 * (1 + mm);
-    for (int i = tid - first_thread; i < nblk + 6; i += nthreads) {
-      if (i < 36) dst[i] = po_ld_strong(d.Hb + (size_t)cn * 36 + i);
-      else if (i < nblk) dst[i] = po_ld_strong(d.Hb + (size_t)(Kf + oa) * 36 + (i - 36));
-      else bdst[i - nblk] = po_ld_strong(d.bz + 6 * cn + (i - nblk));
-    }
+    const int nblk = 36 * (1 + mm), n1 = nblk + 6, n2 = n1 + (ntr <= PO_SP_TRICAP ? ntr : 0), n3 = n2 + mm;
     int2* ts = tri_s + (cn & 1) * PO_SP_TRICAP;
-    if (ntr <= PO_SP_TRICAP) for (int i = tid - first_thread; i < ntr; i += nthreads) ts[i] = d.tri[ta + i];
     int* rs = rp_s + (cn & 1) * PO_SP_MAXROWS;
-    for (int i = tid - first_thread; i < mm; i += nthreads) rs[i] = d.row_pos[oa + i];
+    for (int i0 = tid - first_thread; i0 < n3; i0 += 2 * nthreads) {
+      const int i1 = i0 + nthreads;
+      double v0 = 0.0, v1 = 0.0; int2 w0 = make_int2(0, 0), w1 = make_int2(0, 0); int r0 = 0, r1 = 0;
+      if (i0 < 36) v0 = po_ld_strong(d.Hb + (size_t)cn * 36 + i0);
+      else if (i0 < nblk) v0 = po_ld_strong(d.Hb + (size_t)(Kf + oa) * 36 + (i0 - 36));
+      else if (i0 < n1) v0 = po_ld_strong(d.bz + 6 * cn + (i0 - nblk));
+      else if (i0 < n2) w0 = d.tri[ta + (i0 - n1)];
+      else r0 = d.row_pos[oa + (i0 - n2)];
+      if (i1 < n3) {
+        if (i1 < 36) v1 = po_ld_strong(d.Hb + (size_t)cn * 36 + i1);
+        else if (i1 < nblk) v1 = po_ld_strong(d.Hb + (size_t)(Kf + oa) * 36 + (i1 - 36));
+        else if (i1 < n1) v1 = po_ld_strong(d.bz + 6 * cn + (i1 - nblk));
+        else if (i1 < n2) w1 = d.tri[ta + (i1 - n1)];
+        else r1 = d.row_pos[oa + (i1 - n2)];
+      }
+      if (i0 < nblk) dst[i0] = v0; else if (i0 < n1) bdst[i0 - nblk] = v0; else if (i0 < n2) ts[i0 - n1] = w0; else rs[i0 - n2] = r0;
+      if (i1 < n3) { if (i1 < nblk) dst[i1] = v1; else if (i1 < n1) bdst[i1 - nblk] = v1; else if (i1 < n2) ts[i1 - n1] = w1; else rs[i1 - n2] = r1; }
+    }
   };
   fetch_column(0, cache0, bzc, 0, PO_SP_NT);
   __syncthreads();
@@ -564,8 +577,10 @@ __global__ void __launch_bounds__(PO_SP_NT, 1) po_sp_factor_solve(PoDev d) {
   }
   __syncthreads();
   for (int c = 0; c < Kf; ++c) {
-    double* cur = (c & 1) ? cache1 : cache0;
-    double* nxt = (c & 1) ? cache0 : cache1;
+    // (offsets from the one shared-memory base, not selected pointers: the accesses then stay LDS / STS instead of
+    // generic loads, and nothing is spilled to an indexed local array)
+    double* cur = spsm + (c & 1) * PO_SP_CACHE;
+    double* nxt = spsm + ((c + 1) & 1) * PO_SP_CACHE;
     const double* Wc = Wsm + 36 * (c & 1);
     double* Wn = Wsm + 36 * ((c + 1) & 1);
     double* bcur = bzc + 8 * (c & 1);
@@ -670,15 +685,15 @@ __global__ void __launch_bounds__(PO_SP_NT, 1) po_sp_factor_solve(PoDev d) {
   // ---- back-substitution, descending: y_c = u_c - sum_a P_ac^T y_row(a).  The P blocks of a chunk of columns (a
   // contiguous range of Hb), their u, row positions and offsets are staged in shared memory by all threads, then warp 0
   // walks the chunk's columns while the other warps stage the next chunk.
-  double* yv = (d.n <= PO_SP_YMAX) ? ysm : d.yp;
-  double* stageP[2] = {cache0, cache1};
+  const bool y_in_smem = d.n <= PO_SP_YMAX;
+  double* yv = y_in_smem ? ysm : d.yp;
   double* us_s = reinterpret_cast<double*>(tri_s);                // [2][6 * MAXROWS] (the update lists are dead by now)
   const int nchunk = d.bs_nchunk;
   auto stage_chunk = [&](int k, int first_thread, int nthreads) {
     if (k >= nchunk) return;
     const int c_hi = d.bs_chunk[k], c_lo = d.bs_chunk[k + 1];           // columns [c_lo, c_hi)
     const int b0 = d.col_off[c_lo], nb = d.col_off[c_hi] - b0, ncol = c_hi - c_lo;
-    double* dst = stageP[k & 1];
+    double* dst = spsm + (k & 1) * PO_SP_CACHE;
     for (int i = tid - first_thread; i < 36 * nb; i += nthreads) dst[i] = __ldcg(d.Hb + (size_t)(Kf + b0) * 36 + i);
     double* ud = us_s + (k & 1) * 6 * PO_SP_MAXROWS;
     for (int i = tid - first_thread; i < 6 * ncol; i += nthreads) ud[i] = __ldcg(d.us + 6 * c_lo + i);
@@ -693,7 +708,7 @@ __global__ void __launch_bounds__(PO_SP_NT, 1) po_sp_factor_solve(PoDev d) {
       stage_chunk(k + 1, 32, PO_SP_NT - 32);
     } else {
       const int c_hi = d.bs_chunk[k], c_lo = d.bs_chunk[k + 1];
-      const double* Ps = stageP[k & 1];
+      const double* Ps = spsm + (k & 1) * PO_SP_CACHE;
       const double* ud = us_s + (k & 1) * 6 * PO_SP_MAXROWS;
       const int* id = bs_i + (k & 1) * 400;
       for (int c = c_hi - 1; c >= c_lo; --c) {
@@ -701,7 +716,8 @@ __global__ void __launch_bounds__(PO_SP_NT, 1) po_sp_factor_solve(PoDev d) {
         double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         for (int r = lane; r < 6 * m; r += 32) {
           const int a = r / 6, p = r - 6 * a;
-          const double yr = yv[6 * id[200 + o0 + a] + p];
+          const int yi = 6 * id[200 + o0 + a] + p;
+          const double yr = y_in_smem ? ysm[yi] : d.yp[yi];
           const double* prow = Ps + 36 * (o0 + a) + 6 * p;
 #pragma unroll
           for (int q = 0; q < 6; ++q) acc[q] += prow[q] * yr;
@@ -711,7 +727,10 @@ __global__ void __launch_bounds__(PO_SP_NT, 1) po_sp_factor_solve(PoDev d) {
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
         }
-        if (lane < 6) yv[6 * c + lane] = ud[6 * (c - c_lo) + lane] - (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : lane == 3 ? acc[3] : lane == 4 ? acc[4] : acc[5]);
+        if (lane < 6) {
+          const double yc_ = ud[6 * (c - c_lo) + lane] - (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : lane == 3 ? acc[3] : lane == 4 ? acc[4] : acc[5]);
+          if (y_in_smem) ysm[6 * c + lane] = yc_; else d.yp[6 * c + lane] = yc_;
+        }
         __syncwarp();
       }
     }
