@@ -237,6 +237,71 @@ def workload_config(windows):
             "l2": "flushed between timed steps (256 MiB write)"}
 
 
+def bench_pose_graph(capi, device, fp64_peak_tflops, cpu=True):
+    """BASELINE.json configs[4] (substitute): pose-graph optimisation of a myungdong-scale graph -- the 253
+    keyframes of the reference's own output trajectory (tests/golden/traj_myungdong_wolc.npy), neighbour edges and 10
+    loop closures, max 10 LM iterations (POProblem(.., 10), reference src/slam.cpp:1283).  One step = one slslam_po_solve
+    call with host buffers (H2D, the whole LM loop, D2H); `value` = LM iterations / s of device time."""
+    import torch
+    traj = np.load(os.path.join(ROOT, "tests", "golden", "traj_myungdong_wolc.npy"))
+    g = synth.pose_graph_from_trajectory(traj, seed=0, num_loops=10)
+    for _ in range(3):
+        p, s = capi.po_solve(g, max_iters=10)
+    K = 20
+    dev_ms, wall = [], []
+    for _ in range(K):
+        t0 = time.perf_counter()
+        p, s = capi.po_solve(g, max_iters=10)
+        wall.append(time.perf_counter() - t0)
+        dev_ms.append(float(capi.lib().slslam_po_last_solve_ms()))
+    st = capi.po_last_stats()
+    iters = s["iterations"]
+    # fp64 work one factorisation + its substitutions need (block-sparse factor): per block update 6x6x6 FMAs, per panel
+    # block another 6x6x6, per pivot ~300 flops for the inverse, 2 x 36 per block for the two substitutions
+    nb_off = st["factor_blocks"] - st["free_poses"]
+    flops_factor = 432.0 * st["block_updates"] + 432.0 * nb_off + 300.0 * st["free_poses"] + 4 * 72.0 * nb_off
+    cyc = st["factor_cycles"]
+    sm_hz = 1e6 * float(torch.cuda.clock_rate() if hasattr(torch.cuda, "clock_rate") else 1965.0)
+    out = {
+        "workload": f"{g.num_poses} poses / {g.num_edges} edges (myungdong output trajectory + 10 loop closures), max 10 LM iterations",
+        "metric": "po_lm_iterations_per_s", "value": iters / (np.median(dev_ms) * 1e-3), "unit": UNIT,
+        "ms_per_solve_device": float(np.median(dev_ms)), "lm_iterations": iters, "termination": s["termination"],
+        "final_cost": s["final_cost"], "initial_cost": s["initial_cost"],
+        "e2e": {"value": iters / float(np.median(wall)), "unit": UNIT, "ms_per_solve": 1e3 * float(np.median(wall)),
+                "api": "slslam_po_solve (host buffers in and out, cached workspace)"},
+        "factorisation": {"path": "block-sparse" if st["sparse"] else "dense", "free_poses": st["free_poses"],
+                          "factor_blocks": st["factor_blocks"], "dense_blocks": st["free_poses"] * (st["free_poses"] + 1) // 2,
+                          "block_updates": st["block_updates"], "max_column_rows": st["max_column_rows"],
+                          "iterations_enqueued": st["iterations_enqueued"],
+                          "kernel_cycles": {"panel": cyc[0], "update": cyc[1], "back_substitution": cyc[2], "total": cyc[3]}},
+        "roofline": {"bound": "fp64 (the factorisation is a chain of dependent 6x6 block columns: latency bound, one CTA)",
+                     "kernel": "po_sp_factor_solve", "achieved": flops_factor / max(cyc[3], 1) * 1.965e9 / 1e12 if cyc[3] else None,
+                     "peak": fp64_peak_tflops, "unit": "TFLOP/s",
+                     "frac": (flops_factor / max(cyc[3], 1) * 1.965e9 / 1e12 / fp64_peak_tflops) if (cyc[3] and fp64_peak_tflops) else None,
+                     "algorithmic_flops_per_launch": flops_factor, "traffic": None,
+                     "note": "achieved = fp64 flops the sparse factor needs / kernel cycles x 1.965 GHz; a dense factor of the same "
+                             "graph would need %.2e flops" % (6.0 ** 3 * st["free_poses"] ** 3 / 3 * 2)},
+    }
+    if cpu:
+        from oracle import oracle
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            po, so = oracle.po_solve(g, max_iters=10, solver=1)
+        dt = (time.perf_counter() - t0) / reps
+        rel = abs(s["final_cost"] - so["final_cost"]) / so["final_cost"]
+        ok = rel <= 1e-6 and s["iterations"] == so["iterations"] and s["termination"] == so["termination"] and float(np.abs(p - po).max()) < 1e-5
+        if not ok:
+            raise SystemExit(f"bench.py: PO result differs from the oracle: {s} vs {so}")
+        out["parity_checked"] = True
+        out["parity"] = {"rel_final_cost": rel, "max_abs_pose": float(np.abs(p - po).max()), "tolerance": "final cost rel 1e-6, poses 1e-5, same iterations / termination"}
+        out["cpu_baseline"] = {"value": so["iterations"] / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"{reps} solves of the same graph, oracle with its SPARSE Cholesky (minimum-degree order, "
+                                         "elimination tree, up-looking factorisation: what SPARSE_NORMAL_CHOLESKY, po_problem.cpp:68, ends in)",
+                               "ms_per_solve": 1e3 * dt}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -447,12 +512,18 @@ def main():
         # what actually bounds the kernel: the fp64 pipe (64 DFMA / clk / SM).  Not the contract's roofline object, a reading aid.
         flops = ncu_fp64_flops()
         sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
-        fp64_peak = sm_count * 64 * 2 * float(clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+        fp64_nominal = sm_count * 64 * 2 * float(clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+        try:
+            fp64_peak_meas, _clk = capi.measure_fp64_peak(local_rank)
+        except Exception:
+            fp64_peak_meas = None
+        fp64_peak = fp64_peak_meas or fp64_nominal
         compute = {"bound": "fp64 pipe", "achieved": (flops / (kernel_ms * 1e-3) / 1e12) if flops else None, "peak": fp64_peak,
                    "unit": "TFLOP/s", "frac": (flops / (kernel_ms * 1e-3) / 1e12 / fp64_peak) if flops else None,
                    "fp64_flops_per_launch": flops,
                    "source": "executed DFMA/DMUL/DADD thread instructions of the committed ncu capture (profiles/) / live kernel time; "
-                             "peak = SMs x 64 DFMA/clk x 2 x max SM clock (nominal, not measured)"}
+                             "peak = measured on this device by slslam_measure_fp64_peak (register-only DFMA chains; nominal "
+                             f"SMs x 64 DFMA/clk x 2 x max SM clock = {fp64_nominal:.2f})"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -500,6 +571,8 @@ def main():
             line["single_window"] = {"value": s1[0]["iterations"] * 20 / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT,
                                      "ctas_per_window": b1.info()["ctas_per_window"], "l2": "warm"}
             b1.close()
+        if not args.no_extras:
+            line["pose_graph"] = bench_pose_graph(capi, local_rank, fp64_peak_meas, cpu=(world == 1 and not args.no_cpu_baseline))
         if world == 1 and not args.no_cpu_baseline:
             reps = 2
             iters_c, secs_c = 0, 0.0
