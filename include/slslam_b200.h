@@ -183,6 +183,48 @@ int slslam_lba_pipeline_submit(slslam_lba_pipeline* p, int32_t n, const slslam_l
 int slslam_lba_pipeline_wait(slslam_lba_pipeline* p, int64_t ticket);
 void slslam_lba_pipeline_destroy(slslam_lba_pipeline* p);
 
+/* ---- device-resident map: window assembly and write-back around the LBA solve ----
+ * What SLAM::bundle_adjustment does on the host before and after ceres::Solve (reference src/slam.cpp:799-920, 957-972),
+ * with the map kept in device memory between keyframes: keyframe poses keyframe_t::T as (R row-major 9 | t 3), landmark
+ * lines landmark_t::line as (closest point, direction) in the frame of landmark_t::init_kfid, and every keyframe's
+ * observations (landmark id + 8 normalised stereo endpoint coordinates, the obs_vec entries).  Per keyframe the caller
+ * uploads the new keyframe with its observations, the new landmarks, and -- after its own metric_embedding
+ * (slam.cpp:1317-1366, graph code that stays on the host) -- the re-anchored poses of the <= 2W window keyframes.
+ * slslam_map_bundle_adjust then selects the landmarks seen by >= 2 free keyframes (slam.cpp:838-845), builds the index /
+ * flag / observation arrays and the parameters (gc_Rt_to_wt, gc_line_from_pose + gc_av_to_orth, src/gc.cpp:24-50, 79-81,
+ * 361-417) on the device, solves the window where it was assembled, and writes poses (gc_wt_to_Rt) and lines
+ * (gc_orth_to_av + gc_line_to_pose, src/gc.cpp:419-460, 63-77) back into the map.  Differences from the reference's
+ * packing that no result depends on: observations are emitted chronologically instead of grouped by landmark (their
+ * order inside a line is the same), constant keyframes are numbered by id and kept even when they observe no selected
+ * landmark (an unobserved block is never touched). */
+typedef struct slslam_map slslam_map;
+typedef struct slslam_map_timings {
+  double assemble_ms;             /* host wall clock: small upload + selection kernels + read-back of the two sizes */
+  double solve_and_writeback_ms;  /* emit + parameters + plan + solve + write-back, until the stream is idle */
+  double total_ms;
+  int64_t h2d_bytes;              /* bytes uploaded by the call (window keyframe list and ranges) */
+  int32_t candidates;             /* observations of the window keyframes that were looked at */
+} slslam_map_timings;
+int slslam_map_create(int32_t device, int32_t max_keyframes, int32_t max_landmarks, int32_t max_observations, slslam_map** out);
+void slslam_map_destroy(slslam_map* m);
+int slslam_map_add_keyframe(slslam_map* m, int32_t kf_id, const double* T12, int32_t n_obs, const int32_t* lm_ids, const double* obs8);
+int slslam_map_add_landmarks(slslam_map* m, int32_t n, const int32_t* lm_ids, const int32_t* init_kf_ids, const double* line_av6);
+int slslam_map_set_poses(slslam_map* m, int32_t n, const int32_t* kf_ids, const double* T12);
+int slslam_map_get_poses(slslam_map* m, int32_t n, const int32_t* kf_ids, double* T12_out);
+int slslam_map_get_landmarks(slslam_map* m, int32_t n, const int32_t* lm_ids, double* line_av6_out);
+/* ba_order[i] = graph-distance rank of ba_kf_ids[i] (ba_kfs, slam.cpp:1376-1382): rank < window_size => free camera.
+ * sizes3_out (optional) receives cameras, lines, observations of the assembled window. */
+int slslam_map_bundle_adjust(slslam_map* m, int32_t n_ba, const int32_t* ba_kf_ids, const int32_t* ba_order, int32_t window_size,
+                             int32_t max_iterations, int32_t robust, slslam_summary* summary_out, int32_t* sizes3_out);
+void slslam_map_last_timings(const slslam_map* m, slslam_map_timings* out);
+/* Diagnostics / parity: the window the last slslam_map_bundle_adjust assembled (reference array layout; parameters as
+ * assembled, before the solve).  Any pointer may be NULL.  line_landmark [L], camera_keyframe [C]. */
+int slslam_map_last_window(slslam_map* m, int32_t* camera_index, int32_t* line_index, int32_t* fixed_index, double* observations,
+                           double* parameters, int32_t* line_landmark, int32_t* camera_keyframe);
+/* Batch geometry conversions on the device: mode 0 gc_av_to_orth (av[6n] -> orth[4n]), 1 gc_orth_to_av, 2 rotation
+ * matrix (row-major 9) -> angle-axis (RotationMatrixToAngleAxis behind gc_Rt_to_wt), 3 angle-axis -> rotation matrix. */
+int slslam_geometry_convert(int32_t mode, int32_t n, const double* in, double* out);
+
 /* ---- K1 alone: residuals (Huber-unscaled) and analytic Jacobians of every observation, for parity tests ----
  * residuals [4N]; jac_camera [24N] row-major 4x6; jac_line [16N] row-major 4x4; cost_out = 1/2 sum rho. */
 int slslam_lba_evaluate(const slslam_lba_desc* desc, const double* params, double* residuals, double* jac_camera,

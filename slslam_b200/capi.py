@@ -24,6 +24,9 @@ EXPORTS = [
     "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_max_active_clusters", "slslam_lba_batch_transfer_bytes", "slslam_lba_batch_phase_cycles", "slslam_lba_batch_plan_cycles", "slslam_lba_batch_destroy",
     "slslam_lba_plan_check", "slslam_lba_launch_shape", "slslam_lba_pipeline_create", "slslam_lba_pipeline_submit", "slslam_lba_pipeline_wait", "slslam_lba_pipeline_destroy",
     "slslam_ransac_score", "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate", "slslam_po_last_solve_ms", "slslam_po_last_stats", "slslam_po_get_limits",
+    "slslam_map_create", "slslam_map_destroy", "slslam_map_add_keyframe", "slslam_map_add_landmarks", "slslam_map_set_poses",
+    "slslam_map_get_poses", "slslam_map_get_landmarks", "slslam_map_bundle_adjust", "slslam_map_last_timings", "slslam_map_last_window",
+    "slslam_geometry_convert",
 ]
 
 dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
@@ -447,3 +450,101 @@ def ransac_score(poses, lines, obs, baseline=0.12, thr=5.0 / 406.05, want_inlier
                                      inl.ctypes.data_as(C.POINTER(C.c_uint8)) if want_inliers else None,
                                      err.ctypes.data_as(C.POINTER(C.c_float)) if want_errors else None))
     return scores, inl, err
+
+
+class MapTimings(C.Structure):
+    _fields_ = [("assemble_ms", C.c_double), ("solve_and_writeback_ms", C.c_double), ("total_ms", C.c_double),
+                ("h2d_bytes", C.c_int64), ("candidates", C.c_int32)]
+
+
+def geometry_convert(mode, arr):
+    """slslam_geometry_convert: 0 av[n,6] -> orth[n,4]; 1 orth -> av; 2 R[n,9] (row-major) -> w[n,3]; 3 w -> R."""
+    L = lib()
+    L.slslam_geometry_convert.argtypes = [C.c_int32, C.c_int32, dp, dp]
+    a = np.ascontiguousarray(arr, np.float64)
+    n = a.shape[0]
+    out = np.zeros((n, (4, 6, 3, 9)[mode]))
+    _check(L.slslam_geometry_convert(mode, n, _d(a), _d(out)))
+    return out
+
+
+class DeviceMap:
+    """slslam_map_*: keyframe poses, landmark lines and observations resident on the device; per keyframe only the new
+    observations go up, the window is assembled, solved and written back where it lives."""
+
+    def __init__(self, max_keyframes, max_landmarks, max_observations, device=-1):
+        L = lib()
+        L.slslam_map_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        L.slslam_map_destroy.argtypes = [C.c_void_p]; L.slslam_map_destroy.restype = None
+        L.slslam_map_add_keyframe.argtypes = [C.c_void_p, C.c_int32, dp, C.c_int32, ip, dp]
+        L.slslam_map_add_landmarks.argtypes = [C.c_void_p, C.c_int32, ip, ip, dp]
+        L.slslam_map_set_poses.argtypes = [C.c_void_p, C.c_int32, ip, dp]
+        L.slslam_map_get_poses.argtypes = [C.c_void_p, C.c_int32, ip, dp]
+        L.slslam_map_get_landmarks.argtypes = [C.c_void_p, C.c_int32, ip, dp]
+        L.slslam_map_bundle_adjust.argtypes = [C.c_void_p, C.c_int32, ip, ip, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Summary), ip]
+        L.slslam_map_last_timings.argtypes = [C.c_void_p, C.POINTER(MapTimings)]; L.slslam_map_last_timings.restype = None
+        L.slslam_map_last_window.argtypes = [C.c_void_p, ip, ip, ip, dp, dp, ip, ip]
+        self._h = C.c_void_p()
+        _check(L.slslam_map_create(device, max_keyframes, max_landmarks, max_observations, C.byref(self._h)))
+        self.sizes = (0, 0, 0)
+
+    def add_keyframe(self, kf_id, T12, lm_ids, obs8):
+        T = np.ascontiguousarray(T12, np.float64).ravel()
+        li = np.ascontiguousarray(lm_ids, np.int32)
+        ob = np.ascontiguousarray(obs8, np.float64).ravel()
+        _check(lib().slslam_map_add_keyframe(self._h, kf_id, _d(T), int(li.shape[0]), _i(li), _d(ob)))
+
+    def add_landmarks(self, lm_ids, init_kf_ids, lines_av6):
+        li = np.ascontiguousarray(lm_ids, np.int32); ki = np.ascontiguousarray(init_kf_ids, np.int32)
+        av = np.ascontiguousarray(lines_av6, np.float64).ravel()
+        _check(lib().slslam_map_add_landmarks(self._h, int(li.shape[0]), _i(li), _i(ki), _d(av)))
+
+    def set_poses(self, kf_ids, T12):
+        ki = np.ascontiguousarray(kf_ids, np.int32); T = np.ascontiguousarray(T12, np.float64).ravel()
+        _check(lib().slslam_map_set_poses(self._h, int(ki.shape[0]), _i(ki), _d(T)))
+
+    def get_poses(self, kf_ids):
+        ki = np.ascontiguousarray(kf_ids, np.int32)
+        out = np.zeros((ki.shape[0], 12))
+        _check(lib().slslam_map_get_poses(self._h, int(ki.shape[0]), _i(ki), _d(out)))
+        return out
+
+    def get_landmarks(self, lm_ids):
+        li = np.ascontiguousarray(lm_ids, np.int32)
+        out = np.zeros((li.shape[0], 6))
+        _check(lib().slslam_map_get_landmarks(self._h, int(li.shape[0]), _i(li), _d(out)))
+        return out
+
+    def bundle_adjust(self, ba_kf_ids, ba_order, window_size, max_iters=10, robust=True):
+        ki = np.ascontiguousarray(ba_kf_ids, np.int32); oi = np.ascontiguousarray(ba_order, np.int32)
+        s = Summary()
+        sz = (C.c_int32 * 3)()
+        _check(lib().slslam_map_bundle_adjust(self._h, int(ki.shape[0]), _i(ki), _i(oi), window_size, max_iters, int(robust), C.byref(s), sz))
+        self.sizes = tuple(sz)
+        return summary_dict(s)
+
+    def last_timings(self):
+        t = MapTimings()
+        lib().slslam_map_last_timings(self._h, C.byref(t))
+        return {k: getattr(t, k) for k, _ in MapTimings._fields_}
+
+    def last_window(self):
+        """The window the last bundle_adjust assembled: dict of arrays (parameters as assembled, before the solve)."""
+        Cc, Ll, Nn = self.sizes
+        ci, li, fi = np.zeros(Nn, np.int32), np.zeros(Nn, np.int32), np.zeros(2 * Nn, np.int32)
+        ob, pr = np.zeros(8 * Nn), np.zeros(6 * Cc + 4 * Ll)
+        llm, ckf = np.zeros(Ll, np.int32), np.zeros(Cc, np.int32)
+        _check(lib().slslam_map_last_window(self._h, _i(ci), _i(li), _i(fi), _d(ob), _d(pr), _i(llm), _i(ckf)))
+        return dict(num_cameras=Cc, num_lines=Ll, camera_index=ci, line_index=li, fixed_index=fi, observations=ob,
+                    parameters=pr, line_landmark=llm, camera_keyframe=ckf)
+
+    def close(self):
+        if self._h:
+            lib().slslam_map_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
