@@ -302,6 +302,62 @@ def bench_pose_graph(capi, device, fp64_peak_tflops, cpu=True):
     return out
 
 
+def bench_map_resident(capi, w, max_iters=MAX_ITERS, reps=20):
+    """the per-keyframe blocking solve of one M window when the map (keyframe poses, landmark lines,
+    observations) is resident on the device: slslam_map_bundle_adjust assembles the window from the map with kernels,
+    solves it where it was assembled and writes poses and lines back; the call uploads only the window's keyframe list.
+    Beside it the blocking host-buffer call slslam_lba_solve on the same window (what round 1 measured at 0.67 ms)."""
+    from slslam_b200.synth import orth_to_av, rodrigues
+    C, L = w.num_cameras, w.num_lines
+    cam = w.parameters[:6 * C].reshape(C, 6)
+    T12 = np.stack([np.concatenate([rodrigues(c[:3]).ravel(), c[3:]]) for c in cam])
+    lines = w.parameters[6 * C:].reshape(L, 4)
+    obs = w.observations.reshape(-1, 8)
+    first_cam = np.full(L, -1, np.int64)
+    for i in range(len(w.line_index)):
+        if first_cam[w.line_index[i]] < 0:
+            first_cam[w.line_index[i]] = w.camera_index[i]
+    av = np.zeros((L, 6))
+    for l in range(L):
+        cp, dv = orth_to_av(lines[l])
+        R, t = T12[first_cam[l]][:9].reshape(3, 3), T12[first_cam[l]][9:]
+        av[l, :3] = R @ cp + t; av[l, 3:] = R @ dv
+    dm = capi.DeviceMap(C + 2, L + 8, len(obs) + 64)
+    for c in range(C):
+        idx = np.flatnonzero(w.camera_index == c)
+        dm.add_keyframe(c, T12[c], w.line_index[idx], obs[idx])
+    fixed_cam = set(int(c) for c, f in zip(w.camera_index, w.fixed_index[0::2]) if f)
+    order = [C + 1 if c in fixed_cam else c for c in range(C)]          # rank >= window size: constant camera
+    ids = list(range(C))
+    tms, its, cost = [], 0, None
+    for r in range(reps + 3):
+        dm.set_poses(ids, T12)                                          # restore the start (untimed): every repetition solves the same window
+        dm.add_landmarks(np.arange(L), first_cam, av)
+        t0 = time.perf_counter()
+        sm = dm.bundle_adjust(ids, order, C, max_iters=max_iters)
+        dt = time.perf_counter() - t0
+        if r >= 3:
+            tms.append(dt); its += sm["iterations"]; cost = sm["final_cost"]
+    tm = dm.last_timings()
+    dm.close()
+    hb = []
+    for r in range(reps + 3):
+        t0 = time.perf_counter()
+        p, sh = capi.lba_solve(w, max_iters=max_iters)
+        if r >= 3:
+            hb.append(time.perf_counter() - t0)
+    split = capi.last_timings()
+    return {"workload": f"one M window ({C} KF / {L} lines / {len(obs)} obs), blocking call per keyframe, max {max_iters} LM iterations",
+            "resident_map": {"ms_per_solve": 1e3 * float(np.median(tms)), "lm_iterations_per_s": its / float(np.sum(tms)),
+                             "h2d_bytes_per_solve": tm["h2d_bytes"], "assemble_ms": tm["assemble_ms"],
+                             "solve_and_writeback_ms": tm["solve_and_writeback_ms"], "final_cost": cost,
+                             "api": "slslam_map_bundle_adjust (assembly + solve + write-back on the device)"},
+            "host_buffers": {"ms_per_solve": 1e3 * float(np.median(hb)), "final_cost": sh["final_cost"], "h2d_bytes_per_solve":
+                             int(16 * len(obs) + 64 * len(obs) + 8 * (6 * C + 4 * L)), "split_ms": split,
+                             "api": "slslam_lba_solve (pageable host arrays in, parameters out)"},
+            "rel_cost_difference": abs(cost - sh["final_cost"]) / sh["final_cost"]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -572,6 +628,7 @@ def main():
                                      "ctas_per_window": b1.info()["ctas_per_window"], "l2": "warm"}
             b1.close()
         if not args.no_extras:
+            line["per_keyframe_blocking_solve"] = bench_map_resident(capi, windows[0])
             line["pose_graph"] = bench_pose_graph(capi, local_rank, fp64_peak_meas, cpu=(world == 1 and not args.no_cpu_baseline))
         if world == 1 and not args.no_cpu_baseline:
             reps = 2

@@ -30,7 +30,7 @@ def test_geometry_conversions(gpu):
     # a non-unit direction and a scaled closest point give the same line parameters
     av2 = av.copy(); av2[:, 3:] *= 3.7
     assert np.abs(gpu.geometry_convert(0, av2) - orth).max() < 1e-12
-    w = rng.normal(size=(n, 3)) * rng.uniform(0.0, 1.0, (n, 1)) * 2.5
+    w = rng.normal(size=(n, 3)); w = w / np.linalg.norm(w, axis=1, keepdims=True) * rng.uniform(0.0, 3.0, (n, 1))   # |w| < pi
     w[0] = 0.0; w[1] = [1e-9, 0, 0]; w[2] = [np.pi - 1e-7, 0, 0]
     R = gpu.geometry_convert(3, w)
     Rref = np.stack([rodrigues(x).ravel() for x in w])
