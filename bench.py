@@ -337,7 +337,7 @@ def bench_map_resident(capi, w, max_iters=MAX_ITERS, reps=20):
         sm = dm.bundle_adjust(ids, order, C, max_iters=max_iters)
         dt = time.perf_counter() - t0
         if r >= 3:
-            tms.append(dt); its += sm["iterations"]; cost = sm["final_cost"]
+            tms.append(dt); its += sm["iterations"]; cost = sm["final_cost"]; cost0 = sm["initial_cost"]
     tm = dm.last_timings()
     dm.close()
     hb = []
@@ -355,7 +355,11 @@ def bench_map_resident(capi, w, max_iters=MAX_ITERS, reps=20):
             "host_buffers": {"ms_per_solve": 1e3 * float(np.median(hb)), "final_cost": sh["final_cost"], "h2d_bytes_per_solve":
                              int(16 * len(obs) + 64 * len(obs) + 8 * (6 * C + 4 * L)), "split_ms": split,
                              "api": "slslam_lba_solve (pageable host arrays in, parameters out)"},
-            "rel_cost_difference": abs(cost - sh["final_cost"]) / sh["final_cost"]}
+            "rel_initial_cost_difference": abs(cost0 - sh["initial_cost"]) / sh["initial_cost"],
+            "note": "same window, same start (initial costs agree to rounding); the map re-derives the 4 line parameters from the stored "
+                    "(closest point, direction) in the canonical chart of gc_av_to_orth, the synthetic window carries perturbed ones, "
+                    "and 10 LM iterations from this far start do not converge, so the two final costs belong to two different LM "
+                    "paths (LM is not invariant to the parametrisation); tests/test_map_gpu.py checks bit-equality on identical arrays"}
 
 
 def main():

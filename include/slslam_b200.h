@@ -84,11 +84,16 @@ typedef struct slslam_summary {
  * cost, trial_cost, model_cost_change, radius, step_norm, accepted(1/0/-1 invalid), gradient_max_norm, relative_decrease */
 #define SLSLAM_TRACE_WIDTH 8
 
+/* Limits of the tiled solve kernel (the fast path; also what the device-resident, pipelined and slslam_lba_batch_* entry
+ * points accept).  slslam_lba_solve / slslam_lba_solve_batch route windows beyond them -- the reference's
+ * --ba_window_size 20 / 40 shapes: up to 2 W camera blocks, W free, lines seen by most cameras -- to a general kernel
+ * (one CTA per window, no limit on camera blocks or observations per line, max_free_cameras_general free cameras). */
 typedef struct slslam_lba_limits {
   int32_t max_cameras;            /* parameter blocks, free + constant */
   int32_t max_free_cameras;       /* reduced camera system is 6*max_free_cameras square */
   int32_t max_observations_per_line;
   int32_t max_cluster_size;
+  int32_t max_free_cameras_general;   /* general kernel: reduced camera system up to 6*64 square */
 } slslam_lba_limits;
 
 int slslam_version(void);

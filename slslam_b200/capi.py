@@ -65,7 +65,8 @@ class PoLimits(C.Structure):
 
 class Limits(C.Structure):
     _fields_ = [("max_cameras", C.c_int32), ("max_free_cameras", C.c_int32),
-                ("max_observations_per_line", C.c_int32), ("max_cluster_size", C.c_int32)]
+                ("max_observations_per_line", C.c_int32), ("max_cluster_size", C.c_int32),
+                ("max_free_cameras_general", C.c_int32)]
 
 
 class SlslamError(RuntimeError):

@@ -23,6 +23,7 @@
 #include "lba_kernel.cuh"
 #include "moba_kernel.cuh"
 #include "lba_plan_kernel.cuh"
+#include "wide_kernel.cuh"
 
 namespace slslam {
 
@@ -638,6 +639,7 @@ static int batch_create_impl(int32_t n, const slslam_lba_desc* descs, const doub
 }  // namespace slslam
 
 #include "moba_host.inl"
+#include "wide_host.inl"
 
 extern "C" {
 
@@ -645,6 +647,7 @@ void slslam_lba_get_limits(slslam_lba_limits* out) {
   if (!out) return;
   out->max_cameras = MAX_CAMS; out->max_free_cameras = MAX_FREE_CAMS; out->max_observations_per_line = 32;
   out->max_cluster_size = MAX_G;
+  out->max_free_cameras_general = WIDE_MAX_FREE;
 }
 
 int slslam_lba_plan_check(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t cluster_size,
@@ -849,6 +852,49 @@ int slslam_lba_solve_batch(int32_t n, const slslam_lba_desc* descs, double* cons
       all = all && moba_candidate(descs[i], &fc[i], &nf[i]);
     }
     if (all) return moba_solve_batch(n, descs, params_inout, summaries_out, fc.data(), nf.data());
+  }
+  // windows beyond the tiled kernel's limits (more than 32 camera blocks / 24 free cameras / 32 observations of a line:
+  // the reference's --ba_window_size 20 / 40 shapes) go to the general kernel, the whole batch with them
+  {
+    bool any_wide = false, plannable = true;
+    std::vector<WidePlan> wplans((size_t)n);
+    for (int i = 0; i < n && plannable; ++i) {
+      const slslam_lba_desc& d = descs[i];
+      if (d.num_cameras < 0 || d.num_lines < 0 || d.num_observations < 0 || d.max_iterations < 0 || !params_inout[i] ||
+          (d.num_observations > 0 && (!d.camera_index || !d.line_index || !d.fixed_index || !d.observations))) { plannable = false; break; }
+      if (d.num_cameras <= MAX_CAMS) {
+        // cheap screen first: only windows with many cameras or long lines can need the general kernel
+        bool maybe = false;
+        if (d.num_cameras > MAX_FREE_CAMS || d.num_observations > 32 * std::max(1, d.num_lines)) maybe = true;
+        if (!maybe) {
+          // a line with more than 32 observations needs more observations than 32 in total
+          if (d.num_observations > 32) {
+            std::vector<int> cnt((size_t)std::max(1, d.num_lines), 0);
+            for (int k = 0; k < d.num_observations && !maybe; ++k) {
+              const int l = d.line_index[k];
+              if (l >= 0 && l < d.num_lines && ++cnt[l] > 32) maybe = true;
+            }
+          }
+        }
+        if (!maybe) continue;
+      }
+      bool w = false;
+      const int prc = wide_plan(d, wplans[i], &w);
+      if (prc != SLSLAM_OK) return prc;
+      any_wide = any_wide || w;
+    }
+    if (plannable && any_wide) {
+      for (int i = 0; i < n; ++i) {
+        const int np = 6 * descs[i].num_cameras + 4 * descs[i].num_lines;
+        for (int k = 0; k < np; ++k) if (!std::isfinite(params_inout[i][k])) return SLSLAM_ERR_NUMERICAL;
+        if (wplans[i].N != descs[i].num_observations || wplans[i].order.empty()) {      // windows the screen skipped
+          bool w = false;
+          const int prc = wide_plan(descs[i], wplans[i], &w);
+          if (prc != SLSLAM_OK) return prc;
+        }
+      }
+      return wide_solve_batch(n, descs, params_inout, summaries_out, wplans);
+    }
   }
   // plan -> pinned staging -> H2D -> one cluster launch -> D2H, all on the calling thread's cached workspace
   slslam_lba_batch* b = nullptr;

@@ -76,13 +76,13 @@ def make_scene(poses_wc, seed=0, lines_per_kf=30):
 
 def observe(poses_cw, P, Q, sigma_px, seed, lines_per_kf, reach=14):
     """Per keyframe: {line id: 8 normalised coordinates}.  A line is observed when its four stereo endpoints fall in
-    the image and lie 1-40 m ahead.  Only lines created within `reach` keyframes are tested."""
+    the image and lie 1-40 m ahead.  Only lines created within `reach` keyframes are tested (reach None: all lines)."""
     rng = np.random.default_rng(seed + 1)
     obs = []
     K = len(poses_cw)
     for k, T in enumerate(poses_cw):
         R = rodrigues(T[:3])
-        lo, hi = max(0, k - reach) * lines_per_kf, min(K, k + reach + 1) * lines_per_kf
+        lo, hi = (0, len(P)) if reach is None else (max(0, k - reach) * lines_per_kf, min(K, k + reach + 1) * lines_per_kf)
         cur = {}
         pa, qa = (R @ P[lo:hi].T).T + T[3:], (R @ Q[lo:hi].T).T + T[3:]
         for j in range(hi - lo):
@@ -111,7 +111,7 @@ def export_dataset(obs_dir, poses_wc_true, sigma_px=0.5, seed=0, lines_per_kf=30
 
 
 def run(poses_wc_true, solve, window_size=10, max_iters=10, sigma_px=0.5, seed=0, lines_per_kf=30,
-        odo_noise=(2e-3, 2e-2), anchor_first=True, max_keyframes=None, record=None, obs_dir=None, motion_only=None):
+        odo_noise=(2e-3, 2e-2), anchor_first=True, max_keyframes=None, record=None, obs_dir=None, motion_only=None, scene=None):
     """Replays the trajectory.  Returns the estimated camera->world poses [K][6] and per-window statistics.
     obs_dir: read the observations from the reference's per-frame files (export_dataset) instead of generating them.
     motion_only: optional solver for the per-frame motion-only BA (reference src/slam.cpp:578-675): before a keyframe
@@ -121,6 +121,10 @@ def run(poses_wc_true, solve, window_size=10, max_iters=10, sigma_px=0.5, seed=0
     if obs_dir is not None:
         from . import dataset_io
         obs = [dataset_io.read_frame_observations(obs_dir, k) for k in range(K)]
+    elif scene is not None:
+        # a given line model seen from every keyframe (the reference's house simulation: every segment tested in every view)
+        P, Q = scene
+        obs = observe(truth_cw, np.asarray(P), np.asarray(Q), sigma_px, seed, lines_per_kf, reach=None)
     else:
         P, Q = make_scene(poses_wc_true[:K], seed, lines_per_kf)
         obs = observe(truth_cw, P, Q, sigma_px, seed, lines_per_kf)

@@ -372,3 +372,76 @@ def pose_graph_from_trajectory(poses_wc: np.ndarray, seed: int = 0, neighbours: 
         p0[k] = _compose(C, p0[k - 1])
     return PoseGraph(K, e1a, e2a, np.ascontiguousarray(consa.ravel()), np.ascontiguousarray(p0.ravel()),
                      np.ascontiguousarray(truth.ravel()), dict(seed=seed, source="trajectory"))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's house simulation (matlab_script/house.m): the 74-segment line model its published LBA table
+# (matlab_script/result_comp_ancdir_orthonorm/ba_result_*) was measured on.  The helpers house.m calls (zSegment,
+# XYRectangle, ...) are not in the repository; their names say what they build.  The ground-truth trajectory
+# (gt_trajectory_wave.txt) is not shipped either: house_trajectory() circles the model with a vertical wave.
+# ---------------------------------------------------------------------------------------------------------------------
+def house_segments(x=0.0, y=0.0, z=0.0):
+    """[(P, Q)] x 74, reference matlab_script/house.m:20-133 (l = w = 4.5, h = 3.5 as overwritten at :20-22)."""
+    l, w, h = 4.5, 4.5, 3.5
+    a, b, c, d = .2, .4, .6, .8
+    p, q, r = .25, .5, .65
+    S = []
+
+    def seg(P, Q):
+        S.append((np.asarray(P, float), np.asarray(Q, float)))
+
+    def zseg(x_, y_, z1, z2): seg([x_, y_, z1], [x_, y_, z2])
+    def xseg(x1, x2, y_, z_): seg([x1, y_, z_], [x2, y_, z_])
+    def yseg(x_, y1, y2, z_): seg([x_, y1, z_], [x_, y2, z_])
+
+    def xyrect(x1, x2, y1, y2, z_):
+        xseg(x1, x2, y1, z_); yseg(x2, y1, y2, z_); xseg(x2, x1, y2, z_); yseg(x1, y2, y1, z_)
+
+    def yzrect(x_, y1, y2, z1, z2):
+        yseg(x_, y1, y2, z1); zseg(x_, y2, z1, z2); yseg(x_, y2, y1, z2); zseg(x_, y1, z2, z1)
+
+    zseg(x, y, z, z + r * h); zseg(x + l, y, z, z + r * h); zseg(x + l, y + w, z, z + r * h); zseg(x, y + w, z, z + r * h)   # 1-4 walls
+    xyrect(x, x + l, y, y + w, z)                                                                                          # 5-8 floor
+    seg([x, y, z + r * h], [x, y + w / 2, z + h]); seg([x, y + w / 2, z + h], [x, y + w, z + r * h])                        # 9-12 roof slopes
+    seg([x + l, y, z + r * h], [x + l, y + w / 2, z + h]); seg([x + l, y + w / 2, z + h], [x + l, y + w, z + r * h])
+    xseg(x, x + l, y + .5 * w, z + h); xseg(x, x + l, y, z + r * h); xseg(x, x + l, y + w, z + r * h)                        # 13-15 roof
+    yzrect(x, y + c * w, y + d * w, z, z + q * h)                                                                          # 16-19 door
+    yzrect(x, y + a * w, y + b * w, z + p * h, z + q * h)                                                                  # 20-23 window
+    yseg(x, y, y + w, z + r * h); yseg(x + l, y, y + w, z + r * h)                                                          # 24-25
+    yseg(x, y + a * w, y + b * w, (z + p * h + z + q * h) / 2); zseg(x, (y + a * w + y + b * w) / 2, z + p * h, z + q * h)   # 26-27
+    for fx in (.5, .25, .75):                                                                                              # 28-30
+        seg([x + l * fx, y, z + r * h], [x + l * fx, y + w / 2, z + h])
+    for fx in (.5, .25, .75):                                                                                              # 31-33
+        seg([x + l * fx, y + w / 2, z + h], [x + l * fx, y + w, z + r * h])
+    for k in (1, 2, 3):                                                                                                    # 34-36
+        xseg(x, x + l, y + w * k / 8, z + r * h + (h - r * h) * k / 4)
+    for k, m in ((5, 3), (6, 2), (7, 1)):                                                                                  # 37-39
+        xseg(x, x + l, y + w * k / 8, z + r * h + (h - r * h) * m / 4)
+    for k in (1, 2, 3): zseg(x + l * k / 4, y, z, z + r * h)                                                                # 40-42
+    for k in (1, 2, 3): zseg(x + l * k / 4, y + w, z, z + r * h)                                                            # 43-45
+    for k in (1, 2, 3): zseg(x + l, y + w * k / 4, z, z + r * h)                                                            # 46-48
+    seg([x, y + c * w, z], [x, y + d * w, z + q * h]); seg([x, y + d * w, z], [x, y + c * w, z + q * h])                    # 49-50
+    for k in range(4):                                                                                                     # 51-58 front braces
+        seg([x + k / 4 * l, y, z], [x + (k + 1) / 4 * l, y, z + r * h]); seg([x + (k + 1) / 4 * l, y, z], [x + k / 4 * l, y, z + r * h])
+    for k in range(4):                                                                                                     # 59-66 side braces
+        seg([x + l, y + k / 4 * w, z], [x + l, y + (k + 1) / 4 * w, z + r * h]); seg([x + l, y + (k + 1) / 4 * w, z], [x + l, y + k / 4 * w, z + r * h])
+    for k in range(4):                                                                                                     # 67-74 back braces
+        seg([x + k / 4 * l, y + w, z], [x + (k + 1) / 4 * l, y + w, z + r * h]); seg([x + (k + 1) / 4 * l, y + w, z], [x + k / 4 * l, y + w, z + r * h])
+    assert len(S) == 74
+    return S
+
+
+def house_trajectory(num_keyframes=402, radius=11.0, wave=0.6, turns=1.0):
+    """Camera->world poses (angle-axis, t) [K][6] circling the house at `radius` m, optical axis towards its centre, height
+    on a vertical wave.  Consecutive keyframes are ~0.17 m apart at the defaults (402 frames per turn)."""
+    centre = np.array([2.25, 2.25, 1.6])
+    out = np.zeros((num_keyframes, 6))
+    for k in range(num_keyframes):
+        ang = 2 * np.pi * turns * k / num_keyframes
+        c = centre + np.array([radius * np.cos(ang), radius * np.sin(ang), wave * np.sin(6 * ang)])
+        zc = centre - c; zc /= np.linalg.norm(zc)                  # optical axis
+        xc = np.cross(zc, [0.0, 0.0, 1.0]); xc /= np.linalg.norm(xc)  # image x: horizontal
+        yc = np.cross(zc, xc)                                      # image y: down
+        Rwc = np.stack([xc, yc, zc], axis=1)
+        out[k, :3] = log_so3(Rwc); out[k, 3:] = c
+    return out
