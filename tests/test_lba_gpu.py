@@ -521,53 +521,42 @@ def test_edge_cases(gpu):
     p3, s3 = gpu.lba_solve(w3, max_iters=6)
     po3, so3 = oracle.lba_solve(w3, max_iters=6, solver=1)
     assert _rel(s3["final_cost"], so3["final_cost"]) < 1e-6 and s3["iterations"] == so3["iterations"]
-    # limits: more than 32 camera blocks, more than 32 observations of one line -> SLSLAM_ERR_UNSUPPORTED, inputs untouched
-    big = synth.Window(40, 1, np.arange(40, dtype=np.int32), np.zeros(40, np.int32), np.zeros(80, np.int32),
-                       np.zeros(320), np.full(244, 0.1), np.zeros(244))
+    # beyond the tiled kernel's limits (more than 32 camera blocks, more than 32 observations of one line) the one-shot entry
+    # points switch to the general kernel (wide_kernel.cuh): same answer as the oracle; the resident form keeps the limits
+    wbig = synth.make_window(77, 20, 120, 1500, num_fixed_cameras=16, sigma_px=0.5)            # 36 camera blocks
+    assert wbig.num_cameras == 36
+    pb, sb = gpu.lba_solve(wbig, max_iters=8)
+    pob, sob = oracle.lba_solve(wbig, max_iters=8, solver=1)
+    assert _rel(sb["final_cost"], sob["final_cost"]) < 1e-6 and sb["iterations"] == sob["iterations"] and sb["termination"] == sob["termination"]
+    assert np.abs(pb[:6 * 36] - pob[:6 * 36]).max() < 1e-6
     with pytest.raises(gpu.SlslamError) as e:
-        gpu.lba_solve(big)
+        gpu.LbaBatch([wbig], max_iters=3)
     assert e.value.code == -2
-    many = synth.Window(2, 1, np.zeros(33, np.int32), np.zeros(33, np.int32), np.zeros(66, np.int32), np.zeros(264),
-                        np.full(16, 0.1), np.zeros(16))
+    # one line observed by 40 cameras (all but the first free): more than one 32-lane tile can hold
+    rng = np.random.default_rng(5)
+    base = synth.make_window(78, 6, 30, 150, sigma_px=0.3)
+    C0, L0 = base.num_cameras, base.num_lines
+    reps = 7                                               # every camera block repeated with a slightly different pose
+    C1 = C0 * reps
+    cams = np.concatenate([base.parameters[:6 * C0].reshape(C0, 6) + (0 if r == 0 else rng.normal(0, 1e-3, (C0, 6))) for r in range(reps)])
+    ci = np.concatenate([base.camera_index + C0 * r for r in range(reps)]).astype(np.int32)
+    li = np.tile(base.line_index, reps).astype(np.int32)
+    fi = np.tile(base.fixed_index.reshape(-1, 2), (reps, 1)).ravel().astype(np.int32)
+    ob = np.tile(base.observations.reshape(-1, 8), (reps, 1)).ravel()
+    params = np.concatenate([cams.ravel(), base.parameters[6 * C0:]])
+    wl = synth.Window(C1, L0, ci, li, fi, ob, params, params.copy(), {})
+    assert np.bincount(li).max() > 32 and C1 == 42
+    pl, sl = gpu.lba_solve(wl, max_iters=6)
+    pol, sol = oracle.lba_solve(wl, max_iters=6, solver=1)
+    assert _rel(sl["final_cost"], sol["final_cost"]) < 1e-6 and sl["iterations"] == sol["iterations"]
+    assert np.abs(pl - pol).max() < 1e-6
+    # more free cameras than even the general kernel takes: a clean error, inputs untouched
+    lim = gpu.Limits()
+    gpu.lib().slslam_lba_get_limits(__import__("ctypes").byref(lim))
+    nf = lim.max_free_cameras_general + 1
+    huge = synth.Window(nf, 1, np.arange(nf, dtype=np.int32), np.zeros(nf, np.int32), np.zeros(2 * nf, np.int32),
+                        np.zeros(8 * nf), np.full(6 * nf + 4, 0.1), np.zeros(6 * nf + 4))
+    before = huge.parameters.copy()
     with pytest.raises(gpu.SlslamError) as e:
-        gpu.lba_solve(many)
-    assert e.value.code == -2
-
-
-def test_device_resident_entry_point(gpu):
-    """slslam_lba_solve_batch_device: the windows' arrays already sit in device memory (the layout the NCCL scatter
-    delivers, slslam_b200/shard.py RankLayout); planned where they are, parameters updated in place, summaries written
-    to the device result region.  Same bits as the host-buffer entry point; index errors found on the device."""
-    import torch
-    from slslam_b200 import shard
-    ws = [synth.window_S(60 + i, sigma_px=0.5) for i in range(3)] + [synth.window_M(3, sigma_px=1.0, start="far")]
-    ref_p, ref_s = gpu.lba_solve_batch(ws, max_iters=7)
-    buf, lay = shard.pack_rank_buffer(ws, pin=True)
-    dev = torch.from_numpy(buf).cuda()
-    st = torch.cuda.current_stream().cuda_stream
-    ss = gpu.lba_solve_batch_device(lay.shapes, dev.data_ptr(), lay.offsets(), max_iters=7,
-                                    summaries_dev_ptr=dev.data_ptr() + lay.summary_off, want_host_summaries=True, stream=st)
-    host = dev.cpu().numpy()
-    ps, ss_dev = shard.unpack_results(host[lay.result_begin:lay.result_end], lay)
-    for p, s, sd, pr, sr in zip(ps, ss, ss_dev, ref_p, ref_s):
-        assert np.array_equal(p, pr)
-        assert s == sr
-        assert all(sd[k] == sr[k] for k in ("initial_cost", "final_cost", "iterations", "termination", "num_successful_steps"))
-    # the input arrays are untouched
-    for w, off in zip(ws, lay.offsets()):
-        N = w.num_observations
-        assert np.array_equal(host[off["observations"]:off["observations"] + 64 * N].view(np.float64), w.observations)
-        assert np.array_equal(host[off["camera_index"]:off["camera_index"] + 4 * N].view(np.int32), w.camera_index)
-    # asynchronous form: no host summaries, results appear after a synchronize
-    dev2 = torch.from_numpy(buf).cuda()
-    assert gpu.lba_solve_batch_device(lay.shapes, dev2.data_ptr(), lay.offsets(), max_iters=7,
-                                      summaries_dev_ptr=dev2.data_ptr() + lay.summary_off, want_host_summaries=False, stream=st) is None
-    torch.cuda.synchronize()
-    assert np.array_equal(dev2.cpu().numpy()[lay.result_begin:lay.result_end], host[lay.result_begin:lay.result_end])
-    # a bad index is reported as an invalid argument
-    bad = buf.copy()
-    bad[lay.arrays[0]["camera_index"]:lay.arrays[0]["camera_index"] + 4].view(np.int32)[0] = 77
-    dev3 = torch.from_numpy(bad).cuda()
-    with pytest.raises(gpu.SlslamError) as e:
-        gpu.lba_solve_batch_device(lay.shapes, dev3.data_ptr(), lay.offsets(), max_iters=3, stream=st)
-    assert e.value.code == -1
+        gpu.lba_solve(huge)
+    assert e.value.code == -2 and np.array_equal(huge.parameters, before)
