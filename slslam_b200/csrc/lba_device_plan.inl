@@ -26,7 +26,7 @@ static bool is_page_locked(const void* p) {
 // parameters in place and writes the summaries to `summ_dev` when given.  Only the headers (< 1 KB per window) go up.
 static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, const double* const* params, int32_t device,
                                     int32_t cluster_size, Workspace* ws, cudaStream_t stream, slslam_lba_batch** out,
-                                    bool device_inputs = false, slslam_summary* summ_dev = nullptr) {
+                                    bool device_inputs = false, slslam_summary* summ_dev = nullptr, bool deferred = false) {
   if (!out) return SLSLAM_ERR_INVALID;
   *out = nullptr;
   if (n <= 0 || !descs || !params) return SLSLAM_ERR_INVALID;
@@ -227,6 +227,23 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
       e = cudaGetLastError();
     }
   }
+  b->d_info = (PlanInfo*)(dp + o_info); b->Cmax = Cmax; b->smem_optin = smem_optin; b->want_zg = want_zg;
+  if (deferred && e == cudaSuccess) {
+    // `deferred`: nothing is read back here.  The solve kernel is launched right behind the planner with the maximal
+    // shared-memory size and derives every window's layout itself; the planner's flags are looked at after the solve
+    // (device_plan_check below), together with the results -- one synchronisation per call instead of two.
+    b->deferred = true;
+    b->lay = SmemLayout(); memset(&b->lay, 0, sizeof(b->lay));
+    b->lay.G = CS; b->lay.smem_limit = smem_optin; b->lay.total = 0;
+    b->smem_bytes = (size_t)smem_optin;
+    for (int i = 0; i < n; ++i) b->plans[i].has_unobserved_blocks = true;      // unknown yet: keep the pre-copy of the parameters
+    rc = set_solve_kernel_smem_limit(dev, smem_optin);
+    if (rc != SLSLAM_OK) { slslam_lba_batch_destroy(b); return rc; }
+    b->max_active = balanced_wave(n, cap / CS);
+    if (ws) { g_timing[0] = now_ms() - t_staged; g_timing[1] = t_staged - t_begin; }
+    *out = b;
+    return SLSLAM_OK;
+  }
   if (e == cudaSuccess) e = cudaMemcpyAsync(h_info, dp + o_info, sizeof(PlanInfo) * n, cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); cudaGetLastError(); slslam_lba_batch_destroy(b); return SLSLAM_ERR_CUDA; }
@@ -259,3 +276,19 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
   return SLSLAM_OK;
 }
 
+
+
+// After the solve of a `deferred` batch: the planner's records (already copied to `info`, host memory) say whether every
+// window was planned and fitted -- the same checks batch_create_device_plan makes before the launch otherwise.
+static int device_plan_check_deferred(const slslam_lba_batch* b, const PlanInfo* info) {
+  int flags = 0;
+  for (int i = 0; i < b->n; ++i) flags |= info[i].error;
+  if (flags & PLAN_ERR_INDEX) return SLSLAM_ERR_INVALID;
+  if (flags) return SLSLAM_PLAN_FALLBACK;
+  for (int i = 0; i < b->n; ++i) {
+    const SmemLayout l = lba_layout(b->plans[i].C, info[i].Cf, info[i].max_lines_cta, info[i].max_slots_cta, b->CS, (size_t)b->smem_optin,
+                                    info[i].max_items_cta);
+    if ((size_t)l.total * 8 > (size_t)b->smem_optin || (!l.z_in_smem && !b->want_zg)) return SLSLAM_PLAN_FALLBACK;
+  }
+  return SLSLAM_OK;
+}

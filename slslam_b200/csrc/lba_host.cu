@@ -256,6 +256,8 @@ struct slslam_lba_batch {
   int max_active = 0;   // windows of this shape the device keeps resident at once (a larger batch runs in waves)
   unsigned int* d_bar = nullptr; size_t bar_bytes = 0;   // group barrier counters, zeroed before every launch
   bool inplace = false;    // device-resident inputs: parameters are read and written where the caller keeps them
+  bool deferred = false;   // launched without reading the planner's sizes back: its flags are checked after the solve
+  slslam::PlanInfo* d_info = nullptr; int Cmax = 1, smem_optin = 0; bool want_zg = false;
   bool borrowed = false;   // device pool and pinned staging belong to a Workspace (the calling thread's or a pipeline slot's)
   slslam::Workspace* ws = nullptr;
   // device-side plan (lba_plan_kernel.cuh): where its outputs live in the pool, for the planner parity check
@@ -899,7 +901,12 @@ int slslam_lba_solve_batch(int32_t n, const slslam_lba_desc* descs, double* cons
   // plan -> pinned staging -> H2D -> one cluster launch -> D2H, all on the calling thread's cached workspace
   slslam_lba_batch* b = nullptr;
   const double t0 = now_ms();
-  int rc = batch_create_impl(n, descs, (const double* const*)params_inout, -1, 0, &g_ws, nullptr, &b);
+  // First attempt: planner and solve kernel enqueued back to back, ONE synchronisation (the planner's flags come back
+  // with the results).  A batch the planner could not handle that way is solved again through the checked path.
+  int rc = SLSLAM_PLAN_FALLBACK;
+  if (!getenv("SLSLAM_HOST_PLAN") && !getenv("SLSLAM_NO_DEFERRED_PLAN"))
+    rc = batch_create_device_plan(n, descs, (const double* const*)params_inout, -1, 0, &g_ws, nullptr, &b, false, nullptr, true);
+  if (rc == SLSLAM_PLAN_FALLBACK) rc = batch_create_impl(n, descs, (const double* const*)params_inout, -1, 0, &g_ws, nullptr, &b);
   if (rc != SLSLAM_OK) return rc;
   const double t1 = now_ms();
   double t2 = t1;
@@ -907,12 +914,35 @@ int slslam_lba_solve_batch(int32_t n, const slslam_lba_desc* descs, double* cons
   rc = slslam_lba_batch_solve(b, nullptr);
   if (rc == SLSLAM_OK) {
     slslam_summary* h_summ = (slslam_summary*)(b->h_params + b->total_params);
+    PlanInfo* h_info = (PlanInfo*)(g_ws.h_res + ((b->total_params * 8 + sizeof(slslam_summary) * n + 255) & ~(size_t)255));
     cudaEventRecord(g_ws.ev[2], nullptr);
     cudaError_t e = cudaMemcpyAsync(b->h_params, b->d_params_out, b->total_params * 8, cudaMemcpyDeviceToHost, nullptr);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_summ, b->d_summ, sizeof(slslam_summary) * n, cudaMemcpyDeviceToHost, nullptr);
+    if (e == cudaSuccess && b->deferred) e = cudaMemcpyAsync(h_info, b->d_info, sizeof(PlanInfo) * n, cudaMemcpyDeviceToHost, nullptr);
     if (e == cudaSuccess) e = cudaEventRecord(g_ws.ev[3], nullptr);
     if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
     if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); cudaGetLastError(); rc = SLSLAM_ERR_CUDA; }
+    if (rc == SLSLAM_OK && b->deferred) {
+      const int chk = device_plan_check_deferred(b, h_info);
+      if (chk == SLSLAM_PLAN_FALLBACK) {
+        // (rare: a camera observing a line twice, a shape that needs the group-size search) nothing was solved: again,
+        // through the path that checks the plan before it launches
+        slslam_lba_batch_destroy(b);
+        b = nullptr;
+        rc = batch_create_impl(n, descs, (const double* const*)params_inout, -1, 0, &g_ws, nullptr, &b);
+        if (rc != SLSLAM_OK) return rc;
+        rc = slslam_lba_batch_solve(b, nullptr);
+        if (rc == SLSLAM_OK) {
+          h_summ = (slslam_summary*)(b->h_params + b->total_params);
+          e = cudaMemcpyAsync(b->h_params, b->d_params_out, b->total_params * 8, cudaMemcpyDeviceToHost, nullptr);
+          if (e == cudaSuccess) e = cudaMemcpyAsync(h_summ, b->d_summ, sizeof(slslam_summary) * n, cudaMemcpyDeviceToHost, nullptr);
+          if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+          if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); cudaGetLastError(); rc = SLSLAM_ERR_CUDA; }
+        }
+      } else if (chk != SLSLAM_OK) {
+        rc = chk;
+      }
+    }
     t2 = now_ms();
     if (rc == SLSLAM_OK) {
       float ms = 0.f;
@@ -939,20 +969,26 @@ int slslam_lba_solve_batch_device(int32_t n, const slslam_lba_desc* descs, doubl
   cudaStream_t st = (cudaStream_t)cuda_stream;
   slslam_lba_batch* b = nullptr;
   const double t0 = now_ms();
-  int rc = batch_create_device_plan(n, descs, (const double* const*)params_dev_inout, -1, 0, &g_ws, st, &b, true, summaries_dev_out);
-  if (rc == SLSLAM_PLAN_FALLBACK) {
-    set_last_error("window shape needs the host planner (a camera observing a line twice, or a group-size search), which cannot read device-resident inputs");
-    return SLSLAM_ERR_UNSUPPORTED;
-  }
+  // With host summaries requested the call waits for the solve anyway: the planner's flags are then read back together
+  // with them (one synchronisation); without, the plan is checked before the launch so that errors are still reported.
+  const bool deferred = summaries_host_out != nullptr && !getenv("SLSLAM_NO_DEFERRED_PLAN");
+  static const char* kNeedsHostPlan = "window shape needs the host planner (a camera observing a line twice, or a group-size search), which cannot read device-resident inputs";
+  int rc = batch_create_device_plan(n, descs, (const double* const*)params_dev_inout, -1, 0, &g_ws, st, &b, true, summaries_dev_out, deferred);
+  if (rc == SLSLAM_PLAN_FALLBACK) { set_last_error(kNeedsHostPlan); return SLSLAM_ERR_UNSUPPORTED; }
   if (rc != SLSLAM_OK) return rc;
   const double t1 = now_ms();
   rc = slslam_lba_batch_solve(b, st);
   if (rc == SLSLAM_OK && summaries_host_out) {
     // the summaries are the only thing read back; without this the call returns as soon as the solve is enqueued
     slslam_summary* h_summ = (slslam_summary*)(b->h_params);
+    PlanInfo* h_info = (PlanInfo*)(g_ws.h_res + ((b->total_params * 8 + sizeof(slslam_summary) * n + 255) & ~(size_t)255));
     cudaError_t e = cudaMemcpyAsync(h_summ, summaries_dev_out ? summaries_dev_out : b->d_summ, sizeof(slslam_summary) * n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && b->deferred) e = cudaMemcpyAsync(h_info, b->d_info, sizeof(PlanInfo) * n, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); cudaGetLastError(); rc = SLSLAM_ERR_CUDA; }
+    else if (b->deferred && (rc = device_plan_check_deferred(b, h_info)) != SLSLAM_OK) {
+      if (rc == SLSLAM_PLAN_FALLBACK) { set_last_error(kNeedsHostPlan); rc = SLSLAM_ERR_UNSUPPORTED; }
+    }
     else memcpy(summaries_host_out, h_summ, sizeof(slslam_summary) * n);
   }
   slslam_lba_batch_destroy(b);

@@ -55,6 +55,8 @@ struct WinHdr {
   double* scalg;            // [G][8] per-CTA partial scalars of the trial sweep
   unsigned int* bar;        // arrive counter of the group barrier (zeroed by the host before every launch)
   int vpad;
+  // written by the device planner for launches whose shared-memory layout is derived on the device (lay.total == 0):
+  int plan_error, max_lines_cta, max_slots_cta, max_items_cta;
   int cta_slot_off[MAX_G + 1];
   int cta_line_off[MAX_G + 1];
   signed char cam_free[MAX_CAMS];   // reduced block index of each camera or -1
@@ -67,6 +69,7 @@ struct SmemLayout {
   int G;   // CTAs per window of this launch
   int koff;                   // pair-block offsets of the CTA [nkeys + 1] ints (always staged)
   int items, items_in_smem;   // the CTA's pair list staged in shared memory when it fits (offset in doubles)
+  int smem_limit;             // bytes of dynamic shared memory the launch was given (total == 0: the kernel derives the layout)
 };
 
 __host__ __device__ inline int lba_vlen(int Cf) {
@@ -74,9 +77,10 @@ __host__ __device__ inline int lba_vlen(int Cf) {
   return nkeys * 36 + 3 * n + NSCAL;   // S blocks | g_c | sum Z u | diag H_cc | scalars
 }
 
-__host__ inline SmemLayout lba_layout(int C, int Cf, int max_lines_cta, int max_slots_cta, int CS, size_t smem_limit_bytes,
-                                      int max_items_cta = 0) {
+__host__ __device__ inline SmemLayout lba_layout(int C, int Cf, int max_lines_cta, int max_slots_cta, int CS, size_t smem_limit_bytes,
+                                                 int max_items_cta = 0) {
   SmemLayout l;
+  l.smem_limit = (int)smem_limit_bytes;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
   const int vlen = lba_vlen(Cf);
@@ -849,6 +853,16 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
   const int win = (int)(blockIdx.x / (unsigned)lay.G);
   unsigned int bar_target = 0;
   const WinHdr& h = hdrs[win];
+  if (lay.total == 0) {
+    // One-shot calls launch right behind the device planner without reading its sizes back: the layout of this window is
+    // derived here from what the planner left in the header (same function, same arguments as the host would use).  A
+    // window the planner flagged, or whose layout does not fit, is left alone by all of its CTAs; the host sees the
+    // same flags after the launch and takes the slower path.
+    const int G = lay.G, limit = lay.smem_limit;
+    if (h.plan_error) return;
+    lay = lba_layout(h.C, h.Cf, h.max_lines_cta, h.max_slots_cta, G, (size_t)limit, h.max_items_cta);
+    if ((size_t)lay.total * 8 > (size_t)limit || (!lay.z_in_smem && !h.Zg)) return;
+  }
   c.h = &h; c.sm = sm; c.lay = lay;
   c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
   c.slot0 = h.cta_slot_off[c.rank]; c.nslots = h.cta_slot_off[c.rank + 1] - c.slot0; c.ntiles = c.nslots / 32;

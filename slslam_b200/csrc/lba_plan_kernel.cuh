@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
   }
   __syncthreads();
   if (s_err & PLAN_ERR_INDEX) {
-    if (tid == 0) { PlanInfo o = {}; o.error = s_err; o.Cf = 0; o.max_lines_cta = 1; o.max_slots_cta = 32; o.max_items_cta = 0; o.nslots = 0; o.nitems = 0; o.has_unobserved = 0; *p.info = o; }
+    if (tid == 0) { PlanInfo o = {}; o.error = s_err; o.Cf = 0; o.max_lines_cta = 1; o.max_slots_cta = 32; o.max_items_cta = 0; o.nslots = 0; o.nitems = 0; o.has_unobserved = 0; *p.info = o; p.hdr->plan_error = s_err; }
     return;
   }
   PLAN_PHASE(0)
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
   }
   __syncthreads();
   if (s_err) {
-    if (tid == 0) { PlanInfo o = {}; o.error = s_err; o.Cf = s_Cf; o.max_lines_cta = 1; o.max_slots_cta = 32; o.max_items_cta = 0; o.nslots = 0; o.nitems = 0; o.has_unobserved = s_unobs; *p.info = o; }
+    if (tid == 0) { PlanInfo o = {}; o.error = s_err; o.Cf = s_Cf; o.max_lines_cta = 1; o.max_slots_cta = 32; o.max_items_cta = 0; o.nslots = 0; o.nitems = 0; o.has_unobserved = s_unobs; *p.info = o; p.hdr->plan_error = s_err; }
     return;
   }
   const int nd = s_nd, Cf = s_Cf, nkeys = s_nkeys;
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
   }
   __syncthreads();
   if (s_err) {
-    if (tid == 0) { PlanInfo o = {}; o.error = s_err; o.Cf = Cf; o.max_lines_cta = s_max_lines; o.max_slots_cta = s_max_slots; o.max_items_cta = 0; o.nslots = 0; o.nitems = 0; o.has_unobserved = s_unobs; *p.info = o; }
+    if (tid == 0) { PlanInfo o = {}; o.error = s_err; o.Cf = Cf; o.max_lines_cta = s_max_lines; o.max_slots_cta = s_max_slots; o.max_items_cta = 0; o.nslots = 0; o.nitems = 0; o.has_unobserved = s_unobs; *p.info = o; p.hdr->plan_error = s_err; }
     return;
   }
   const int total_slots = s_total_slots;
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
   __syncthreads();
   if (s_err) {
     // a camera observing the same line twice: the host planner handles that (rare; never produced by the reference)
-    if (tid == 0) { PlanInfo o = {}; o.error = s_err; o.Cf = Cf; o.max_lines_cta = s_max_lines; o.max_slots_cta = s_max_slots; o.max_items_cta = 0; o.nslots = total_slots; o.nitems = 0; o.has_unobserved = s_unobs; *p.info = o; }
+    if (tid == 0) { PlanInfo o = {}; o.error = s_err; o.Cf = Cf; o.max_lines_cta = s_max_lines; o.max_slots_cta = s_max_slots; o.max_items_cta = 0; o.nslots = total_slots; o.nitems = 0; o.has_unobserved = s_unobs; *p.info = o; p.hdr->plan_error = s_err; }
     return;
   }
   PLAN_PHASE(5)
@@ -364,6 +364,7 @@ __global__ void __launch_bounds__(PLAN_NT, 1) lba_plan_kernel(const PlanIn* __re
   WinHdr* h = p.hdr;
   if (tid == 0) {
     h->Cf = Cf; h->n = 6 * Cf; h->nkeys = nkeys; h->vlen = lba_vlen(Cf); h->vpad = (lba_vlen(Cf) + 31) & ~31;
+    h->plan_error = s_err; h->max_lines_cta = s_max_lines; h->max_slots_cta = s_max_slots; h->max_items_cta = s_max_items;
     PlanInfo o = {};
     o.error = s_err; o.Cf = Cf; o.max_lines_cta = s_max_lines; o.max_slots_cta = s_max_slots; o.max_items_cta = s_max_items;
     o.nslots = total_slots; o.nitems = s_total_items; o.has_unobserved = s_unobs;
