@@ -159,6 +159,18 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
   b->d_params_in = (double*)(dp + o_par); b->d_params_out = (double*)(dp + o_pout);
   b->d_trace = (double*)(dp + o_trace); b->d_summ = (slslam_summary*)(dp + o_summ);
   b->d_phase = (long long*)(dp + o_phase); b->d_bar = (unsigned int*)(dp + o_bar);
+  // observations that sit in page-locked caller memory are DMA'd straight from there, FIRST: those copies (most of the
+  // bytes) then run while this thread stages the small arrays below
+  cudaError_t e = cudaSuccess;
+  if (ws) cudaEventRecord(ws->ev[0], stream);
+  size_t direct_bytes = 0;
+  for (int i = 0; i < n && e == cudaSuccess; ++i) {
+    if (!direct[i]) continue;
+    const size_t bytes = 64 * (size_t)descs[i].num_observations;
+    e = cudaMemcpyAsync(dp + o_raw[i], descs[i].observations, bytes, cudaMemcpyHostToDevice, stream);
+    direct_bytes += bytes;
+  }
+  if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); cudaGetLastError(); slslam_lba_batch_destroy(b); return SLSLAM_ERR_CUDA; }
   // ---- staging: headers and the caller's arrays as they are (one thread, one buffer, one copy) ----
   for (int i = 0; i < n; ++i) {
     const slslam_lba_desc& d = descs[i];
@@ -208,16 +220,8 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
   }
   b->inplace = device_inputs;
   const double t_staged = now_ms();
-  b->upload_bytes = upload;
-  cudaError_t e = cudaSuccess;
-  if (ws) cudaEventRecord(ws->ev[0], stream);
+  b->upload_bytes = upload + direct_bytes;
   e = cudaMemcpyAsync(dp, host, upload, cudaMemcpyHostToDevice, stream);
-  for (int i = 0; i < n && e == cudaSuccess; ++i) {
-    if (!direct[i]) continue;
-    const size_t bytes = 64 * (size_t)descs[i].num_observations;
-    e = cudaMemcpyAsync(dp + o_raw[i], descs[i].observations, bytes, cudaMemcpyHostToDevice, stream);
-    b->upload_bytes += bytes;
-  }
   if (e == cudaSuccess) {
     lba_plan_kernel<<<n, PLAN_NT, plan_smem, stream>>>((const PlanIn*)(dp + o_pin_in));
     e = cudaGetLastError();
