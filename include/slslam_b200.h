@@ -253,8 +253,6 @@ typedef struct slslam_po_stats {
   int32_t max_column_rows;
   int32_t iterations_enqueued;    /* LM iterations whose kernels were launched (<= max_iterations: early stop) */
   int64_t factor_cycles[4];       /* last factorisation (sparse path), SM cycles: panel phase, update phase, back-substitution, total */
-  int32_t backsub_levels;         /* levels of the elimination tree the back-substitution walks (columns of a level in parallel) */
-  int32_t reserved;
 } slslam_po_stats;
 void slslam_po_last_stats(slslam_po_stats* out);
 typedef struct slslam_po_limits {

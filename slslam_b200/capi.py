@@ -56,7 +56,7 @@ class Summary(C.Structure):
 class PoStats(C.Structure):
     _fields_ = [("sparse", C.c_int32), ("free_poses", C.c_int32), ("factor_blocks", C.c_int64),
                 ("block_updates", C.c_int64), ("max_column_rows", C.c_int32), ("iterations_enqueued", C.c_int32),
-                ("factor_cycles", C.c_int64 * 4), ("backsub_levels", C.c_int32), ("reserved", C.c_int32)]
+                ("factor_cycles", C.c_int64 * 4)]
 
 
 class PoLimits(C.Structure):

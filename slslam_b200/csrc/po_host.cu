@@ -25,7 +25,7 @@ struct PoPlan {
   bool sparse = false;
   int nsb = 0, max_rows = 0;
   long long dense_blocks = 0;
-  std::vector<int> slot_pos, col_off, row_pos, tri_off, blk_dst, bs_chunk, bs_cols;
+  std::vector<int> slot_pos, col_off, row_pos, tri_off, blk_dst, bs_chunk;
   std::vector<int2> tri;
 };
 
@@ -109,24 +109,14 @@ static bool build_po_sparse(const slslam_po_desc& d, PoPlan& p) {
     }
     p.blk_dst[b] = block_id(p.slot_pos[p.blk_i[b]], p.slot_pos[p.blk_j[b]]);
   }
-  // Back-substitution by LEVELS of the elimination tree: y_c needs y of the rows of column c only (all of them later in
-  // the order), so every column whose rows are solved can go at once.  level(c) = 1 + max level(rows of c); the columns
-  // of one level are independent (a warp each), levels are separated by a CTA barrier.  A chain-like pose graph under
-  // minimum-degree order has a bushy tree: a few dozen levels instead of one step per pose.
-  {
-    std::vector<int> level(Kf, 0);
-    int nlev = 0;
-    for (int c = Kf - 1; c >= 0; --c) {
-      int lv = 0;
-      for (int t = p.col_off[c]; t < p.col_off[c + 1]; ++t) lv = std::max(lv, level[p.row_pos[t]] + 1);
-      level[c] = lv; nlev = std::max(nlev, lv + 1);
-    }
-    p.bs_chunk.assign(nlev + 1, 0);                     // offsets of the levels in bs_cols
-    for (int c = 0; c < Kf; ++c) ++p.bs_chunk[level[c] + 1];
-    for (int l = 0; l < nlev; ++l) p.bs_chunk[l + 1] += p.bs_chunk[l];
-    p.bs_cols.assign(Kf, 0);
-    std::vector<int> fill(p.bs_chunk.begin(), p.bs_chunk.end() - 1);
-    for (int c = Kf - 1; c >= 0; --c) p.bs_cols[fill[level[c]]++] = c;
+  // chunks of consecutive columns (descending) whose panels fit one shared-memory stage of the back-substitution
+  p.bs_chunk.clear();
+  p.bs_chunk.push_back(Kf);
+  for (int c = Kf; c > 0;) {
+    int lo = c, blocks = 0;
+    while (lo > 0 && c - lo < PO_SP_MAXROWS && blocks + (p.col_off[lo] - p.col_off[lo - 1]) <= PO_SP_MAXROWS) { blocks += p.col_off[lo] - p.col_off[lo - 1]; --lo; }
+    p.bs_chunk.push_back(lo);
+    c = lo;
   }
   p.sparse = true;
   return true;
@@ -267,7 +257,7 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   const size_t o_boff = pool.reserve(4 * (size_t)(nblk + 2)), o_contrib = pool.reserve(4 * (p.contrib.size() + 1));
   const size_t o_spos = pool.reserve(4 * Kfz), o_coff = pool.reserve(4 * (Kfz + 1)), o_rpos = pool.reserve(4 * (p.row_pos.size() + 1));
   const size_t o_toff = pool.reserve(4 * (Kfz + 1)), o_tri = pool.reserve(8 * (p.tri.size() + 1)), o_bdst = pool.reserve(4 * (size_t)(nblk + 1));
-  const size_t o_bsc = pool.reserve(4 * (p.bs_chunk.size() + 1)), o_bscol = pool.reserve(4 * (p.bs_cols.size() + 1));
+  const size_t o_bsc = pool.reserve(4 * (p.bs_chunk.size() + 1));
   const size_t o_x = pool.reserve(48 * Kz);
   const size_t o_state = pool.reserve(sizeof(PoState));
   const size_t upload_end = pool.off;
@@ -316,7 +306,6 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
     if (!p.tri.empty()) memcpy(host + o_tri, p.tri.data(), 8 * p.tri.size());
     if (nblk > 0) memcpy(host + o_bdst, p.blk_dst.data(), 4 * (size_t)nblk);
     memcpy(host + o_bsc, p.bs_chunk.data(), 4 * p.bs_chunk.size());
-    if (!p.bs_cols.empty()) memcpy(host + o_bscol, p.bs_cols.data(), 4 * p.bs_cols.size());
   }
   PoState st; memset(&st, 0, sizeof(st));
   st.radius = desc->initial_trust_region_radius > 0 ? desc->initial_trust_region_radius : 1e4;   // Ceres 1.7.0 defaults
@@ -348,8 +337,7 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   d.slot_pos = (const int*)(B + o_spos); d.col_off = (const int*)(B + o_coff); d.row_pos = (const int*)(B + o_rpos);
   d.tri_off = (const int*)(B + o_toff); d.tri = (const int2*)(B + o_tri); d.blk_dst = (const int*)(B + o_bdst);
   d.sp_cycles = (long long*)(B + o_spc);
-  d.bs_chunk = (const int*)(B + o_bsc); d.bs_nchunk = sparse ? (int)p.bs_chunk.size() - 1 : 0; d.bs_cols = (const int*)(B + o_bscol);
-  g_po_stats.backsub_levels = d.bs_nchunk;
+  d.bs_chunk = (const int*)(B + o_bsc); d.bs_nchunk = sparse ? (int)p.bs_chunk.size() - 1 : 0;
 
   cudaStream_t s = nullptr;
   unsigned int* d_flags = (unsigned int*)(B + o_flags);

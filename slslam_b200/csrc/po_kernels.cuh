@@ -68,8 +68,7 @@ struct PoDev {
   const int* tri_off;             // [Kf + 1] updates of column c
   const int2* tri;                // x: destination block id, y: a | b << 16 (sources: off-diagonal blocks a >= b of the column)
   const int* blk_dst;             // [nblk] where po_sp_assemble writes the structurally non-zero blocks of J^T J
-  const int* bs_chunk;            // [bs_nchunk + 1] offsets of the back-substitution's levels in bs_cols
-  const int* bs_cols;             // [Kf] columns grouped by level of the elimination tree (a level's columns are independent)
+  const int* bs_chunk;            // [bs_nchunk + 1] descending column boundaries of the back-substitution's staging chunks
   int bs_nchunk;
   long long* sp_cycles;           // [4] diagnostics of po_sp_factor_solve: phase 1, phase 2, back-substitution, total (SM cycles)
 };
@@ -683,34 +682,57 @@ __global__ void __launch_bounds__(PO_SP_NT, 1) po_sp_factor_solve(PoDev d) {
     if (tid == 0) { const long long now = clock64(); t_p2 += now - t_mark; t_mark = now; }
   }
   if (tid == 0 && bad) d.st->chol_fail = 1;
-  // ---- back-substitution: y_c = u_c - sum_a P_ac^T y_row(a), by levels of the elimination tree (po_host.cu): the
-  // columns of a level only need y of earlier levels, so a level is one pass of warp-per-column work and a barrier.
-  // Lane (g, q), g < 5, q < 6, sums the (row block, row) pairs j = g, g + 5, ... of entry q; three shuffle steps fold
-  // the five partial sums (fixed order).
+  // ---- back-substitution, descending: y_c = u_c - sum_a P_ac^T y_row(a).  The P blocks of a chunk of columns (a
+  // contiguous range of Hb), their u, row positions and offsets are staged in shared memory by all threads, then warp 0
+  // walks the chunk's columns while the other warps stage the next chunk.
   const bool y_in_smem = d.n <= PO_SP_YMAX;
   double* yv = y_in_smem ? ysm : d.yp;
-  const int warp = tid >> 5, nwarps = PO_SP_NT / 32;
-  const int g = lane / 6, q = lane - 6 * g;
-  for (int lv = 0; lv < d.bs_nchunk; ++lv) {
-    const int l0 = d.bs_chunk[lv], l1 = d.bs_chunk[lv + 1];
-    for (int ci = l0 + warp; ci < l1; ci += nwarps) {
-      const int c = d.bs_cols[ci];
-      const int o0 = d.col_off[c], m = d.col_off[c + 1] - o0;
-      double acc = 0.0;
-      if (lane < 30) {
-        for (int j = g; j < 6 * m; j += 5) {
-          const int a = j / 6, p = j - 6 * a;
-          const int yi = 6 * d.row_pos[o0 + a] + p;
-          const double yr = y_in_smem ? ysm[yi] : d.yp[yi];
-          acc += __ldcg(d.Hb + (size_t)(Kf + o0 + a) * 36 + 6 * p + q) * yr;
+  double* us_s = reinterpret_cast<double*>(tri_s);                // [2][6 * MAXROWS] (the update lists are dead by now)
+  const int nchunk = d.bs_nchunk;
+  auto stage_chunk = [&](int k, int first_thread, int nthreads) {
+    if (k >= nchunk) return;
+    const int c_hi = d.bs_chunk[k], c_lo = d.bs_chunk[k + 1];           // columns [c_lo, c_hi)
+    const int b0 = d.col_off[c_lo], nb = d.col_off[c_hi] - b0, ncol = c_hi - c_lo;
+    double* dst = spsm + (k & 1) * PO_SP_CACHE;
+    for (int i = tid - first_thread; i < 36 * nb; i += nthreads) dst[i] = __ldcg(d.Hb + (size_t)(Kf + b0) * 36 + i);
+    double* ud = us_s + (k & 1) * 6 * PO_SP_MAXROWS;
+    for (int i = tid - first_thread; i < 6 * ncol; i += nthreads) ud[i] = __ldcg(d.us + 6 * c_lo + i);
+    int* id = bs_i + (k & 1) * 400;                                     // [0, ncol]: column offsets, [200, 200 + nb): row positions
+    for (int i = tid - first_thread; i <= ncol; i += nthreads) id[i] = d.col_off[c_lo + i] - b0;
+    for (int i = tid - first_thread; i < nb; i += nthreads) id[200 + i] = d.row_pos[b0 + i];
+  };
+  stage_chunk(0, 0, PO_SP_NT);
+  __syncthreads();
+  for (int k = 0; k < nchunk; ++k) {
+    if (tid >= 32) {
+      stage_chunk(k + 1, 32, PO_SP_NT - 32);
+    } else {
+      const int c_hi = d.bs_chunk[k], c_lo = d.bs_chunk[k + 1];
+      const double* Ps = spsm + (k & 1) * PO_SP_CACHE;
+      const double* ud = us_s + (k & 1) * 6 * PO_SP_MAXROWS;
+      const int* id = bs_i + (k & 1) * 400;
+      // lane (g, q), g < 5, q < 6, sums the (row block, row) pairs j = g, g + 5, ... of entry q of P^T y; four shuffles
+      // fold the five partial sums in a fixed order (the instruction count of this single-warp chain is what it costs:
+      // six 5-level butterflies per column were 3x slower)
+      const int g = lane / 6, q = lane - 6 * g;
+      for (int c = c_hi - 1; c >= c_lo; --c) {
+        const int o0 = id[c - c_lo], m = id[c - c_lo + 1] - o0;
+        double acc = 0.0;
+        if (lane < 30) {
+          for (int j = g; j < 6 * m; j += 5) {
+            const int a = j / 6, p = j - 6 * a;
+            const int yi = 6 * id[200 + o0 + a] + p;
+            const double yr = y_in_smem ? ysm[yi] : d.yp[yi];
+            acc += Ps[36 * (o0 + a) + 6 * p + q] * yr;
+          }
         }
-      }
-      // fold g = 0..4 for every q: lanes q, q + 6, q + 12, q + 18, q + 24
-      const double a1 = __shfl_down_sync(0xffffffffu, acc, 6), a2 = __shfl_down_sync(0xffffffffu, acc, 12);
-      const double a3 = __shfl_down_sync(0xffffffffu, acc, 18), a4 = __shfl_down_sync(0xffffffffu, acc, 24);
-      if (lane < 6) {
-        const double yc_ = d.us[6 * c + lane] - ((((acc + a1) + a2) + a3) + a4);
-        if (y_in_smem) ysm[6 * c + lane] = yc_; else d.yp[6 * c + lane] = yc_;
+        const double a1 = __shfl_down_sync(0xffffffffu, acc, 6), a2 = __shfl_down_sync(0xffffffffu, acc, 12);
+        const double a3 = __shfl_down_sync(0xffffffffu, acc, 18), a4 = __shfl_down_sync(0xffffffffu, acc, 24);
+        if (lane < 6) {
+          const double yc_ = ud[6 * (c - c_lo) + lane] - ((((acc + a1) + a2) + a3) + a4);
+          if (y_in_smem) ysm[6 * c + lane] = yc_; else d.yp[6 * c + lane] = yc_;
+        }
+        __syncwarp();
       }
     }
     __syncthreads();
