@@ -161,15 +161,21 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
   b->d_phase = (long long*)(dp + o_phase); b->d_bar = (unsigned int*)(dp + o_bar);
   // observations that sit in page-locked caller memory are DMA'd straight from there, FIRST: those copies (most of the
   // bytes) then run while this thread stages the small arrays below
+  // -- on the workspace's copy stream, so that they also overlap the planner (which reads the index arrays only; the
+  // kernel that gathers the observations into slot order waits for them)
   cudaError_t e = cudaSuccess;
   if (ws) cudaEventRecord(ws->ev[0], stream);
   size_t direct_bytes = 0;
+  cudaStream_t obs_stream = (ws && ws->copy_stream) ? ws->copy_stream : stream;
+  if (obs_stream != stream) { cudaEventRecord(ws->ev_obs, stream); cudaStreamWaitEvent(obs_stream, ws->ev_obs, 0); }   // the pool may still be in use on `stream`
   for (int i = 0; i < n && e == cudaSuccess; ++i) {
     if (!direct[i]) continue;
     const size_t bytes = 64 * (size_t)descs[i].num_observations;
-    e = cudaMemcpyAsync(dp + o_raw[i], descs[i].observations, bytes, cudaMemcpyHostToDevice, stream);
+    e = cudaMemcpyAsync(dp + o_raw[i], descs[i].observations, bytes, cudaMemcpyHostToDevice, obs_stream);
     direct_bytes += bytes;
   }
+  const bool obs_on_copy_stream = obs_stream != stream && direct_bytes > 0;
+  if (obs_on_copy_stream && e == cudaSuccess) e = cudaEventRecord(ws->ev_obs, obs_stream);
   if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); cudaGetLastError(); slslam_lba_batch_destroy(b); return SLSLAM_ERR_CUDA; }
   // ---- staging: headers and the caller's arrays as they are (one thread, one buffer, one copy) ----
   for (int i = 0; i < n; ++i) {
@@ -225,6 +231,7 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
   if (e == cudaSuccess) {
     lba_plan_kernel<<<n, PLAN_NT, plan_smem, stream>>>((const PlanIn*)(dp + o_pin_in));
     e = cudaGetLastError();
+    if (e == cudaSuccess && obs_on_copy_stream) e = cudaStreamWaitEvent(stream, ws->ev_obs, 0);
     if (e == cudaSuccess) {
       const int gx = (int)std::max<long long>(1, std::min<long long>(32, (max_obs * 4 + 2047) / 2048));
       lba_gather_obs_kernel<<<dim3((unsigned)gx, (unsigned)n), 256, 0, stream>>>((const PlanIn*)(dp + o_pin_in));

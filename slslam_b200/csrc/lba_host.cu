@@ -277,10 +277,14 @@ struct Workspace {
   char* h_pin = nullptr; size_t h_cap = 0;     // upload staging: write-combined, written once by one thread, read only by the DMA engine
   char* h_res = nullptr; size_t r_cap = 0;     // results: ordinary pinned memory (the CPU reads it)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;          // page-locked observation arrays are DMA'd on their own stream, beside staging + planner
+  cudaEvent_t ev_obs = nullptr;
   std::vector<WindowPlan> plans;               // plan objects of the previous call, reused for their capacity
   int ensure(int dev, size_t d_bytes, size_t h_bytes, size_t r_bytes) {
     if (device != dev) { release(); device = dev; }
     for (int k = 0; k < 4; ++k) if (!ev[k]) CUDA_TRY(cudaEventCreate(&ev[k]));
+    if (!copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    if (!ev_obs) CUDA_TRY(cudaEventCreateWithFlags(&ev_obs, cudaEventDisableTiming));
     if (d_bytes > d_cap) {
       if (d_pool) cudaFree(d_pool);
       d_pool = nullptr; d_cap = 0;
@@ -310,6 +314,9 @@ struct Workspace {
     if (h_res) cudaFreeHost(h_res);
     d_pool = nullptr; h_pin = nullptr; h_res = nullptr; d_cap = h_cap = r_cap = 0;
     for (int k = 0; k < 4; ++k) { if (ev[k]) cudaEventDestroy(ev[k]); ev[k] = nullptr; }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (ev_obs) cudaEventDestroy(ev_obs);
+    copy_stream = nullptr; ev_obs = nullptr;
   }
 };
 static thread_local Workspace g_ws;
