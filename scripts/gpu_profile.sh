@@ -20,7 +20,12 @@ timeout 300 python scripts/po_profile.py 3 2>&1 | tee gpurun_out/po_${tag}.txt
 timeout 300 python scripts/phase_profile.py all > gpurun_out/phase_${tag}.txt 2>&1
 timeout 300 python scripts/phase_profile.py scale > gpurun_out/phase_scale_${tag}.txt 2>&1
 timeout 300 python scripts/e2e_profile.py > gpurun_out/e2e_${tag}.txt 2>&1
-timeout 300 python scripts/h2d_test2.py > gpurun_out/h2d_${tag}.txt 2>&1
+timeout 300 python scripts/h2d_staging_probe2.py > gpurun_out/h2d_${tag}.txt 2>&1
 timeout 300 python scripts/motion_only_profile.py > gpurun_out/moba_${tag}.txt 2>&1
 timeout 300 python scripts/ransac_profile.py > gpurun_out/ransac_${tag}.txt 2>&1
+# every other kernel family once, full metric set (the summaries go to profiles/<round>_other_kernels_ncu.csv)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'^(?!.*(lba_solve_kernel|elementwise|at::|vectorized)).*$' -c 60 -f -o gpurun_out/prof_other_${tag} \
+    python scripts/all_kernels_driver.py > gpurun_out/ncu_c_${tag}.log 2>&1
+./build/ubench_latency > gpurun_out/ubench_${tag}.txt 2>&1
+timeout 120 python -c "from slslam_b200 import capi; print('measured fp64 peak TFLOP/s, SM MHz:', capi.measure_fp64_peak())" >> gpurun_out/ubench_${tag}.txt 2>&1
 ls -la gpurun_out | tail -25

@@ -65,6 +65,29 @@ for src, dst in ((f"launches_{tag}.csv", f"{rnd}_launches_bench_lba.csv"), (f"la
     if os.path.exists(os.path.join(G, src)):
         shutil.copy(os.path.join(G, src), os.path.join(P, dst))
 
+for src, dst in ((f"ubench_{tag}.txt", f"{rnd}_latency_and_fp64_peak.txt"),):
+    if os.path.exists(os.path.join(G, src)):
+        shutil.copy(os.path.join(G, src), os.path.join(P, dst))
+
+# the other kernel families: one row per launch of the `ncu --set full` capture of scripts/all_kernels_driver.py
+rep2 = os.path.join(G, f"prof_other_{tag}.ncu-rep")
+if os.path.exists(rep2):
+    raw = subprocess.run(["ncu", "-i", rep2, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    if len(rows) > 2:
+        hdr, units = rows[0], rows[1]
+        name_col = hdr.index("Kernel Name")
+        cols = [i for i, h in enumerate(hdr) if h in KEEP or h in ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+                                                                   "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+                                                                   "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+                                                                   "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio")]
+        with open(os.path.join(P, f"{rnd}_other_kernels_ncu.csv"), "w") as f:
+            w = csv.writer(f)
+            w.writerow(["# ncu --set full --clock-control none, scripts/all_kernels_driver.py: one row per launch"])
+            w.writerow(["kernel"] + [hdr[i] + (" [" + units[i] + "]" if units[i] else "") for i in cols])
+            for r in rows[2:]:
+                w.writerow([r[name_col].split("(")[0]] + [r[i] for i in cols])
+
 # per-kernel totals of the PO launch list
 po = os.path.join(G, f"launches_po_{tag}.csv")
 if os.path.exists(po):
