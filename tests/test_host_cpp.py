@@ -95,6 +95,11 @@ def test_no_gpu_leaves_parameters_untouched(demo, tmp_path):
     head, params, stdout = _run(demo, "lba", inp, out)
     assert head["error_code"] == -3 and "failed" in stdout
     assert np.array_equal(params, w.parameters)
+    # a failed solve contributes ZEROS to the statistics the reference accumulates without looking (src/slam.cpp:949-952),
+    # never the -1 "did not run" markers, and says so on stderr although LBAProblem::set_options forces SILENT
+    assert head["initial_cost"] == 0.0 and head["final_cost"] == 0.0 and head["successful"] == 0 and head["unsuccessful"] == 0
+    p = subprocess.run([demo, "lba", inp, out], capture_output=True, text=True, timeout=120)
+    assert "solve failed" in p.stderr
 
 
 @pytest.mark.gpu
@@ -143,3 +148,20 @@ def test_po_through_cpp_boundary(demo, gpu, tmp_path):
     assert head["error_code"] == 0
     assert abs(head["final_cost"] - so["final_cost"]) < 1e-6 * so["final_cost"]
     assert np.abs(params - po).max() < 1e-6
+
+
+@pytest.mark.gpu
+def test_wide_window_through_cpp_boundary(demo, gpu, tmp_path):
+    """A --ba_window_size 20 window (20 free + 20 constant keyframes = 40 camera blocks, beyond the tiled kernel) through
+    LBAProblem -> ceres::Solve: routed to the general kernel, no silent no-op (reference src/slam.cpp:1376-1382)."""
+    from oracle import oracle
+    w = synth.make_window(31, 20, 150, 1900, num_fixed_cameras=20, sigma_px=0.5)
+    assert w.num_cameras == 40
+    inp, out = str(tmp_path / "w.bin"), str(tmp_path / "o.bin")
+    _write_lba(inp, w, 10)
+    head, params, _ = _run(demo, "lba", inp, out)
+    po, so = oracle.lba_solve(w, max_iters=10, solver=1)
+    assert head["error_code"] == 0
+    assert abs(head["final_cost"] - so["final_cost"]) < 1e-6 * so["final_cost"]
+    assert head["successful"] == so["num_successful_steps"] and head["unsuccessful"] == so["num_unsuccessful_steps"]
+    assert np.abs(params[:6 * 40] - po[:6 * 40]).max() < 1e-6
