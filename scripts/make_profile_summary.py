@@ -51,8 +51,7 @@ if os.path.exists(rep):
                     or h.startswith("smsp__pcsamp_warps_issue_stalled") and not h.endswith("not_issued"):
                 w.writerow([h, units[i]] + [r[i] for r in rows[2:]])
     by = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_by_line.py"), rep,
-                         os.path.join(G, f"lib_{tag}.so") if os.path.exists(os.path.join(G, f"lib_{tag}.so"))
-                         else os.path.join(ROOT, "slslam_b200", "libslslam_b200.so"), "lba_solve", "60"], capture_output=True, text=True).stdout
+                         os.path.join(ROOT, "slslam_b200", "libslslam_b200.so"), "lba_solve", "60"], capture_output=True, text=True).stdout
     open(os.path.join(P, f"{rnd}_lba_solve_kernel_by_source_line.txt"), "w").write(
         "# ncu --set full --import-source on, samples and instructions aggregated by CUDA source line (scripts/ncu_by_line.py)\n" + by)
 
@@ -70,10 +69,9 @@ for src, dst in ((f"ubench_{tag}.txt", f"{rnd}_latency_and_fp64_peak.txt"),):
         shutil.copy(os.path.join(G, src), os.path.join(P, dst))
 
 # the other kernel families: one row per launch of the `ncu --set full` capture of scripts/all_kernels_driver.py
-rep2 = os.path.join(G, f"prof_other_{tag}.ncu-rep")
+rep2 = os.path.join(G, f"other_raw_{tag}.csv")
 if os.path.exists(rep2):
-    raw = subprocess.run(["ncu", "-i", rep2, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
+    rows = list(csv.reader(open(rep2)))
     if len(rows) > 2:
         hdr, units = rows[0], rows[1]
         name_col = hdr.index("Kernel Name")

@@ -25,3 +25,23 @@ if which in ("all", "po"):
     g = synth.make_pose_graph(0, num_poses=16, neighbours=2, num_loops=2)
     p, s = capi.po_solve(g, max_iters=3)
     print("po", s["final_cost"])
+if which in ("all", "po"):
+    os.environ["SLSLAM_PO_DENSE"] = "1"                          # the dense fallback path as well
+    p, s = capi.po_solve(synth.make_pose_graph(0, num_poses=16, neighbours=2, num_loops=2), max_iters=2)
+    del os.environ["SLSLAM_PO_DENSE"]
+    print("po dense", s["final_cost"])
+if which in ("all", "wide"):
+    w = synth.make_window(31, 18, 60, 700, num_fixed_cameras=16, sigma_px=0.5)      # 34 camera blocks: the general kernel
+    p, s = capi.lba_solve(w, max_iters=2)
+    print("lba wide", w.num_cameras, s["iterations"], s["final_cost"])
+if which in ("all", "map"):
+    exec(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "all_kernels_driver.py")).read().split("# resident map")[1].replace('print("all kernel families launched")', 'print("map ok")'))
+if which in ("all", "device"):
+    import torch
+    from slslam_b200 import shard
+    ws = [synth.make_window(40 + i, 5, 40, 150) for i in range(2)]
+    buf, lay = shard.pack_rank_buffer(ws, pin=True)
+    dev = torch.from_numpy(buf).cuda()
+    ss = capi.lba_solve_batch_device(lay.shapes, dev.data_ptr(), lay.offsets(), max_iters=2, summaries_dev_ptr=dev.data_ptr() + lay.summary_off,
+                                     stream=torch.cuda.current_stream().cuda_stream)
+    print("lba device", [x["final_cost"] for x in ss])
