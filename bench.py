@@ -193,10 +193,19 @@ def ensure_built(capi):
         time.sleep(2.0)
 
 
+def _ncu_capture():
+    """The committed `ncu --set full` capture of lba_solve_kernel on this workload: the newest round's."""
+    for rnd in ("r2", "r1"):
+        p = os.path.join(ROOT, "profiles", f"{rnd}_lba_solve_kernel_ncu_raw.csv")
+        if os.path.exists(p):
+            return p
+    return os.path.join(ROOT, "profiles", "r1_lba_solve_kernel_ncu_raw.csv")
+
+
 def ncu_dram_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of one lba_solve_kernel launch of this workload, from the committed
     `ncu --set full` capture (profiles/, same command line as this bench); None when no capture is committed."""
-    path = os.path.join(ROOT, "profiles", "r1_lba_solve_kernel_ncu_raw.csv")
+    path = _ncu_capture()
     try:
         vals = {}
         for ln in open(path):
@@ -205,7 +214,7 @@ def ncu_dram_traffic():
                 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[1]]
                 vals[f[0]] = float(f[2]) * scale
         if len(vals) == 2:
-            return int(sum(vals.values())), "profiles/r1_lba_solve_kernel_ncu_raw.csv (ncu --set full, 1 launch)"
+            return int(sum(vals.values())), f"profiles/{os.path.basename(path)} (ncu --set full, 1 launch)"
     except Exception:
         pass
     return None, None
@@ -214,7 +223,7 @@ def ncu_dram_traffic():
 def ncu_fp64_flops():
     """fp64 flops one lba_solve_kernel launch of this workload executes (2 x DFMA + DMUL + DADD thread instructions, from
     the committed `ncu --set full` capture: rate per elapsed cycle x elapsed cycles); the work per launch is deterministic."""
-    path = os.path.join(ROOT, "profiles", "r1_lba_solve_kernel_ncu_raw.csv")
+    path = _ncu_capture()
     try:
         v = {}
         for ln in open(path):
