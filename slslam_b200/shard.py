@@ -414,25 +414,83 @@ class DeviceSharder:
                 self.host_bufs = [own]
                 for r in range(1, self.world):
                     t = torch.zeros(self.layouts[r].total, dtype=torch.uint8, device=self.dev)
-                    dist.recv(t, r, group=group)
+                    for req in dist.batch_isend_irecv([dist.P2POp(dist.irecv, t, r, group=group)]):
+                        req.wait()
                     h = torch.zeros(self.layouts[r].total, dtype=torch.uint8)
                     if pin and cuda:
                         h = h.pin_memory()
                     h.copy_(t)
                     self.host_bufs.append(h.numpy())
             else:
-                dist.send(torch.from_numpy(own).to(self.dev), 0, group=group)
+                for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, torch.from_numpy(own).to(self.dev), 0, group=group)]):
+                    req.wait()
         elif self.rank == 0:
             self.host_bufs = [pack_rank_buffer([windows[w] for w in local_indices(self.num_windows, r, self.world)], pin=pin and cuda)[0]
                               for r in range(self.world)]
+        self.res_off = np.concatenate([[0], np.cumsum([_up(self.layouts[r].result_bytes) for r in range(self.world)])]).astype(np.int64)
+        self.shm = None
         if self.rank == 0:
             self.stage = [torch.zeros(self.layouts[r].total, dtype=torch.uint8, device=self.dev) for r in range(self.world)]
-            self.res_off = np.concatenate([[0], np.cumsum([_up(self.layouts[r].result_bytes) for r in range(self.world)])]).astype(np.int64)
             self.res_dev = torch.zeros(int(self.res_off[-1]), dtype=torch.uint8, device=self.dev)
             self.res_host = torch.zeros(int(self.res_off[-1]), dtype=torch.uint8)
             if cuda:
                 self.res_host = self.res_host.pin_memory()
         self._pending = []
+
+    def enable_shared_host(self):
+        """origin = "host_shared" (one node): the packed windows live in ONE page-locked host segment that every rank's
+        process maps (POSIX shared memory, registered with CUDA in each process).  A rank then pulls its own slice over
+        its OWN PCIe link and writes its results back the same way: N links instead of rank 0's one, no NCCL on the data
+        path (a one-element all-reduce joins the ranks at the end).  This is how a single host producer -- the SLAM front
+        end -- would feed N GPUs; the NCCL origins above remain for data that starts on rank 0's GPU or in its private
+        memory.  Set-up (untimed): rank 0 copies its packed buffers into the segment."""
+        from multiprocessing import resource_tracker, shared_memory
+        torch, dist = self.torch, self.dist
+        self.seg_off = np.concatenate([[0], np.cumsum([_up(self.layouts[r].total) for r in range(self.world)])]).astype(np.int64)
+        self.seg_res = int(self.seg_off[-1])
+        size = self.seg_res + int(self.res_off[-1])
+        name = [None]
+        if self.rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=size)
+            name[0] = self.shm.name
+        dist.broadcast_object_list(name, 0, group=self.group)
+        if self.rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+            try:                      # only the creator unlinks (Python < 3.13 tracks attachments as if it owned them)
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.seg_np = np.ndarray((size,), np.uint8, buffer=self.shm.buf)
+        self.seg = torch.from_numpy(self.seg_np)
+        self._registered = False
+        if self.dev.type == "cuda":
+            rc = torch.cuda.cudart().cudaHostRegister(self.seg.data_ptr(), size, 0)
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister of the shared window segment failed: {rc}")
+            self._registered = True
+        if self.rank == 0:
+            for r in range(self.world):
+                o = int(self.seg_off[r])
+                self.seg_np[o:o + self.layouts[r].total] = self.host_bufs[r]
+        self._join = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        dist.barrier(group=self.group)
+
+    def close_shared_host(self):
+        if self.shm is None:
+            return
+        if self.dev.type == "cuda":
+            self.torch.cuda.synchronize(self.dev)
+        self.dist.barrier(group=self.group)
+        if self._registered:
+            self.torch.cuda.cudart().cudaHostUnregister(self.seg.data_ptr())
+        del self.seg, self.seg_np
+        shm, self.shm = self.shm, None
+        try:
+            shm.close()
+        except BufferError:
+            pass
+        if self.rank == 0:
+            shm.unlink()
 
     def preload_device(self):
         """origin = "device": put rank 0's packed buffers into its HBM (untimed; the windows then start on the device)."""
@@ -445,6 +503,10 @@ class DeviceSharder:
     def scatter(self, origin="host"):
         """After this call self.recv holds this rank's buffer (device).  Asynchronous on CUDA: the recv is enqueued."""
         torch, dist = self.torch, self.dist
+        if origin == "host_shared":
+            o = int(self.seg_off[self.rank])
+            self.recv.copy_(self.seg[o:o + self.lay.total], non_blocking=True)     # this rank's own PCIe link
+            return
         if self.rank == 0 and origin == "device" and self.dev.type == "cuda":
             # everything is already in HBM: ONE grouped launch sends to all peers side by side (separate sends would
             # queue behind one another on NCCL's stream: 0.54 ms instead of ~0.15 ms for 7 x 6.9 MB, measured)
@@ -533,9 +595,23 @@ class DeviceSharder:
             torch.cuda.current_stream(self.dev).synchronize()
         return True
 
-    def unpack_gathered(self):
-        """Rank 0: (params, summaries) of all windows in window order from self.res_host."""
-        host = self.res_host.numpy()
+    def gather_raw_shared(self):
+        """origin = "host_shared": every rank copies its result region into the shared host segment over its own link; a
+        one-element all-reduce, stream-ordered behind the copies, tells rank 0 that all of them have landed."""
+        lay = self.lay
+        if lay.result_bytes:
+            o = self.seg_res + int(self.res_off[self.rank])
+            self.seg[o:o + lay.result_bytes].copy_(self.recv[lay.result_begin:lay.result_end], non_blocking=True)
+        self.dist.all_reduce(self._join, group=self.group)
+        if self.rank != 0:
+            return False
+        if self.dev.type == "cuda":
+            self.torch.cuda.current_stream(self.dev).synchronize()
+        return True
+
+    def unpack_gathered(self, shared=False):
+        """Rank 0: (params, summaries) of all windows in window order from self.res_host (or the shared segment)."""
+        host = self.seg_np[self.seg_res:] if shared else self.res_host.numpy()
         out_p, out_s = [None] * self.num_windows, [None] * self.num_windows
         for r in range(self.world):
             n = self.layouts[r].result_bytes

@@ -105,6 +105,24 @@ def _worker(rank, world, port, out_dir):
     if rank == 0:
         assert [s_["final_cost"] for s_ in gs2] == [0.5, 1.5, 0.5, 1.5]
         assert np.array_equal(gp2[0], mine_l[0].parameters + 1.0) and np.array_equal(gp2[2], mine_l[1].parameters + 1.0)
+    # the shared page-locked segment path (one node): every rank pulls its slice from / writes its results to ONE host
+    # segment mapped by all processes; no send / recv at all
+    ds2.enable_shared_host()
+    ds2.scatter(origin="host_shared"); ds2.wait_scatter()
+    for w_, m_ in zip(ds2.views(), mine_l):
+        assert np.array_equal(w_.observations, m_.observations) and np.array_equal(w_.parameters, m_.parameters)
+        w_.parameters[:] = w_.parameters + 2.0
+    for i in range(2):
+        ds2.store_summary(i, dict(initial_cost=1.0, final_cost=2.5 + rank, num_successful_steps=1, num_unsuccessful_steps=0,
+                                  termination="NO_CONVERGENCE", iterations=1))
+    if ds2.gather_raw_shared():
+        gp3, gs3 = ds2.unpack_gathered(shared=True)
+        assert [s_["final_cost"] for s_ in gs3] == [2.5, 3.5, 2.5, 3.5]
+        assert np.array_equal(gp3[0], mine_l[0].parameters + 2.0) and np.array_equal(gp3[2], mine_l[1].parameters + 2.0)
+        del gp3, gs3
+    else:
+        assert rank != 0
+    ds2.close_shared_host()
     if rank == 0:
         np.save(os.path.join(out_dir, "cost.npy"), np.array([s["final_cost"] for s in ss]))
         np.save(os.path.join(out_dir, "iters.npy"), np.array([s["iterations"] for s in ss]))
