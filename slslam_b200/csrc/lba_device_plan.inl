@@ -99,6 +99,8 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
       o_ci[i] = reserve(4 * N); o_li[i] = reserve(4 * N); o_fi[i] = reserve(8 * N);
     }
     // observations last, so that the ones that are DMA'd directly leave no hole in the staged prefix
+    // (page-locked index / flag arrays are staged all the same: 24 small DMAs ahead of the planner were slower than one
+    // cache-hot staged copy, 1.08 against 1.01 ms per 8-window call)
     for (int i = 0; i < n; ++i) {
       const size_t N = (size_t)descs[i].num_observations;
       direct[i] = (N * 64 >= 65536 && is_page_locked(descs[i].observations)) ? 1 : 0;
@@ -222,16 +224,40 @@ static int batch_create_device_plan(int32_t n, const slslam_lba_desc* descs, con
     memcpy(host + o_ci[i], d.camera_index, 4 * N);
     memcpy(host + o_li[i], d.line_index, 4 * N);
     memcpy(host + o_fi[i], d.fixed_index, 8 * N);
-    if (!direct[i]) memcpy(host + o_raw[i], d.observations, 64 * N);
   }
   b->inplace = device_inputs;
-  const double t_staged = now_ms();
   b->upload_bytes = upload + direct_bytes;
-  e = cudaMemcpyAsync(dp, host, upload, cudaMemcpyHostToDevice, stream);
+  // The staged prefix (headers, parameters, index and flag arrays of every window) goes up first and the planner, which
+  // reads nothing else, starts behind it.  Pageable observations follow in pieces of <= 1 MB: piece k is copied into the
+  // page-locked staging buffer while the DMA of piece k-1 runs (on the copy stream when there is one, so the pieces also
+  // overlap the planner), and a piece that has just been written is still in the cache the DMA reads from (measured on the
+  // bench host: 49 GB/s for a freshly written buffer, 13-28 GB/s otherwise, profiles/r2_h2d_staging.txt).
+  size_t prefix = upload;
+  if (!device_inputs) for (int i = 0; i < n; ++i) if (!direct[i] && descs[i].num_observations > 0) prefix = std::min(prefix, o_raw[i]);
+  e = cudaMemcpyAsync(dp, host, prefix, cudaMemcpyHostToDevice, stream);
   if (e == cudaSuccess) {
     lba_plan_kernel<<<n, PLAN_NT, plan_smem, stream>>>((const PlanIn*)(dp + o_pin_in));
     e = cudaGetLastError();
-    if (e == cudaSuccess && obs_on_copy_stream) e = cudaStreamWaitEvent(stream, ws->ev_obs, 0);
+  }
+  bool staged_obs = false;
+  if (!device_inputs) {
+    constexpr size_t PIECE = (size_t)1 << 20;
+    for (int i = 0; i < n && e == cudaSuccess; ++i) {
+      if (direct[i]) continue;
+      const size_t bytes = 64 * (size_t)descs[i].num_observations;
+      const char* src = reinterpret_cast<const char*>(descs[i].observations);
+      for (size_t o = 0; o < bytes && e == cudaSuccess; o += PIECE) {
+        const size_t m = std::min(PIECE, bytes - o);
+        memcpy(host + o_raw[i] + o, src + o, m);
+        e = cudaMemcpyAsync(dp + o_raw[i] + o, host + o_raw[i] + o, m, cudaMemcpyHostToDevice, obs_stream);
+        staged_obs = true;
+      }
+    }
+    if (e == cudaSuccess && staged_obs && obs_stream != stream) e = cudaEventRecord(ws->ev_obs, obs_stream);
+  }
+  const double t_staged = now_ms();
+  if (e == cudaSuccess) {
+    if ((obs_on_copy_stream || (staged_obs && obs_stream != stream))) e = cudaStreamWaitEvent(stream, ws->ev_obs, 0);
     if (e == cudaSuccess) {
       const int gx = (int)std::max<long long>(1, std::min<long long>(32, (max_obs * 4 + 2047) / 2048));
       lba_gather_obs_kernel<<<dim3((unsigned)gx, (unsigned)n), 256, 0, stream>>>((const PlanIn*)(dp + o_pin_in));
