@@ -29,6 +29,8 @@ constexpr int MAX_G = 64;              // CTAs cooperating on one window (a CTA 
 constexpr int ZS = 24;               // doubles per Z block (6 x 4, row-major)
 constexpr int ZST = 26;              // row stride of the Z staging: 13 x 16 B, so 8 consecutive rows cover all 32 banks
 constexpr int ACC = 39;              // per-camera accumulators: H_cc - sum Z Z^T (21, lower) | g_c (6) | sum Z u (6) | diag H_cc (6)
+constexpr int ACCS = 42;             // their stride in shared memory: even (16-byte read-modify-writes) and = 2 mod 4, so the
+                                     // 16-byte accesses of 8 lanes on 8 consecutive cameras fall on 8 distinct bank groups
 constexpr int LLU = 22;              // per-line: L (10, lower) | u = L^-1 g_l (4) | D_l (4) | 1 / l_kk (4)
 constexpr int NSCAL = 8;
 constexpr int NPHASE = 14;         // init | linearise | pairs | fold | allreduce | gradient | reduced solve | trial | decide | total | solve: prep, factor+panel, trailing, back-substitution
@@ -91,7 +93,7 @@ __host__ __device__ inline SmemLayout lba_layout(int C, int Cf, int max_lines_ct
   l.lineLU = take(LLU * max_lines_cta);
   l.ltrig = take(8 * max_lines_cta); l.ltrigt = take(8 * max_lines_cta);   // sin/cos of the line angles at x and at x'
   l.V = take(vlen); l.Vred = l.V; l.G = CS;
-  l.wacc = take(LBA_NW * ACC * (Cf > 0 ? Cf : 1));
+  l.wacc = take(LBA_NW * ACCS * (Cf > 0 ? Cf : 1));
   l.yc = take(6 * (Cf > 0 ? Cf : 1) + 8);
   l.misc = take(64 + LBA_NW * NSCAL);
   l.tri = take((Cf * (Cf + 1) / 2 + 2) / 2 + 1);   // int table: key -> (I, K)
@@ -206,10 +208,10 @@ __device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, d
   double* lscale = sm + c.lay.lscale;
   double* lineLU = sm + c.lay.lineLU;
   const int Cf = h.Cf;
-  double* wacc = sm + c.lay.wacc + c.warp * ACC * (Cf > 0 ? Cf : 1);
+  double* wacc = sm + c.lay.wacc + c.warp * ACCS * (Cf > 0 ? Cf : 1);
   constexpr int NACC = (MODE == 0) ? 6 : ACC;
   // clear the warp-private camera accumulators
-  for (int i = c.lane; i < ACC * Cf; i += 32) wacc[i] = 0.0;
+  for (int i = c.lane; i < ACCS * Cf; i += 32) wacc[i] = 0.0;
   __syncwarp();
   double cost = 0.0, fixed_cost = 0.0, gmax = 0.0, fail = 0.0;
   const bool robust = h.robust != 0;
@@ -373,13 +375,19 @@ __device__ void linearize_sweep(const Ctx& c, double radius, double* out_cost, d
     const int nrounds = __reduce_max_sync(0xffffffffu, valid ? round + 1 : 0);
     for (int rd = 0; rd < nrounds; ++rd) {
       if (cam_free && round == rd && cf >= 0) {
-        double* a = wacc + ACC * cf;
+        // 16-byte read-modify-writes (same sums in the same order as scalar ones; a third fewer shared-memory instructions)
+        double2* a2 = reinterpret_cast<double2*>(wacc + ACCS * cf);
         if constexpr (MODE == 0) {
 #pragma unroll
-          for (int k = 0; k < 6; ++k) a[k] += acc[k];
+          for (int j = 0; j < 3; ++j) { double2 t = a2[j]; t.x += acc[2 * j]; t.y += acc[2 * j + 1]; a2[j] = t; }
         } else {
 #pragma unroll
-          for (int k = 0; k < ACC; ++k) a[k] += acc[k];
+          for (int j = 0; j < (ACC + 1) / 2; ++j) {
+            double2 t = a2[j];
+            t.x += acc[2 * j];
+            if (2 * j + 1 < ACC) t.y += acc[2 * j + 1];
+            a2[j] = t;
+          }
         }
       }
       __syncwarp();
@@ -477,7 +485,7 @@ __device__ void fold_cameras(const Ctx& c, bool norms_only) {
   for (int i = c.tid; i < Cf * nacc; i += LBA_NT) {
     const int f = i / nacc, e = i % nacc;
     double s = 0.0;
-    for (int w = 0; w < LBA_NW; ++w) s += wacc[(w * Cf + f) * ACC + e];
+    for (int w = 0; w < LBA_NW; ++w) s += wacc[(w * Cf + f) * ACCS + e];
     if (norms_only) { V[hd_off + 6 * f + e] = s; continue; }
     if (e < 21) {
       int p = 0; while ((p + 1) * (p + 2) / 2 <= e) ++p;
