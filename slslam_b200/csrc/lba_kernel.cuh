@@ -1067,7 +1067,14 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
       if (c.tid < C) cam_precompute(camxt + 6 * c.tid, camRt + CAM_STRIDE * c.tid, true);
       __syncthreads();
       double part[4];
+#ifdef SLSLAM_TRIAL_PHASES
+      PHASE(10)
+#endif
       trial_sweep(c, part);
+#ifdef SLSLAM_TRIAL_PHASES
+      __syncthreads();
+      PHASE(11)
+#endif
       cta_sum<4>(c, part, scal);
       if (c.G > 1) {
         if (c.tid < 4) h.scalg[c.rank * 8 + c.tid] = scal[c.tid];
@@ -1086,7 +1093,11 @@ __global__ void __launch_bounds__(LBA_NT, 1) lba_solve_kernel(const WinHdr* __re
         for (int k = 0; k < 4; ++k) trial[k] = scal[k];
       }
     }
+#ifdef SLSLAM_TRIAL_PHASES
+    PHASE(12)
+#else
     PHASE(7)
+#endif
     const double model = trial[1] + model_c;
     if (tr) tr[2] = model;
     if (!ok || model < 0.0) {
