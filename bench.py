@@ -311,6 +311,53 @@ def bench_pose_graph(capi, device, fp64_peak_tflops, cpu=True):
     return out
 
 
+def bench_wide_windows(capi, cpu=True):
+    """The reference's --ba_window_size 20 / 40 configurations (matlab_script/result_comp_ancdir_orthonorm/ba_result_*_basize{20,40}_*):
+    the house simulation (74 segments of house.m, circular trajectory), 2 W keyframes per window of which W are free, every
+    line seen by nearly every camera.  40 / 80 camera blocks are beyond the tiled kernel: these windows run through the
+    general kernel (csrc/wide_kernel.cuh).  One step = one blocking slslam_lba_solve call with host buffers on the last
+    window of a short replay; the oracle solves the same window on one host thread."""
+    from slslam_b200 import replay
+    S = synth.house_segments()
+    P, Q = np.stack([a for a, _ in S]), np.stack([b for _, b in S])
+    traj = synth.house_trajectory()
+    out = {}
+    for W in (20, 40):
+        windows = []
+        replay.run(traj, lambda w_, it_: capi.lba_solve(w_, max_iters=it_), window_size=W, max_iters=MAX_ITERS, sigma_px=0.2, seed=1,
+                   max_keyframes=2 * W + 6, scene=(P, Q), odo_noise=(5e-4, 2e-3), record=windows)
+        w = windows[-1]
+        assert w.num_cameras == 2 * W
+        wall = []
+        for _ in range(6):
+            t0 = time.perf_counter()
+            p, s = capi.lba_solve(w, max_iters=MAX_ITERS)
+            wall.append(time.perf_counter() - t0)
+        ms = 1e3 * float(np.median(wall[1:]))
+        rec = {"workload": f"house simulation, W = {W}: {w.num_cameras} camera blocks ({W} free) / {w.num_lines} lines / "
+                           f"{w.num_observations} observations, sigma 0.2 px, max {MAX_ITERS} LM iterations",
+               "kernel": "lba_wide_kernel (one CTA per window, intermediates in L2)", "ms_per_solve": ms, "lm_iterations": s["iterations"],
+               "value": s["iterations"] / (ms * 1e-3), "unit": UNIT, "final_cost": s["final_cost"], "termination": s["termination"],
+               "api": "slslam_lba_solve (host buffers in, parameters out, blocking)"}
+        if cpu:
+            from oracle import oracle
+            t0 = time.perf_counter()
+            po, so = oracle.lba_solve(w, max_iters=MAX_ITERS, solver=1)
+            dt = time.perf_counter() - t0
+            rel = abs(s["final_cost"] - so["final_cost"]) / so["final_cost"]
+            C = w.num_cameras
+            dpose = float(np.abs(p[:6 * C] - po[:6 * C]).max())
+            ok = rel <= 1e-6 and s["iterations"] == so["iterations"] and s["termination"] == so["termination"] and dpose < 1e-6
+            if not ok:
+                raise SystemExit(f"bench.py: wide-window result differs from the oracle (W = {W}): {s} vs {so}")
+            rec["parity_checked"] = True
+            rec["parity"] = {"rel_final_cost": rel, "max_abs_pose": dpose, "tolerance": "final cost rel 1e-6, poses 1e-6, same iterations / termination"}
+            rec["cpu_baseline"] = {"value": so["iterations"] / dt, "unit": UNIT, "cores": 1, "kind": "port", "ms_per_solve": 1e3 * dt,
+                                   "sample": "one solve of the same window, oracle (sparse Schur path), 1 thread"}
+        out[f"W{W}"] = rec
+    return out
+
+
 def bench_map_resident(capi, w, max_iters=MAX_ITERS, reps=20):
     """the per-keyframe blocking solve of one M window when the map (keyframe poses, landmark lines,
     observations) is resident on the device: slslam_map_bundle_adjust assembles the window from the map with kernels,
@@ -687,6 +734,8 @@ def main():
         if not args.no_extras:
             line["per_keyframe_blocking_solve"] = bench_map_resident(capi, windows[0])
             line["pose_graph"] = bench_pose_graph(capi, local_rank, fp64_peak_meas, cpu=(world == 1 and not args.no_cpu_baseline))
+            if world == 1:
+                line["wide_windows"] = bench_wide_windows(capi, cpu=not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
             reps = 2
             iters_c, secs_c = 0, 0.0

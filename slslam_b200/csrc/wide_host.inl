@@ -85,7 +85,7 @@ static int wide_solve_batch(int n, const slslam_lba_desc* descs, double* const* 
   size_t res = 0;
   for (int i = 0; i < n; ++i) { o_po[i] = res; res += (np[i] + 1) & ~(size_t)1; }
   const size_t o_pout = reserve(res * 8 + 8), o_summ = reserve(sizeof(slslam_summary) * n);
-  struct Scr { size_t camx, camxt, camR, camRt, linex, linext, cscale, lscale, r, Jc, Jl, Z, lineLU, S, gc, zu, hd, yc, ub, ab; };
+  struct Scr { size_t camx, camxt, camR, camRt, linex, linext, ltrig, ltrigt, cscale, lscale, r, Jc, Jl, Z, lineLU, S, gc, zu, hd, yc, ub, ab, part, flag; };
   std::vector<Scr> sc(n);
   for (int i = 0; i < n; ++i) {
     const WidePlan& p = plans[i];
@@ -96,7 +96,10 @@ static int wide_solve_batch(int n, const slslam_lba_desc* descs, double* const* 
     s.r = reserve(32 * N + 8); s.Jc = reserve(192 * N + 8); s.Jl = reserve(128 * N + 8); s.Z = reserve(192 * N + 8); s.lineLU = reserve(176 * L + 8);
     s.S = reserve(8 * nn * nn + 8); s.gc = reserve(8 * nn + 8); s.zu = reserve(8 * nn + 8); s.hd = reserve(8 * nn + 8);
     s.yc = reserve(8 * nn + 8); s.ub = reserve(8 * nn + 8); s.ab = reserve(8 * nn + 8);
+    s.ltrig = reserve(64 * L + 8); s.ltrigt = reserve(64 * L + 8);
+    s.part = reserve(8 * 2 * WIDE_MAX_G * WIDE_NPART); s.flag = reserve(8);
   }
+  const size_t o_bar = reserve((size_t)n * 128);          // one barrier counter per window, on its own line
   const size_t result_bytes = res * 8 + sizeof(slslam_summary) * n + 256;
   rc = g_ws.ensure(device, off, upload, result_bytes);
   if (rc != SLSLAM_OK) return rc;
@@ -119,11 +122,13 @@ static int wide_solve_batch(int n, const slslam_lba_desc* descs, double* const* 
     h.params_in = (const double*)(dev + o[i].par); h.params_out = (double*)(dev + o_pout) + o_po[i];
     h.summary = (slslam_summary*)(dev + o_summ) + i; h.trace = nullptr;
     const Scr& s = sc[i];
-    h.camx = (double*)(dev + s.camx); h.camxt = (double*)(dev + s.camxt); h.camR = (double*)(dev + s.camR); h.camRt = (double*)(dev + s.camRt);
-    h.linex = (double*)(dev + s.linex); h.linext = (double*)(dev + s.linext); h.cscale = (double*)(dev + s.cscale); h.lscale = (double*)(dev + s.lscale);
+    h.camx[0] = (double*)(dev + s.camx); h.camx[1] = (double*)(dev + s.camxt); h.camR[0] = (double*)(dev + s.camR); h.camR[1] = (double*)(dev + s.camRt);
+    h.linex[0] = (double*)(dev + s.linex); h.linex[1] = (double*)(dev + s.linext); h.ltrig[0] = (double*)(dev + s.ltrig); h.ltrig[1] = (double*)(dev + s.ltrigt);
+    h.cscale = (double*)(dev + s.cscale); h.lscale = (double*)(dev + s.lscale);
+    h.part = (double*)(dev + s.part); h.flag = (double*)(dev + s.flag); h.bar = (unsigned int*)(dev + o_bar + (size_t)i * 128);
     h.r = (double*)(dev + s.r); h.Jc = (double*)(dev + s.Jc); h.Jl = (double*)(dev + s.Jl); h.Z = (double*)(dev + s.Z); h.lineLU = (double*)(dev + s.lineLU);
     h.S = (double*)(dev + s.S); h.gc = (double*)(dev + s.gc); h.zu = (double*)(dev + s.zu); h.hd = (double*)(dev + s.hd);
-    h.yc = (double*)(dev + s.yc); h.ub = (double*)(dev + s.ub); h.ab = (double*)(dev + s.ab); h.red = nullptr;
+    h.yc = (double*)(dev + s.yc); h.ub = (double*)(dev + s.ub); h.ab = (double*)(dev + s.ab);
     memcpy(host + o_hdr + sizeof(WideHdr) * i, &h, sizeof(h));
     int* cs = (int*)(host + o[i].cam_s); int* ls = (int*)(host + o[i].line_s); double* os = (double*)(host + o[i].obs_s);
     for (int k = 0; k < p.N; ++k) {
@@ -140,12 +145,31 @@ static int wide_solve_batch(int n, const slslam_lba_desc* descs, double* const* 
     memcpy(host + o[i].par, params_inout[i], 8 * np[i]);
   }
   const double t1 = now_ms();
-  const size_t smem = (size_t)(WIDE_NT + WIDE_MAX_FREE * 36 + 36 + 16) * 8;
+  const size_t smem = (size_t)(WIDE_NPART * WIDE_NT + WIDE_MAX_FREE * 36 + 36 + 16) * 8 + (size_t)(WIDE_MAX_FREE * (WIDE_MAX_FREE + 1) / 2) * 4;
+  // group size: as many CTAs per window as stay co-resident with every window of the call (cooperative launch: the
+  // group barrier spins), at most WIDE_MAX_G; more windows than SMs run in waves of one CTA each
+  static int wide_cap[16] = {0};
+  if (device >= 16 || wide_cap[device] == 0) {
+    int per_sm = 0, sms = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lba_wide_kernel, WIDE_NT, smem));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (per_sm < 1) { set_last_error("the general LBA kernel does not fit on this device"); return SLSLAM_ERR_UNSUPPORTED; }
+    if (device < 16) wide_cap[device] = per_sm * sms;
+    else wide_cap[0] = per_sm * sms;
+  }
+  const int cap = wide_cap[device < 16 ? device : 0];
+  const int G = std::max(1, std::min((int)WIDE_MAX_G, cap / std::max(1, n)));
+  const int groups = std::min(n, cap / G);
   CUDA_TRY(cudaEventRecord(g_ws.ev[0], nullptr));
   CUDA_TRY(cudaMemcpyAsync(dev, host, upload, cudaMemcpyHostToDevice, nullptr));
+  CUDA_TRY(cudaMemsetAsync(dev + o_bar, 0, (size_t)n * 128, nullptr));
   CUDA_TRY(cudaEventRecord(g_ws.ev[1], nullptr));
-  lba_wide_kernel<<<n, WIDE_NT, smem>>>((const WideHdr*)(dev + o_hdr));
-  CUDA_TRY(cudaGetLastError());
+  {
+    const WideHdr* d_hdrs = (const WideHdr*)(dev + o_hdr);
+    int nwin = n, gsz = G;
+    void* args[] = {(void*)&d_hdrs, (void*)&nwin, (void*)&gsz};
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)lba_wide_kernel, dim3((unsigned)(groups * G)), dim3(WIDE_NT), args, smem, nullptr));
+  }
   CUDA_TRY(cudaEventRecord(g_ws.ev[2], nullptr));
   double* h_par = (double*)g_ws.h_res;
   slslam_summary* h_summ = (slslam_summary*)(h_par + res);

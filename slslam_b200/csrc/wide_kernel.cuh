@@ -3,18 +3,22 @@
 // up to 2 W = 80 cameras, 40 of them free, and in the house simulation nearly every camera sees every line) build such
 // windows (src/slam.cpp:1376-1382, 811-871).  Same algorithm -- Huber-corrected, Jacobi-scaled LM on the Schur
 // complement of the line blocks, Ceres 1.7.0 control -- in a shape that has no such limits:
-// one CTA per window, every intermediate in global memory (it stays in L2 / L1: a W = 40 house window is < 3 MB), any
-// number of cameras and of observations per line, up to WIDE_MAX_FREE free cameras (reduced system 6 * 64 square).
-// All reductions have a fixed order: results are bit-reproducible.
+// a GROUP of G co-resident CTAs per window (cooperative launch; round 2: round 1 of this kernel ran one CTA per window and
+// was bound by the latency of its own global loads), every intermediate in global memory (it stays in L2: a W = 40 house
+// window is < 3 MB), any number of cameras and of observations per line, up to WIDE_MAX_FREE free cameras (reduced
+// system 6 * 64 square).  Work items of a phase are strided over all threads (or warps) of the group; phases are
+// separated by an arrive / spin barrier on an L2 counter (release / acquire, as in lba_kernel.cuh); scalars are reduced
+// per CTA and then over the group in rank order.  All reductions have a fixed order: results are bit-reproducible.
 //   linearise   thread per observation (line-sorted order): residual, analytic Jacobian, corrector, Jacobi scale -> r, Jc, Jl
 //   lines       warp per line: H_ll, g_l over its observations (lane-strided partial sums, butterfly), 4x4 Cholesky,
 //               Z_i = (Jc_i^T Jl_i) L^-T per observation
 //   cameras     thread per (free camera, accumulator): H_cc - Z Z^T, g_c, Z u, diag H_cc over the camera's observations
 //   pairs       thread per entry of every off-diagonal block (I > K): - sum over the lines seen by both of Z_I Z_K^T
 //               (lookup table line x free camera -> observation)
-//   solve       right-looking block elimination of the dense reduced system with explicit 6x6 pivot inverses, the
-//               current panel in shared memory; back-substitution without solves
-//   trial       thread per line: y_l, trial line; thread per observation: residual at the trial point
+//   solve       CTA 0 of the group: right-looking block elimination of the dense reduced system with explicit 6x6 pivot
+//               inverses, the current panel in shared memory; back-substitution without solves
+//   trial       thread per camera: trial pose and rotation table; warp per line: y_l, trial line and its sines / cosines;
+//               thread per observation: residual at the trial point
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,6 +30,8 @@ namespace slslam {
 
 constexpr int WIDE_NT = 256;
 constexpr int WIDE_MAX_FREE = 64;
+constexpr int WIDE_MAX_G = 32;       // CTAs per window
+constexpr int WIDE_NPART = 4;        // scalars per group reduction
 
 struct WideHdr {
   int C, Cf, L, N, n, max_iters, robust, pad;
@@ -44,53 +50,118 @@ struct WideHdr {
   double* params_out;
   slslam_summary* summary;
   double* trace;
-  // scratch
-  double *camx, *camxt, *camR, *camRt, *linex, *linext, *cscale, *lscale;
+  // scratch: two copies (x and the trial point x') of the parameters, the rotation tables and the line sines / cosines
+  double *camx[2], *camR[2], *linex[2], *ltrig[2];
+  double *cscale, *lscale;
   double *r, *Jc, *Jl, *Z, *lineLU;        // [4N] [24N] [16N] [24N] [22L]
   double *S, *gc, *zu, *hd, *yc, *ub, *ab; // [n*n] [n] ...
-  double* red;                             // [WIDE_NT] block reduction scratch
+  double* part;                            // [2][WIDE_MAX_G][WIDE_NPART] per-CTA partial scalars (double-buffered)
+  double* flag;                            // [1] failure flag of the reduced solve (written by CTA 0)
+  unsigned int* bar;                       // arrive counter of the group barrier (zeroed by the host before every launch)
 };
 
-__device__ __forceinline__ double wide_block_sum(double v, double* sh) {
-  const int tid = threadIdx.x;
+struct WideCtx {
+  int tid, lane, warp, rank, G;
+  int gt, gsize, gw, gwarps;      // thread / warp index inside the group and their counts
+  unsigned int target, xchg;
+  unsigned int* bar;
+  double* sh;                     // [WIDE_NPART][WIDE_NT] block reduction scratch (shared)
+};
+
+// Barrier over the G CTAs of a window: arrive (release) + spin (acquire) by thread 0 on a counter in L2; the acquire also
+// drops this SM's stale L1 lines, so plain loads after it see what the other CTAs wrote before it.
+__device__ __forceinline__ void wide_sync(WideCtx& c) {
+  if (c.G == 1) { __syncthreads(); return; }
+  c.target += (unsigned int)c.G;
   __syncthreads();
-  sh[tid] = v;
-  __syncthreads();
-  for (int s = WIDE_NT >> 1; s > 0; s >>= 1) {
-    if (tid < s) sh[tid] += sh[tid + s];
-    __syncthreads();
+  if (c.tid == 0) {
+    __threadfence();
+    atomicAdd(c.bar, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(c.bar) : "memory");
+    } while ((int)(seen - c.target) < 0);
+    __threadfence();
   }
-  const double out = sh[0];
   __syncthreads();
-  return out;
-}
-__device__ __forceinline__ double wide_block_max(double v, double* sh) {
-  const int tid = threadIdx.x;
-  __syncthreads();
-  sh[tid] = v;
-  __syncthreads();
-  for (int s = WIDE_NT >> 1; s > 0; s >>= 1) {
-    if (tid < s) sh[tid] = fmax(sh[tid], sh[tid + s]);
-    __syncthreads();
-  }
-  const double out = sh[0];
-  __syncthreads();
-  return out;
 }
 
-// residual (+ Jacobian) sweep at (cam precompute table `cR`, lines `lx`).  MODE 0: column norms for the Jacobi scale (J
-// Huber-scaled only), 1: full linearisation (stores r, Jc, Jl scaled), 2: cost only.
+// v[0..K) of every thread -> the same K totals on every thread of every CTA of the group.  Bit k of `maxmask`: combine
+// value k with max (values >= 0) instead of +.  Tree inside the CTA, rank order over the group; includes a group barrier.
+template <int K>
+__device__ __forceinline__ void wide_group_reduce(WideCtx& c, const WideHdr& h, double* v, unsigned int maxmask) {
+  static_assert(K <= WIDE_NPART, "WIDE_NPART");
+  double* sh = c.sh;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) sh[k * WIDE_NT + c.tid] = v[k];
+  __syncthreads();
+  for (int s = WIDE_NT >> 1; s > 0; s >>= 1) {
+    if (c.tid < s) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const double a = sh[k * WIDE_NT + c.tid], b = sh[k * WIDE_NT + c.tid + s];
+        sh[k * WIDE_NT + c.tid] = ((maxmask >> k) & 1u) ? fmax(a, b) : a + b;
+      }
+    }
+    __syncthreads();
+  }
+  if (c.G > 1) {
+    double* slot = h.part + (size_t)(c.xchg & 1u) * WIDE_MAX_G * WIDE_NPART;
+    ++c.xchg;
+    if (c.tid < K) slot[c.rank * WIDE_NPART + c.tid] = sh[c.tid * WIDE_NT];
+    wide_sync(c);
+    if (c.tid < K) {
+      double a = 0.0;
+      for (int r = 0; r < c.G; ++r) {
+        const double b = __ldcg(slot + r * WIDE_NPART + c.tid);
+        a = ((maxmask >> c.tid) & 1u) ? fmax(a, b) : a + b;
+      }
+      sh[c.tid * WIDE_NT] = a;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = sh[k * WIDE_NT];
+  __syncthreads();
+}
+
+// CTA-local reduction (every CTA of the group holds the same data and gets the same bits): no exchange.
+template <int K>
+__device__ __forceinline__ void wide_block_reduce(WideCtx& c, double* v, unsigned int maxmask) {
+  double* sh = c.sh;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) sh[k * WIDE_NT + c.tid] = v[k];
+  __syncthreads();
+  for (int s = WIDE_NT >> 1; s > 0; s >>= 1) {
+    if (c.tid < s) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const double a = sh[k * WIDE_NT + c.tid], b = sh[k * WIDE_NT + c.tid + s];
+        sh[k * WIDE_NT + c.tid] = ((maxmask >> k) & 1u) ? fmax(a, b) : a + b;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = sh[k * WIDE_NT];
+  __syncthreads();
+}
+
+// residual (+ Jacobian) sweep at (cam precompute table `cR`, line sines / cosines `ltr`).  MODE 0: column norms for the
+// Jacobi scale (J Huber-scaled only), 1: full linearisation (stores r, Jc, Jl scaled), 2: cost only.
 template <int MODE>
-__device__ void wide_sweep(const WideHdr& h, const double* cR, const double* lx, double* cost_out, double* fixed_out) {
+__device__ void wide_sweep(const WideCtx& c, const WideHdr& h, const double* cR, const double* ltr, double* cost_out, double* fixed_out) {
   double cost = 0.0, fixed = 0.0;
   const bool robust = h.robust != 0;
-  for (int s = threadIdx.x; s < h.N; s += WIDE_NT) {
+  for (int s = c.gt; s < h.N; s += c.gsize) {
     const int cam = h.cam_s[s], l = h.line_s[s];
     const int cf = h.cam_free[cam];
     const bool lfree = h.line_free[l] != 0;
     if (MODE == 2 && cf < 0 && !lfree) continue;
     LineTrig lt;
-    line_trig(lx + 4 * (size_t)l, lt);
+    line_trig_sc(ltr + 8 * (size_t)l, lt);
     double ob[8], r[4], Jc[24], Jl[16];
 #pragma unroll
     for (int k = 0; k < 8; ++k) ob[k] = h.obs_s[8 * (size_t)s + k];
@@ -121,30 +192,194 @@ __device__ __forceinline__ double wide_warp_sum(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __restrict__ hdrs) {
-  const WideHdr& h = hdrs[blockIdx.x];
+// Reduced solve (S + D_c) y = g_c - sum Z u by ONE CTA: right-looking block elimination in global memory (L1 / L2), the
+// unscaled panel of the current block column in shared memory.  Returns false when a pivot block is not positive.
+__device__ bool wide_reduced_solve(const WideHdr& h, double inv_radius, double* pan, double* Wsm, double* bcast, const int* tri) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Cf = h.Cf, n = h.n;
+  for (int i = tid; i < n; i += WIDE_NT) {
+    h.yc[i] = h.gc[i] - h.zu[i];
+    h.ab[i] = 0.0;
+    h.S[(size_t)i * n + i] += fmin(fmax(h.hd[i], 1e-6), 1e32) * inv_radius;
+  }
+  if (tid == 0) bcast[0] = 0.0;
+  __syncthreads();
+  for (int J = 0; J < Cf; ++J) {
+    const int nb = Cf - J - 1;
+    // pivot inverse by warp 0 (all lanes the same values), to shared memory
+    if (warp == 0) {
+      double A[21], Ai[6], Si[6], M[9], S3[6], W[21];
+#define L6I(p, q) ((p) * ((p) + 1) / 2 + (q))
+#define SY3(mm, r, cc) mm[(r) <= (cc) ? ((r) == 0 ? (cc) : (r) == 1 ? 2 + (cc) : 5) : ((cc) == 0 ? (r) : (cc) == 1 ? 2 + (r) : 5)]
+#pragma unroll
+      for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = 0; q <= p; ++q) A[L6I(p, q)] = h.S[(size_t)(6 * J + p) * n + 6 * J + q];
+      bool ok = spd3_inverse(A[L6I(0, 0)], A[L6I(1, 0)], A[L6I(2, 0)], A[L6I(1, 1)], A[L6I(2, 1)], A[L6I(2, 2)], Ai);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+          M[3 * r + cc] = A[L6I(3 + r, 0)] * SY3(Ai, 0, cc) + A[L6I(3 + r, 1)] * SY3(Ai, 1, cc) + A[L6I(3 + r, 2)] * SY3(Ai, 2, cc);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = r; cc < 3; ++cc)
+          SY3(S3, r, cc) = A[L6I(3 + cc, 3 + r)] - (M[3 * r] * A[L6I(3 + cc, 0)] + M[3 * r + 1] * A[L6I(3 + cc, 1)] + M[3 * r + 2] * A[L6I(3 + cc, 2)]);
+      ok = spd3_inverse(S3[0], S3[1], S3[2], S3[3], S3[4], S3[5], Si) && ok;
+      double W21[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+          W21[3 * r + cc] = -(SY3(Si, r, 0) * M[cc] + SY3(Si, r, 1) * M[3 + cc] + SY3(Si, r, 2) * M[6 + cc]);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc <= r; ++cc) {
+          W[L6I(r, cc)] = SY3(Ai, r, cc) - (M[r] * W21[cc] + M[3 + r] * W21[3 + cc] + M[6 + r] * W21[6 + cc]);
+          W[L6I(3 + r, 3 + cc)] = SY3(Si, r, cc);
+        }
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) W[L6I(3 + r, cc)] = W21[3 * r + cc];
+#undef SY3
+      if (lane == 0) {
+        if (!ok) bcast[0] = 1.0;
+#pragma unroll
+        for (int p = 0; p < 6; ++p)
+#pragma unroll
+          for (int q = 0; q < 6; ++q) Wsm[6 * p + q] = W[p >= q ? L6I(p, q) : L6I(q, p)];
+      }
+#undef L6I
+    }
+    __syncthreads();
+    // panel rows P_I = A_IJ W (original rows kept in shared memory), u_J = W b_J
+    for (int t = tid; t < 6 * nb + 6; t += WIDE_NT) {
+      if (t < 6 * nb) {
+        const int bI = t / 6, p = t - 6 * bI, I = J + 1 + bI;
+        double* a = h.S + (size_t)(6 * I + p) * n + 6 * J;
+        double av[6], pv[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) av[k] = a[k];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) pv[q] = (av[0] * Wsm[q] + av[1] * Wsm[6 + q] + av[2] * Wsm[12 + q]) + (av[3] * Wsm[18 + q] + av[4] * Wsm[24 + q] + av[5] * Wsm[30 + q]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { pan[36 * bI + 6 * p + k] = av[k]; a[k] = pv[k]; }
+      } else {
+        const int q = t - 6 * nb;
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sacc += h.yc[6 * J + k] * Wsm[6 * k + q];
+        h.ub[6 * J + q] = sacc;
+      }
+    }
+    __syncthreads();
+    // trailing update A_IK -= P_I A_KJ^T (I >= K > J): a thread owns row p of a block; b_I -= P_I b_J
+    const int nrow = nb * (nb + 1) / 2 * 6;
+    for (int e = tid; e < nrow + 6 * nb; e += WIDE_NT) {
+      if (e < nrow) {
+        const int blk = e / 6, p = e - 6 * blk;
+        const int bi = tri[blk] >> 8, bk = tri[blk] & 0xff;
+        const int I = J + 1 + bi, K = J + 1 + bk;
+        const double* pi = h.S + (size_t)(6 * I + p) * n + 6 * J;
+        const double* ak = pan + 36 * bk;
+        double* dst = h.S + (size_t)(6 * I + p) * n + 6 * K;
+        double a6[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a6[k] = pi[k];
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+          dst[q] -= (a6[0] * ak[6 * q] + a6[1] * ak[6 * q + 1] + a6[2] * ak[6 * q + 2]) + (a6[3] * ak[6 * q + 3] + a6[4] * ak[6 * q + 4] + a6[5] * ak[6 * q + 5]);
+      } else {
+        const int rI = e - nrow, bI = rI / 6, p = rI - 6 * bI, I = J + 1 + bI;
+        const double* pi = h.S + (size_t)(6 * I + p) * n + 6 * J;
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sacc += pi[k] * h.yc[6 * J + k];
+        h.yc[6 * I + p] -= sacc;
+      }
+    }
+    __syncthreads();
+  }
+  const bool ok = bcast[0] == 0.0;
+  // back-substitution (warp 0): y_J = u_J - acc_J, acc_K += P_JK^T y_J for K < J
+  if (warp == 0 && ok) {
+    for (int J = Cf - 1; J >= 0; --J) {
+      double y[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) y[k] = h.ub[6 * J + k] - h.ab[6 * J + k];
+      __syncwarp();
+      if (lane < 6) h.yc[6 * J + lane] = h.ub[6 * J + lane] - h.ab[6 * J + lane];
+      for (int e = lane; e < 6 * J; e += 32) {
+        const int K = e / 6, q = e - 6 * K;
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sacc += h.S[(size_t)(6 * J + k) * n + 6 * K + q] * y[k];
+        h.ab[6 * K + q] += sacc;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  return ok;
+}
+
+// grid = (windows resident at a time) x G CTAs; window w of a launch is solved by the group blockIdx.x / G, then w +
+// groups, ... (every window has its own barrier counter and partial-sum slots)
+__global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __restrict__ hdrs, int nwin, int G) {
   extern __shared__ __align__(16) double wsm[];
-  double* sh = wsm;                               // [WIDE_NT] reductions
-  double* pan = sh + WIDE_NT;                     // [WIDE_MAX_FREE][36] original panel rows of the current block column
+  double* pan = wsm + WIDE_NPART * WIDE_NT;       // [WIDE_MAX_FREE][36] original panel rows of the current block column
   double* Wsm = pan + WIDE_MAX_FREE * 36;         // [36] pivot inverse
   double* bcast = Wsm + 36;                       // [16] broadcast scalars
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = WIDE_NT / 32;
+  int* tri = reinterpret_cast<int*>(bcast + 16);  // block of a lower block triangle -> row << 8 | column
+  for (int k = threadIdx.x; k < WIDE_MAX_FREE * (WIDE_MAX_FREE + 1) / 2; k += WIDE_NT) {
+    int I = 0;
+    while ((I + 1) * (I + 2) / 2 <= k) ++I;
+    tri[k] = (I << 8) | (k - I * (I + 1) / 2);
+  }
+  __syncthreads();
+  WideCtx c;
+  c.sh = wsm;
+  c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
+  c.G = G; c.rank = (int)(blockIdx.x % (unsigned)G);
+  c.gt = c.rank * WIDE_NT + c.tid; c.gsize = G * WIDE_NT;
+  c.gw = c.rank * (WIDE_NT / 32) + c.warp; c.gwarps = G * (WIDE_NT / 32);
+  const int tid = c.tid, lane = c.lane;
+  const int groups = (int)(gridDim.x / (unsigned)G);
+  for (int win = (int)(blockIdx.x / (unsigned)G); win < nwin; win += groups) {
+  const WideHdr& h = hdrs[win];
+  c.bar = h.bar; c.target = 0; c.xchg = 0;
   const int C = h.C, Cf = h.Cf, L = h.L, N = h.N, n = h.n;
-  // ---- parameters ----
-  for (int i = tid; i < 6 * C; i += WIDE_NT) h.camx[i] = h.params_in[i];
-  for (int i = tid; i < 4 * L; i += WIDE_NT) h.linex[i] = h.params_in[6 * (size_t)C + i];
-  __syncthreads();
-  for (int c = tid; c < C; c += WIDE_NT) cam_precompute(h.camx + 6 * (size_t)c, h.camR + CAM_STRIDE * (size_t)c, true);
-  for (int i = tid; i < 4 * L; i += WIDE_NT) h.lscale[i] = 1.0;
-  for (int i = tid; i < n; i += WIDE_NT) h.cscale[i] = 1.0;
-  __syncthreads();
+  int cur = 0;                                    // which copy holds x (the other one the trial point)
+  // ---- parameters, rotation tables, line sines / cosines at x0 ----
+  for (int cc = c.gt; cc < C; cc += c.gsize) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) h.camx[0][6 * (size_t)cc + j] = h.params_in[6 * (size_t)cc + j];
+    cam_precompute(h.camx[0] + 6 * (size_t)cc, h.camR[0] + CAM_STRIDE * (size_t)cc, true);
+  }
+  for (int i = c.gt; i < 4 * L; i += c.gsize) {
+    const double v = h.params_in[6 * (size_t)C + i];
+    h.linex[0][i] = v;
+    double sv, cv;
+    sincos(v, &sv, &cv);
+    h.ltrig[0][2 * (size_t)i] = sv; h.ltrig[0][2 * (size_t)i + 1] = cv;
+    h.lscale[i] = 1.0;
+  }
+  for (int i = c.gt; i < n; i += c.gsize) h.cscale[i] = 1.0;
+  wide_sync(c);
   // ---- Jacobi scale from the column norms at x0 (Huber-scaled Jacobian), initial and fixed cost ----
   double pc, pf;
-  wide_sweep<0>(h, h.camR, h.linex, &pc, &pf);
-  double cost = wide_block_sum(pc, sh);
-  const double fixed_cost = wide_block_sum(pf, sh);
+  wide_sweep<0>(c, h, h.camR[0], h.ltrig[0], &pc, &pf);
+  double cost, fixed_cost;
+  {
+    double v[2] = {pc, pf};
+    wide_group_reduce<2>(c, h, v, 0u);
+    cost = v[0]; fixed_cost = v[1];
+  }
   const double initial_cost = cost + fixed_cost;
-  for (int l = warp; l < L; l += nwarp) {
+  for (int l = c.gw; l < L; l += c.gwarps) {
     double cn[4] = {0, 0, 0, 0};
     for (int s = h.line_start[l] + lane; s < h.line_start[l + 1]; s += 32) {
       const double* J = h.Jl + 16 * (size_t)s;
@@ -154,7 +389,7 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
 #pragma unroll
     for (int j = 0; j < 4; ++j) { cn[j] = wide_warp_sum(cn[j]); if (lane == 0) h.lscale[4 * (size_t)l + j] = 1.0 / (1.0 + sqrt(cn[j])); }
   }
-  for (int i = tid; i < n; i += WIDE_NT) {
+  for (int i = c.gt; i < n; i += c.gsize) {
     const int f = i / 6, j = i - 6 * f;
     double cn = 0.0;
     for (int t = h.cam_start[f]; t < h.cam_start[f + 1]; ++t) {
@@ -163,7 +398,7 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
     }
     h.cscale[i] = 1.0 / (1.0 + sqrt(cn));
   }
-  __syncthreads();
+  wide_sync(c);
 
   double radius = h.radius0, decrease_factor = 2.0, gmax = 0.0, gtol_abs = 0.0;
   int successful = 0, unsuccessful = 0, invalid = 0, term = SLSLAM_NO_CONVERGENCE, iters = 0;
@@ -171,13 +406,21 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
   for (int it = 0; it <= h.max_iters; ++it) {
     const bool last = it == h.max_iters;
     if (last && !grad_pending) break;
+    double* camx = h.camx[cur]; double* camxt = h.camx[cur ^ 1];
+    double* camR = h.camR[cur]; double* camRt = h.camR[cur ^ 1];
+    double* linex = h.linex[cur]; double* linext = h.linex[cur ^ 1];
+    double* ltrig = h.ltrig[cur]; double* ltrigt = h.ltrig[cur ^ 1];
     // ---- linearise at x ----
-    wide_sweep<1>(h, h.camR, h.linex, &pc, &pf);
-    cost = wide_block_sum(pc, sh);
+    wide_sweep<1>(c, h, camR, ltrig, &pc, &pf);
+    {
+      double v[1] = {pc};
+      wide_group_reduce<1>(c, h, v, 0u);          // (the barrier inside also publishes r, Jc, Jl)
+      cost = v[0];
+    }
     // ---- lines: H_ll, g_l, LM diagonal, Cholesky, u; Z per observation; line part of the gradient norm ----
     double gm = 0.0, failf = 0.0;
     const double inv_radius = 1.0 / radius;
-    for (int l = warp; l < L; l += nwarp) {
+    for (int l = c.gw; l < L; l += c.gwarps) {
       const int s0 = h.line_start[l], s1 = h.line_start[l + 1];
       if (!h.line_free[l] || s0 == s1) continue;
       double hg[14];
@@ -244,13 +487,17 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
       }
     }
     // constant lines: their observations have Jl = 0, no Schur term: Z = 0
-    for (int s = tid; s < N; s += WIDE_NT) {
+    for (int s = c.gt; s < N; s += c.gsize) {
       if (!h.line_free[h.line_s[s]]) { double* Zo = h.Z + 24 * (size_t)s; for (int k = 0; k < 24; ++k) Zo[k] = 0.0; }
     }
-    const bool line_fail = wide_block_max(failf, sh) != 0.0;
-    gm = wide_block_max(gm, sh);
+    bool line_fail;
+    {
+      double v[2] = {failf, gm};
+      wide_group_reduce<2>(c, h, v, 3u);          // (publishes Z and lineLU)
+      line_fail = v[0] != 0.0; gm = v[1];
+    }
     // ---- cameras: diagonal blocks, g_c, Z u, diag H_cc ----
-    for (int i = tid; i < Cf * 39; i += WIDE_NT) {
+    for (int i = c.gt; i < Cf * 39; i += c.gsize) {
       const int f = i / 39, e = i - 39 * f;
       double acc = 0.0;
       int p = 0, q = 0;
@@ -282,9 +529,9 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
       else h.hd[6 * f + p] = acc;
     }
     // ---- pairs: off-diagonal blocks (I > K) ----
-    {
+    if (!last) {
       const int nblk = Cf * (Cf - 1) / 2;
-      for (int i = tid; i < nblk * 36; i += WIDE_NT) {
+      for (int i = c.gt; i < nblk * 36; i += c.gsize) {
         const int b = i / 36, pq = i - 36 * b, p = pq / 6, q = pq - 6 * p;
         int I = 1; while (I * (I + 1) / 2 <= b) ++I;          // b = I (I - 1) / 2 + K, K < I
         const int K = b - I * (I - 1) / 2;
@@ -301,208 +548,114 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
         h.S[(size_t)(6 * I + p) * n + 6 * K + q] = -acc;
       }
     }
-    __syncthreads();
-    // ---- gradient max norm (unscaled Jacobian), |x|^2 of the free blocks ----
-    double pg = 0.0, px = 0.0;
-    for (int i = tid; i < n; i += WIDE_NT) pg = fmax(pg, fabs(h.gc[i] / h.cscale[i]));
-    for (int c = tid; c < C; c += WIDE_NT) if (h.cam_free[c] >= 0) for (int j = 0; j < 6; ++j) px += h.camx[6 * c + j] * h.camx[6 * c + j];
-    for (int l = tid; l < L; l += WIDE_NT) if (h.line_free[l] && h.line_start[l + 1] > h.line_start[l]) for (int j = 0; j < 4; ++j) px += h.linex[4 * l + j] * h.linex[4 * l + j];
-    gmax = fmax(gm, wide_block_max(pg, sh));
-    const double x_norm2 = wide_block_sum(px, sh);
+    wide_sync(c);
+    // ---- gradient max norm (unscaled Jacobian), |x|^2 of the free blocks: the same on every CTA, no exchange ----
+    double x_norm2;
+    {
+      double pg = 0.0, px = 0.0;
+      for (int i = tid; i < n; i += WIDE_NT) pg = fmax(pg, fabs(h.gc[i] / h.cscale[i]));
+      for (int cc = tid; cc < C; cc += WIDE_NT) if (h.cam_free[cc] >= 0) for (int j = 0; j < 6; ++j) px += camx[6 * cc + j] * camx[6 * cc + j];
+      for (int l = tid; l < L; l += WIDE_NT) if (h.line_free[l] && h.line_start[l + 1] > h.line_start[l]) for (int j = 0; j < 4; ++j) px += linex[4 * l + j] * linex[4 * l + j];
+      double v[2] = {pg, px};
+      wide_block_reduce<2>(c, v, 1u);
+      gmax = fmax(gm, v[0]); x_norm2 = v[1];
+    }
     if (first_lin) { gtol_abs = h.gtol * fmax(gmax, 2.220446049250313e-16); first_lin = false; }
     grad_pending = false;
     if (gmax <= gtol_abs) { term = SLSLAM_GRADIENT_TOLERANCE; break; }
     if (last) break;
     iters = it + 1;
-    double* tr = (h.trace && tid == 0) ? h.trace + (size_t)it * SLSLAM_TRACE_WIDTH : nullptr;
+    double* tr = (h.trace && c.gt == 0) ? h.trace + (size_t)it * SLSLAM_TRACE_WIDTH : nullptr;
     if (tr) { tr[0] = cost; tr[1] = 0; tr[2] = 0; tr[3] = radius; tr[4] = 0; tr[5] = 0; tr[6] = gmax; tr[7] = 0; }
-    // ---- reduced solve: (S + D_c) y = g_c - sum Z u ----
-    for (int i = tid; i < n; i += WIDE_NT) {
-      h.yc[i] = h.gc[i] - h.zu[i];
-      h.ab[i] = 0.0;
-      h.S[(size_t)i * n + i] += fmin(fmax(h.hd[i], 1e-6), 1e32) * inv_radius;
+    // ---- reduced solve by CTA 0 of the group ----
+    if (c.rank == 0) {
+      const bool sok = wide_reduced_solve(h, inv_radius, pan, Wsm, bcast, tri);
+      if (tid == 0) *h.flag = sok ? 0.0 : 1.0;
     }
-    if (tid == 0) bcast[0] = 0.0;
-    __syncthreads();
-    for (int J = 0; J < Cf; ++J) {
-      const int nb = Cf - J - 1;
-      // pivot inverse by warp 0 (all lanes the same values), to shared memory
-      if (warp == 0) {
-        double A36[36];
-#pragma unroll
-        for (int p = 0; p < 6; ++p)
-#pragma unroll
-          for (int q = 0; q <= p; ++q) A36[6 * p + q] = h.S[(size_t)(6 * J + p) * n + 6 * J + q];
-        double A[21], Ai[6], Si[6], M[9], S3[6], W[21];
-#define L6I(p, q) ((p) * ((p) + 1) / 2 + (q))
-#define SY3(mm, r, cc) mm[(r) <= (cc) ? ((r) == 0 ? (cc) : (r) == 1 ? 2 + (cc) : 5) : ((cc) == 0 ? (r) : (cc) == 1 ? 2 + (r) : 5)]
-#pragma unroll
-        for (int p = 0; p < 6; ++p)
-#pragma unroll
-          for (int q = 0; q <= p; ++q) A[L6I(p, q)] = A36[6 * p + q];
-        bool ok = spd3_inverse(A[L6I(0, 0)], A[L6I(1, 0)], A[L6I(2, 0)], A[L6I(1, 1)], A[L6I(2, 1)], A[L6I(2, 2)], Ai);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int cc = 0; cc < 3; ++cc)
-            M[3 * r + cc] = A[L6I(3 + r, 0)] * SY3(Ai, 0, cc) + A[L6I(3 + r, 1)] * SY3(Ai, 1, cc) + A[L6I(3 + r, 2)] * SY3(Ai, 2, cc);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int cc = r; cc < 3; ++cc)
-            SY3(S3, r, cc) = A[L6I(3 + cc, 3 + r)] - (M[3 * r] * A[L6I(3 + cc, 0)] + M[3 * r + 1] * A[L6I(3 + cc, 1)] + M[3 * r + 2] * A[L6I(3 + cc, 2)]);
-        ok = spd3_inverse(S3[0], S3[1], S3[2], S3[3], S3[4], S3[5], Si) && ok;
-        double W21[9];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int cc = 0; cc < 3; ++cc)
-            W21[3 * r + cc] = -(SY3(Si, r, 0) * M[cc] + SY3(Si, r, 1) * M[3 + cc] + SY3(Si, r, 2) * M[6 + cc]);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int cc = 0; cc <= r; ++cc) {
-            W[L6I(r, cc)] = SY3(Ai, r, cc) - (M[r] * W21[cc] + M[3 + r] * W21[3 + cc] + M[6 + r] * W21[6 + cc]);
-            W[L6I(3 + r, 3 + cc)] = SY3(Si, r, cc);
-          }
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int cc = 0; cc < 3; ++cc) W[L6I(3 + r, cc)] = W21[3 * r + cc];
-#undef SY3
-        if (lane == 0) {
-          if (!ok) bcast[0] = 1.0;
-#pragma unroll
-          for (int p = 0; p < 6; ++p)
-#pragma unroll
-            for (int q = 0; q < 6; ++q) Wsm[6 * p + q] = W[p >= q ? L6I(p, q) : L6I(q, p)];
-        }
-#undef L6I
-      }
-      __syncthreads();
-      // panel rows P_I = A_IJ W (original rows kept in shared memory), u_J = W b_J
-      for (int t = tid; t < 6 * nb + 6; t += WIDE_NT) {
-        if (t < 6 * nb) {
-          const int bI = t / 6, p = t - 6 * bI, I = J + 1 + bI;
-          double* a = h.S + (size_t)(6 * I + p) * n + 6 * J;
-          double av[6], pv[6];
-#pragma unroll
-          for (int k = 0; k < 6; ++k) av[k] = a[k];
-#pragma unroll
-          for (int q = 0; q < 6; ++q) pv[q] = (av[0] * Wsm[q] + av[1] * Wsm[6 + q] + av[2] * Wsm[12 + q]) + (av[3] * Wsm[18 + q] + av[4] * Wsm[24 + q] + av[5] * Wsm[30 + q]);
-#pragma unroll
-          for (int k = 0; k < 6; ++k) { pan[36 * bI + 6 * p + k] = av[k]; a[k] = pv[k]; }
-        } else {
-          const int q = t - 6 * nb;
-          double s = 0.0;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) s += h.yc[6 * J + k] * Wsm[6 * k + q];
-          h.ub[6 * J + q] = s;
+    wide_sync(c);
+    bool ok = !line_fail && __ldcg(h.flag) == 0.0;
+    // camera part of the model decrease, |delta|^2, finiteness (the same on every CTA)
+    double model = 0.0, dn2 = 0.0;
+    {
+      double v[3] = {0.0, 0.0, 0.0};
+      if (ok) {
+        for (int i = tid; i < n; i += WIDE_NT) {
+          const double y = h.yc[i];
+          v[0] += 0.5 * y * (h.gc[i] + fmin(fmax(h.hd[i], 1e-6), 1e32) * inv_radius * y);
+          const double dl = y * h.cscale[i];
+          v[1] += dl * dl;
+          if (!isfinite(y)) v[2] = 1.0;
         }
       }
-      __syncthreads();
-      // trailing update A_IK -= P_I A_KJ^T (I >= K > J), b_I -= P_I b_J
-      const int nitem = nb * (nb + 1) / 2 * 36;
-      for (int e = tid; e < nitem + 6 * nb; e += WIDE_NT) {
-        if (e < nitem) {
-          const int blk = e / 36, pq = e - 36 * blk, p = pq / 6, q = pq - 6 * p;
-          int bi = 0; while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
-          const int bk = blk - bi * (bi + 1) / 2;
-          const int I = J + 1 + bi, K = J + 1 + bk;
-          const double* pi = h.S + (size_t)(6 * I + p) * n + 6 * J;
-          const double* ak = pan + 36 * bk + 6 * q;
-          h.S[(size_t)(6 * I + p) * n + 6 * K + q] -= (pi[0] * ak[0] + pi[1] * ak[1] + pi[2] * ak[2]) + (pi[3] * ak[3] + pi[4] * ak[4] + pi[5] * ak[5]);
-        } else {
-          const int rI = e - nitem, bI = rI / 6, p = rI - 6 * bI, I = J + 1 + bI;
-          const double* pi = h.S + (size_t)(6 * I + p) * n + 6 * J;
-          double s = 0.0;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) s += pi[k] * h.yc[6 * J + k];
-          h.yc[6 * I + p] -= s;
-        }
-      }
-      __syncthreads();
+      wide_block_reduce<3>(c, v, 4u);
+      model = v[0]; dn2 = v[1];
+      if (v[2] != 0.0) ok = false;
     }
-    bool ok = !line_fail && bcast[0] == 0.0;
-    // back-substitution (warp 0): y_J = u_J - acc_J, acc_K += P_JK^T y_J for K < J
-    if (warp == 0 && ok) {
-      for (int J = Cf - 1; J >= 0; --J) {
-        double y[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) y[k] = h.ub[6 * J + k] - h.ab[6 * J + k];
-        __syncwarp();
-        if (lane < 6) h.yc[6 * J + lane] = h.ub[6 * J + lane] - h.ab[6 * J + lane];
-        for (int e = lane; e < 6 * J; e += 32) {
-          const int K = e / 6, q = e - 6 * K;
-          double s = 0.0;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) s += h.S[(size_t)(6 * J + k) * n + 6 * K + q] * y[k];
-          h.ab[6 * K + q] += s;
-        }
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    // camera part of the model decrease, |delta|^2, finiteness
-    double pm = 0.0, pd = 0.0, pbad = 0.0;
-    if (ok) {
-      for (int i = tid; i < n; i += WIDE_NT) {
-        const double y = h.yc[i];
-        pm += 0.5 * y * (h.gc[i] + fmin(fmax(h.hd[i], 1e-6), 1e32) * inv_radius * y);
-        const double dl = y * h.cscale[i];
-        pd += dl * dl;
-        if (!isfinite(y)) pbad = 1.0;
-      }
-    }
-    double model = wide_block_sum(pm, sh), dn2 = wide_block_sum(pd, sh);
-    if (wide_block_max(pbad, sh) != 0.0) ok = false;
     double new_cost = 0.0;
     if (ok) {
       // ---- trial point: cameras, lines (y_l = L^-T (u - sum Z^T y_c)), cost ----
-      for (int i = tid; i < 6 * C; i += WIDE_NT) {
-        const int cf = h.cam_free[i / 6];
-        h.camxt[i] = h.camx[i] - (cf >= 0 ? h.yc[6 * cf + i % 6] * h.cscale[6 * cf + i % 6] : 0.0);
+      for (int cc = c.gt; cc < C; cc += c.gsize) {
+        const int cf = h.cam_free[cc];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) camxt[6 * (size_t)cc + j] = camx[6 * (size_t)cc + j] - (cf >= 0 ? h.yc[6 * cf + j] * h.cscale[6 * cf + j] : 0.0);
+        cam_precompute(camxt + 6 * (size_t)cc, camRt + CAM_STRIDE * (size_t)cc, true);
       }
       double plm = 0.0, pld = 0.0;
-      for (int l = tid; l < L; l += WIDE_NT) {
+      for (int l = c.gw; l < L; l += c.gwarps) {
         const int s0 = h.line_start[l], s1 = h.line_start[l + 1];
+        double nl[4];
         if (!h.line_free[l] || s0 == s1) {
-          for (int k = 0; k < 4; ++k) h.linext[4 * (size_t)l + k] = h.linex[4 * (size_t)l + k];
-          continue;
-        }
-        double v[4] = {0, 0, 0, 0};
-        for (int s = s0; s < s1; ++s) {
-          const int cf = h.cam_free[h.cam_s[s]];
-          if (cf < 0) continue;
-          const double* Z = h.Z + 24 * (size_t)s;
-          const double* y = h.yc + 6 * cf;
 #pragma unroll
-          for (int p = 0; p < 6; ++p) { v[0] += Z[4 * p] * y[p]; v[1] += Z[4 * p + 1] * y[p]; v[2] += Z[4 * p + 2] * y[p]; v[3] += Z[4 * p + 3] * y[p]; }
-        }
-        const double* lu = h.lineLU + 22 * (size_t)l;
-        double yl[4];
-        const double w3 = lu[13] - v[3], w2 = lu[12] - v[2], w1 = lu[11] - v[1], w0 = lu[10] - v[0];
-        yl[3] = w3 * lu[21];
-        yl[2] = (w2 - lu[8] * yl[3]) * lu[20];
-        yl[1] = (w1 - lu[4] * yl[2] - lu[7] * yl[3]) * lu[19];
-        yl[0] = (w0 - lu[1] * yl[1] - lu[3] * yl[2] - lu[6] * yl[3]) * lu[18];
-        const double u0 = lu[10], u1 = lu[11], u2 = lu[12], u3 = lu[13];
-        const double g0 = lu[0] * u0, g1 = lu[1] * u0 + lu[2] * u1, g2 = lu[3] * u0 + lu[4] * u1 + lu[5] * u2,
-                     g3 = lu[6] * u0 + lu[7] * u1 + lu[8] * u2 + lu[9] * u3;
-        plm += 0.5 * (yl[0] * (g0 + lu[14] * yl[0]) + yl[1] * (g1 + lu[15] * yl[1]) + yl[2] * (g2 + lu[16] * yl[2]) + yl[3] * (g3 + lu[17] * yl[3]));
+          for (int k = 0; k < 4; ++k) nl[k] = linex[4 * (size_t)l + k];
+        } else {
+          double v[4] = {0, 0, 0, 0};
+          for (int s = s0 + lane; s < s1; s += 32) {
+            const int cf = h.cam_free[h.cam_s[s]];
+            if (cf < 0) continue;
+            const double* Z = h.Z + 24 * (size_t)s;
+            const double* y = h.yc + 6 * cf;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const double dl = yl[k] * h.lscale[4 * (size_t)l + k];
-          pld += dl * dl;
-          h.linext[4 * (size_t)l + k] = h.linex[4 * (size_t)l + k] - dl;
+            for (int p = 0; p < 6; ++p) { v[0] += Z[4 * p] * y[p]; v[1] += Z[4 * p + 1] * y[p]; v[2] += Z[4 * p + 2] * y[p]; v[3] += Z[4 * p + 3] * y[p]; }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = wide_warp_sum(v[k]);
+          const double* lu = h.lineLU + 22 * (size_t)l;
+          double yl[4];
+          const double w3 = lu[13] - v[3], w2 = lu[12] - v[2], w1 = lu[11] - v[1], w0 = lu[10] - v[0];
+          yl[3] = w3 * lu[21];
+          yl[2] = (w2 - lu[8] * yl[3]) * lu[20];
+          yl[1] = (w1 - lu[4] * yl[2] - lu[7] * yl[3]) * lu[19];
+          yl[0] = (w0 - lu[1] * yl[1] - lu[3] * yl[2] - lu[6] * yl[3]) * lu[18];
+          const double u0 = lu[10], u1 = lu[11], u2 = lu[12], u3 = lu[13];
+          const double g0 = lu[0] * u0, g1 = lu[1] * u0 + lu[2] * u1, g2 = lu[3] * u0 + lu[4] * u1 + lu[5] * u2,
+                       g3 = lu[6] * u0 + lu[7] * u1 + lu[8] * u2 + lu[9] * u3;
+          if (lane == 0) plm += 0.5 * (yl[0] * (g0 + lu[14] * yl[0]) + yl[1] * (g1 + lu[15] * yl[1]) + yl[2] * (g2 + lu[16] * yl[2]) + yl[3] * (g3 + lu[17] * yl[3]));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const double dl = yl[k] * h.lscale[4 * (size_t)l + k];
+            if (lane == 0) pld += dl * dl;
+            nl[k] = linex[4 * (size_t)l + k] - dl;
+          }
+        }
+        if (lane < 4) {
+          const double v = lane == 0 ? nl[0] : lane == 1 ? nl[1] : lane == 2 ? nl[2] : nl[3];
+          double sv, cv;
+          sincos(v, &sv, &cv);
+          linext[4 * (size_t)l + lane] = v;
+          ltrigt[8 * (size_t)l + 2 * lane] = sv; ltrigt[8 * (size_t)l + 2 * lane + 1] = cv;
         }
       }
-      model += wide_block_sum(plm, sh);
-      dn2 += wide_block_sum(pld, sh);
-      for (int c = tid; c < C; c += WIDE_NT) cam_precompute(h.camxt + 6 * (size_t)c, h.camRt + CAM_STRIDE * (size_t)c, true);
-      __syncthreads();
-      wide_sweep<2>(h, h.camRt, h.linext, &pc, &pf);
-      new_cost = wide_block_sum(pc, sh);
+      {
+        double v[2] = {plm, pld};
+        wide_group_reduce<2>(c, h, v, 0u);        // (publishes the trial cameras and lines)
+        model += v[0]; dn2 += v[1];
+      }
+      wide_sweep<2>(c, h, camRt, ltrigt, &pc, &pf);
+      {
+        double v[1] = {pc};
+        wide_group_reduce<1>(c, h, v, 0u);
+        new_cost = v[0];
+      }
     }
     if (tr) tr[2] = model;
     if (!ok || model < 0.0) {
@@ -524,11 +677,7 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
     if (rel > 1e-3) {
       ++successful;
       if (tr) tr[5] = 1.0;
-      __syncthreads();
-      for (int i = tid; i < 6 * C; i += WIDE_NT) h.camx[i] = h.camxt[i];
-      for (int i = tid; i < 4 * L; i += WIDE_NT) h.linex[i] = h.linext[i];
-      for (int i = tid; i < CAM_STRIDE * C; i += WIDE_NT) h.camR[i] = h.camRt[i];
-      __syncthreads();
+      cur ^= 1;                                   // the trial point becomes x: no copies
       cost = new_cost;
       grad_pending = true;
       const double t = 2.0 * rel - 1.0;
@@ -541,16 +690,17 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
     }
     if (radius < 1e-32) { term = SLSLAM_PARAMETER_TOLERANCE; break; }
   }
-  __syncthreads();
   // ---- write back: blocks no observation touches keep their input bits (the host pre-copies the input) ----
-  for (int i = tid; i < 6 * C; i += WIDE_NT) h.params_out[i] = h.camx[i];
-  for (int i = tid; i < 4 * L; i += WIDE_NT) h.params_out[6 * (size_t)C + i] = h.linex[i];
-  if (tid == 0) {
+  wide_sync(c);
+  for (int i = c.gt; i < 6 * C; i += c.gsize) h.params_out[i] = h.camx[cur][i];
+  for (int i = c.gt; i < 4 * L; i += c.gsize) h.params_out[6 * (size_t)C + i] = h.linex[cur][i];
+  if (c.gt == 0) {
     slslam_summary s;
     s.initial_cost = initial_cost; s.final_cost = cost + fixed_cost; s.fixed_cost = fixed_cost; s.gradient_max_norm = gmax;
     s.num_successful_steps = successful; s.num_unsuccessful_steps = unsuccessful; s.termination_type = term; s.iterations = iters;
     *h.summary = s;
   }
+  }   // windows of this group
 }
 
 }  // namespace slslam
