@@ -85,7 +85,7 @@ static int wide_solve_batch(int n, const slslam_lba_desc* descs, double* const* 
   size_t res = 0;
   for (int i = 0; i < n; ++i) { o_po[i] = res; res += (np[i] + 1) & ~(size_t)1; }
   const size_t o_pout = reserve(res * 8 + 8), o_summ = reserve(sizeof(slslam_summary) * n);
-  struct Scr { size_t camx, camxt, camR, camRt, linex, linext, ltrig, ltrigt, cscale, lscale, r, Jc, Jl, Z, lineLU, S, gc, zu, hd, yc, ub, ab, part, flag; };
+  struct Scr { size_t P, camx, camxt, camR, camRt, linex, linext, ltrig, ltrigt, cscale, lscale, r, Jc, Jl, Z, lineLU, S, gc, zu, hd, yc, ub, ab, part, flag; };
   std::vector<Scr> sc(n);
   for (int i = 0; i < n; ++i) {
     const WidePlan& p = plans[i];
@@ -94,7 +94,7 @@ static int wide_solve_batch(int n, const slslam_lba_desc* descs, double* const* 
     s.camx = reserve(48 * C + 8); s.camxt = reserve(48 * C + 8); s.camR = reserve(8 * CAM_STRIDE * C + 8); s.camRt = reserve(8 * CAM_STRIDE * C + 8);
     s.linex = reserve(32 * L + 8); s.linext = reserve(32 * L + 8); s.cscale = reserve(8 * nn + 8); s.lscale = reserve(32 * L + 8);
     s.r = reserve(32 * N + 8); s.Jc = reserve(192 * N + 8); s.Jl = reserve(128 * N + 8); s.Z = reserve(192 * N + 8); s.lineLU = reserve(176 * L + 8);
-    s.S = reserve(8 * nn * nn + 8); s.gc = reserve(8 * nn + 8); s.zu = reserve(8 * nn + 8); s.hd = reserve(8 * nn + 8);
+    s.S = reserve(8 * nn * nn + 8); s.P = reserve(8 * nn * nn + 8); s.gc = reserve(8 * nn + 8); s.zu = reserve(8 * nn + 8); s.hd = reserve(8 * nn + 8);
     s.yc = reserve(8 * nn + 8); s.ub = reserve(8 * nn + 8); s.ab = reserve(8 * nn + 8);
     s.ltrig = reserve(64 * L + 8); s.ltrigt = reserve(64 * L + 8);
     s.part = reserve(8 * 2 * WIDE_MAX_G * WIDE_NPART); s.flag = reserve(8);
@@ -127,7 +127,7 @@ static int wide_solve_batch(int n, const slslam_lba_desc* descs, double* const* 
     h.cscale = (double*)(dev + s.cscale); h.lscale = (double*)(dev + s.lscale);
     h.part = (double*)(dev + s.part); h.flag = (double*)(dev + s.flag); h.bar = (unsigned int*)(dev + o_bar + (size_t)i * 128);
     h.r = (double*)(dev + s.r); h.Jc = (double*)(dev + s.Jc); h.Jl = (double*)(dev + s.Jl); h.Z = (double*)(dev + s.Z); h.lineLU = (double*)(dev + s.lineLU);
-    h.S = (double*)(dev + s.S); h.gc = (double*)(dev + s.gc); h.zu = (double*)(dev + s.zu); h.hd = (double*)(dev + s.hd);
+    h.S = (double*)(dev + s.S); h.P = (double*)(dev + s.P); h.gc = (double*)(dev + s.gc); h.zu = (double*)(dev + s.zu); h.hd = (double*)(dev + s.hd);
     h.yc = (double*)(dev + s.yc); h.ub = (double*)(dev + s.ub); h.ab = (double*)(dev + s.ab);
     memcpy(host + o_hdr + sizeof(WideHdr) * i, &h, sizeof(h));
     int* cs = (int*)(host + o[i].cam_s); int* ls = (int*)(host + o[i].line_s); double* os = (double*)(host + o[i].obs_s);
@@ -145,7 +145,7 @@ static int wide_solve_batch(int n, const slslam_lba_desc* descs, double* const* 
     memcpy(host + o[i].par, params_inout[i], 8 * np[i]);
   }
   const double t1 = now_ms();
-  const size_t smem = (size_t)(WIDE_NPART * WIDE_NT + WIDE_MAX_FREE * 36 + 36 + 16) * 8 + (size_t)(WIDE_MAX_FREE * (WIDE_MAX_FREE + 1) / 2) * 4;
+  const size_t smem = (size_t)(WIDE_NPART * WIDE_NT + 36 + 16) * 8 + (size_t)(WIDE_MAX_FREE * (WIDE_MAX_FREE + 1) / 2) * 4;
   // group size: as many CTAs per window as stay co-resident with every window of the call (cooperative launch: the
   // group barrier spins), at most WIDE_MAX_G; more windows than SMs run in waves of one CTA each
   static int wide_cap[16] = {0};

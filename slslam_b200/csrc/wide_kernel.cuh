@@ -22,8 +22,10 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "../../include/slslam_b200.h"
+#include "lba_kernel.cuh"     // warp_reduce_scatter32, warp_sum
 #include "lba_math.cuh"
 
 namespace slslam {
@@ -54,7 +56,7 @@ struct WideHdr {
   double *camx[2], *camR[2], *linex[2], *ltrig[2];
   double *cscale, *lscale;
   double *r, *Jc, *Jl, *Z, *lineLU;        // [4N] [24N] [16N] [24N] [22L]
-  double *S, *gc, *zu, *hd, *yc, *ub, *ab; // [n*n] [n] ...
+  double *S, *P, *gc, *zu, *hd, *yc, *ub, *ab; // [n*n] [n*n] [n] ...  (P: the scaled panels A_IJ W_J of the block elimination)
   double* part;                            // [2][WIDE_MAX_G][WIDE_NPART] per-CTA partial scalars (double-buffered)
   double* flag;                            // [1] failure flag of the reduced solve (written by CTA 0)
   unsigned int* bar;                       // arrive counter of the group barrier (zeroed by the host before every launch)
@@ -192,137 +194,186 @@ __device__ __forceinline__ double wide_warp_sum(double v) {
   return v;
 }
 
-// Reduced solve (S + D_c) y = g_c - sum Z u by ONE CTA: right-looking block elimination in global memory (L1 / L2), the
-// unscaled panel of the current block column in shared memory.  Returns false when a pivot block is not positive.
-__device__ bool wide_reduced_solve(const WideHdr& h, double inv_radius, double* pan, double* Wsm, double* bcast, const int* tri) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// W = A^-1 of the 6x6 pivot block J of S (lower triangle read from global memory) by one warp, all lanes the same values;
+// lane 0 stores W (full, symmetric) to shared memory.  false when the block is not positive definite.
+__device__ __forceinline__ bool wide_pivot_inverse(const WideHdr& h, int J, double* Wsm, int lane) {
+  const int n = h.n;
+  double A[21], Ai[6], Si[6], M[9], S3[6], W[21];
+#define L6I(p, q) ((p) * ((p) + 1) / 2 + (q))
+#define SY3(mm, r, cc) mm[(r) <= (cc) ? ((r) == 0 ? (cc) : (r) == 1 ? 2 + (cc) : 5) : ((cc) == 0 ? (r) : (cc) == 1 ? 2 + (r) : 5)]
+#pragma unroll
+  for (int p = 0; p < 6; ++p)
+#pragma unroll
+    for (int q = 0; q <= p; ++q) A[L6I(p, q)] = h.S[(size_t)(6 * J + p) * n + 6 * J + q];
+  bool ok = spd3_inverse(A[L6I(0, 0)], A[L6I(1, 0)], A[L6I(2, 0)], A[L6I(1, 1)], A[L6I(2, 1)], A[L6I(2, 2)], Ai);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+      M[3 * r + cc] = A[L6I(3 + r, 0)] * SY3(Ai, 0, cc) + A[L6I(3 + r, 1)] * SY3(Ai, 1, cc) + A[L6I(3 + r, 2)] * SY3(Ai, 2, cc);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = r; cc < 3; ++cc)
+      SY3(S3, r, cc) = A[L6I(3 + cc, 3 + r)] - (M[3 * r] * A[L6I(3 + cc, 0)] + M[3 * r + 1] * A[L6I(3 + cc, 1)] + M[3 * r + 2] * A[L6I(3 + cc, 2)]);
+  ok = spd3_inverse(S3[0], S3[1], S3[2], S3[3], S3[4], S3[5], Si) && ok;
+  double W21[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+      W21[3 * r + cc] = -(SY3(Si, r, 0) * M[cc] + SY3(Si, r, 1) * M[3 + cc] + SY3(Si, r, 2) * M[6 + cc]);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc <= r; ++cc) {
+      W[L6I(r, cc)] = SY3(Ai, r, cc) - (M[r] * W21[cc] + M[3 + r] * W21[3 + cc] + M[6 + r] * W21[6 + cc]);
+      W[L6I(3 + r, 3 + cc)] = SY3(Si, r, cc);
+    }
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) W[L6I(3 + r, cc)] = W21[3 * r + cc];
+#undef SY3
+  if (lane == 0) {
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) Wsm[6 * p + q] = W[p >= q ? L6I(p, q) : L6I(q, p)];
+  }
+#undef L6I
+  return ok;
+}
+
+// Reduced solve (S + D_c) y = g_c - sum Z u by the whole group: right-looking block elimination in global memory (L2) with
+// explicit 6x6 pivot inverses.  Per block column J ONE group barrier: every CTA inverts the pivot block itself (same
+// bits), then the rows of the trailing blocks (I, K), I >= K > J, are strided over all threads of the group; a thread
+// recomputes its scaled panel row P_I[p,:] = A_IJ[p,:] W_J (36 FMAs) rather than wait for it, the column-J blocks of S
+// stay unscaled (so nobody reads what another thread overwrites), and the owner of block (I, J+1) stores the panel row
+// to P and updates the right-hand side row.  Back-substitution without solves by one warp: y_J = u_J - sum P_IJ^T y_I.
+__device__ bool wide_reduced_solve(WideCtx& c, const WideHdr& h, double inv_radius, double* Wsm, double* bcast, const int* tri) {
+  const int tid = c.tid, lane = c.lane, warp = c.warp;
   const int Cf = h.Cf, n = h.n;
-  for (int i = tid; i < n; i += WIDE_NT) {
+  for (int i = c.gt; i < n; i += c.gsize) {
     h.yc[i] = h.gc[i] - h.zu[i];
     h.ab[i] = 0.0;
     h.S[(size_t)i * n + i] += fmin(fmax(h.hd[i], 1e-6), 1e32) * inv_radius;
   }
   if (tid == 0) bcast[0] = 0.0;
-  __syncthreads();
+  wide_sync(c);
+#ifdef SLSLAM_WIDE_PHASES
+  long long sp[4] = {0, 0, 0, 0}, st0 = clock64();
+#define SPHASE(i) { const long long now_ = clock64(); sp[i] += now_ - st0; st0 = now_; }
+#else
+#define SPHASE(i)
+#endif
   for (int J = 0; J < Cf; ++J) {
     const int nb = Cf - J - 1;
-    // pivot inverse by warp 0 (all lanes the same values), to shared memory
     if (warp == 0) {
-      double A[21], Ai[6], Si[6], M[9], S3[6], W[21];
-#define L6I(p, q) ((p) * ((p) + 1) / 2 + (q))
-#define SY3(mm, r, cc) mm[(r) <= (cc) ? ((r) == 0 ? (cc) : (r) == 1 ? 2 + (cc) : 5) : ((cc) == 0 ? (r) : (cc) == 1 ? 2 + (r) : 5)]
-#pragma unroll
-      for (int p = 0; p < 6; ++p)
-#pragma unroll
-        for (int q = 0; q <= p; ++q) A[L6I(p, q)] = h.S[(size_t)(6 * J + p) * n + 6 * J + q];
-      bool ok = spd3_inverse(A[L6I(0, 0)], A[L6I(1, 0)], A[L6I(2, 0)], A[L6I(1, 1)], A[L6I(2, 1)], A[L6I(2, 2)], Ai);
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc)
-          M[3 * r + cc] = A[L6I(3 + r, 0)] * SY3(Ai, 0, cc) + A[L6I(3 + r, 1)] * SY3(Ai, 1, cc) + A[L6I(3 + r, 2)] * SY3(Ai, 2, cc);
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cc = r; cc < 3; ++cc)
-          SY3(S3, r, cc) = A[L6I(3 + cc, 3 + r)] - (M[3 * r] * A[L6I(3 + cc, 0)] + M[3 * r + 1] * A[L6I(3 + cc, 1)] + M[3 * r + 2] * A[L6I(3 + cc, 2)]);
-      ok = spd3_inverse(S3[0], S3[1], S3[2], S3[3], S3[4], S3[5], Si) && ok;
-      double W21[9];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc)
-          W21[3 * r + cc] = -(SY3(Si, r, 0) * M[cc] + SY3(Si, r, 1) * M[3 + cc] + SY3(Si, r, 2) * M[6 + cc]);
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cc = 0; cc <= r; ++cc) {
-          W[L6I(r, cc)] = SY3(Ai, r, cc) - (M[r] * W21[cc] + M[3 + r] * W21[3 + cc] + M[6 + r] * W21[6 + cc]);
-          W[L6I(3 + r, 3 + cc)] = SY3(Si, r, cc);
-        }
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc) W[L6I(3 + r, cc)] = W21[3 * r + cc];
-#undef SY3
-      if (lane == 0) {
-        if (!ok) bcast[0] = 1.0;
-#pragma unroll
-        for (int p = 0; p < 6; ++p)
-#pragma unroll
-          for (int q = 0; q < 6; ++q) Wsm[6 * p + q] = W[p >= q ? L6I(p, q) : L6I(q, p)];
-      }
-#undef L6I
+      const bool pok = wide_pivot_inverse(h, J, Wsm, lane);
+      if (lane == 0 && !pok) bcast[0] = 1.0;
     }
     __syncthreads();
-    // panel rows P_I = A_IJ W (original rows kept in shared memory), u_J = W b_J
-    for (int t = tid; t < 6 * nb + 6; t += WIDE_NT) {
-      if (t < 6 * nb) {
-        const int bI = t / 6, p = t - 6 * bI, I = J + 1 + bI;
-        double* a = h.S + (size_t)(6 * I + p) * n + 6 * J;
-        double av[6], pv[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) av[k] = a[k];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) pv[q] = (av[0] * Wsm[q] + av[1] * Wsm[6 + q] + av[2] * Wsm[12 + q]) + (av[3] * Wsm[18 + q] + av[4] * Wsm[24 + q] + av[5] * Wsm[30 + q]);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) { pan[36 * bI + 6 * p + k] = av[k]; a[k] = pv[k]; }
-      } else {
-        const int q = t - 6 * nb;
-        double sacc = 0.0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) sacc += h.yc[6 * J + k] * Wsm[6 * k + q];
-        h.ub[6 * J + q] = sacc;
-      }
-    }
-    __syncthreads();
-    // trailing update A_IK -= P_I A_KJ^T (I >= K > J): a thread owns row p of a block; b_I -= P_I b_J
+    SPHASE(0)
+    const double* bJ = h.yc + 6 * J;
     const int nrow = nb * (nb + 1) / 2 * 6;
-    for (int e = tid; e < nrow + 6 * nb; e += WIDE_NT) {
+    for (int e = c.gt; e < nrow + 6; e += c.gsize) {
       if (e < nrow) {
         const int blk = e / 6, p = e - 6 * blk;
         const int bi = tri[blk] >> 8, bk = tri[blk] & 0xff;
         const int I = J + 1 + bi, K = J + 1 + bk;
-        const double* pi = h.S + (size_t)(6 * I + p) * n + 6 * J;
-        const double* ak = pan + 36 * bk;
+        const double* ai = h.S + (size_t)(6 * I + p) * n + 6 * J;
         double* dst = h.S + (size_t)(6 * I + p) * n + 6 * K;
-        double a6[6];
+        // every load first (one L2 round trip for all of them), then the arithmetic, then the stores: the arrays may alias
+        // as far as the compiler knows, and a store in between would serialise the round trips
+        double av[6], pv[6], o[6], akv[36], bv[6], ycv = 0.0;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) a6[k] = pi[k];
+        for (int k = 0; k < 6; ++k) { av[k] = ai[k]; o[k] = dst[k]; }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const double* ak = h.S + (size_t)(6 * K + q) * n + 6 * J;      // row q of the unscaled block (K, J)
+#pragma unroll
+          for (int k = 0; k < 6; ++k) akv[6 * q + k] = ak[k];
+        }
+        if (bk == 0) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) bv[k] = bJ[k];
+          ycv = h.yc[6 * I + p];
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) pv[q] = (av[0] * Wsm[q] + av[1] * Wsm[6 + q] + av[2] * Wsm[12 + q]) + (av[3] * Wsm[18 + q] + av[4] * Wsm[24 + q] + av[5] * Wsm[30 + q]);
 #pragma unroll
         for (int q = 0; q < 6; ++q)
-          dst[q] -= (a6[0] * ak[6 * q] + a6[1] * ak[6 * q + 1] + a6[2] * ak[6 * q + 2]) + (a6[3] * ak[6 * q + 3] + a6[4] * ak[6 * q + 4] + a6[5] * ak[6 * q + 5]);
+          o[q] -= (pv[0] * akv[6 * q] + pv[1] * akv[6 * q + 1] + pv[2] * akv[6 * q + 2]) + (pv[3] * akv[6 * q + 3] + pv[4] * akv[6 * q + 4] + pv[5] * akv[6 * q + 5]);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) dst[q] = o[q];
+        if (bk == 0) {
+          double* pdst = h.P + (size_t)(6 * I + p) * n + 6 * J;
+          double sacc = 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { pdst[k] = pv[k]; sacc += pv[k] * bv[k]; }
+          h.yc[6 * I + p] = ycv - sacc;
+        }
       } else {
-        const int rI = e - nrow, bI = rI / 6, p = rI - 6 * bI, I = J + 1 + bI;
-        const double* pi = h.S + (size_t)(6 * I + p) * n + 6 * J;
+        const int q = e - nrow;                      // u_J = W_J b_J
         double sacc = 0.0;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) sacc += pi[k] * h.yc[6 * J + k];
-        h.yc[6 * I + p] -= sacc;
+        for (int k = 0; k < 6; ++k) sacc += bJ[k] * Wsm[6 * k + q];
+        h.ub[6 * J + q] = sacc;
       }
     }
-    __syncthreads();
+    SPHASE(1)
+    wide_sync(c);
+    SPHASE(2)
   }
+#ifdef SLSLAM_WIDE_PHASES
+  if (c.gt == 0) printf("  solve: inverse %lld  items %lld  barrier %lld (cycles, %d columns)\n", sp[0], sp[1], sp[2], Cf);
+#endif
+#undef SPHASE
   const bool ok = bcast[0] == 0.0;
-  // back-substitution (warp 0): y_J = u_J - acc_J, acc_K += P_JK^T y_J for K < J
-  if (warp == 0 && ok) {
-    for (int J = Cf - 1; J >= 0; --J) {
-      double y[6];
+  // back-substitution by CTA 0: y_J = u_J - acc_J, acc_K += P_JK^T y_J for K < J.  u and acc live in shared memory
+  // meanwhile; thread e owns entry (K, q) = (e / 6, e % 6) (and e + WIDE_NT), and the P values of the next column are
+  // loaded while the current one is being applied, so the dependent chain runs through shared memory only
+  if (c.rank == 0 && ok) {
+    double* ubs = c.sh;              // [n]  (the reduction scratch is free here: 2 n <= 12 * WIDE_MAX_FREE <= WIDE_NT * WIDE_NPART)
+    double* abs_ = c.sh + n;         // [n]
+    for (int i = tid; i < n; i += WIDE_NT) { ubs[i] = h.ub[i]; abs_[i] = 0.0; }
+    const int e0 = tid, e1 = tid + WIDE_NT;
+    const int K0 = e0 / 6, q0 = e0 - 6 * K0, K1 = e1 / 6, q1 = e1 - 6 * K1;
+    double pa[6], pb[6];
+    auto fetch = [&](int J) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) y[k] = h.ub[6 * J + k] - h.ab[6 * J + k];
-      __syncwarp();
-      if (lane < 6) h.yc[6 * J + lane] = h.ub[6 * J + lane] - h.ab[6 * J + lane];
-      for (int e = lane; e < 6 * J; e += 32) {
-        const int K = e / 6, q = e - 6 * K;
+      for (int k = 0; k < 6; ++k) {
+        pa[k] = (J >= 0 && e0 < 6 * J) ? h.P[(size_t)(6 * J + k) * n + 6 * K0 + q0] : 0.0;
+        pb[k] = (J >= 0 && e1 < 6 * J) ? h.P[(size_t)(6 * J + k) * n + 6 * K1 + q1] : 0.0;
+      }
+    };
+    fetch(Cf - 1);
+    __syncthreads();
+    for (int J = Cf - 1; J >= 0; --J) {
+      double y[6], ca[6], cb[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { y[k] = ubs[6 * J + k] - abs_[6 * J + k]; ca[k] = pa[k]; cb[k] = pb[k]; }
+      fetch(J - 1);
+      __syncthreads();               // everybody has read u_J and acc_J
+      if (tid < 6) ubs[6 * J + tid] = (tid == 0 ? y[0] : tid == 1 ? y[1] : tid == 2 ? y[2] : tid == 3 ? y[3] : tid == 4 ? y[4] : y[5]);
+      if (e0 < 6 * J) {
         double sacc = 0.0;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) sacc += h.S[(size_t)(6 * J + k) * n + 6 * K + q] * y[k];
-        h.ab[6 * K + q] += sacc;
+        for (int k = 0; k < 6; ++k) sacc += ca[k] * y[k];
+        abs_[e0] += sacc;
       }
-      __syncwarp();
+      if (e1 < 6 * J) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sacc += cb[k] * y[k];
+        abs_[e1] += sacc;
+      }
+      __syncthreads();
     }
+    for (int i = tid; i < n; i += WIDE_NT) h.yc[i] = ubs[i];     // y over u
   }
-  __syncthreads();
+  wide_sync(c);
   return ok;
 }
 
@@ -330,8 +381,7 @@ __device__ bool wide_reduced_solve(const WideHdr& h, double inv_radius, double* 
 // groups, ... (every window has its own barrier counter and partial-sum slots)
 __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __restrict__ hdrs, int nwin, int G) {
   extern __shared__ __align__(16) double wsm[];
-  double* pan = wsm + WIDE_NPART * WIDE_NT;       // [WIDE_MAX_FREE][36] original panel rows of the current block column
-  double* Wsm = pan + WIDE_MAX_FREE * 36;         // [36] pivot inverse
+  double* Wsm = wsm + WIDE_NPART * WIDE_NT;       // [36] pivot inverse
   double* bcast = Wsm + 36;                       // [16] broadcast scalars
   int* tri = reinterpret_cast<int*>(bcast + 16);  // block of a lower block triangle -> row << 8 | column
   for (int k = threadIdx.x; k < WIDE_MAX_FREE * (WIDE_MAX_FREE + 1) / 2; k += WIDE_NT) {
@@ -403,6 +453,17 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
   double radius = h.radius0, decrease_factor = 2.0, gmax = 0.0, gtol_abs = 0.0;
   int successful = 0, unsuccessful = 0, invalid = 0, term = SLSLAM_NO_CONVERGENCE, iters = 0;
   bool first_lin = true, grad_pending = false;
+#ifdef SLSLAM_WIDE_PHASES
+  {
+    const long long b0 = clock64();
+    for (int k = 0; k < 20; ++k) wide_sync(c);
+    if (c.gt == 0) printf("wide_sync: %lld cycles each (G = %d)\n", (clock64() - b0) / 20, c.G);
+  }
+  long long wph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, wt0 = clock64();
+#define WPHASE(i) { const long long now_ = clock64(); wph[i] += now_ - wt0; wt0 = now_; }
+#else
+#define WPHASE(i)
+#endif
   for (int it = 0; it <= h.max_iters; ++it) {
     const bool last = it == h.max_iters;
     if (last && !grad_pending) break;
@@ -417,6 +478,7 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
       wide_group_reduce<1>(c, h, v, 0u);          // (the barrier inside also publishes r, Jc, Jl)
       cost = v[0];
     }
+    WPHASE(0)
     // ---- lines: H_ll, g_l, LM diagonal, Cholesky, u; Z per observation; line part of the gradient norm ----
     double gm = 0.0, failf = 0.0;
     const double inv_radius = 1.0 / radius;
@@ -470,9 +532,14 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
         for (int k = 0; k < 4; ++k) gm = fmax(gm, fabs(hg[10 + k] / h.lscale[4 * (size_t)l + k]));
       }
       for (int s = s0 + lane; s < s1; s += 32) {
-        const double* Jc = h.Jc + 24 * (size_t)s;
-        const double* Jl = h.Jl + 16 * (size_t)s;
+        const double* Jcp = h.Jc + 24 * (size_t)s;
+        const double* Jlp = h.Jl + 16 * (size_t)s;
         double* Zo = h.Z + 24 * (size_t)s;
+        double Jc[24], Jl[16], Zv[24];           // loads first, stores last (see the reduced solve)
+#pragma unroll
+        for (int k = 0; k < 24; ++k) Jc[k] = Jcp[k];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) Jl[k] = Jlp[k];
 #pragma unroll
         for (int p = 0; p < 6; ++p) {
           double W[4];
@@ -482,8 +549,10 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
           const double z1 = (W[1] - z0 * Lm[1]) * inv[1];
           const double z2 = (W[2] - z0 * Lm[3] - z1 * Lm[4]) * inv[2];
           const double z3 = (W[3] - z0 * Lm[6] - z1 * Lm[7] - z2 * Lm[8]) * inv[3];
-          Zo[4 * p] = z0; Zo[4 * p + 1] = z1; Zo[4 * p + 2] = z2; Zo[4 * p + 3] = z3;
+          Zv[4 * p] = z0; Zv[4 * p + 1] = z1; Zv[4 * p + 2] = z2; Zv[4 * p + 3] = z3;
         }
+#pragma unroll
+        for (int k = 0; k < 24; ++k) Zo[k] = Zv[k];
       }
     }
     // constant lines: their observations have Jl = 0, no Schur term: Z = 0
@@ -496,59 +565,90 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
       wide_group_reduce<2>(c, h, v, 3u);          // (publishes Z and lineLU)
       line_fail = v[0] != 0.0; gm = v[1];
     }
-    // ---- cameras: diagonal blocks, g_c, Z u, diag H_cc ----
-    for (int i = c.gt; i < Cf * 39; i += c.gsize) {
-      const int f = i / 39, e = i - 39 * f;
-      double acc = 0.0;
-      int p = 0, q = 0;
-      if (e < 21) { while ((p + 1) * (p + 2) / 2 <= e) ++p; q = e - p * (p + 1) / 2; }
-      else p = (e - 21) % 6;
-      for (int t = h.cam_start[f]; t < h.cam_start[f + 1]; ++t) {
+    WPHASE(1)
+    // ---- cameras: diagonal blocks, g_c, Z u, diag H_cc.  Warp per free camera, lanes over its observations, transposing
+    // warp reduction (lane k ends up with accumulator k) ----
+    for (int f = c.gw; f < Cf; f += c.gwarps) {
+      double acc[39];
+#pragma unroll
+      for (int k = 0; k < 39; ++k) acc[k] = 0.0;
+      for (int t = h.cam_start[f] + lane; t < h.cam_start[f + 1]; t += 32) {
         const int s = h.cam_obs[t];
-        const double* Jc = h.Jc + 24 * (size_t)s;
-        const double* Z = h.Z + 24 * (size_t)s;
-        if (e < 21) {
-          acc += Jc[p] * Jc[q] + Jc[6 + p] * Jc[6 + q] + Jc[12 + p] * Jc[12 + q] + Jc[18 + p] * Jc[18 + q]
-                 - (Z[4 * p] * Z[4 * q] + Z[4 * p + 1] * Z[4 * q + 1] + Z[4 * p + 2] * Z[4 * q + 2] + Z[4 * p + 3] * Z[4 * q + 3]);
-        } else if (e < 27) {
-          const double* r = h.r + 4 * (size_t)s;
-          acc += Jc[p] * r[0] + Jc[6 + p] * r[1] + Jc[12 + p] * r[2] + Jc[18 + p] * r[3];
-        } else if (e < 33) {
-          const int l = h.line_s[s];
-          if (h.line_free[l]) {
-            const double* u = h.lineLU + 22 * (size_t)l + 10;
-            acc += Z[4 * p] * u[0] + Z[4 * p + 1] * u[1] + Z[4 * p + 2] * u[2] + Z[4 * p + 3] * u[3];
-          }
-        } else {
-          acc += Jc[p] * Jc[p] + Jc[6 + p] * Jc[6 + p] + Jc[12 + p] * Jc[12 + p] + Jc[18 + p] * Jc[18 + p];
+        const double* Jcp = h.Jc + 24 * (size_t)s;
+        const double* Zp = h.Z + 24 * (size_t)s;
+        const double* rp = h.r + 4 * (size_t)s;
+        double Jc[24], Z[24], r[4], u[4];
+#pragma unroll
+        for (int k = 0; k < 24; ++k) { Jc[k] = Jcp[k]; Z[k] = Zp[k]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r[k] = rp[k];
+        const int l = h.line_s[s];
+        const bool lf = h.line_free[l] != 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = lf ? h.lineLU[22 * (size_t)l + 10 + k] : 0.0;
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+#pragma unroll
+          for (int q = 0; q <= p; ++q)
+            acc[p * (p + 1) / 2 + q] += Jc[p] * Jc[q] + Jc[6 + p] * Jc[6 + q] + Jc[12 + p] * Jc[12 + q] + Jc[18 + p] * Jc[18 + q]
+                                        - (Z[4 * p] * Z[4 * q] + Z[4 * p + 1] * Z[4 * q + 1] + Z[4 * p + 2] * Z[4 * q + 2] + Z[4 * p + 3] * Z[4 * q + 3]);
+          acc[21 + p] += Jc[p] * r[0] + Jc[6 + p] * r[1] + Jc[12 + p] * r[2] + Jc[18 + p] * r[3];
+          acc[27 + p] += Z[4 * p] * u[0] + Z[4 * p + 1] * u[1] + Z[4 * p + 2] * u[2] + Z[4 * p + 3] * u[3];
+          acc[33 + p] += Jc[p] * Jc[p] + Jc[6 + p] * Jc[6 + p] + Jc[12 + p] * Jc[12 + p] + Jc[18 + p] * Jc[18 + p];
         }
       }
-      if (e < 21) { h.S[(size_t)(6 * f + p) * n + 6 * f + q] = acc; h.S[(size_t)(6 * f + q) * n + 6 * f + p] = acc; }
-      else if (e < 27) h.gc[6 * f + p] = acc;
-      else if (e < 33) h.zu[6 * f + p] = acc;
-      else h.hd[6 * f + p] = acc;
+      double tail[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) tail[k] = warp_sum(acc[32 + k]);
+      warp_reduce_scatter32(acc, lane);
+      const double tot = acc[0];                 // accumulator `lane`
+      if (lane < 21) {
+        int p = 0; while ((p + 1) * (p + 2) / 2 <= lane) ++p;
+        const int q = lane - p * (p + 1) / 2;
+        h.S[(size_t)(6 * f + p) * n + 6 * f + q] = tot; h.S[(size_t)(6 * f + q) * n + 6 * f + p] = tot;
+      } else if (lane < 27) h.gc[6 * f + lane - 21] = tot;
+      else h.zu[6 * f + lane - 27] = tot;        // lanes 27..31: entries 0..4
+      if (lane == 0) {
+        h.zu[6 * f + 5] = tail[0];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) h.hd[6 * f + k] = tail[1 + k];
+      }
     }
-    // ---- pairs: off-diagonal blocks (I > K) ----
+    // ---- pairs: off-diagonal blocks (I > K).  Warp per block, lanes over the lines (lookup table line x free camera) ----
     if (!last) {
       const int nblk = Cf * (Cf - 1) / 2;
-      for (int i = c.gt; i < nblk * 36; i += c.gsize) {
-        const int b = i / 36, pq = i - 36 * b, p = pq / 6, q = pq - 6 * p;
-        int I = 1; while (I * (I + 1) / 2 <= b) ++I;          // b = I (I - 1) / 2 + K, K < I
-        const int K = b - I * (I - 1) / 2;
-        double acc = 0.0;
-        for (int l = 0; l < L; ++l) {
-          const int sa = h.pos[(size_t)l * Cf + I];
-          if (sa < 0) continue;
-          const int sb = h.pos[(size_t)l * Cf + K];
-          if (sb < 0) continue;
-          const double* Za = h.Z + 24 * (size_t)sa + 4 * p;
-          const double* Zb = h.Z + 24 * (size_t)sb + 4 * q;
-          acc += Za[0] * Zb[0] + Za[1] * Zb[1] + Za[2] * Zb[2] + Za[3] * Zb[3];
+      for (int b = c.gw; b < nblk; b += c.gwarps) {
+        const int I = (tri[b] >> 8) + 1, K = tri[b] & 0xff;      // b = I (I - 1) / 2 + K, K < I
+        double acc[36];
+#pragma unroll
+        for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+        for (int l = lane; l < L; l += 32) {
+          const int sa = h.pos[(size_t)l * Cf + I], sb = h.pos[(size_t)l * Cf + K];
+          if (sa < 0 || sb < 0) continue;
+          const double* Zap = h.Z + 24 * (size_t)sa;
+          const double* Zbp = h.Z + 24 * (size_t)sb;
+          double Za[24], Zb[24];
+#pragma unroll
+          for (int k = 0; k < 24; ++k) { Za[k] = Zap[k]; Zb[k] = Zbp[k]; }
+#pragma unroll
+          for (int p = 0; p < 6; ++p)
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+              acc[6 * p + q] += Za[4 * p] * Zb[4 * q] + Za[4 * p + 1] * Zb[4 * q + 1] + Za[4 * p + 2] * Zb[4 * q + 2] + Za[4 * p + 3] * Zb[4 * q + 3];
         }
-        h.S[(size_t)(6 * I + p) * n + 6 * K + q] = -acc;
+        double tail[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tail[k] = warp_sum(acc[32 + k]);
+        warp_reduce_scatter32(acc, lane);
+        {
+          const int p = lane / 6, q = lane - 6 * p;
+          h.S[(size_t)(6 * I + p) * n + 6 * K + q] = -acc[0];
+        }
+        if (lane < 4) h.S[(size_t)(6 * I + 5) * n + 6 * K + 2 + lane] = -(lane == 0 ? tail[0] : lane == 1 ? tail[1] : lane == 2 ? tail[2] : tail[3]);
       }
     }
     wide_sync(c);
+    WPHASE(2)
     // ---- gradient max norm (unscaled Jacobian), |x|^2 of the free blocks: the same on every CTA, no exchange ----
     double x_norm2;
     {
@@ -567,13 +667,25 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
     iters = it + 1;
     double* tr = (h.trace && c.gt == 0) ? h.trace + (size_t)it * SLSLAM_TRACE_WIDTH : nullptr;
     if (tr) { tr[0] = cost; tr[1] = 0; tr[2] = 0; tr[3] = radius; tr[4] = 0; tr[5] = 0; tr[6] = gmax; tr[7] = 0; }
-    // ---- reduced solve by CTA 0 of the group ----
-    if (c.rank == 0) {
-      const bool sok = wide_reduced_solve(h, inv_radius, pan, Wsm, bcast, tri);
-      if (tid == 0) *h.flag = sok ? 0.0 : 1.0;
+    WPHASE(3)
+    // ---- reduced solve by the whole group (the pivot test is evaluated identically on every CTA) ----
+#ifdef SLSLAM_WIDE_SOLO_SOLVE
+    bool sok;
+    {
+      WideCtx solo = c;
+      solo.G = 1; solo.gt = c.tid; solo.gsize = WIDE_NT; solo.gw = c.warp; solo.gwarps = WIDE_NT / 32;
+      if (c.rank == 0) {
+        const bool r0 = wide_reduced_solve(solo, h, inv_radius, Wsm, bcast, tri);
+        if (tid == 0) *h.flag = r0 ? 0.0 : 1.0;
+      }
+      wide_sync(c);
+      sok = __ldcg(h.flag) == 0.0;
     }
-    wide_sync(c);
-    bool ok = !line_fail && __ldcg(h.flag) == 0.0;
+#else
+    const bool sok = wide_reduced_solve(c, h, inv_radius, Wsm, bcast, tri);
+#endif
+    WPHASE(4)
+    bool ok = !line_fail && sok;
     // camera part of the model decrease, |delta|^2, finiteness (the same on every CTA)
     double model = 0.0, dn2 = 0.0;
     {
@@ -650,12 +762,14 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
         wide_group_reduce<2>(c, h, v, 0u);        // (publishes the trial cameras and lines)
         model += v[0]; dn2 += v[1];
       }
+      WPHASE(5)
       wide_sweep<2>(c, h, camRt, ltrigt, &pc, &pf);
       {
         double v[1] = {pc};
         wide_group_reduce<1>(c, h, v, 0u);
         new_cost = v[0];
       }
+      WPHASE(6)
     }
     if (tr) tr[2] = model;
     if (!ok || model < 0.0) {
@@ -690,6 +804,11 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
     }
     if (radius < 1e-32) { term = SLSLAM_PARAMETER_TOLERANCE; break; }
   }
+#ifdef SLSLAM_WIDE_PHASES
+  if (c.gt == 0) printf("wide phases (cycles, %d iterations, G=%d): linearise %lld  lines %lld  cameras+pairs %lld  gradient %lld  solve %lld  trial point %lld  trial sweep %lld\n",
+                        iters, c.G, wph[0], wph[1], wph[2], wph[3], wph[4], wph[5], wph[6]);
+#endif
+#undef WPHASE
   // ---- write back: blocks no observation touches keep their input bits (the host pre-copies the input) ----
   wide_sync(c);
   for (int i = c.gt; i < 6 * C; i += c.gsize) h.params_out[i] = h.camx[cur][i];
