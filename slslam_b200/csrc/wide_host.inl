@@ -145,7 +145,15 @@ static int wide_solve_batch(int n, const slslam_lba_desc* descs, double* const* 
     memcpy(host + o[i].par, params_inout[i], 8 * np[i]);
   }
   const double t1 = now_ms();
-  const size_t smem = (size_t)(WIDE_NPART * WIDE_NT + 36 + 16) * 8 + (size_t)(WIDE_MAX_FREE * (WIDE_MAX_FREE + 1) / 2) * 4;
+  const size_t smem = (size_t)(WIDE_NPART * WIDE_NT + 36 + 16 + (WIDE_MAX_FREE * (WIDE_MAX_FREE + 1) / 2 + 1) / 2 +
+                               WIDE_TAIL_MAX * (WIDE_TAIL_MAX + 1) / 2 * 36 + (WIDE_TAIL_MAX - 1) * 36 + 12 * WIDE_TAIL_MAX) * 8;
+  {
+    static bool attr_set[16] = {false};
+    if (device >= 16 || !attr_set[device]) {
+      CUDA_TRY(cudaFuncSetAttribute(lba_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (device < 16) attr_set[device] = true;
+    }
+  }
   // group size: as many CTAs per window as stay co-resident with every window of the call (cooperative launch: the
   // group barrier spins), at most WIDE_MAX_G; more windows than SMs run in waves of one CTA each
   static int wide_cap[16] = {0};

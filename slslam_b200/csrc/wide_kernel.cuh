@@ -194,17 +194,16 @@ __device__ __forceinline__ double wide_warp_sum(double v) {
   return v;
 }
 
-// W = A^-1 of the 6x6 pivot block J of S (lower triangle read from global memory) by one warp, all lanes the same values;
+// W = A^-1 of a 6x6 pivot block (lower triangle read from A0, row stride ld) by one warp, all lanes the same values;
 // lane 0 stores W (full, symmetric) to shared memory.  false when the block is not positive definite.
-__device__ __forceinline__ bool wide_pivot_inverse(const WideHdr& h, int J, double* Wsm, int lane) {
-  const int n = h.n;
+__device__ __forceinline__ bool wide_pivot_inverse(const double* A0, size_t ld, double* Wsm, int lane) {
   double A[21], Ai[6], Si[6], M[9], S3[6], W[21];
 #define L6I(p, q) ((p) * ((p) + 1) / 2 + (q))
 #define SY3(mm, r, cc) mm[(r) <= (cc) ? ((r) == 0 ? (cc) : (r) == 1 ? 2 + (cc) : 5) : ((cc) == 0 ? (r) : (cc) == 1 ? 2 + (r) : 5)]
 #pragma unroll
   for (int p = 0; p < 6; ++p)
 #pragma unroll
-    for (int q = 0; q <= p; ++q) A[L6I(p, q)] = h.S[(size_t)(6 * J + p) * n + 6 * J + q];
+    for (int q = 0; q <= p; ++q) A[L6I(p, q)] = A0[(size_t)p * ld + q];
   bool ok = spd3_inverse(A[L6I(0, 0)], A[L6I(1, 0)], A[L6I(2, 0)], A[L6I(1, 1)], A[L6I(2, 1)], A[L6I(2, 2)], Ai);
 #pragma unroll
   for (int r = 0; r < 3; ++r)
@@ -245,13 +244,102 @@ __device__ __forceinline__ bool wide_pivot_inverse(const WideHdr& h, int J, doub
   return ok;
 }
 
+constexpr int WIDE_TAIL_MAX = 24;    // the last block columns, whose trailing matrix (lower block triangle, 24 * 25 / 2 blocks = 86 KB) is kept in
+                                     // shared memory: big columns are cheaper spread over the group, small ones without barriers and L2 trips
+
+// The last m <= WIDE_TAIL_MAX block columns of the elimination by ONE CTA with the trailing matrix in shared memory (packed
+// lower block triangle): no group barrier and no L2 round trip per column any more.  Panel rows are scaled in place, their
+// unscaled copies kept in `pan` for the trailing update, and also written to P in global memory for the back-substitution;
+// right-hand side and u in shared memory, copied back at the end.  Returns false when a pivot block is not positive.
+__device__ bool wide_solve_tail(const WideHdr& h, int c0, double* T, double* pan, double* ycs, double* ubs, double* Wsm, const int* tri) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Cf = h.Cf, n = h.n, m = Cf - c0;
+  bool ok = true;
+  for (int i = tid; i < m * (m + 1) / 2 * 36; i += WIDE_NT) {
+    const int blk = i / 36, pq = i - 36 * blk, p = pq / 6, q = pq - 6 * p;
+    const int bi = tri[blk] >> 8, bk = tri[blk] & 0xff;
+    T[i] = h.S[(size_t)(6 * (c0 + bi) + p) * n + 6 * (c0 + bk) + q];
+  }
+  for (int i = tid; i < 6 * m; i += WIDE_NT) ycs[i] = h.yc[6 * c0 + i];
+  __syncthreads();
+  for (int Jl = 0; Jl < m; ++Jl) {
+    const int nb = m - Jl - 1, J = c0 + Jl;
+    double* AJJ = T + (Jl * (Jl + 1) / 2 + Jl) * 36;
+    if (warp == 0) {
+      const bool pok = wide_pivot_inverse(AJJ, 6, Wsm, lane);
+      ok = ok && pok;
+    }
+    __syncthreads();
+    for (int t = tid; t < 6 * nb + 6; t += WIDE_NT) {
+      if (t < 6 * nb) {
+        const int bI = t / 6, p = t - 6 * bI, Il = Jl + 1 + bI;
+        double* a = T + (Il * (Il + 1) / 2 + Jl) * 36 + 6 * p;
+        double av[6], pv[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) av[k] = a[k];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) pv[q] = (av[0] * Wsm[q] + av[1] * Wsm[6 + q] + av[2] * Wsm[12 + q]) + (av[3] * Wsm[18 + q] + av[4] * Wsm[24 + q] + av[5] * Wsm[30 + q]);
+        double* pg = h.P + (size_t)(6 * (c0 + Il) + p) * n + 6 * J;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { pan[36 * bI + 6 * p + k] = av[k]; a[k] = pv[k]; pg[k] = pv[k]; }
+      } else {
+        const int q = t - 6 * nb;
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sacc += ycs[6 * Jl + k] * Wsm[6 * k + q];
+        ubs[6 * Jl + q] = sacc;
+      }
+    }
+    __syncthreads();
+    const int nrow = nb * (nb + 1) / 2 * 6;
+    for (int e = tid; e < nrow + 6 * nb; e += WIDE_NT) {
+      if (e < nrow) {
+        const int blk = e / 6, p = e - 6 * blk;
+        const int bi = tri[blk] >> 8, bk = tri[blk] & 0xff;
+        const int Il = Jl + 1 + bi, Kl = Jl + 1 + bk;
+        const double* pi = T + (Il * (Il + 1) / 2 + Jl) * 36 + 6 * p;
+        const double* ak = pan + 36 * bk;
+        double* dst = T + (Il * (Il + 1) / 2 + Kl) * 36 + 6 * p;
+        double a6[6], o[6];
+        const double2* pi2 = reinterpret_cast<const double2*>(pi);
+        const double2* ak2 = reinterpret_cast<const double2*>(ak);
+        double2* dst2 = reinterpret_cast<double2*>(dst);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const double2 t0 = pi2[k], t1 = dst2[k]; a6[2 * k] = t0.x; a6[2 * k + 1] = t0.y; o[2 * k] = t1.x; o[2 * k + 1] = t1.y; }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const double2 k0 = ak2[3 * q], k1 = ak2[3 * q + 1], k2 = ak2[3 * q + 2];
+          o[q] -= (a6[0] * k0.x + a6[1] * k0.y + a6[2] * k1.x) + (a6[3] * k1.y + a6[4] * k2.x + a6[5] * k2.y);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dst2[k] = make_double2(o[2 * k], o[2 * k + 1]);
+      } else {
+        const int rI = e - nrow, bI = rI / 6, p = rI - 6 * bI, Il = Jl + 1 + bI;
+        const double* pi = T + (Il * (Il + 1) / 2 + Jl) * 36 + 6 * p;
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sacc += pi[k] * ycs[6 * Jl + k];
+        ycs[6 * Il + p] -= sacc;
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < 6 * m; i += WIDE_NT) { h.ub[6 * c0 + i] = ubs[i]; h.yc[6 * c0 + i] = ycs[i]; }
+  // every lane of warp 0 saw the same pivots; hand the verdict to the whole CTA
+  if (tid == 0) Wsm[0] = ok ? 0.0 : 1.0;
+  __syncthreads();
+  const bool all_ok = Wsm[0] == 0.0;
+  __syncthreads();
+  return all_ok;
+}
+
 // Reduced solve (S + D_c) y = g_c - sum Z u by the whole group: right-looking block elimination in global memory (L2) with
 // explicit 6x6 pivot inverses.  Per block column J ONE group barrier: every CTA inverts the pivot block itself (same
 // bits), then the rows of the trailing blocks (I, K), I >= K > J, are strided over all threads of the group; a thread
 // recomputes its scaled panel row P_I[p,:] = A_IJ[p,:] W_J (36 FMAs) rather than wait for it, the column-J blocks of S
 // stay unscaled (so nobody reads what another thread overwrites), and the owner of block (I, J+1) stores the panel row
 // to P and updates the right-hand side row.  Back-substitution without solves by one warp: y_J = u_J - sum P_IJ^T y_I.
-__device__ bool wide_reduced_solve(WideCtx& c, const WideHdr& h, double inv_radius, double* Wsm, double* bcast, const int* tri) {
+__device__ bool wide_reduced_solve(WideCtx& c, const WideHdr& h, double inv_radius, double* Wsm, double* bcast, const int* tri, double* tail_sm) {
   const int tid = c.tid, lane = c.lane, warp = c.warp;
   const int Cf = h.Cf, n = h.n;
   for (int i = c.gt; i < n; i += c.gsize) {
@@ -267,10 +355,12 @@ __device__ bool wide_reduced_solve(WideCtx& c, const WideHdr& h, double inv_radi
 #else
 #define SPHASE(i)
 #endif
-  for (int J = 0; J < Cf; ++J) {
+  // the first c0 block columns by the whole group in global memory, the rest (<= WIDE_TAIL_MAX) by CTA 0 in shared memory
+  const int c0 = Cf > WIDE_TAIL_MAX ? Cf - WIDE_TAIL_MAX : 0;
+  for (int J = 0; J < c0; ++J) {
     const int nb = Cf - J - 1;
     if (warp == 0) {
-      const bool pok = wide_pivot_inverse(h, J, Wsm, lane);
+      const bool pok = wide_pivot_inverse(h.S + (size_t)(6 * J) * n + 6 * J, (size_t)n, Wsm, lane);
       if (lane == 0 && !pok) bcast[0] = 1.0;
     }
     __syncthreads();
@@ -330,7 +420,16 @@ __device__ bool wide_reduced_solve(WideCtx& c, const WideHdr& h, double inv_radi
   if (c.gt == 0) printf("  solve: inverse %lld  items %lld  barrier %lld (cycles, %d columns)\n", sp[0], sp[1], sp[2], Cf);
 #endif
 #undef SPHASE
-  const bool ok = bcast[0] == 0.0;
+  if (c.rank == 0) {
+    double* T = tail_sm;                                             // [TAIL (TAIL + 1) / 2][36]
+    double* pan = T + WIDE_TAIL_MAX * (WIDE_TAIL_MAX + 1) / 2 * 36;    // [TAIL - 1][36]
+    double* ycs = pan + (WIDE_TAIL_MAX - 1) * 36;                    // [6 TAIL]
+    double* ubs = ycs + 6 * WIDE_TAIL_MAX;                           // [6 TAIL]
+    const bool tok = wide_solve_tail(h, c0, T, pan, ycs, ubs, Wsm, tri);
+    if (tid == 0) *h.flag = (tok && bcast[0] == 0.0) ? 0.0 : 1.0;
+  }
+  wide_sync(c);
+  const bool ok = c.G == 1 ? (*h.flag == 0.0) : (__ldcg(h.flag) == 0.0);
   // back-substitution by CTA 0: y_J = u_J - acc_J, acc_K += P_JK^T y_J for K < J.  u and acc live in shared memory
   // meanwhile; thread e owns entry (K, q) = (e / 6, e % 6) (and e + WIDE_NT), and the P values of the next column are
   // loaded while the current one is being applied, so the dependent chain runs through shared memory only
@@ -384,6 +483,7 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
   double* Wsm = wsm + WIDE_NPART * WIDE_NT;       // [36] pivot inverse
   double* bcast = Wsm + 36;                       // [16] broadcast scalars
   int* tri = reinterpret_cast<int*>(bcast + 16);  // block of a lower block triangle -> row << 8 | column
+  double* tail_sm = bcast + 16 + (WIDE_MAX_FREE * (WIDE_MAX_FREE + 1) / 2 + 1) / 2;   // trailing matrix of the reduced solve
   for (int k = threadIdx.x; k < WIDE_MAX_FREE * (WIDE_MAX_FREE + 1) / 2; k += WIDE_NT) {
     int I = 0;
     while ((I + 1) * (I + 2) / 2 <= k) ++I;
@@ -675,14 +775,14 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
       WideCtx solo = c;
       solo.G = 1; solo.gt = c.tid; solo.gsize = WIDE_NT; solo.gw = c.warp; solo.gwarps = WIDE_NT / 32;
       if (c.rank == 0) {
-        const bool r0 = wide_reduced_solve(solo, h, inv_radius, Wsm, bcast, tri);
+        const bool r0 = wide_reduced_solve(solo, h, inv_radius, Wsm, bcast, tri, tail_sm);
         if (tid == 0) *h.flag = r0 ? 0.0 : 1.0;
       }
       wide_sync(c);
       sok = __ldcg(h.flag) == 0.0;
     }
 #else
-    const bool sok = wide_reduced_solve(c, h, inv_radius, Wsm, bcast, tri);
+    const bool sok = wide_reduced_solve(c, h, inv_radius, Wsm, bcast, tri, tail_sm);
 #endif
     WPHASE(4)
     bool ok = !line_fail && sok;
