@@ -128,6 +128,22 @@ __device__ __forceinline__ void wide_group_reduce(WideCtx& c, const WideHdr& h, 
   __syncthreads();
 }
 
+// 16-byte global loads / stores of rows of doubles (rows are 16-byte aligned): lanes read rows of their own, so every
+// load instruction touches 32 sectors; pairs of doubles halve the number of sector requests, which is what bounds the
+// row-gathering phases
+template <int NV>
+__device__ __forceinline__ void ld_row(const double* __restrict__ src, double* dst) {
+  const double2* s2 = reinterpret_cast<const double2*>(src);
+#pragma unroll
+  for (int k = 0; k < NV / 2; ++k) { const double2 t = s2[k]; dst[2 * k] = t.x; dst[2 * k + 1] = t.y; }
+}
+template <int NV>
+__device__ __forceinline__ void st_row(double* dst, const double* src) {
+  double2* d2 = reinterpret_cast<double2*>(dst);
+#pragma unroll
+  for (int k = 0; k < NV / 2; ++k) d2[k] = make_double2(src[2 * k], src[2 * k + 1]);
+}
+
 // CTA-local reduction (every CTA of the group holds the same data and gets the same bits): no exchange.
 template <int K>
 __device__ __forceinline__ void wide_block_reduce(WideCtx& c, double* v, unsigned int maxmask) {
@@ -165,8 +181,7 @@ __device__ void wide_sweep(const WideCtx& c, const WideHdr& h, const double* cR,
     LineTrig lt;
     line_trig_sc(ltr + 8 * (size_t)l, lt);
     double ob[8], r[4], Jc[24], Jl[16];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) ob[k] = h.obs_s[8 * (size_t)s + k];
+    ld_row<8>(h.obs_s + 8 * (size_t)s, ob);
     if (MODE == 2) obs_eval<false>(cR + CAM_STRIDE * (size_t)cam, lt, ob, h.baseline, r, nullptr, nullptr);
     else obs_eval<true>(cR + CAM_STRIDE * (size_t)cam, lt, ob, h.baseline, r, Jc, Jl);
     double w;
@@ -174,16 +189,17 @@ __device__ void wide_sweep(const WideCtx& c, const WideHdr& h, const double* cR,
     if (cf >= 0 || lfree) cost += 0.5 * rho; else fixed += 0.5 * rho;
     if (MODE == 2) continue;
     const double wc = cf >= 0 ? w : 0.0, wl = lfree ? w : 0.0;
-    double* Jco = h.Jc + 24 * (size_t)s;
-    double* Jlo = h.Jl + 16 * (size_t)s;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      h.r[4 * (size_t)s + k] = r[k] * w;
+      r[k] *= w;
 #pragma unroll
-      for (int j = 0; j < 6; ++j) Jco[6 * k + j] = Jc[6 * k + j] * wc * (MODE == 1 && cf >= 0 ? h.cscale[6 * cf + j] : 1.0);
+      for (int j = 0; j < 6; ++j) Jc[6 * k + j] = Jc[6 * k + j] * wc * (MODE == 1 && cf >= 0 ? h.cscale[6 * cf + j] : 1.0);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) Jlo[4 * k + j] = Jl[4 * k + j] * wl * (MODE == 1 ? h.lscale[4 * (size_t)l + j] : 1.0);
+      for (int j = 0; j < 4; ++j) Jl[4 * k + j] = Jl[4 * k + j] * wl * (MODE == 1 ? h.lscale[4 * (size_t)l + j] : 1.0);
     }
+    st_row<4>(h.r + 4 * (size_t)s, r);
+    st_row<24>(h.Jc + 24 * (size_t)s, Jc);
+    st_row<16>(h.Jl + 16 * (size_t)s, Jl);
   }
   *cost_out = cost; *fixed_out = fixed;
 }
@@ -495,7 +511,7 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
   c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
   c.G = G; c.rank = (int)(blockIdx.x % (unsigned)G);
   c.gt = c.rank * WIDE_NT + c.tid; c.gsize = G * WIDE_NT;
-  c.gw = c.rank * (WIDE_NT / 32) + c.warp; c.gwarps = G * (WIDE_NT / 32);
+  c.gw = c.warp * G + c.rank; c.gwarps = G * (WIDE_NT / 32);      // interleaved: consecutive warp-items land on different SMs
   const int tid = c.tid, lane = c.lane;
   const int groups = (int)(gridDim.x / (unsigned)G);
   for (int win = (int)(blockIdx.x / (unsigned)G); win < nwin; win += groups) {
@@ -589,8 +605,9 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
 #pragma unroll
       for (int k = 0; k < 14; ++k) hg[k] = 0.0;
       for (int s = s0 + lane; s < s1; s += 32) {
-        const double* J = h.Jl + 16 * (size_t)s;
-        const double* r = h.r + 4 * (size_t)s;
+        double J[16], r[4];
+        ld_row<16>(h.Jl + 16 * (size_t)s, J);
+        ld_row<4>(h.r + 4 * (size_t)s, r);
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
 #pragma unroll
@@ -636,10 +653,8 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
         const double* Jlp = h.Jl + 16 * (size_t)s;
         double* Zo = h.Z + 24 * (size_t)s;
         double Jc[24], Jl[16], Zv[24];           // loads first, stores last (see the reduced solve)
-#pragma unroll
-        for (int k = 0; k < 24; ++k) Jc[k] = Jcp[k];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) Jl[k] = Jlp[k];
+        ld_row<24>(Jcp, Jc);
+        ld_row<16>(Jlp, Jl);
 #pragma unroll
         for (int p = 0; p < 6; ++p) {
           double W[4];
@@ -651,13 +666,12 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
           const double z3 = (W[3] - z0 * Lm[6] - z1 * Lm[7] - z2 * Lm[8]) * inv[3];
           Zv[4 * p] = z0; Zv[4 * p + 1] = z1; Zv[4 * p + 2] = z2; Zv[4 * p + 3] = z3;
         }
-#pragma unroll
-        for (int k = 0; k < 24; ++k) Zo[k] = Zv[k];
+        st_row<24>(Zo, Zv);
       }
     }
     // constant lines: their observations have Jl = 0, no Schur term: Z = 0
     for (int s = c.gt; s < N; s += c.gsize) {
-      if (!h.line_free[h.line_s[s]]) { double* Zo = h.Z + 24 * (size_t)s; for (int k = 0; k < 24; ++k) Zo[k] = 0.0; }
+      if (!h.line_free[h.line_s[s]]) { double2* Zo = reinterpret_cast<double2*>(h.Z + 24 * (size_t)s); for (int k = 0; k < 12; ++k) Zo[k] = make_double2(0.0, 0.0); }
     }
     bool line_fail;
     {
@@ -678,10 +692,9 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
         const double* Zp = h.Z + 24 * (size_t)s;
         const double* rp = h.r + 4 * (size_t)s;
         double Jc[24], Z[24], r[4], u[4];
-#pragma unroll
-        for (int k = 0; k < 24; ++k) { Jc[k] = Jcp[k]; Z[k] = Zp[k]; }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) r[k] = rp[k];
+        ld_row<24>(Jcp, Jc);
+        ld_row<24>(Zp, Z);
+        ld_row<4>(rp, r);
         const int l = h.line_s[s];
         const bool lf = h.line_free[l] != 0;
 #pragma unroll
@@ -728,8 +741,8 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
           const double* Zap = h.Z + 24 * (size_t)sa;
           const double* Zbp = h.Z + 24 * (size_t)sb;
           double Za[24], Zb[24];
-#pragma unroll
-          for (int k = 0; k < 24; ++k) { Za[k] = Zap[k]; Zb[k] = Zbp[k]; }
+          ld_row<24>(Zap, Za);
+          ld_row<24>(Zbp, Zb);
 #pragma unroll
           for (int p = 0; p < 6; ++p)
 #pragma unroll
@@ -824,7 +837,8 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
           for (int s = s0 + lane; s < s1; s += 32) {
             const int cf = h.cam_free[h.cam_s[s]];
             if (cf < 0) continue;
-            const double* Z = h.Z + 24 * (size_t)s;
+            double Z[24];
+            ld_row<24>(h.Z + 24 * (size_t)s, Z);
             const double* y = h.yc + 6 * cf;
 #pragma unroll
             for (int p = 0; p < 6; ++p) { v[0] += Z[4 * p] * y[p]; v[1] += Z[4 * p + 1] * y[p]; v[2] += Z[4 * p + 2] * y[p]; v[3] += Z[4 * p + 3] * y[p]; }
