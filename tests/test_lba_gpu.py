@@ -560,3 +560,25 @@ def test_edge_cases(gpu):
     with pytest.raises(gpu.SlslamError) as e:
         gpu.lba_solve(huge)
     assert e.value.code == -2 and np.array_equal(huge.parameters, before)
+
+
+@pytest.mark.gpu
+def test_general_kernel_groups_are_deterministic_and_agree(gpu):
+    """The general kernel runs a window on a group of CTAs whose size depends on how many windows share the launch (32 for
+    one window, fewer for more, 1 when there are more windows than SMs).  Same window, same group size: identical bits run
+    after run (every cross-CTA hand-over is behind the group barrier).  Different group sizes reduce in a different order:
+    same LM path, costs to rounding."""
+    w = synth.make_window(91, 18, 70, 900, num_fixed_cameras=18, sigma_px=0.5)            # 36 camera blocks
+    assert w.num_cameras == 36
+    p0, s0 = gpu.lba_solve(w, max_iters=8)
+    for _ in range(4):
+        p, s = gpu.lba_solve(w, max_iters=8)
+        assert np.array_equal(p, p0) and s["final_cost"] == s0["final_cost"] and s["iterations"] == s0["iterations"]
+    others = [synth.make_window(92 + i, 17, 60, 700, num_fixed_cameras=17, sigma_px=0.5) for i in range(5)]
+    for batch in ([w] + others, [w] * 7 + others, [w] + others * 32):      # groups of 24, 12 and 1 CTA(s)
+        ps, ss = gpu.lba_solve_batch(batch, max_iters=8)
+        assert ss[0]["iterations"] == s0["iterations"] and ss[0]["termination"] == s0["termination"]
+        assert abs(ss[0]["final_cost"] - s0["final_cost"]) <= 1e-9 * s0["final_cost"]
+        assert np.abs(ps[0][:6 * 36] - p0[:6 * 36]).max() < 1e-8
+        ps2, ss2 = gpu.lba_solve_batch(batch, max_iters=8)
+        assert all(np.array_equal(a, b) for a, b in zip(ps, ps2))
