@@ -358,6 +358,63 @@ def bench_wide_windows(capi, cpu=True):
     return out
 
 
+def bench_per_frame(capi, cpu=True):
+    """The two per-FRAME hot loops of the reference's tracking thread, through the C ABI with
+    host buffers: motion-only BA (src/slam.cpp:578-675: one free camera, every line constant; the dedicated kernel) and RANSAC
+    hypothesis scoring (src/slam.cpp:363-425, 691-726: every hypothesis against every line).  Oracle on one host thread beside
+    them; motion-only BA checked to 1e-9 on the cost, RANSAC scores and inlier masks bit for bit."""
+    out = {}
+    w = synth.motion_only_window(11, num_lines=200)
+    for _ in range(5):
+        capi.lba_solve(w, max_iters=MAX_ITERS)
+    ts, ks = [], []
+    for _ in range(40):
+        t0 = time.perf_counter()
+        p, s = capi.lba_solve(w, max_iters=MAX_ITERS)
+        ts.append(time.perf_counter() - t0)
+        ks.append(capi.last_timings()["dev_kernel_ms"])
+    mo = {"workload": f"one frame: 1 free camera / {w.num_lines} constant lines / {w.num_observations} observations, max {MAX_ITERS} LM iterations",
+          "kernel": "lba_motion_only_kernel", "api": "slslam_lba_solve (recognised as motion-only BA)", "ms_per_solve": 1e3 * float(np.median(ts)),
+          "kernel_ms": float(np.median(ks)), "lm_iterations": s["iterations"], "value": s["iterations"] / float(np.median(ts)), "unit": UNIT}
+    poses, lines, obs, _ = synth.ransac_case(0, 300, 1000)
+    thr = 5.0 / 406.05
+    for _ in range(3):
+        capi.ransac_score(poses, lines, obs, 0.12, thr, want_errors=False)
+    tr = []
+    for _ in range(20):
+        t0 = time.perf_counter()
+        sg, ig, _ = capi.ransac_score(poses, lines, obs, 0.12, thr, want_errors=False)
+        tr.append(time.perf_counter() - t0)
+    ra = {"workload": "1000 pose hypotheses x 300 lines (stereo reprojection test of every pair)", "kernel": "ransac_score_kernel",
+          "api": "slslam_ransac_score (host buffers in, scores + inlier masks out)", "ms_per_call": 1e3 * float(np.median(tr)),
+          "value": 1000 * 300 / float(np.median(tr)), "unit": "line tests/s"}
+    if cpu:
+        from oracle import oracle
+        tc = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            po, so = oracle.lba_solve(w, max_iters=MAX_ITERS, solver=1)
+            tc.append(time.perf_counter() - t0)
+        rel = abs(s["final_cost"] - so["final_cost"]) / so["final_cost"]
+        if not (rel <= 1e-9 and s["iterations"] == so["iterations"] and float(np.abs(p[:6] - po[:6]).max()) < 1e-8):
+            raise SystemExit(f"bench.py: motion-only BA differs from the oracle: {s} vs {so}")
+        mo["parity_checked"] = True
+        mo["parity"] = {"rel_final_cost": rel, "max_abs_pose": float(np.abs(p[:6] - po[:6]).max())}
+        mo["cpu_baseline"] = {"ms_per_solve": 1e3 * float(np.median(tc)), "value": so["iterations"] / float(np.median(tc)), "unit": UNIT,
+                              "cores": 1, "kind": "port"}
+        t0 = time.perf_counter()
+        so_, io_, _ = oracle.ransac_score(poses, lines, obs, 0.12, thr)
+        dt = time.perf_counter() - t0
+        if not (np.array_equal(sg, so_) and np.array_equal(ig, io_)):
+            raise SystemExit("bench.py: RANSAC scores / inlier masks differ from the oracle")
+        ra["parity_checked"] = True
+        ra["parity"] = "scores and inlier masks identical to the oracle"
+        ra["cpu_baseline"] = {"ms_per_call": 1e3 * dt, "value": 1000 * 300 / dt, "unit": "line tests/s", "cores": 1, "kind": "port"}
+    out["motion_only_ba"] = mo
+    out["ransac_scoring"] = ra
+    return out
+
+
 def bench_map_resident(capi, w, max_iters=MAX_ITERS, reps=20):
     """the per-keyframe blocking solve of one M window when the map (keyframe poses, landmark lines,
     observations) is resident on the device: slslam_map_bundle_adjust assembles the window from the map with kernels,
@@ -736,6 +793,7 @@ def main():
             line["pose_graph"] = bench_pose_graph(capi, local_rank, fp64_peak_meas, cpu=(world == 1 and not args.no_cpu_baseline))
             if world == 1:
                 line["wide_windows"] = bench_wide_windows(capi, cpu=not args.no_cpu_baseline)
+                line["per_frame"] = bench_per_frame(capi, cpu=not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
             reps = 2
             iters_c, secs_c = 0, 0.0

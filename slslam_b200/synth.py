@@ -445,3 +445,27 @@ def house_trajectory(num_keyframes=402, radius=11.0, wave=0.6, turns=1.0):
         Rwc = np.stack([xc, yc, zc], axis=1)
         out[k, :3] = log_so3(Rwc); out[k, 3:] = c
     return out
+
+
+def ransac_case(seed, n_lines=120, n_hyp=64, sigma_px=0.3, baseline=0.12):
+    """RANSAC scoring input (reference src/slam.cpp:363-425).  Lines in the previous keyframe's frame, a true motion T (previous -> current), stereo observations in the current
+    frame, and hypotheses = T perturbed by growing amounts (a few with |t| > 1, which the reference skips)."""
+    rng = np.random.default_rng(seed)
+    w = rng.normal(0, 0.03, 3); t = np.array([rng.normal(0, 0.05), rng.normal(0, 0.05), -0.75 + rng.normal(0, 0.05)])
+    R = rodrigues(w)
+    lines, obs = np.zeros((n_lines, 6)), np.zeros((n_lines, 8))
+    for k in range(n_lines):
+        z = rng.uniform(3, 12)
+        mid = np.array([rng.uniform(-0.6, 0.6) * z, rng.uniform(-0.4, 0.4) * z, z])
+        v = rng.normal(size=3); v /= np.linalg.norm(v)
+        lines[k, :3], lines[k, 3:] = mid - v * (mid @ v), v
+        P, Q = R @ (mid - 0.6 * v) + t, R @ (mid + 0.6 * v) + t
+        ends = [P, Q, P - [baseline, 0, 0], Q - [baseline, 0, 0]]
+        obs[k] = np.concatenate([[e[0] / e[2], e[1] / e[2]] for e in ends]) + rng.normal(0, sigma_px / 406.05, 8)
+    poses = np.zeros((n_hyp, 12))
+    for h in range(n_hyp):
+        s = 0.0 if h == 0 else 10.0 ** rng.uniform(-4, -0.5)
+        Rh = rodrigues(w + rng.normal(0, s, 3))
+        th = t + rng.normal(0, 3 * s, 3) + (np.array([0, 0, 2.0]) if h % 17 == 5 else 0)
+        poses[h, :9], poses[h, 9:] = Rh.ravel(), th
+    return poses, lines, obs, (R, t)
