@@ -795,7 +795,7 @@ def main():
                 line["wide_windows"] = bench_wide_windows(capi, cpu=not args.no_cpu_baseline)
                 line["per_frame"] = bench_per_frame(capi, cpu=not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
-            reps = 2
+            reps = 8                 # ~6 s timed on one thread; the parity check below adds 16 more oracle solves (~12 s, untimed)
             iters_c, secs_c = 0, 0.0
             for _ in range(reps):
                 a, b_, res_c = oracle_solve_windows(windows, 1)
