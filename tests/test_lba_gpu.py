@@ -582,3 +582,36 @@ def test_general_kernel_groups_are_deterministic_and_agree(gpu):
         assert np.abs(ps[0][:6 * 36] - p0[:6 * 36]).max() < 1e-8
         ps2, ss2 = gpu.lba_solve_batch(batch, max_iters=8)
         assert all(np.array_equal(a, b) for a, b in zip(ps, ps2))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [
+    dict(cams=33, fixed=0, lines=60, obs=600, robust=True, const_lines=0),       # all free, tail solve only (24 < Cf = 33: 9 distributed columns)
+    dict(cams=12, fixed=24, lines=80, obs=900, robust=False, const_lines=7),     # few free cameras, many constant ones, constant lines, no loss
+    dict(cams=60, fixed=4, lines=90, obs=2200, robust=True, const_lines=3),      # 60 free cameras: 36 distributed block columns
+])
+def test_general_kernel_shapes_against_oracle(gpu, shape):
+    """The general kernel on windows of very different shapes (how many block columns the group eliminates before the
+    shared-memory tail takes over depends on the number of free cameras), constant lines and cameras, with and without the
+    Huber loss: iteration count, steps, termination as the oracle, cost 1e-6, poses 1e-6."""
+    from oracle import oracle
+    w = synth.make_window(300 + shape["cams"], shape["cams"], shape["lines"], shape["obs"], num_fixed_cameras=shape["fixed"], sigma_px=0.5)
+    if shape["const_lines"]:
+        fx = w.fixed_index.reshape(-1, 2).copy()
+        fx[np.isin(w.line_index, np.arange(shape["const_lines"])), 1] = 1
+        w.fixed_index = np.ascontiguousarray(fx.ravel())
+    assert w.num_cameras > 32
+    p, s = gpu.lba_solve(w, max_iters=10, robust=shape["robust"])
+    po, so = oracle.lba_solve(w, max_iters=10, solver=1, robust=shape["robust"])
+    assert s["iterations"] == so["iterations"] and s["termination"] == so["termination"], (s, so)
+    assert s["num_successful_steps"] == so["num_successful_steps"] and s["num_unsuccessful_steps"] == so["num_unsuccessful_steps"]
+    assert abs(s["initial_cost"] - so["initial_cost"]) <= 1e-11 * so["initial_cost"]
+    assert abs(s["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"], (s, so)
+    C = w.num_cameras
+    assert np.abs(p[:6 * C] - po[:6 * C]).max() < 1e-6
+    # constant blocks keep their input bits
+    const_cams = np.unique(w.camera_index[w.fixed_index.reshape(-1, 2)[:, 0] != 0])
+    for c in const_cams:
+        assert np.array_equal(p[6 * c:6 * c + 6], w.parameters[6 * c:6 * c + 6])
+    for l in range(shape["const_lines"]):
+        assert np.array_equal(p[6 * C + 4 * l:6 * C + 4 * l + 4], w.parameters[6 * C + 4 * l:6 * C + 4 * l + 4])
