@@ -615,3 +615,20 @@ def test_general_kernel_shapes_against_oracle(gpu, shape):
         assert np.array_equal(p[6 * c:6 * c + 6], w.parameters[6 * c:6 * c + 6])
     for l in range(shape["const_lines"]):
         assert np.array_equal(p[6 * C + 4 * l:6 * C + 4 * l + 4], w.parameters[6 * C + 4 * l:6 * C + 4 * l + 4])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W", [20, 40])
+def test_solve_W40(gpu, W):
+    """--ba_window_size 20 / 40 as the reference's published table runs them (matlab_script/result_comp_ancdir_orthonorm/
+    ba_result_*_basize{20,40}_*): 2 W camera blocks, W of them free (src/slam.cpp:1376-1382).  Synthetic window of that shape
+    against the oracle (the house-simulation windows themselves: tests/test_house.py)."""
+    from oracle import oracle
+    w = synth.make_window(500 + W, W, 160, 60 * W, num_fixed_cameras=W, sigma_px=0.5)
+    assert w.num_cameras == 2 * W
+    p, s = gpu.lba_solve(w, max_iters=10)
+    po, so = oracle.lba_solve(w, max_iters=10, solver=1)
+    assert s["iterations"] == so["iterations"] and s["termination"] == so["termination"], (s, so)
+    assert s["num_successful_steps"] == so["num_successful_steps"]
+    assert abs(s["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"], (s, so)
+    assert np.abs(p[:12 * W] - po[:12 * W]).max() < 1e-6
