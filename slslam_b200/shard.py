@@ -449,31 +449,66 @@ class DeviceSharder:
         self.seg_off = np.concatenate([[0], np.cumsum([_up(self.layouts[r].total) for r in range(self.world)])]).astype(np.int64)
         self.seg_res = int(self.seg_off[-1])
         size = self.seg_res + int(self.res_off[-1])
-        name = [None]
-        if self.rank == 0:
-            self.shm = shared_memory.SharedMemory(create=True, size=size)
-            name[0] = self.shm.name
-        dist.broadcast_object_list(name, 0, group=self.group)
-        if self.rank != 0:
-            self.shm = shared_memory.SharedMemory(name=name[0])
-            try:                      # only the creator unlinks (Python < 3.13 tracks attachments as if it owned them)
-                resource_tracker.unregister(self.shm._name, "shared_memory")
-            except Exception:
-                pass
-        self.seg_np = np.ndarray((size,), np.uint8, buffer=self.shm.buf)
-        self.seg = torch.from_numpy(self.seg_np)
+        name, err = [None], None
         self._registered = False
-        if self.dev.type == "cuda":
-            rc = torch.cuda.cudart().cudaHostRegister(self.seg.data_ptr(), size, 0)
-            if int(rc) != 0:
-                raise RuntimeError(f"cudaHostRegister of the shared window segment failed: {rc}")
-            self._registered = True
+        if self.rank == 0:
+            try:
+                self.shm = shared_memory.SharedMemory(create=True, size=size)
+                name[0] = self.shm.name
+            except Exception as e:          # e.g. /dev/shm too small in a container
+                err = f"shared memory segment of {size} bytes: {e}"
+        dist.broadcast_object_list(name, 0, group=self.group)
+        try:
+            if name[0] is None:
+                raise RuntimeError(err or "rank 0 could not create the shared segment")
+            if self.rank != 0:
+                self.shm = shared_memory.SharedMemory(name=name[0])
+                try:                  # only the creator unlinks (Python < 3.13 tracks attachments as if it owned them)
+                    resource_tracker.unregister(self.shm._name, "shared_memory")
+                except Exception:
+                    pass
+            self.seg_np = np.ndarray((size,), np.uint8, buffer=self.shm.buf)
+            self.seg = torch.from_numpy(self.seg_np)
+            if self.dev.type == "cuda":
+                rc = torch.cuda.cudart().cudaHostRegister(self.seg.data_ptr(), size, 0)
+                if int(rc) != 0:
+                    raise RuntimeError(f"cudaHostRegister of the shared window segment failed: {rc}")
+                self._registered = True
+        except Exception as e:
+            err = str(e)
+        # every rank must have the segment, or nobody uses it
+        good = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(good, op=dist.ReduceOp.MIN, group=self.group)
+        if int(good.item()) == 0:
+            self.shared_host_error = err or "another rank could not map the shared segment"
+            self._drop_segment()
+            return False
         if self.rank == 0:
             for r in range(self.world):
                 o = int(self.seg_off[r])
                 self.seg_np[o:o + self.layouts[r].total] = self.host_bufs[r]
         self._join = torch.zeros(1, dtype=torch.int32, device=self.dev)
         dist.barrier(group=self.group)
+        return True
+
+    def _drop_segment(self):
+        if getattr(self, "_registered", False):
+            self.torch.cuda.cudart().cudaHostUnregister(self.seg.data_ptr())
+            self._registered = False
+        for a_ in ("seg", "seg_np"):
+            if hasattr(self, a_):
+                delattr(self, a_)
+        shm, self.shm = self.shm, None
+        if shm is not None:
+            try:
+                shm.close()
+            except BufferError:
+                pass
+            if self.rank == 0:
+                try:
+                    shm.unlink()
+                except FileNotFoundError:
+                    pass
 
     def close_shared_host(self):
         if self.shm is None:
@@ -481,16 +516,7 @@ class DeviceSharder:
         if self.dev.type == "cuda":
             self.torch.cuda.synchronize(self.dev)
         self.dist.barrier(group=self.group)
-        if self._registered:
-            self.torch.cuda.cudart().cudaHostUnregister(self.seg.data_ptr())
-        del self.seg, self.seg_np
-        shm, self.shm = self.shm, None
-        try:
-            shm.close()
-        except BufferError:
-            pass
-        if self.rank == 0:
-            shm.unlink()
+        self._drop_segment()
 
     def preload_device(self):
         """origin = "device": put rank 0's packed buffers into its HBM (untimed; the windows then start on the device)."""
