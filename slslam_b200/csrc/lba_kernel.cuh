@@ -511,13 +511,13 @@ __device__ __forceinline__ void group_barrier(const Ctx& c, unsigned int& target
   __syncthreads();
   if (c.tid == 0) {
     unsigned int* bar = c.h->bar;
-    __threadfence();
-    atomicAdd(bar, 1u);
+    // arrive with release semantics (cumulative over the CTA barrier above: everything this CTA wrote is visible before
+    // the count), spin with acquire loads: no separate fences
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     unsigned int seen;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
     } while ((int)(seen - target) < 0);
-    __threadfence();
   }
   __syncthreads();
 }

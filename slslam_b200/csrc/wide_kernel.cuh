@@ -77,13 +77,11 @@ __device__ __forceinline__ void wide_sync(WideCtx& c) {
   c.target += (unsigned int)c.G;
   __syncthreads();
   if (c.tid == 0) {
-    __threadfence();
-    atomicAdd(c.bar, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(c.bar) : "memory");
     unsigned int seen;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(c.bar) : "memory");
     } while ((int)(seen - c.target) < 0);
-    __threadfence();
   }
   __syncthreads();
 }
