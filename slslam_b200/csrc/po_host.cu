@@ -361,7 +361,7 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   PO_TRY(cudaMemcpyAsync(B, host, upload_end, cudaMemcpyHostToDevice, s));
   if (trace_out) PO_TRY(cudaMemsetAsync(B + o_trace, 0, 8 * (size_t)SLSLAM_TRACE_WIDTH * std::max(max_iters, 1), s));
   PO_TRY(cudaEventRecord(ws.ev0, s));
-  if (E > 0) po_linearize<<<(E + 127) / 128, 128, 0, s>>>(d, 0, 1, evaluate_only ? 1 : 0);
+  if (E > 0) po_linearize<<<(PO_LIN_PARTS * E + 127) / 128, 128, 0, s>>>(d, 0, 1, evaluate_only ? 1 : 0);
   if (evaluate_only) {
     PO_TRY(cudaGetLastError());
     PO_TRY(cudaStreamSynchronize(s));
@@ -423,7 +423,7 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
         PO_TRY(cudaLaunchCooperativeKernel((const void*)po_backsolve, dim3((unsigned)bs_ctas), dim3(256), args, 0, s));
       }
       po_step<<<(6 * K + E + 255) / 256, 256, 0, s>>>(d);
-      po_linearize<<<(E + 127) / 128, 128, 0, s>>>(d, 1, 0, 0);
+      po_linearize<<<(PO_LIN_PARTS * E + 127) / 128, 128, 0, s>>>(d, 1, 0, 0);
       po_decide<<<1, 256, 0, s>>>(d);
       po_accept<<<(6 * K + 255) / 256, 256, 0, s>>>(d);
       po_colnorm_grad<<<(n + 127) / 128, 128, 0, s>>>(d, 1);

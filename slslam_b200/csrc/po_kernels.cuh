@@ -77,9 +77,14 @@ struct PoDev {
 // K5: residual and Jacobians of every edge at x (which_x = 0) or at the trial point (1), into buffer set `use_cur ?
 // cur : 1 - cur`.  all_free = 1 ignores the constant pose (evaluate-only entry point).
 // ------------------------------------------------------------------------------------------------------------
+// Four threads per edge (round 2; one thread carried all 12 partials in two passes before: 38 us per call, twice per LM
+// iteration): thread `part` evaluates the residual with the three partials (part & 1) * 3 .. + 2 of pose1 (part < 2) or of
+// pose2 (part >= 2).  Every partial is computed by the same operations as before, so the Jacobians keep their bits.
+constexpr int PO_LIN_PARTS = 4;
 __global__ void po_linearize(PoDev d, int which_x, int use_cur, int all_free) {
   if (d.st->done) return;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = t / PO_LIN_PARTS, part = t - e * PO_LIN_PARTS;
   if (e >= d.E) return;
   const int set = use_cur ? d.st->cur : 1 - d.st->cur;
   const double* x = which_x ? d.xt : d.x;
@@ -91,33 +96,38 @@ __global__ void po_linearize(PoDev d, int which_x, int use_cur, int all_free) {
   double p1[6], p2[6], c[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) { p1[k] = x[6 * a + k]; p2[k] = x[6 * b + k]; c[k] = d.cons[6 * (size_t)e + k]; }
-  typedef Dual<6> D6;
-  D6 A[6], B[6], res[6];
-  // derivatives with respect to pose1 (a self edge aliases one block for both arguments: directions coincide)
+  const int d0 = 3 * (part & 1);            // first direction of this thread
+  const bool second = part >= 2;            // derivatives with respect to pose2
+  if (second && (a == b || !f2)) {
+    // (a self edge aliases one block for both arguments: its directions coincide and go to J1)
 #pragma unroll
-  for (int k = 0; k < 6; ++k) { A[k] = dvar<6>(p1[k], k); B[k] = (a == b) ? dvar<6>(p2[k], k) : dconst<6>(p2[k]); }
-  pose_constraint_residual<6>(A, B, c, res);
-  double cost = 0.0;
+    for (int k = 0; k < 6; ++k)
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    r[k] = res[k].a;
-    cost += 0.5 * res[k].a * res[k].a;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) J1[6 * k + j] = f1 ? res[k].v[j] : 0.0;
-  }
-  d.cost_e[(size_t)set * d.E + e] = cost;
-  if (a == b || !f2) {
-#pragma unroll
-    for (int k = 0; k < 36; ++k) J2[k] = 0.0;
+      for (int j = 0; j < 3; ++j) J2[6 * k + d0 + j] = 0.0;
     return;
   }
+  typedef Dual<3> D3;
+  D3 A[6], B[6], res[6];
 #pragma unroll
-  for (int k = 0; k < 6; ++k) { A[k] = dconst<6>(p1[k]); B[k] = dvar<6>(p2[k], k); }
-  pose_constraint_residual<6>(A, B, c, res);
+  for (int k = 0; k < 6; ++k) {
+    const bool mine = k >= d0 && k < d0 + 3;
+    const bool va = mine && !second, vb = mine && (second || a == b);
+    A[k] = va ? dvar<3>(p1[k], k - d0) : dconst<3>(p1[k]);
+    B[k] = vb ? dvar<3>(p2[k], k - d0) : dconst<3>(p2[k]);
+  }
+  pose_constraint_residual<3>(A, B, c, res);
+  if (part == 0) {
+    double cost = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { r[k] = res[k].a; cost += 0.5 * res[k].a * res[k].a; }
+    d.cost_e[(size_t)set * d.E + e] = cost;
+  }
+  double* J = second ? J2 : J1;
+  const bool fr = second ? true : f1;
 #pragma unroll
   for (int k = 0; k < 6; ++k)
 #pragma unroll
-    for (int j = 0; j < 6; ++j) J2[6 * k + j] = res[k].v[j];
+    for (int j = 0; j < 3; ++j) J[6 * k + d0 + j] = fr ? res[k].v[j] : 0.0;
 }
 
 // squared column norms and gradient of the unscaled Jacobian (current set), thread per unknown
