@@ -278,13 +278,17 @@ def bench_pose_graph(capi, device, fp64_peak_tflops, cpu=True):
         "final_cost": s["final_cost"], "initial_cost": s["initial_cost"],
         "e2e": {"value": iters / float(np.median(wall)), "unit": UNIT, "ms_per_solve": 1e3 * float(np.median(wall)),
                 "api": "slslam_po_solve (host buffers in and out, cached workspace)"},
-        "factorisation": {"path": "block-sparse" if st["sparse"] else "dense", "free_poses": st["free_poses"],
+        "factorisation": {"path": {0: "dense", 1: "block-sparse, minimum-degree order, column at a time",
+                                   2: "block-sparse, level order (independent poses side by side), warp per column"}[int(st["sparse"])],
+                          "free_poses": st["free_poses"],
                           "factor_blocks": st["factor_blocks"], "dense_blocks": st["free_poses"] * (st["free_poses"] + 1) // 2,
                           "block_updates": st["block_updates"], "max_column_rows": st["max_column_rows"],
                           "iterations_enqueued": st["iterations_enqueued"],
-                          "kernel_cycles": {"panel": cyc[0], "update": cyc[1], "back_substitution": cyc[2], "total": cyc[3]}},
-        "roofline": {"bound": "fp64 (the factorisation is a chain of dependent 6x6 block columns: latency bound, one CTA)",
-                     "kernel": "po_sp_factor_solve", "achieved": flops_factor / max(cyc[3], 1) * 1.965e9 / 1e12 if cyc[3] else None,
+                          "kernel_cycles": ({"stages_warp_per_column": cyc[0], "stages_cta_per_column": cyc[1], "back_substitution": cyc[2], "total": cyc[3]}
+                                            if int(st["sparse"]) == 2 else
+                                            {"panel": cyc[0], "update": cyc[1], "back_substitution": cyc[2], "total": cyc[3]})},
+        "roofline": {"bound": "fp64 (the factorisation is a chain of dependent stages of 6x6 block columns: latency bound, one CTA)",
+                     "kernel": "po_sp_factor_levels" if int(st["sparse"]) == 2 else "po_sp_factor_solve", "achieved": flops_factor / max(cyc[3], 1) * 1.965e9 / 1e12 if cyc[3] else None,
                      "peak": fp64_peak_tflops, "unit": "TFLOP/s",
                      "frac": (flops_factor / max(cyc[3], 1) * 1.965e9 / 1e12 / fp64_peak_tflops) if (cyc[3] and fp64_peak_tflops) else None,
                      "algorithmic_flops_per_launch": flops_factor, "traffic": None,

@@ -246,13 +246,16 @@ float slslam_po_last_solve_ms(void);
  * included) are eliminated by one CTA in one launch per LM iteration.  A graph whose factor is more than a third full,
  * or with more than max_column_blocks_sparse blocks in one column, goes to the dense blocked factorisation instead. */
 typedef struct slslam_po_stats {
-  int32_t sparse;                 /* 1 = block-sparse path, 0 = dense path */
+  int32_t sparse;                 /* 2 = block-sparse, level order (warp per column); 1 = block-sparse, minimum-degree order
+                                     (column at a time); 0 = dense path */
   int32_t free_poses;
   int64_t factor_blocks;          /* 6x6 blocks of L (dense path: Kf (Kf + 1) / 2) */
   int64_t block_updates;          /* 6x6x6 block products of one numeric factorisation (sparse path) */
   int32_t max_column_rows;
   int32_t iterations_enqueued;    /* LM iterations whose kernels were launched (<= max_iterations: early stop) */
-  int64_t factor_cycles[4];       /* last factorisation (sparse path), SM cycles: panel phase, update phase, back-substitution, total */
+  int64_t factor_cycles[4];       /* last factorisation (sparse paths), SM cycles.  sparse = 1: panel phase, update phase,
+                                     back-substitution, total; sparse = 2: stages with a warp per column, stages with the CTA per
+                                     column, back-substitution, total */
 } slslam_po_stats;
 void slslam_po_last_stats(slslam_po_stats* out);
 typedef struct slslam_po_limits {

@@ -27,6 +27,11 @@ if which in ("all", "po"):
     p, s = capi.po_solve(g, max_iters=3)
     print("po", s["final_cost"])
 if which in ("all", "po"):
+    os.environ["SLSLAM_PO_COLUMNS"] = "1"                        # minimum-degree order, column-at-a-time kernel
+    p, s = capi.po_solve(synth.make_pose_graph(0, num_poses=16, neighbours=2, num_loops=2), max_iters=2)
+    del os.environ["SLSLAM_PO_COLUMNS"]
+    print("po columns", s["final_cost"])
+if which in ("all", "po"):
     os.environ["SLSLAM_PO_DENSE"] = "1"                          # the dense fallback path as well
     p, s = capi.po_solve(synth.make_pose_graph(0, num_poses=16, neighbours=2, num_loops=2), max_iters=2)
     del os.environ["SLSLAM_PO_DENSE"]

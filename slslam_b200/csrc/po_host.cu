@@ -3,6 +3,7 @@
 // contribution lists), upload, the stream-ordered LM loop (no host round trip inside), download.
 // Replaces what POProblem::build + ceres::Solve do (reference src/po_problem.cpp:40-77, src/slam.cpp:1283-1293).
 #include <algorithm>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -27,15 +28,20 @@ struct PoPlan {
   long long dense_blocks = 0;
   std::vector<int> slot_pos, col_off, row_pos, tri_off, blk_dst, bs_chunk;
   std::vector<int2> tri;
+  // level order (build_po_sparse with levels = true): columns [stage_off[s], stage_off[s + 1]) are mutually independent
+  // and touch disjoint blocks of the factor, so one warp each can eliminate them side by side
+  bool levels = false;
+  std::vector<int> stage_off;
 };
 
 // Symbolic analysis of the block graph of the free poses: exact greedy minimum-degree order (ties by index), the
 // structure of every column of L (the eliminated node's remaining neighbours, which become a clique), block numbering
 // and, per column, the (destination, source a, source b) list of its updates.  Returns false when the factor is too
 // full for the sparse kernel to pay (or a column exceeds its shared-memory panel): the dense path takes over.
-static bool build_po_sparse(const slslam_po_desc& d, PoPlan& p) {
+static bool build_po_sparse(const slslam_po_desc& d, PoPlan& p, bool levels) {
   const int Kf = p.Kf;
   p.dense_blocks = (long long)Kf * (Kf + 1) / 2;
+  p.levels = false; p.stage_off.clear(); p.max_rows = 0;
   if (Kf == 0) return false;
   std::vector<std::set<int> > adj(Kf);
   for (int e = 0; e < d.num_edges; ++e) {
@@ -47,9 +53,9 @@ static bool build_po_sparse(const slslam_po_desc& d, PoPlan& p) {
   std::vector<int> order; order.reserve(Kf);
   std::vector<std::vector<int> > col_nodes(Kf);         // by elimination step: the remaining neighbours
   long long nblocks = Kf, ntri = 0;
-  for (int step = 0; step < Kf; ++step) {
-    const int v = queue.begin()->second;
-    queue.erase(queue.begin());
+  auto eliminate = [&](int v) -> bool {
+    queue.erase(std::make_pair((int)adj[v].size(), v));
+    const int step = (int)order.size();
     order.push_back(v);
     std::vector<int> nb(adj[v].begin(), adj[v].end());
     for (int u : nb) { queue.erase(std::make_pair((int)adj[u].size(), u)); adj[u].erase(v); }
@@ -63,6 +69,55 @@ static bool build_po_sparse(const slslam_po_desc& d, PoPlan& p) {
     col_nodes[step].swap(nb);
     if (nblocks * 3 > p.dense_blocks && Kf > 64) return false;      // more than a third of the dense factor: not sparse
     if (ntri > (1LL << 24)) return false;
+    return true;
+  };
+  if (!levels) {
+    for (int step = 0; step < Kf; ++step)
+      if (!eliminate(queue.begin()->second)) return false;
+  } else {
+    // Multiple elimination: per level an independent set of (near-)minimum-degree nodes -- on a trajectory graph every
+    // other pose of the chain -- whose eliminations do not depend on one another; inside a level, nodes that share a
+    // neighbour would update the same blocks, so they are coloured apart (greedy): a (level, colour) class is a STAGE
+    // whose columns the kernel eliminates concurrently, one warp each, without atomics and in a fixed order.
+    p.stage_off.push_back(0);
+    std::vector<int> mark(Kf, -1), colour_of(Kf, 0);
+    int level = 0;
+    while (!queue.empty()) {
+      const int dmin = queue.begin()->first;
+      const int thr = std::max(2 * dmin, 2);           // generous: the interior of a band graph has twice the degree of its ends
+      std::vector<int> picked;
+      for (auto it = queue.begin(); it != queue.end() && it->first <= thr; ++it) {
+        const int v = it->second;
+        if (mark[v] == level) continue;                  // a neighbour was picked in this level
+        picked.push_back(v);
+        for (int u : adj[v]) mark[u] = level;
+      }
+      // colours: nodes sharing a neighbour get different ones
+      std::vector<std::vector<int> > used(0);
+      std::map<int, std::vector<int> > nb_colours;       // neighbour -> colours taken by the picked nodes around it
+      int ncol = 0;
+      for (int v : picked) {
+        std::vector<char> taken(ncol + 1, 0);
+        for (int u : adj[v]) for (int cc : nb_colours[u]) taken[cc] = 1;
+        int cc = 0;
+        while (cc < ncol && taken[cc]) ++cc;
+        if (cc == ncol) ++ncol;
+        colour_of[v] = cc;
+        for (int u : adj[v]) nb_colours[u].push_back(cc);
+      }
+      for (int cc = 0; cc < ncol; ++cc) {
+        for (int v : picked) if (colour_of[v] == cc) { if (!eliminate(v)) return false; }
+        p.stage_off.push_back((int)order.size());
+      }
+      ++level;
+    }
+    if (getenv("SLSLAM_PO_DEBUG")) {
+      fprintf(stderr, "po level order: %d levels, %d stages, max rows %d, blocks %lld; columns per stage:", level, (int)p.stage_off.size() - 1, p.max_rows, nblocks);
+      for (size_t k = 0; k + 1 < p.stage_off.size(); ++k) fprintf(stderr, " %d", p.stage_off[k + 1] - p.stage_off[k]);
+      fprintf(stderr, "\n");
+    }
+    if (p.max_rows > PO_LV_MAXROWS) return false;
+    p.levels = true;
   }
   if (p.max_rows > PO_SP_MAXROWS) return false;
   p.slot_pos.assign(Kf, 0);
@@ -238,12 +293,18 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   cudaGetDevice(&dev);
   PoPlan p;
   build_po_plan(*desc, evaluate_only, p);
-  const bool sparse = !evaluate_only && !getenv("SLSLAM_PO_DENSE") && build_po_sparse(*desc, p);
+  bool sparse = false;
+  if (!evaluate_only && !getenv("SLSLAM_PO_DENSE")) {
+    // level order + warp-per-column kernel when every column of that order is short enough; the minimum-degree order with
+    // the column-at-a-time kernel otherwise (SLSLAM_PO_COLUMNS forces it)
+    sparse = !getenv("SLSLAM_PO_COLUMNS") && build_po_sparse(*desc, p, true);
+    if (!sparse) sparse = build_po_sparse(*desc, p, false);
+  }
   const int n = p.n, M = n + 1, ld = (M + 7) & ~7, nblk = (int)p.blk_i.size();
   const int max_iters = desc->max_iterations;
   const int nb32 = (n + PO_NB - 1) / PO_NB;
   memset(&g_po_stats, 0, sizeof(g_po_stats));
-  g_po_stats.free_poses = p.Kf; g_po_stats.sparse = sparse ? 1 : 0;
+  g_po_stats.free_poses = p.Kf; g_po_stats.sparse = sparse ? (p.levels ? 2 : 1) : 0;   // 2: level order, warp per column
   g_po_stats.factor_blocks = sparse ? p.nsb : (int64_t)p.Kf * (p.Kf + 1) / 2;
   g_po_stats.block_updates = sparse ? (int64_t)p.tri.size() : 0;
   g_po_stats.max_column_rows = sparse ? p.max_rows : p.Kf;
@@ -258,6 +319,7 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   const size_t o_spos = pool.reserve(4 * Kfz), o_coff = pool.reserve(4 * (Kfz + 1)), o_rpos = pool.reserve(4 * (p.row_pos.size() + 1));
   const size_t o_toff = pool.reserve(4 * (Kfz + 1)), o_tri = pool.reserve(8 * (p.tri.size() + 1)), o_bdst = pool.reserve(4 * (size_t)(nblk + 1));
   const size_t o_bsc = pool.reserve(4 * (p.bs_chunk.size() + 1));
+  const size_t o_stg = pool.reserve(4 * (p.stage_off.size() + 1));
   const size_t o_x = pool.reserve(48 * Kz);
   const size_t o_state = pool.reserve(sizeof(PoState));
   const size_t upload_end = pool.off;
@@ -306,6 +368,7 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
     if (!p.tri.empty()) memcpy(host + o_tri, p.tri.data(), 8 * p.tri.size());
     if (nblk > 0) memcpy(host + o_bdst, p.blk_dst.data(), 4 * (size_t)nblk);
     memcpy(host + o_bsc, p.bs_chunk.data(), 4 * p.bs_chunk.size());
+    if (!p.stage_off.empty()) memcpy(host + o_stg, p.stage_off.data(), 4 * p.stage_off.size());
   }
   PoState st; memset(&st, 0, sizeof(st));
   st.radius = desc->initial_trust_region_radius > 0 ? desc->initial_trust_region_radius : 1e4;   // Ceres 1.7.0 defaults
@@ -338,6 +401,7 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   d.tri_off = (const int*)(B + o_toff); d.tri = (const int2*)(B + o_tri); d.blk_dst = (const int*)(B + o_bdst);
   d.sp_cycles = (long long*)(B + o_spc);
   d.bs_chunk = (const int*)(B + o_bsc); d.bs_nchunk = sparse ? (int)p.bs_chunk.size() - 1 : 0;
+  d.stage_off = (const int*)(B + o_stg); d.nstage = (sparse && p.levels) ? (int)p.stage_off.size() - 1 : 0;
 
   cudaStream_t s = nullptr;
   unsigned int* d_flags = (unsigned int*)(B + o_flags);
@@ -355,6 +419,7 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
     static bool attr_set[16] = {false};
     if (dev < 0 || dev >= 16 || !attr_set[dev]) {
       PO_TRY(cudaFuncSetAttribute(po_sp_factor_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
+      PO_TRY(cudaFuncSetAttribute(po_sp_factor_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PO_LV_SMEM));
       if (dev >= 0 && dev < 16) attr_set[dev] = true;
     }
   }
@@ -406,7 +471,8 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
       if (sparse) {
         PO_TRY(cudaMemsetAsync(d.Hb, 0, hb_bytes, s));
         po_sp_assemble<<<(nblk * 36 + n + 255) / 256, 256, 0, s>>>(d);
-        po_sp_factor_solve<<<1, PO_SP_NT, sp_smem, s>>>(d);
+        if (p.levels) po_sp_factor_levels<<<1, PO_LV_NT, PO_LV_SMEM, s>>>(d);
+        else po_sp_factor_solve<<<1, PO_SP_NT, sp_smem, s>>>(d);
       } else {
         PO_TRY(cudaMemsetAsync(d.H, 0, 8 * (size_t)M * ld, s));
         po_assemble<<<(nblk * 36 + n + 255) / 256, 256, 0, s>>>(d);

@@ -71,6 +71,8 @@ struct PoDev {
   const int* bs_chunk;            // [bs_nchunk + 1] descending column boundaries of the back-substitution's staging chunks
   int bs_nchunk;
   long long* sp_cycles;           // [4] diagnostics of po_sp_factor_solve: phase 1, phase 2, back-substitution, total (SM cycles)
+  const int* stage_off;           // level order: columns [stage_off[s], stage_off[s + 1]) are eliminated side by side
+  int nstage;
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -753,6 +755,266 @@ __global__ void __launch_bounds__(PO_SP_NT, 1) po_sp_factor_solve(PoDev d) {
   }
   // solution back in slot order
   for (int i = tid; i < d.n; i += PO_SP_NT) d.y[i] = yv[6 * d.slot_pos[i / 6] + i % 6];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Level-ordered factorisation (round 2, second form).  The minimum-degree order peels a trajectory graph from its ends:
+// the elimination tree is a path and po_sp_factor_solve walks ~250 dependent block columns at ~3.3 k cycles each.  The
+// host now orders by LEVELS of independent, near-minimum-degree poses (every other pose of the chain, then every other
+// of what is left, ...; po_host.cu) and splits a level into stages whose columns touch disjoint blocks.  Here ONE WARP
+// eliminates a column -- pivot inverse, scaled panel (written over the column: the back-substitution reads it), update of
+// the blocks between its rows, right-hand side -- and the 16 warps of the CTA take the columns of a stage side by side:
+// plain read-modify-writes, fixed order, no atomics; a __syncthreads separates the stages.  Back-substitution by stages in
+// reverse, warp per column.  Everything the stages exchange goes through L2 (loads with .cg).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PO_LV_NT = 256;         // 8 warps: the column code wants more than the 128 registers 512 threads would leave
+constexpr int PO_LV_COOP = 4;         // stages with fewer columns than this: the whole CTA works on one column at a time
+constexpr int PO_LV_MAXROWS = 12;       // off-diagonal blocks per column the per-warp staging holds
+constexpr int PO_LV_MAXTRI = PO_LV_MAXROWS * (PO_LV_MAXROWS + 1) / 2;
+constexpr size_t PO_LV_SMEM = (size_t)(PO_LV_NT / 32) * (2 * PO_LV_MAXROWS * 36 + PO_LV_MAXTRI) * 8;
+
+__global__ void __launch_bounds__(PO_LV_NT, 1) po_sp_factor_levels(PoDev d) {
+  if (d.st->done) return;
+  extern __shared__ __align__(16) double lvsm[];
+  __shared__ int bad;
+  __shared__ double cW[36], cbc[8];                   // cooperative mode: pivot inverse and right-hand-side block
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = PO_LV_NT / 32, Kf = d.Kf;
+  double* stA = lvsm + (size_t)warp * (2 * PO_LV_MAXROWS * 36 + PO_LV_MAXTRI);     // unscaled blocks of the warp's column
+  double* stP = stA + PO_LV_MAXROWS * 36;                         // scaled panel P = A W
+  int2* tri_s = reinterpret_cast<int2*>(stP + PO_LV_MAXROWS * 36);   // the column's update list
+  if (tid == 0) bad = 0;
+  long long t_start = 0, t_mid = 0, t_coop = 0;
+  if (tid == 0) t_start = clock64();
+  __syncthreads();
+  for (int s = 0; s < d.nstage; ++s) {
+    const int c0 = d.stage_off[s], c1 = d.stage_off[s + 1];
+    long long t_st = 0;
+    if (tid == 0) t_st = clock64();
+    if (c1 - c0 < PO_LV_COOP) {
+      // few columns (the dense end of the elimination: long columns, one per stage): the whole CTA takes them one at a
+      // time -- warp 0 inverts the pivot, 6 m threads scale the panel, the update rows are spread over all threads
+      double* cA = lvsm;                                   // warp 0's staging, shared by everybody here
+      double* cP = cA + PO_LV_MAXROWS * 36;
+      int2* ctri = reinterpret_cast<int2*>(cP + PO_LV_MAXROWS * 36);
+      for (int c = c0; c < c1; ++c) {
+        const int o0 = d.col_off[c], m = d.col_off[c + 1] - o0;
+        const int t0 = d.tri_off[c], nt = d.tri_off[c + 1] - t0;
+        for (int i = tid; i < nt; i += PO_LV_NT) ctri[i] = d.tri[t0 + i];
+        if (tid < 6) cbc[tid] = __ldcg(d.bz + 6 * c + tid);
+        if (warp == 0) {
+          double A36[36], W[21];
+#pragma unroll
+          for (int pp = 0; pp < 6; ++pp)
+#pragma unroll
+            for (int q = 0; q <= pp; ++q) A36[6 * pp + q] = __ldcg(d.Hb + (size_t)c * 36 + 6 * pp + q);
+          const bool ok = po_spd6_inverse(A36, W);
+          if (lane == 0) {
+            if (!ok) bad = 1;
+#pragma unroll
+            for (int pp = 0; pp < 6; ++pp)
+#pragma unroll
+              for (int q = 0; q < 6; ++q) cW[6 * pp + q] = W[pp >= q ? pp * (pp + 1) / 2 + q : q * (q + 1) / 2 + pp];
+          }
+        }
+        __syncthreads();
+        if (tid < 6 * m) {
+          const int a = tid / 6, pr = tid - 6 * a;
+          double* blk = d.Hb + (size_t)(Kf + o0 + a) * 36 + 6 * pr;
+          double av[6], pv[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) av[k] = __ldcg(blk + k);
+          const int rrow = 6 * d.row_pos[o0 + a] + pr;
+          const double bold = __ldcg(d.bz + rrow);
+#pragma unroll
+          for (int q = 0; q < 6; ++q)
+            pv[q] = (av[0] * cW[q] + av[1] * cW[6 + q] + av[2] * cW[12 + q]) + (av[3] * cW[18 + q] + av[4] * cW[24 + q] + av[5] * cW[30 + q]);
+          double sacc = 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { cA[36 * a + 6 * pr + k] = av[k]; cP[36 * a + 6 * pr + k] = pv[k]; sacc += pv[k] * cbc[k]; }
+#pragma unroll
+          for (int k = 0; k < 6; ++k) blk[k] = pv[k];
+          d.bz[rrow] = bold - sacc;
+        } else if (tid >= 96 && tid < 102) {
+          const int q = tid - 96;
+          double u = 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) u += cW[6 * q + k] * cbc[k];
+          d.us[6 * c + q] = u;
+        }
+        __syncthreads();
+        for (int base = 0; base < 6 * nt; base += 2 * PO_LV_NT) {
+          double o[2][6];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = base + PO_LV_NT * u + tid;
+            if (i < 6 * nt) {
+              const int t = i / 6, pr = i - 6 * t;
+              const double* dst = d.Hb + (size_t)ctri[t].x * 36 + 6 * pr;
+#pragma unroll
+              for (int k = 0; k < 6; ++k) o[u][k] = __ldcg(dst + k);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = base + PO_LV_NT * u + tid;
+            if (i < 6 * nt) {
+              const int t = i / 6, pr = i - 6 * t;
+              const int2 tr = ctri[t];
+              const int a = tr.y & 0xffff, b = tr.y >> 16;
+              const double* Pa = cP + 36 * a + 6 * pr;
+              const double* Ab = cA + 36 * b;
+              double* dst = d.Hb + (size_t)tr.x * 36 + 6 * pr;
+              double pa[6];
+#pragma unroll
+              for (int k = 0; k < 6; ++k) pa[k] = Pa[k];
+#pragma unroll
+              for (int q = 0; q < 6; ++q)
+                o[u][q] -= (pa[0] * Ab[6 * q] + pa[1] * Ab[6 * q + 1] + pa[2] * Ab[6 * q + 2]) + (pa[3] * Ab[6 * q + 3] + pa[4] * Ab[6 * q + 4] + pa[5] * Ab[6 * q + 5]);
+#pragma unroll
+              for (int q = 0; q < 6; ++q) dst[q] = o[u][q];
+            }
+          }
+        }
+        __syncthreads();
+      }
+      if (tid == 0) t_coop += clock64() - t_st;
+      continue;
+    }
+    for (int c = c0 + warp; c < c1; c += nw) {
+      const int o0 = d.col_off[c], m = d.col_off[c + 1] - o0;
+      const int t0 = d.tri_off[c], nt = d.tri_off[c + 1] - t0;
+      for (int i = lane; i < nt; i += 32) tri_s[i] = d.tri[t0 + i];          // in flight with the pivot loads
+      // pivot inverse (every lane the same values) and right-hand-side block
+      double A36[36], W[21], bc[6];
+#pragma unroll
+      for (int pp = 0; pp < 6; ++pp)
+#pragma unroll
+        for (int q = 0; q <= pp; ++q) A36[6 * pp + q] = __ldcg(d.Hb + (size_t)c * 36 + 6 * pp + q);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) bc[k] = __ldcg(d.bz + 6 * c + k);
+      const bool ok = po_spd6_inverse(A36, W);
+      if (!ok && lane == 0) bad = 1;
+#define WF(i, j) W[(i) >= (j) ? (i) * ((i) + 1) / 2 + (j) : (j) * ((j) + 1) / 2 + (i)]
+      if (lane < 6) {
+        double u = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          // (W symmetric) row `lane` of W times b_c, with compile-time indices into W
+          const double w = lane == 0 ? WF(0, k) : lane == 1 ? WF(1, k) : lane == 2 ? WF(2, k) : lane == 3 ? WF(3, k) : lane == 4 ? WF(4, k) : WF(5, k);
+          u += w * bc[k];
+        }
+        d.us[6 * c + lane] = u;
+      }
+      // panel: row p of P_a = A_a W; the unscaled row kept for the updates; right-hand side of the row block.  At most
+      // three rows per lane (m <= 12): every load first, then the arithmetic, then the stores (one L2 round trip)
+      {
+        double av[3][6], bold[3];
+        int rrow[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int i = lane + 32 * u;
+          rrow[u] = 0; bold[u] = 0.0;
+          if (i < 6 * m) {
+            const int a = i / 6, pr = i - 6 * a;
+            const double* blk = d.Hb + (size_t)(Kf + o0 + a) * 36 + 6 * pr;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) av[u][k] = __ldcg(blk + k);
+            rrow[u] = 6 * d.row_pos[o0 + a] + pr;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) if (lane + 32 * u < 6 * m) bold[u] = __ldcg(d.bz + rrow[u]);
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int i = lane + 32 * u;
+          if (i < 6 * m) {
+            const int a = i / 6, pr = i - 6 * a;
+            double* blk = d.Hb + (size_t)(Kf + o0 + a) * 36 + 6 * pr;
+            double pv[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+              pv[q] = (av[u][0] * WF(0, q) + av[u][1] * WF(1, q) + av[u][2] * WF(2, q)) + (av[u][3] * WF(3, q) + av[u][4] * WF(4, q) + av[u][5] * WF(5, q));
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { stA[36 * a + 6 * pr + k] = av[u][k]; stP[36 * a + 6 * pr + k] = pv[k]; sacc += pv[k] * bc[k]; }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) blk[k] = pv[k];
+            d.bz[rrow[u]] = bold[u] - sacc;
+          }
+        }
+      }
+#undef WF
+      __syncwarp();
+      // updates: destination block (rows of a, columns of b) -= P_a A_b^T, one row per lane-item; two items per lane at a
+      // time with all their destination loads issued first (no two items of a column share a destination row)
+      for (int base = 0; base < 6 * nt; base += 64) {
+        double o[2][6];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int i = base + 32 * u + lane;
+          if (i < 6 * nt) {
+            const int t = i / 6, pr = i - 6 * t;
+            const double* dst = d.Hb + (size_t)tri_s[t].x * 36 + 6 * pr;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) o[u][k] = __ldcg(dst + k);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int i = base + 32 * u + lane;
+          if (i < 6 * nt) {
+            const int t = i / 6, pr = i - 6 * t;
+            const int2 tr = tri_s[t];
+            const int a = tr.y & 0xffff, b = tr.y >> 16;
+            const double* Pa = stP + 36 * a + 6 * pr;
+            const double* Ab = stA + 36 * b;
+            double* dst = d.Hb + (size_t)tr.x * 36 + 6 * pr;
+            double pa[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) pa[k] = Pa[k];
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+              o[u][q] -= (pa[0] * Ab[6 * q] + pa[1] * Ab[6 * q + 1] + pa[2] * Ab[6 * q + 2]) + (pa[3] * Ab[6 * q + 3] + pa[4] * Ab[6 * q + 4] + pa[5] * Ab[6 * q + 5]);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) dst[q] = o[u][q];
+          }
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+  if (tid == 0) { t_mid = clock64(); if (bad) d.st->chol_fail = 1; }
+  // back-substitution, stages in reverse: y_c = u_c - sum_a P_ac^T y_row(a); lanes over (row block, row), butterfly
+  for (int s = d.nstage - 1; s >= 0; --s) {
+    const int c0 = d.stage_off[s], c1 = d.stage_off[s + 1];
+    for (int c = c0 + warp; c < c1; c += nw) {
+      const int o0 = d.col_off[c], m = d.col_off[c + 1] - o0;
+      double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      for (int i = lane; i < 6 * m; i += 32) {
+        const int a = i / 6, pr = i - 6 * a;
+        const double* blk = d.Hb + (size_t)(Kf + o0 + a) * 36 + 6 * pr;
+        const double yr = __ldcg(d.yp + 6 * d.row_pos[o0 + a] + pr);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) acc[q] += __ldcg(blk + q) * yr;
+      }
+#pragma unroll
+      for (int q = 0; q < 6; ++q)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], off);
+      if (lane < 6) {
+        const double sum = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : lane == 3 ? acc[3] : lane == 4 ? acc[4] : acc[5];
+        d.yp[6 * c + lane] = __ldcg(d.us + 6 * c + lane) - sum;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && d.sp_cycles) {
+    const long long now = clock64();
+    d.sp_cycles[0] = t_mid - t_start - t_coop; d.sp_cycles[1] = t_coop; d.sp_cycles[2] = now - t_mid; d.sp_cycles[3] = now - t_start;
+  }
+  // solution back in slot order
+  for (int i = tid; i < d.n; i += PO_LV_NT) d.y[i] = __ldcg(d.yp + 6 * d.slot_pos[i / 6] + i % 6);
 }
 
 // trial point x' = x - scale*y on the free poses, and the per-edge part of the model decrease -(m.(r + m/2)), m = J delta
