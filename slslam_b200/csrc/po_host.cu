@@ -412,6 +412,14 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
   double* h_trace = (double*)(ws.h_res + 48 * Kz + ((sizeof(slslam_summary) + 255) & ~(size_t)255));
   volatile int* h_done = (volatile int*)((char*)h_trace + 8 * (size_t)SLSLAM_TRACE_WIDTH * std::max(max_iters, 1));
   const size_t sp_smem = PO_SP_SMEM;
+  // CTAs of the level kernel's cluster: enough warps for the widest stage, at most PO_LV_CLUSTER (SLSLAM_PO_CLUSTER overrides)
+  int lv_ctas = 1;
+  if (sparse && p.levels) {
+    int widest = 1;
+    for (size_t k = 0; k + 1 < p.stage_off.size(); ++k) widest = std::max(widest, p.stage_off[k + 1] - p.stage_off[k]);
+    lv_ctas = std::max(1, std::min((int)PO_LV_CLUSTER, (widest + PO_LV_NT / 32 - 1) / (PO_LV_NT / 32)));
+    if (const char* ev = getenv("SLSLAM_PO_CLUSTER")) lv_ctas = std::max(1, std::min((int)PO_LV_CLUSTER, atoi(ev)));
+  }
   int enqueued = 0;
   rc = SLSLAM_OK;
 #define PO_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_last_error(cudaGetErrorString(e_)); cudaGetLastError(); rc = SLSLAM_ERR_CUDA; goto done; } } while (0)
@@ -471,8 +479,18 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
       if (sparse) {
         PO_TRY(cudaMemsetAsync(d.Hb, 0, hb_bytes, s));
         po_sp_assemble<<<(nblk * 36 + n + 255) / 256, 256, 0, s>>>(d);
-        if (p.levels) po_sp_factor_levels<<<1, PO_LV_NT, PO_LV_SMEM, s>>>(d);
-        else po_sp_factor_solve<<<1, PO_SP_NT, sp_smem, s>>>(d);
+        if (p.levels) {
+          // one thread-block cluster: the columns of a stage spread over the warps of up to 8 SMs of one GPC
+          cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+          cfg.gridDim = dim3((unsigned)lv_ctas); cfg.blockDim = dim3(PO_LV_NT); cfg.dynamicSmemBytes = PO_LV_SMEM; cfg.stream = s;
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeClusterDimension;
+          at[0].val.clusterDim.x = (unsigned)lv_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+          cfg.attrs = at; cfg.numAttrs = 1;
+          PO_TRY(cudaLaunchKernelEx(&cfg, po_sp_factor_levels, d));
+        } else {
+          po_sp_factor_solve<<<1, PO_SP_NT, sp_smem, s>>>(d);
+        }
       } else {
         PO_TRY(cudaMemsetAsync(d.H, 0, 8 * (size_t)M * ld, s));
         po_assemble<<<(nblk * 36 + n + 255) / 256, 256, 0, s>>>(d);

@@ -768,6 +768,7 @@ __global__ void __launch_bounds__(PO_SP_NT, 1) po_sp_factor_solve(PoDev d) {
 // reverse, warp per column.  Everything the stages exchange goes through L2 (loads with .cg).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int PO_LV_NT = 256;         // 8 warps: the column code wants more than the 128 registers 512 threads would leave
+constexpr int PO_LV_CLUSTER = 8;      // CTAs of the cluster the kernel is launched as (portable maximum)
 constexpr int PO_LV_COOP = 4;         // stages with fewer columns than this: the whole CTA works on one column at a time
 constexpr int PO_LV_MAXROWS = 12;       // off-diagonal blocks per column the per-warp staging holds
 constexpr int PO_LV_MAXTRI = PO_LV_MAXROWS * (PO_LV_MAXROWS + 1) / 2;
@@ -778,8 +779,17 @@ __global__ void __launch_bounds__(PO_LV_NT, 1) po_sp_factor_levels(PoDev d) {
   extern __shared__ __align__(16) double lvsm[];
   __shared__ int bad;
   __shared__ double cW[36], cbc[8];                   // cooperative mode: pivot inverse and right-hand-side block
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = PO_LV_NT / 32, Kf = d.Kf;
-  double* stA = lvsm + (size_t)warp * (2 * PO_LV_MAXROWS * 36 + PO_LV_MAXTRI);     // unscaled blocks of the warp's column
+  // launched as ONE thread-block cluster of gridDim.x CTAs (<= 8, on the SMs of one GPC): the columns of a stage are
+  // spread over the warps of all of them, a hardware cluster barrier (release / acquire) separates the stages, and
+  // everything the CTAs exchange goes through L2 (every load of factor data is .cg)
+  const int ncta = (int)gridDim.x, cta = (int)blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = (tid >> 5) + (PO_LV_NT / 32) * cta, nw = (PO_LV_NT / 32) * ncta, Kf = d.Kf;
+  auto stage_sync = [&]() {
+    if (ncta == 1) { __syncthreads(); return; }
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  };
+  double* stA = lvsm + (size_t)(tid >> 5) * (2 * PO_LV_MAXROWS * 36 + PO_LV_MAXTRI);     // unscaled blocks of the warp's column
   double* stP = stA + PO_LV_MAXROWS * 36;                         // scaled panel P = A W
   int2* tri_s = reinterpret_cast<int2*>(stP + PO_LV_MAXROWS * 36);   // the column's update list
   if (tid == 0) bad = 0;
@@ -791,12 +801,17 @@ __global__ void __launch_bounds__(PO_LV_NT, 1) po_sp_factor_levels(PoDev d) {
     long long t_st = 0;
     if (tid == 0) t_st = clock64();
     if (c1 - c0 < PO_LV_COOP) {
-      // few columns (the dense end of the elimination: long columns, one per stage): the whole CTA takes them one at a
-      // time -- warp 0 inverts the pivot, 6 m threads scale the panel, the update rows are spread over all threads
+      // few columns (the dense end of the elimination: long columns, one per stage): CTA 0 takes them one at a time --
+      // warp 0 inverts the pivot, 6 m threads scale the panel, the update rows are spread over all threads -- and it
+      // takes the whole run of consecutive short stages in one go (one cluster barrier for the run)
       double* cA = lvsm;                                   // warp 0's staging, shared by everybody here
       double* cP = cA + PO_LV_MAXROWS * 36;
       int2* ctri = reinterpret_cast<int2*>(cP + PO_LV_MAXROWS * 36);
-      for (int c = c0; c < c1; ++c) {
+      int s_end = s + 1;
+      while (s_end < d.nstage && d.stage_off[s_end + 1] - d.stage_off[s_end] < PO_LV_COOP) ++s_end;
+      const int c_run = d.stage_off[s_end];
+      s = s_end - 1;
+      for (int c = c0; c < c_run && cta == 0; ++c) {
         const int o0 = d.col_off[c], m = d.col_off[c + 1] - o0;
         const int t0 = d.tri_off[c], nt = d.tri_off[c + 1] - t0;
         for (int i = tid; i < nt; i += PO_LV_NT) ctri[i] = d.tri[t0 + i];
@@ -877,6 +892,7 @@ __global__ void __launch_bounds__(PO_LV_NT, 1) po_sp_factor_levels(PoDev d) {
         }
         __syncthreads();
       }
+      stage_sync();
       if (tid == 0) t_coop += clock64() - t_st;
       continue;
     }
@@ -982,13 +998,18 @@ __global__ void __launch_bounds__(PO_LV_NT, 1) po_sp_factor_levels(PoDev d) {
       }
       __syncwarp();
     }
-    __syncthreads();
+    stage_sync();
   }
   if (tid == 0) { t_mid = clock64(); if (bad) d.st->chol_fail = 1; }
   // back-substitution, stages in reverse: y_c = u_c - sum_a P_ac^T y_row(a); lanes over (row block, row), butterfly
   for (int s = d.nstage - 1; s >= 0; --s) {
     const int c0 = d.stage_off[s], c1 = d.stage_off[s + 1];
-    for (int c = c0 + warp; c < c1; c += nw) {
+    // a short stage: CTA 0 alone, and no cluster barrier until the run of short stages ends
+    const bool small = c1 - c0 < PO_LV_COOP;
+    const bool next_small = small && s > 0 && d.stage_off[s] - d.stage_off[s - 1] < PO_LV_COOP;
+    const int w0 = small ? (tid >> 5) : warp, wn = small ? PO_LV_NT / 32 : nw;
+    if (small && cta != 0) { if (!next_small) stage_sync(); continue; }
+    for (int c = c0 + w0; c < c1; c += wn) {
       const int o0 = d.col_off[c], m = d.col_off[c + 1] - o0;
       double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       for (int i = lane; i < 6 * m; i += 32) {
@@ -1007,14 +1028,14 @@ __global__ void __launch_bounds__(PO_LV_NT, 1) po_sp_factor_levels(PoDev d) {
         d.yp[6 * c + lane] = __ldcg(d.us + 6 * c + lane) - sum;
       }
     }
-    __syncthreads();
+    if (small && next_small) __syncthreads(); else stage_sync();
   }
-  if (tid == 0 && d.sp_cycles) {
+  if (tid == 0 && cta == 0 && d.sp_cycles) {
     const long long now = clock64();
     d.sp_cycles[0] = t_mid - t_start - t_coop; d.sp_cycles[1] = t_coop; d.sp_cycles[2] = now - t_mid; d.sp_cycles[3] = now - t_start;
   }
   // solution back in slot order
-  for (int i = tid; i < d.n; i += PO_LV_NT) d.y[i] = __ldcg(d.yp + 6 * d.slot_pos[i / 6] + i % 6);
+  for (int i = tid + PO_LV_NT * cta; i < d.n; i += PO_LV_NT * ncta) d.y[i] = __ldcg(d.yp + 6 * d.slot_pos[i / 6] + i % 6);
 }
 
 // trial point x' = x - scale*y on the free poses, and the per-edge part of the model decrease -(m.(r + m/2)), m = J delta
