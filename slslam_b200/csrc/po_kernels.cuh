@@ -772,7 +772,10 @@ constexpr int PO_LV_CLUSTER = 8;      // CTAs of the cluster the kernel is launc
 constexpr int PO_LV_COOP = 4;         // stages with fewer columns than this: the whole CTA works on one column at a time
 constexpr int PO_LV_MAXROWS = 12;       // off-diagonal blocks per column the per-warp staging holds
 constexpr int PO_LV_MAXTRI = PO_LV_MAXROWS * (PO_LV_MAXROWS + 1) / 2;
-constexpr size_t PO_LV_SMEM = (size_t)(PO_LV_NT / 32) * (2 * PO_LV_MAXROWS * 36 + PO_LV_MAXTRI) * 8;
+constexpr int PO_LV_WARP_DOUBLES = 2 * PO_LV_MAXROWS * 36 + PO_LV_MAXTRI;            // per-warp staging: blocks, panel, update list
+constexpr int PO_LV_STAGE_DOUBLES = (PO_LV_NT / 32) * PO_LV_WARP_DOUBLES;
+constexpr int PO_LV_TAILCOLS = 96, PO_LV_TAILBLK = 400;                               // dense end kept in shared memory by the back-substitution
+constexpr size_t PO_LV_SMEM = (size_t)(PO_LV_STAGE_DOUBLES + PO_LV_TAILBLK * 36 + 6 * PO_LV_TAILCOLS) * 8 + (size_t)(PO_LV_TAILBLK + PO_LV_TAILCOLS + 2) * 4;
 
 __global__ void __launch_bounds__(PO_LV_NT, 1) po_sp_factor_levels(PoDev d) {
   if (d.st->done) return;
@@ -789,7 +792,7 @@ __global__ void __launch_bounds__(PO_LV_NT, 1) po_sp_factor_levels(PoDev d) {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   };
-  double* stA = lvsm + (size_t)(tid >> 5) * (2 * PO_LV_MAXROWS * 36 + PO_LV_MAXTRI);     // unscaled blocks of the warp's column
+  double* stA = lvsm + (size_t)(tid >> 5) * PO_LV_WARP_DOUBLES;     // unscaled blocks of the warp's column
   double* stP = stA + PO_LV_MAXROWS * 36;                         // scaled panel P = A W
   int2* tri_s = reinterpret_cast<int2*>(stP + PO_LV_MAXROWS * 36);   // the column's update list
   if (tid == 0) bad = 0;
@@ -1001,8 +1004,54 @@ __global__ void __launch_bounds__(PO_LV_NT, 1) po_sp_factor_levels(PoDev d) {
     stage_sync();
   }
   if (tid == 0) { t_mid = clock64(); if (bad) d.st->chol_fail = 1; }
-  // back-substitution, stages in reverse: y_c = u_c - sum_a P_ac^T y_row(a); lanes over (row block, row), butterfly
-  for (int s = d.nstage - 1; s >= 0; --s) {
+  // back-substitution.  First the dense end (the final run of short stages, columns [tail0, Kf)): CTA 0 stages all their
+  // panel blocks, row positions and u in shared memory with one round of loads, then one warp walks the columns downwards
+  // with y in shared memory -- no L2 round trip on the chain.
+  int s_hi = d.nstage - 1;
+  {
+    int s_lo = d.nstage;
+    while (s_lo > 0 && d.stage_off[s_lo] - d.stage_off[s_lo - 1] < PO_LV_COOP) --s_lo;
+    const int tail0 = d.stage_off[s_lo], ntail = Kf - tail0;
+    const int b0 = ntail > 0 ? d.col_off[tail0] : 0, nbt = ntail > 0 ? d.col_off[Kf] - b0 : 0;
+    if (ntail > 0 && ntail <= PO_LV_TAILCOLS && nbt <= PO_LV_TAILBLK) {
+      if (cta == 0) {
+        double* Pt = lvsm + PO_LV_STAGE_DOUBLES;             // [nbt][36]
+        double* yt = Pt + PO_LV_TAILBLK * 36;                // [6 ntail] u, then y
+        int* rpt = reinterpret_cast<int*>(yt + 6 * PO_LV_TAILCOLS);   // [nbt] row positions, then [ntail + 1] column offsets
+        int* cot = rpt + PO_LV_TAILBLK;
+        for (int i = tid; i < 36 * nbt; i += PO_LV_NT) Pt[i] = __ldcg(d.Hb + (size_t)(Kf + b0) * 36 + i);
+        for (int i = tid; i < 6 * ntail; i += PO_LV_NT) yt[i] = __ldcg(d.us + 6 * tail0 + i);
+        for (int i = tid; i < nbt; i += PO_LV_NT) rpt[i] = d.row_pos[b0 + i];
+        for (int i = tid; i <= ntail; i += PO_LV_NT) cot[i] = d.col_off[tail0 + i] - b0;
+        __syncthreads();
+        if ((tid >> 5) == 0) {
+          for (int c = Kf - 1; c >= tail0; --c) {
+            const int o0 = cot[c - tail0], m = cot[c - tail0 + 1] - o0;
+            // lane (g, q), g < 5, q < 6, sums the (row block, row) pairs j = g, g + 5, ... of entry q of P^T y; four
+            // shuffles fold the five partial sums in a fixed order (six 5-level butterflies cost three times as much)
+            const int g = lane / 6, q = lane - 6 * g;
+            double acc = 0.0;
+            if (lane < 30) {
+              for (int j = g; j < 6 * m; j += 5) {
+                const int a = j / 6, pr = j - 6 * a;
+                acc += Pt[36 * (o0 + a) + 6 * pr + q] * yt[6 * (rpt[o0 + a] - tail0) + pr];   // rows of a tail column are later tail columns
+              }
+            }
+            const double a1 = __shfl_down_sync(0xffffffffu, acc, 6), a2 = __shfl_down_sync(0xffffffffu, acc, 12);
+            const double a3 = __shfl_down_sync(0xffffffffu, acc, 18), a4 = __shfl_down_sync(0xffffffffu, acc, 24);
+            if (lane < 6) yt[6 * (c - tail0) + lane] -= (((acc + a1) + a2) + a3) + a4;
+            __syncwarp();
+          }
+        }
+        __syncthreads();
+        for (int i = tid; i < 6 * ntail; i += PO_LV_NT) d.yp[6 * tail0 + i] = yt[i];
+      }
+      stage_sync();
+      s_hi = s_lo - 1;
+    }
+  }
+  // the other stages in reverse: y_c = u_c - sum_a P_ac^T y_row(a); warp per column, lanes over (row block, row), butterfly
+  for (int s = s_hi; s >= 0; --s) {
     const int c0 = d.stage_off[s], c1 = d.stage_off[s + 1];
     // a short stage: CTA 0 alone, and no cluster barrier until the run of short stages ends
     const bool small = c1 - c0 < PO_LV_COOP;
@@ -1011,22 +1060,17 @@ __global__ void __launch_bounds__(PO_LV_NT, 1) po_sp_factor_levels(PoDev d) {
     if (small && cta != 0) { if (!next_small) stage_sync(); continue; }
     for (int c = c0 + w0; c < c1; c += wn) {
       const int o0 = d.col_off[c], m = d.col_off[c + 1] - o0;
-      double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      for (int i = lane; i < 6 * m; i += 32) {
-        const int a = i / 6, pr = i - 6 * a;
-        const double* blk = d.Hb + (size_t)(Kf + o0 + a) * 36 + 6 * pr;
-        const double yr = __ldcg(d.yp + 6 * d.row_pos[o0 + a] + pr);
-#pragma unroll
-        for (int q = 0; q < 6; ++q) acc[q] += __ldcg(blk + q) * yr;
+      const int g = lane / 6, q = lane - 6 * g;          // (see the tail above)
+      double acc = 0.0;
+      if (lane < 30) {
+        for (int j = g; j < 6 * m; j += 5) {
+          const int a = j / 6, pr = j - 6 * a;
+          acc += __ldcg(d.Hb + (size_t)(Kf + o0 + a) * 36 + 6 * pr + q) * __ldcg(d.yp + 6 * d.row_pos[o0 + a] + pr);
+        }
       }
-#pragma unroll
-      for (int q = 0; q < 6; ++q)
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], off);
-      if (lane < 6) {
-        const double sum = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : lane == 3 ? acc[3] : lane == 4 ? acc[4] : acc[5];
-        d.yp[6 * c + lane] = __ldcg(d.us + 6 * c + lane) - sum;
-      }
+      const double a1 = __shfl_down_sync(0xffffffffu, acc, 6), a2 = __shfl_down_sync(0xffffffffu, acc, 12);
+      const double a3 = __shfl_down_sync(0xffffffffu, acc, 18), a4 = __shfl_down_sync(0xffffffffu, acc, 24);
+      if (lane < 6) d.yp[6 * c + lane] = __ldcg(d.us + 6 * c + lane) - ((((acc + a1) + a2) + a3) + a4);
     }
     if (small && next_small) __syncthreads(); else stage_sync();
   }
