@@ -41,7 +41,10 @@ if __name__ == "__main__":
     poses = np.concatenate([np.tile(np.eye(3).ravel(), (H, 1)), rng.normal(0, 0.05, (H, 3))], axis=1)
     lines = np.concatenate([rng.normal(0, 1, (K, 3)) + [0, 0, 6], rng.normal(0, 1, (K, 3))], axis=1)
     capi.ransac_score(poses, lines, rng.normal(0, 0.2, (K, 8)))
-    capi.po_solve(synth.make_pose_graph(0), max_iters=2)
+    capi.po_solve(synth.make_pose_graph(0), max_iters=2)                       # level order: po_sp_factor_levels (a cluster)
+    os.environ["SLSLAM_PO_COLUMNS"] = "1"
+    capi.po_solve(synth.make_pose_graph(0), max_iters=1)                       # minimum-degree order: po_sp_factor_solve
+    del os.environ["SLSLAM_PO_COLUMNS"]
     capi.geometry_convert(0, np.concatenate([rng.normal(0, 1, (64, 3)), rng.normal(0, 1, (64, 3))], axis=1))
     map_case()
     print("all kernel families launched")

@@ -22,8 +22,10 @@ timeout 300 python scripts/e2e_profile.py > gpurun_out/e2e_${tag}.txt 2>&1
 timeout 300 python scripts/h2d_staging_probe2.py > gpurun_out/h2d_${tag}.txt 2>&1
 timeout 300 python scripts/motion_only_profile.py > gpurun_out/moba_${tag}.txt 2>&1
 timeout 300 python scripts/ransac_profile.py > gpurun_out/ransac_${tag}.txt 2>&1
+timeout 300 python scripts/po_compare_orders.py > gpurun_out/po_orders_${tag}.txt 2>&1
+timeout 300 python scripts/wide_probe.py 2>&1 | grep "===\|^ms" > gpurun_out/wide_${tag}.txt
 # every other kernel family once, full metric set (the summaries go to profiles/<round>_other_kernels_ncu.csv)
-timeout 900 ncu --set full --clock-control none -k regex:'^(?!.*(lba_solve_kernel|elementwise|at::|vectorized)).*$' -c 60 -f -o gpurun_out/prof_other_${tag} \
+timeout 900 ncu --set full --clock-control none -k regex:'^(?!.*(lba_solve_kernel|elementwise|at::|vectorized)).*$' -c 100 -f -o gpurun_out/prof_other_${tag} \
     python scripts/all_kernels_driver.py > gpurun_out/ncu_c_${tag}.log 2>&1
 # gpurun merges at most 64 MiB back: keep the raw page of that capture as CSV, not the 50 MB report
 ncu -i gpurun_out/prof_other_${tag}.ncu-rep --page raw --csv > gpurun_out/other_raw_${tag}.csv 2>/dev/null; rm -f gpurun_out/prof_other_${tag}.ncu-rep

@@ -60,7 +60,8 @@ for src, dst in ((f"launches_{tag}.csv", f"{rnd}_launches_bench_lba.csv"), (f"la
                  (f"po_{tag}.txt", f"{rnd}_po_solve_timing.txt"), (f"phase_{tag}.txt", f"{rnd}_lba_phase_cycles.txt"),
                  (f"e2e_{tag}.txt", f"{rnd}_lba_e2e_split.txt"), (f"h2d_{tag}.txt", f"{rnd}_h2d_staging.txt"),
                  (f"phase_scale_{tag}.txt", f"{rnd}_lba_batch_size_scaling.txt"), (f"moba_{tag}.txt", f"{rnd}_motion_only_ba.txt"),
-                 (f"host_{tag}.txt", f"{rnd}_host_cpu.txt"), (f"ransac_{tag}.txt", f"{rnd}_ransac_scoring.txt")):
+                 (f"host_{tag}.txt", f"{rnd}_host_cpu.txt"), (f"ransac_{tag}.txt", f"{rnd}_ransac_scoring.txt"),
+                 (f"po_orders_{tag}.txt", f"{rnd}_po_level_vs_column_order.txt"), (f"wide_{tag}.txt", f"{rnd}_wide_kernel_timing.txt")):
     if os.path.exists(os.path.join(G, src)):
         shutil.copy(os.path.join(G, src), os.path.join(P, dst))
 
