@@ -487,7 +487,15 @@ static int po_run(const slslam_po_desc* desc, const double* poses_in, double* po
           at[0].id = cudaLaunchAttributeClusterDimension;
           at[0].val.clusterDim.x = (unsigned)lv_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
           cfg.attrs = at; cfg.numAttrs = 1;
-          PO_TRY(cudaLaunchKernelEx(&cfg, po_sp_factor_levels, d));
+          cudaError_t le = cudaLaunchKernelEx(&cfg, po_sp_factor_levels, d);
+          if (le != cudaSuccess && lv_ctas > 1) {
+            // no room for the cluster right now (or clusters unavailable): the same kernel as a single CTA
+            cudaGetLastError();
+            lv_ctas = 1;
+            cfg.gridDim = dim3(1); at[0].val.clusterDim.x = 1;
+            le = cudaLaunchKernelEx(&cfg, po_sp_factor_levels, d);
+          }
+          PO_TRY(le);
         } else {
           po_sp_factor_solve<<<1, PO_SP_NT, sp_smem, s>>>(d);
         }
