@@ -780,21 +780,7 @@ __global__ void __launch_bounds__(WIDE_NT, 1) lba_wide_kernel(const WideHdr* __r
     if (tr) { tr[0] = cost; tr[1] = 0; tr[2] = 0; tr[3] = radius; tr[4] = 0; tr[5] = 0; tr[6] = gmax; tr[7] = 0; }
     WPHASE(3)
     // ---- reduced solve by the whole group (the pivot test is evaluated identically on every CTA) ----
-#ifdef SLSLAM_WIDE_SOLO_SOLVE
-    bool sok;
-    {
-      WideCtx solo = c;
-      solo.G = 1; solo.gt = c.tid; solo.gsize = WIDE_NT; solo.gw = c.warp; solo.gwarps = WIDE_NT / 32;
-      if (c.rank == 0) {
-        const bool r0 = wide_reduced_solve(solo, h, inv_radius, Wsm, bcast, tri, tail_sm);
-        if (tid == 0) *h.flag = r0 ? 0.0 : 1.0;
-      }
-      wide_sync(c);
-      sok = __ldcg(h.flag) == 0.0;
-    }
-#else
     const bool sok = wide_reduced_solve(c, h, inv_radius, Wsm, bcast, tri, tail_sm);
-#endif
     WPHASE(4)
     bool ok = !line_fail && sok;
     // camera part of the model decrease, |delta|^2, finiteness (the same on every CTA)
