@@ -163,6 +163,12 @@ def test_sparse_and_dense_paths_agree(gpu, monkeypatch):
         # run to run the level kernel repeats itself bit for bit (no atomics: the stages order every update)
         pg2, sg2 = gpu.po_solve(g, max_iters=10)
         assert np.array_equal(pg2, pg) and sg2["final_cost"] == sg["final_cost"]
+        # ... and whether the level kernel runs as a cluster of CTAs or as one CTA (what it falls back to when the cluster
+        # cannot be launched) changes nothing: the stages fix the order of every update
+        monkeypatch.setenv("SLSLAM_PO_CLUSTER", "1")
+        p1, s1 = gpu.po_solve(g, max_iters=10)
+        monkeypatch.delenv("SLSLAM_PO_CLUSTER")
+        assert gpu.po_last_stats()["sparse"] == 2 and np.array_equal(p1, pg) and s1["final_cost"] == sg["final_cost"]
         monkeypatch.setenv("SLSLAM_PO_DENSE", "1")
         pd, sd = gpu.po_solve(g, max_iters=10)
         monkeypatch.delenv("SLSLAM_PO_DENSE")
