@@ -263,6 +263,16 @@ typedef struct slslam_po_limits {
   int32_t max_free_poses_dense;       /* dense fallback: 6 * free poses <= 32 * 8 * 64 */
 } slslam_po_limits;
 void slslam_po_get_limits(slslam_po_limits* out);
+/* Host only (no device needed): the symbolic plan po_solve would build for this graph, with its invariants verified --
+ * every column's rows are eliminated later; the columns of a stage (level order) are pairwise non-adjacent and update
+ * disjoint blocks and right-hand-side rows; every update destination exists in the structure.  Returns 0 and fills
+ * `out` (order: 2 = level order, 1 = minimum-degree order, 0 = not sparse enough: dense path), SLSLAM_ERR_INVALID for a bad
+ * graph, SLSLAM_ERR_NUMERICAL when an invariant is violated (a bug). */
+typedef struct slslam_po_plan_info {
+  int32_t order, free_poses, stages, widest_stage, max_column_rows, reserved;
+  int64_t factor_blocks, block_updates;
+} slslam_po_plan_info;
+int slslam_po_plan_check(const slslam_po_desc* desc, int32_t force_columns, slslam_po_plan_info* out);
 /* residuals [6E], jac_pose1 / jac_pose2 [36E] row-major 6x6 */
 int slslam_po_evaluate(const slslam_po_desc* desc, const double* poses, double* residuals, double* jac_pose1,
                        double* jac_pose2, double* cost_out);

@@ -23,7 +23,7 @@ EXPORTS = [
     "slslam_lba_solve", "slslam_lba_solve_batch", "slslam_lba_solve_batch_device", "slslam_lba_last_timings", "slslam_lba_batch_create", "slslam_lba_batch_solve",
     "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_max_active_clusters", "slslam_lba_batch_transfer_bytes", "slslam_lba_batch_phase_cycles", "slslam_lba_batch_plan_cycles", "slslam_lba_batch_destroy",
     "slslam_lba_plan_check", "slslam_lba_launch_shape", "slslam_lba_pipeline_create", "slslam_lba_pipeline_submit", "slslam_lba_pipeline_wait", "slslam_lba_pipeline_destroy",
-    "slslam_ransac_score", "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate", "slslam_po_last_solve_ms", "slslam_po_last_stats", "slslam_po_get_limits",
+    "slslam_ransac_score", "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate", "slslam_po_last_solve_ms", "slslam_po_last_stats", "slslam_po_get_limits", "slslam_po_plan_check",
     "slslam_map_create", "slslam_map_destroy", "slslam_map_add_keyframe", "slslam_map_add_landmarks", "slslam_map_set_poses",
     "slslam_map_get_poses", "slslam_map_get_landmarks", "slslam_map_bundle_adjust", "slslam_map_last_timings", "slslam_map_last_window",
     "slslam_geometry_convert",
@@ -57,6 +57,11 @@ class PoStats(C.Structure):
     _fields_ = [("sparse", C.c_int32), ("free_poses", C.c_int32), ("factor_blocks", C.c_int64),
                 ("block_updates", C.c_int64), ("max_column_rows", C.c_int32), ("iterations_enqueued", C.c_int32),
                 ("factor_cycles", C.c_int64 * 4)]
+
+
+class PoPlanInfo(C.Structure):
+    _fields_ = [("order", C.c_int32), ("free_poses", C.c_int32), ("stages", C.c_int32), ("widest_stage", C.c_int32),
+                ("max_column_rows", C.c_int32), ("reserved", C.c_int32), ("factor_blocks", C.c_int64), ("block_updates", C.c_int64)]
 
 
 class PoLimits(C.Structure):
@@ -136,6 +141,8 @@ def lib():
         L.slslam_po_last_stats.restype = None
         L.slslam_po_get_limits.argtypes = [C.POINTER(PoLimits)]
         L.slslam_po_get_limits.restype = None
+        L.slslam_po_plan_check.argtypes = [C.POINTER(PoDesc), C.c_int32, C.POINTER(PoPlanInfo)]
+        L.slslam_po_plan_check.restype = C.c_int32
         _LIB = L
     return _LIB
 
@@ -421,6 +428,14 @@ def po_last_stats():
     st = PoStats()
     lib().slslam_po_last_stats(C.byref(st))
     return {k: (list(getattr(st, k)) if k == "factor_cycles" else getattr(st, k)) for k, _ in PoStats._fields_}
+
+
+def po_plan_check(g, force_columns=False):
+    """slslam_po_plan_check: the symbolic plan of a pose graph, built and verified on the host (no device needed)."""
+    k = po_desc(g)
+    info = PoPlanInfo()
+    _check(lib().slslam_po_plan_check(C.byref(k.desc), 1 if force_columns else 0, C.byref(info)))
+    return {f: getattr(info, f) for f, _ in PoPlanInfo._fields_ if f != "reserved"}
 
 
 def po_limits():

@@ -117,6 +117,9 @@ static bool build_po_sparse(const slslam_po_desc& d, PoPlan& p, bool levels) {
       fprintf(stderr, "\n");
     }
     if (p.max_rows > PO_LV_MAXROWS) return false;
+    // no parallelism to be had (a hub pose adjacent to everything puts every column in a stage of its own): the
+    // column-at-a-time kernel is the faster one then
+    if (Kf > 16 && (int)p.stage_off.size() - 1 > (3 * Kf) / 5) return false;
     p.levels = true;
   }
   if (p.max_rows > PO_SP_MAXROWS) return false;
@@ -573,6 +576,73 @@ int slslam_po_evaluate(const slslam_po_desc* desc, const double* poses, double* 
 float slslam_po_last_solve_ms(void) { return g_po_last_ms; }
 
 void slslam_po_last_stats(slslam_po_stats* out) { if (out) *out = g_po_stats; }
+
+int slslam_po_plan_check(const slslam_po_desc* desc, int32_t force_columns, slslam_po_plan_info* out) {
+  set_last_error("");
+  if (!desc || !out) return SLSLAM_ERR_INVALID;
+  int rc = validate_po(*desc);
+  if (rc != SLSLAM_OK) return rc;
+  PoPlan p;
+  build_po_plan(*desc, false, p);
+  bool sparse = !force_columns && build_po_sparse(*desc, p, true);
+  if (!sparse) sparse = build_po_sparse(*desc, p, false);
+  memset(out, 0, sizeof(*out));
+  out->free_poses = p.Kf;
+  if (!sparse) return SLSLAM_OK;
+  out->order = p.levels ? 2 : 1;
+  out->factor_blocks = p.nsb; out->block_updates = (int64_t)p.tri.size(); out->max_column_rows = p.max_rows;
+  const int Kf = p.Kf;
+  auto fail = [&](const char* what) { set_last_error(what); return SLSLAM_ERR_NUMERICAL; };
+  // structure: rows of a column come later in the order, ascending; positions are a permutation
+  std::vector<char> seen(Kf, 0);
+  for (int s = 0; s < Kf; ++s) { const int c = p.slot_pos[s]; if (c < 0 || c >= Kf || seen[c]) return fail("positions are not a permutation"); seen[c] = 1; }
+  for (int c = 0; c < Kf; ++c)
+    for (int k = p.col_off[c]; k < p.col_off[c + 1]; ++k) {
+      if (p.row_pos[k] <= c || p.row_pos[k] >= Kf) return fail("a row of a column is not eliminated after it");
+      if (k > p.col_off[c] && p.row_pos[k] <= p.row_pos[k - 1]) return fail("rows of a column are not ascending");
+    }
+  // every update targets the diagonal block of its row or an existing off-diagonal block (row a of column row b)
+  for (int c = 0; c < Kf; ++c) {
+    const int o0 = p.col_off[c], m = p.col_off[c + 1] - o0;
+    if (p.tri_off[c + 1] - p.tri_off[c] != m * (m + 1) / 2) return fail("update list of a column has the wrong length");
+    for (int t = p.tri_off[c]; t < p.tri_off[c + 1]; ++t) {
+      const int a = p.tri[t].y & 0xffff, b = p.tri[t].y >> 16, dst = p.tri[t].x;
+      if (a >= m || b > a) return fail("update sources out of range");
+      const int ra = p.row_pos[o0 + a], rb = p.row_pos[o0 + b];
+      if (a == b) { if (dst != ra) return fail("diagonal update does not target its row's pivot block"); continue; }
+      if (dst < Kf || dst >= p.nsb) return fail("off-diagonal update outside the block range");
+      const int k = dst - Kf;
+      if (k < p.col_off[rb] || k >= p.col_off[rb + 1] || p.row_pos[k] != ra) return fail("off-diagonal update targets the wrong block");
+    }
+  }
+  // every block of J^T J has a home
+  for (size_t b = 0; b < p.blk_dst.size(); ++b) if (p.blk_dst[b] < 0 || p.blk_dst[b] >= p.nsb) return fail("a block of J^T J has no home in the factor");
+  if (p.levels) {
+    out->stages = (int)p.stage_off.size() - 1;
+    if (p.stage_off.empty() || p.stage_off.front() != 0 || p.stage_off.back() != Kf) return fail("stages do not cover the columns");
+    std::vector<int> owner_blk(p.nsb, -1), owner_row(Kf, -1);
+    for (int s = 0; s + 1 < (int)p.stage_off.size(); ++s) {
+      const int c0 = p.stage_off[s], c1 = p.stage_off[s + 1];
+      if (c1 <= c0) return fail("empty stage");
+      out->widest_stage = std::max(out->widest_stage, c1 - c0);
+      for (int c = c0; c < c1; ++c) {
+        // no column of the stage is a row of another one (independence), destinations and rhs rows are private
+        for (int k = p.col_off[c]; k < p.col_off[c + 1]; ++k) {
+          if (p.row_pos[k] >= c0 && p.row_pos[k] < c1) return fail("two columns of a stage are adjacent");
+          if (owner_row[p.row_pos[k]] == s) return fail("two columns of a stage update the same right-hand-side rows");
+        }
+        for (int k = p.col_off[c]; k < p.col_off[c + 1]; ++k) owner_row[p.row_pos[k]] = s;
+        for (int t = p.tri_off[c]; t < p.tri_off[c + 1]; ++t) {
+          int& o = owner_blk[p.tri[t].x];
+          if (o == s * Kf + c) continue;
+          if (o >= s * Kf && o < (s + 1) * Kf) return fail("two columns of a stage update the same block");
+          o = s * Kf + c;
+        }
+      }
+    }
+  }
+  return SLSLAM_OK;
+}
 
 void slslam_po_get_limits(slslam_po_limits* out) {
   if (!out) return;
