@@ -162,6 +162,16 @@ void slslam_lba_batch_destroy(slslam_lba_batch* b);
  * waves).  Pure host arithmetic, usable without a device. */
 int slslam_lba_launch_shape(int32_t num_windows, int32_t max_observations, int32_t max_lines, int32_t resident_ctas,
                             int32_t smem_bytes_per_cta, int32_t* ctas_per_window, int32_t* windows_per_wave);
+/* Host only (no device needed): which kernel slslam_lba_solve would hand this window to -- SLSLAM_ROUTE_TILED (the tiled
+ * solve kernel: <= 32 camera blocks, <= 24 free, <= 32 observations per line), SLSLAM_ROUTE_MOTION_ONLY (one free camera,
+ * every line constant: SLAM::motion_only_ba, reference src/slam.cpp:578-675) or SLSLAM_ROUTE_GENERAL (the general kernel:
+ * the reference's --ba_window_size 20 / 40 shapes).  Returns the route (>= 0) or SLSLAM_ERR_INVALID / SLSLAM_ERR_UNSUPPORTED
+ * (more than max_free_cameras_general free cameras, or a camera observing one line twice in a window of that size). */
+#define SLSLAM_ROUTE_TILED 0
+#define SLSLAM_ROUTE_MOTION_ONLY 1
+#define SLSLAM_ROUTE_GENERAL 2
+int slslam_lba_route(const slslam_lba_desc* desc);
+
 /* Test hook: builds the plan of every window twice -- on the device (the product path) and with the host planner --
  * for the same group size and compares every array bit for bit.  0 = identical, 1 = the device planner deferred to the
  * host planner for this batch, 2 = mismatch (detail[0] window, detail[1] field, detail[2] index), < 0 = error. */

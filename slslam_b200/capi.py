@@ -23,7 +23,7 @@ EXPORTS = [
     "slslam_lba_solve", "slslam_lba_solve_batch", "slslam_lba_solve_batch_device", "slslam_lba_last_timings", "slslam_lba_batch_create", "slslam_lba_batch_solve",
     "slslam_lba_batch_upload_params", "slslam_lba_batch_download", "slslam_lba_batch_info", "slslam_lba_batch_max_active_clusters", "slslam_lba_batch_transfer_bytes", "slslam_lba_batch_phase_cycles", "slslam_lba_batch_plan_cycles", "slslam_lba_batch_destroy",
     "slslam_lba_plan_check", "slslam_lba_launch_shape", "slslam_lba_pipeline_create", "slslam_lba_pipeline_submit", "slslam_lba_pipeline_wait", "slslam_lba_pipeline_destroy",
-    "slslam_ransac_score", "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate", "slslam_po_last_solve_ms", "slslam_po_last_stats", "slslam_po_get_limits", "slslam_po_plan_check",
+    "slslam_ransac_score", "slslam_lba_evaluate", "slslam_po_solve", "slslam_po_solve_trace", "slslam_po_evaluate", "slslam_po_last_solve_ms", "slslam_po_last_stats", "slslam_po_get_limits", "slslam_po_plan_check", "slslam_lba_route",
     "slslam_map_create", "slslam_map_destroy", "slslam_map_add_keyframe", "slslam_map_add_landmarks", "slslam_map_set_poses",
     "slslam_map_get_poses", "slslam_map_get_landmarks", "slslam_map_bundle_adjust", "slslam_map_last_timings", "slslam_map_last_window",
     "slslam_geometry_convert",
@@ -141,6 +141,8 @@ def lib():
         L.slslam_po_last_stats.restype = None
         L.slslam_po_get_limits.argtypes = [C.POINTER(PoLimits)]
         L.slslam_po_get_limits.restype = None
+        L.slslam_lba_route.argtypes = [C.POINTER(LbaDesc)]
+        L.slslam_lba_route.restype = C.c_int32
         L.slslam_po_plan_check.argtypes = [C.POINTER(PoDesc), C.c_int32, C.POINTER(PoPlanInfo)]
         L.slslam_po_plan_check.restype = C.c_int32
         _LIB = L
@@ -428,6 +430,17 @@ def po_last_stats():
     st = PoStats()
     lib().slslam_po_last_stats(C.byref(st))
     return {k: (list(getattr(st, k)) if k == "factor_cycles" else getattr(st, k)) for k, _ in PoStats._fields_}
+
+
+ROUTES = {0: "tiled", 1: "motion_only", 2: "general"}
+
+
+def lba_route(w, **kw):
+    """slslam_lba_route: the kernel a window would go to, decided on the host (no device needed)."""
+    k = lba_desc(w, **kw)
+    rc = lib().slslam_lba_route(C.byref(k.desc))
+    _check(rc if rc < 0 else 0)
+    return ROUTES[rc]
 
 
 def po_plan_check(g, force_columns=False):

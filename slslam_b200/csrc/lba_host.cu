@@ -847,6 +847,23 @@ void slslam_lba_batch_destroy(slslam_lba_batch* b) {
   delete b;
 }
 
+int slslam_lba_route(const slslam_lba_desc* desc) {
+  slslam::set_last_error("");
+  if (!desc) return SLSLAM_ERR_INVALID;
+  const slslam_lba_desc& d = *desc;
+  if (d.num_cameras < 0 || d.num_lines < 0 || d.num_observations < 0 ||
+      (d.num_observations > 0 && (!d.camera_index || !d.line_index || !d.fixed_index))) return SLSLAM_ERR_INVALID;
+  int fc = 0, nf = 0;
+  if (d.observations && validate_desc(d) == SLSLAM_OK && d.max_iterations > 0 && moba_candidate(d, &fc, &nf)) return SLSLAM_ROUTE_MOTION_ONLY;
+  WidePlan wp;
+  bool wide = false;
+  int rc = wide_plan(d, wp, &wide);
+  if (rc != SLSLAM_OK) return rc;
+  if (!wide) return SLSLAM_ROUTE_TILED;
+  rc = wide_plan_tables(d, wp);
+  return rc == SLSLAM_OK ? SLSLAM_ROUTE_GENERAL : rc;
+}
+
 int slslam_lba_solve_batch(int32_t n, const slslam_lba_desc* descs, double* const* params_inout, slslam_summary* summaries_out) {
   slslam::set_last_error("");   // a message left by an earlier call must not be attached to this one
   if (n <= 0 || !descs || !params_inout) return SLSLAM_ERR_INVALID;
